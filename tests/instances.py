@@ -1,0 +1,49 @@
+"""Small seeded Ising instances shared by the tests (built with the oracle's GenerateNeighbors restatement)."""
+import numpy as np
+import scipy.sparse as sps
+
+from oracle import oracle as orc
+
+
+def torus(L, seed=0, fields=False, lo=-2.0, hi=2.0):
+    """L x L periodic square lattice, J ~ U(lo, hi), optional local fields on the diagonal."""
+    rng = np.random.RandomState(seed)
+    n = L * L
+    J = sps.dok_matrix((n, n))
+    for r in range(L):
+        for c in range(L):
+            i = r * L + c
+            for j in (r * L + (c + 1) % L, ((r + 1) % L) * L + c):
+                if i != j and (i, j) not in J and (j, i) not in J:
+                    J[i, j] = rng.uniform(lo, hi)
+    if fields:
+        for i in range(n):
+            J[i, i] = rng.uniform(-1.0, 1.0)
+    maxnb = 4 + (1 if fields else 0)
+    if L == 2:
+        maxnb = 2 + (1 if fields else 0)
+    return J, orc.GenerateNeighbors(n, J, maxnb)
+
+
+def random_graph(n, nedges, seed=0, fields=True):
+    """Irregular sparse graph (rows zero-padded to maxnb, tools.pyx:52-59)."""
+    rng = np.random.RandomState(seed)
+    J = sps.dok_matrix((n, n))
+    deg = np.zeros(n, dtype=int)
+    while J.nnz < nedges:
+        i, j = rng.randint(n, size=2)
+        if i == j or (i, j) in J or (j, i) in J:
+            continue
+        J[i, j] = rng.normal()
+        deg[i] += 1
+        deg[j] += 1
+    if fields:
+        for i in range(0, n, 2):
+            J[i, i] = rng.normal()
+            deg[i] += 1
+    maxnb = int(deg.max())
+    return J, orc.GenerateNeighbors(n, J, maxnb)
+
+
+def random_spins(n, seed):
+    return (2 * np.random.RandomState(seed).randint(2, size=n) - 1).astype(np.int64)
