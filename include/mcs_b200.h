@@ -1,0 +1,170 @@
+/*
+ * mcs_b200.h -- C ABI of libmcs_b200.so: B200-native annealing sweeps behind the
+ * MonteCarloSolvers call surface (dtoconnor/MonteCarloSolvers; paths below are relative to
+ * the reference tree).
+ *
+ * The reference exposes the hot path as module-level Cython `cpdef` functions taking NumPy
+ * buffers; it has no C header of its own.  Each entry point here names the
+ * reference function (file:line) whose loop nest it replaces.  The Python package
+ * `montecarlosolvers_b200` binds these with ctypes and reproduces the reference's positional
+ * signatures on top (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success or a negative
+ *     MCS_E* code, with a human-readable message available from mcs_last_error().
+ *   - "host" pointers are ordinary (ideally pinned, see mcs_host_alloc) CPU memory; copies to
+ *     and from the device happen inside the call.  `mcs_state` keeps a replica batch resident
+ *     in HBM between calls for callers that want to avoid the copies.
+ *   - spins are int8 (+1 / -1).  Replica batches are C-ordered [R][N][P] (replica, site,
+ *     Trotter slice) for PIQMC and [R][N] for SA / SVMC; R = 1 is the reference's single call.
+ *   - the neighbour table is the reference's own format: float64 [N][maxnb][2] =
+ *     (neighbour index stored as a float, coupling), rows zero padded, a self entry is a local
+ *     field (tools.pyx:28-96; consumed at qmc.pyx:114-125, sa.pyx:84-94, svmc.pyx:98-108).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     MCS_ENODEVICE.
+ */
+#ifndef MCS_B200_H
+#define MCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCS_ABI_VERSION 1
+
+enum {
+    MCS_OK = 0,
+    MCS_EINVAL = -1,     /* bad argument (shape, range, NULL)                               */
+    MCS_ENODEVICE = -2,  /* no usable CUDA device / CUDA runtime error (see mcs_last_error) */
+    MCS_EZERODIV = -3,   /* temp * P == 0: the reference raises ZeroDivisionError here
+                            (qmc.c:3030-3034; qmc.pyx has no cdivision)                     */
+    MCS_EUNSUPPORTED = -4, /* valid in the reference but outside this build's kernels      */
+    MCS_ENOMEM = -5
+};
+
+typedef struct mcs_instance mcs_instance; /* compiled Ising instance resident on one GPU   */
+typedef struct mcs_state mcs_state;       /* replica batch resident on the same GPU        */
+
+/* ---- library ------------------------------------------------------------------------- */
+int mcs_abi_version(void);
+const char *mcs_last_error(void);   /* thread-local message of the last failing call       */
+int mcs_device_count(void);         /* 0 when no CUDA device is visible                    */
+
+/* pinned host memory for the batched entry points (pageable memory works, but slower)      */
+void *mcs_host_alloc(size_t bytes);
+void mcs_host_free(void *p);
+
+/* ---- instance compiler ---------------------------------------------------------------
+ * Consumes the table tools.GenerateNeighbors produces (tools.pyx:28-96): drops the zero
+ * padding, splits self entries into fields, graph-colours the interaction graph
+ * (2-colouring when bipartite -- the Santoro torus and Chimera are -- else greedy), sorts
+ * sites by colour and uploads fp32 ELL tables (production kernels) and the fp64 table in
+ * the reference's row order (exact / probe kernels).                                        */
+int mcs_instance_create(const double *nbs, int64_t nspins, int64_t maxnb, int device,
+                        mcs_instance **out);
+void mcs_instance_destroy(mcs_instance *inst);
+/* info[0]=nspins info[1]=maxnb info[2]=ncolors info[3]=max degree (fields excluded)
+ * info[4]=1 if any local field  info[5]=device  info[6]=1 if the LUT kernels apply        */
+int mcs_instance_info(const mcs_instance *inst, int64_t info[8]);
+int mcs_instance_colors(const mcs_instance *inst, int32_t *color /* [nspins] */);
+/* CUDA-event stopwatch on the instance's stream: start ... stop returns milliseconds.      */
+int mcs_timer_start(mcs_instance *inst);
+int mcs_timer_stop(mcs_instance *inst, double *ms);
+int mcs_synchronize(mcs_instance *inst);
+/* number of kernels this instance has launched so far (bench.py's gpu_launches)            */
+int64_t mcs_launch_count(const mcs_instance *inst);
+
+/* ---- resident replica batches -------------------------------------------------------- */
+enum { MCS_KIND_PIQMC = 1, MCS_KIND_SA = 2, MCS_KIND_SVMC = 3 };
+/* P is the number of Trotter slices (PIQMC, 2 <= P <= 64) and must be 1 for SA / SVMC.     */
+int mcs_state_create(mcs_instance *inst, int kind, int64_t R, int64_t P, mcs_state **out);
+void mcs_state_destroy(mcs_state *st);
+/* spins: int8 [R][N][P] (PIQMC) or [R][N] (SA); angles: float64 [R][N] (SVMC)              */
+int mcs_state_upload_spins(mcs_state *st, const int8_t *host);
+int mcs_state_download_spins(mcs_state *st, int8_t *host);
+int mcs_state_upload_angles(mcs_state *st, const double *host);
+int mcs_state_download_angles(mcs_state *st, double *host);
+/* replica r starts from Philox(seed, replica_offset + r) spins, identical across slices
+ * (SURVEY.md 8d cfg3); SVMC states start at theta = pi/2.                                   */
+int mcs_state_init_random(mcs_state *st, uint64_t seed, uint64_t replica_offset);
+/* fixed-order fp64 classical energies, bit-identical to the oracle's definition of
+ * tools.ClassicalIsingEnergy (tools.pyx:99-118): out is [R][P] (PIQMC) or [R] (SA).        */
+int mcs_state_energies(mcs_state *st, double *host_out);
+/* SVMC energy B*(sum J cos cos + sum h cos) - A*sum sin per replica, out [R]               */
+int mcs_state_svmc_energies(mcs_state *st, double a, double b, double *host_out);
+
+/* ---- production sweeps (coloured, Philox-driven; statistical parity) ------------------
+ * mcs_piqmc_sweeps replaces the loop nest of qmc.QuantumAnneal (qmc.pyx:93-143) and, with
+ * global_moves != 0, of qmc.QuantumAnnealGlobal (qmc.pyx:358-438): for every schedule step
+ * `mcsteps` sweeps; a sweep attempts every (site, slice) once, colour class by colour class
+ * and Trotter parity by parity, with J_perp = -(P*T/2) ln tanh(A/(P*T)) (qmc.pyx:95) and the
+ * Metropolis rule of qmc.pyx:140-143.  `temp` is a C float as in the reference (qmc.pyx:28).
+ * sweep_offset numbers the first sweep for the counter-based RNG so that a schedule may be
+ * split over several calls (checkpoint / resume = slicing the schedule).                    */
+int mcs_piqmc_sweeps(mcs_state *st, const double *A_sched, const double *B_sched, int64_t schedsize,
+                     int mcsteps, float temp, int global_moves, uint64_t seed,
+                     uint64_t replica_offset, uint64_t sweep_offset);
+/* sa.Anneal (sa.pyx:66-101): Metropolis sweeps at temperature sched[itemp]                 */
+int mcs_sa_sweeps(mcs_state *st, const double *sched, int64_t schedsize, int mcsteps, uint64_t seed,
+                  uint64_t replica_offset, uint64_t sweep_offset);
+/* svmc.SpinVectorMonteCarlo (svmc.pyx:78-117); tf != 0: SpinVectorMonteCarloTF (:181-229)  */
+int mcs_svmc_sweeps(mcs_state *st, const double *A_sched, const double *B_sched, int64_t schedsize,
+                    int mcsteps, float temp, int tf, uint64_t seed, uint64_t replica_offset,
+                    uint64_t sweep_offset);
+
+/* one-shot host-buffer forms (upload, sweep, download [, energies]) -- what the Python
+ * drop-ins call.  energies_out may be NULL.                                                 */
+int mcs_piqmc_anneal(mcs_instance *inst, const double *A_sched, const double *B_sched,
+                     int64_t schedsize, int mcsteps, float temp, int8_t *confs /* [R][N][P] */,
+                     int64_t R, int64_t P, int global_moves, uint64_t seed, uint64_t replica_offset,
+                     double *energies_out /* [R][P] */);
+int mcs_sa_anneal(mcs_instance *inst, const double *sched, int64_t schedsize, int mcsteps,
+                  int8_t *svec /* [R][N] */, int64_t R, uint64_t seed, uint64_t replica_offset,
+                  double *energies_out /* [R] */);
+int mcs_svmc_anneal(mcs_instance *inst, const double *A_sched, const double *B_sched, int64_t schedsize,
+                    int mcsteps, float temp, double *svec /* [R][N] */, int64_t R, int tf, uint64_t seed,
+                    uint64_t replica_offset);
+
+/* ---- exact (sequential-order) kernels: bit-exact replay of the reference ---------------
+ * One GPU thread per replica runs the reference's own visiting order in fp64: Fisher-Yates
+ * shuffle from a glibc rand() stream (qmc.pyx:102-108), sequential Metropolis visits in table
+ * order without FMA contraction.  libc_seeds[r] plays the role of srand(seed) before the
+ * r-th reference call; if rand_stream != NULL it is used instead (int32 [R][stream_len] of
+ * recorded rand() outputs) and consumed[r] returns how many values replica r used.
+ * lookuptable != NULL selects the Dissipative variants (qmc.pyx:149-278, 444-609).          */
+int mcs_exact_qmc(mcs_instance *inst, const double *A_sched, const double *B_sched, int64_t schedsize,
+                  int mcsteps, float temp, const double *lookuptable, int8_t *confs /* [R][N][P] */,
+                  int64_t R, int64_t P, int global_moves, const uint32_t *libc_seeds /* [R] */,
+                  const int32_t *rand_stream, int64_t stream_len, int64_t *consumed /* [R] or NULL */);
+/* sa.Anneal / Anneal_parallel (sa.pyx:19-101, 201-284); randuni != NULL: sa.AnnealMA
+ * (sa.pyx:108-193), float64 [schedsize][mcsteps][N] shared by all replicas                  */
+int mcs_exact_sa(mcs_instance *inst, const double *sched, int64_t schedsize, int mcsteps,
+                 int8_t *svec /* [R][N] */, int64_t R, const uint32_t *libc_seeds, const double *randuni,
+                 int64_t *consumed);
+/* svmc.SpinVectorMonteCarlo[TF] (svmc.pyx:21-229) and ...Compact (:455-554): randuni is the
+ * float64 [schedsize][mcsteps][N][2] array the reference draws from np.random up front
+ * (svmc.pyx:70), shared by all replicas.  serial_stream != 0 reproduces the Compact form's single
+ * rand() stream running through the reads one after another (libc_seeds[0] only); randuni ==
+ * NULL with tf != 0 is SpinVectorMonteCarloTFCompact (:561-674, all uniforms from rand()).  */
+int mcs_exact_svmc(mcs_instance *inst, const double *A_sched, const double *B_sched, int64_t schedsize,
+                   int mcsteps, float temp, double *svec /* [R][N] */, int64_t R, int tf,
+                   const uint32_t *libc_seeds, const double *randuni, int serial_stream);
+
+/* ---- probes (parity tier a): fp64, reference association order, no FMA ---------------- */
+/* ediff of every (site, slice) visit for frozen configurations (qmc.pyx:112-138);
+ * out float64 [R][N][P]                                                                     */
+int mcs_probe_qmc_delta_e(mcs_instance *inst, double a, double b, float temp, const int8_t *confs,
+                          int64_t R, int64_t P, double *out);
+/* world-line flip ediff (qmc.pyx:416-431); out float64 [R][N]                              */
+int mcs_probe_qmc_delta_e_global(mcs_instance *inst, double b, const int8_t *confs, int64_t R,
+                                 int64_t P, double *out);
+/* sa.pyx:84-94; out float64 [R][N]                                                         */
+int mcs_probe_sa_delta_e(mcs_instance *inst, const int8_t *svec, int64_t R, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCS_B200_H */

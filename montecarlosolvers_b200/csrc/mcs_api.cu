@@ -1,0 +1,194 @@
+// mcs_api.cu -- extern "C" entry points over resident replica batches (see include/mcs_b200.h).
+#include <cmath>
+
+#include "mcs_common.cuh"
+
+// implemented next to their kernels
+int mcs_piqmc_pack(mcs_state *st, const int8_t *d_in);
+int mcs_piqmc_unpack(mcs_state *st, int8_t *d_out);
+int mcs_piqmc_init(mcs_state *st, uint64_t seed, uint64_t replica_offset);
+int mcs_piqmc_energy(mcs_state *st, double *d_out);
+int mcs_sa_pack(mcs_state *st, const int8_t *d_in);
+int mcs_sa_unpack(mcs_state *st, int8_t *d_out);
+int mcs_sa_init(mcs_state *st, uint64_t seed, uint64_t replica_offset);
+int mcs_sa_energy(mcs_state *st, double *d_out);
+int mcs_svmc_pack(mcs_state *st, const double *d_in);
+int mcs_svmc_unpack(mcs_state *st, double *d_out);
+int mcs_svmc_init(mcs_state *st);
+int mcs_svmc_energy(mcs_state *st, double a, double b, double *d_out);
+
+static size_t spin_bytes(const mcs_state *st) { return (size_t)st->R * st->inst->N * st->P; }
+
+extern "C" int mcs_state_upload_spins(mcs_state *st, const int8_t *host)
+{
+    MCS_REQUIRE(st && host, MCS_EINVAL, "mcs_state_upload_spins: NULL argument");
+    MCS_REQUIRE(st->kind == MCS_KIND_PIQMC || st->kind == MCS_KIND_SA, MCS_EINVAL,
+                "mcs_state_upload_spins: state holds angles, not spins");
+    MCS_CUDA(cudaSetDevice(st->inst->device));
+    const size_t bytes = spin_bytes(st);
+    MCS_TRY(mcs_state_reserve_stage(st, bytes));
+    MCS_CUDA(cudaMemcpyAsync(st->d_stage, host, bytes, cudaMemcpyHostToDevice, st->inst->stream));
+    return st->kind == MCS_KIND_PIQMC ? mcs_piqmc_pack(st, (const int8_t *)st->d_stage)
+                                      : mcs_sa_pack(st, (const int8_t *)st->d_stage);
+}
+
+extern "C" int mcs_state_download_spins(mcs_state *st, int8_t *host)
+{
+    MCS_REQUIRE(st && host, MCS_EINVAL, "mcs_state_download_spins: NULL argument");
+    MCS_REQUIRE(st->kind == MCS_KIND_PIQMC || st->kind == MCS_KIND_SA, MCS_EINVAL,
+                "mcs_state_download_spins: state holds angles, not spins");
+    MCS_CUDA(cudaSetDevice(st->inst->device));
+    const size_t bytes = spin_bytes(st);
+    MCS_TRY(mcs_state_reserve_stage(st, bytes));
+    MCS_TRY(st->kind == MCS_KIND_PIQMC ? mcs_piqmc_unpack(st, (int8_t *)st->d_stage)
+                                       : mcs_sa_unpack(st, (int8_t *)st->d_stage));
+    MCS_CUDA(cudaMemcpyAsync(host, st->d_stage, bytes, cudaMemcpyDeviceToHost, st->inst->stream));
+    MCS_CUDA(cudaStreamSynchronize(st->inst->stream));
+    return MCS_OK;
+}
+
+extern "C" int mcs_state_upload_angles(mcs_state *st, const double *host)
+{
+    MCS_REQUIRE(st && host, MCS_EINVAL, "mcs_state_upload_angles: NULL argument");
+    MCS_REQUIRE(st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_state_upload_angles: not an SVMC state");
+    MCS_CUDA(cudaSetDevice(st->inst->device));
+    const size_t bytes = (size_t)st->R * st->inst->N * sizeof(double);
+    MCS_TRY(mcs_state_reserve_stage(st, bytes));
+    MCS_CUDA(cudaMemcpyAsync(st->d_stage, host, bytes, cudaMemcpyHostToDevice, st->inst->stream));
+    return mcs_svmc_pack(st, (const double *)st->d_stage);
+}
+
+extern "C" int mcs_state_download_angles(mcs_state *st, double *host)
+{
+    MCS_REQUIRE(st && host, MCS_EINVAL, "mcs_state_download_angles: NULL argument");
+    MCS_REQUIRE(st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_state_download_angles: not an SVMC state");
+    MCS_CUDA(cudaSetDevice(st->inst->device));
+    const size_t bytes = (size_t)st->R * st->inst->N * sizeof(double);
+    MCS_TRY(mcs_state_reserve_stage(st, bytes));
+    MCS_TRY(mcs_svmc_unpack(st, (double *)st->d_stage));
+    MCS_CUDA(cudaMemcpyAsync(host, st->d_stage, bytes, cudaMemcpyDeviceToHost, st->inst->stream));
+    MCS_CUDA(cudaStreamSynchronize(st->inst->stream));
+    return MCS_OK;
+}
+
+extern "C" int mcs_state_init_random(mcs_state *st, uint64_t seed, uint64_t replica_offset)
+{
+    MCS_REQUIRE(st, MCS_EINVAL, "mcs_state_init_random: NULL state");
+    MCS_CUDA(cudaSetDevice(st->inst->device));
+    if (st->kind == MCS_KIND_PIQMC) return mcs_piqmc_init(st, seed, replica_offset);
+    if (st->kind == MCS_KIND_SA) return mcs_sa_init(st, seed, replica_offset);
+    return mcs_svmc_init(st);
+}
+
+extern "C" int mcs_state_energies(mcs_state *st, double *host_out)
+{
+    MCS_REQUIRE(st && host_out, MCS_EINVAL, "mcs_state_energies: NULL argument");
+    MCS_REQUIRE(st->kind == MCS_KIND_PIQMC || st->kind == MCS_KIND_SA, MCS_EINVAL,
+                "mcs_state_energies: use mcs_state_svmc_energies for SVMC states");
+    MCS_CUDA(cudaSetDevice(st->inst->device));
+    const size_t bytes = (size_t)st->R * st->P * sizeof(double);
+    double *d_out = nullptr;
+    MCS_CUDA(cudaMalloc((void **)&d_out, bytes));
+    int rc = st->kind == MCS_KIND_PIQMC ? mcs_piqmc_energy(st, d_out) : mcs_sa_energy(st, d_out);
+    cudaError_t e = cudaSuccess;
+    if (rc == MCS_OK) {
+        e = cudaMemcpyAsync(host_out, d_out, bytes, cudaMemcpyDeviceToHost, st->inst->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st->inst->stream);
+    }
+    cudaFree(d_out);
+    if (rc != MCS_OK) return rc;
+    MCS_CUDA(e);
+    return MCS_OK;
+}
+
+extern "C" int mcs_state_svmc_energies(mcs_state *st, double a, double b, double *host_out)
+{
+    MCS_REQUIRE(st && host_out, MCS_EINVAL, "mcs_state_svmc_energies: NULL argument");
+    MCS_REQUIRE(st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_state_svmc_energies: not an SVMC state");
+    MCS_CUDA(cudaSetDevice(st->inst->device));
+    const size_t bytes = (size_t)st->R * sizeof(double);
+    double *d_out = nullptr;
+    MCS_CUDA(cudaMalloc((void **)&d_out, bytes));
+    int rc = mcs_svmc_energy(st, a, b, d_out);
+    cudaError_t e = cudaSuccess;
+    if (rc == MCS_OK) {
+        e = cudaMemcpyAsync(host_out, d_out, bytes, cudaMemcpyDeviceToHost, st->inst->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st->inst->stream);
+    }
+    cudaFree(d_out);
+    if (rc != MCS_OK) return rc;
+    MCS_CUDA(e);
+    return MCS_OK;
+}
+
+extern "C" int mcs_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
+                                int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
+{
+    MCS_REQUIRE(st && st->kind == MCS_KIND_PIQMC, MCS_EINVAL, "mcs_piqmc_sweeps: not a PIQMC state");
+    MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_piqmc_sweeps: bad schedule");
+    return mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, sweep_offset);
+}
+
+extern "C" int mcs_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcsteps, uint64_t seed,
+                             uint64_t replica_offset, uint64_t sweep_offset)
+{
+    MCS_REQUIRE(st && st->kind == MCS_KIND_SA, MCS_EINVAL, "mcs_sa_sweeps: not an SA state");
+    MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || sched), MCS_EINVAL, "mcs_sa_sweeps: bad schedule");
+    return mcs_launch_sa_sweeps(st, sched, S, mcsteps, seed, replica_offset, sweep_offset);
+}
+
+extern "C" int mcs_svmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
+                               int tf, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
+{
+    MCS_REQUIRE(st && st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_svmc_sweeps: not an SVMC state");
+    MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_svmc_sweeps: bad schedule");
+    return mcs_launch_svmc_sweeps(st, A, B, S, mcsteps, temp, tf, seed, replica_offset, sweep_offset);
+}
+
+// ---- one-shot host-buffer forms ----------------------------------------------------------------
+namespace {
+struct StateGuard {
+    mcs_state *st = nullptr;
+    ~StateGuard() { mcs_state_destroy(st); }
+};
+} // namespace
+
+extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const double *B, int64_t S, int mcsteps,
+                                float temp, int8_t *confs, int64_t R, int64_t P, int global_moves, uint64_t seed,
+                                uint64_t replica_offset, double *energies_out)
+{
+    MCS_REQUIRE(inst && confs, MCS_EINVAL, "mcs_piqmc_anneal: NULL argument");
+    MCS_REQUIRE((double)temp * (double)P != 0.0 || S == 0, MCS_EZERODIV, "float division");
+    StateGuard g;
+    MCS_TRY(mcs_state_create(inst, MCS_KIND_PIQMC, R, P, &g.st));
+    MCS_TRY(mcs_state_upload_spins(g.st, confs));
+    MCS_TRY(mcs_piqmc_sweeps(g.st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, 0));
+    MCS_TRY(mcs_state_download_spins(g.st, confs));
+    if (energies_out) MCS_TRY(mcs_state_energies(g.st, energies_out));
+    return MCS_OK;
+}
+
+extern "C" int mcs_sa_anneal(mcs_instance *inst, const double *sched, int64_t S, int mcsteps, int8_t *svec, int64_t R,
+                             uint64_t seed, uint64_t replica_offset, double *energies_out)
+{
+    MCS_REQUIRE(inst && svec, MCS_EINVAL, "mcs_sa_anneal: NULL argument");
+    StateGuard g;
+    MCS_TRY(mcs_state_create(inst, MCS_KIND_SA, R, 1, &g.st));
+    MCS_TRY(mcs_state_upload_spins(g.st, svec));
+    MCS_TRY(mcs_sa_sweeps(g.st, sched, S, mcsteps, seed, replica_offset, 0));
+    MCS_TRY(mcs_state_download_spins(g.st, svec));
+    if (energies_out) MCS_TRY(mcs_state_energies(g.st, energies_out));
+    return MCS_OK;
+}
+
+extern "C" int mcs_svmc_anneal(mcs_instance *inst, const double *A, const double *B, int64_t S, int mcsteps,
+                               float temp, double *svec, int64_t R, int tf, uint64_t seed, uint64_t replica_offset)
+{
+    MCS_REQUIRE(inst && svec, MCS_EINVAL, "mcs_svmc_anneal: NULL argument");
+    StateGuard g;
+    MCS_TRY(mcs_state_create(inst, MCS_KIND_SVMC, R, 1, &g.st));
+    MCS_TRY(mcs_state_upload_angles(g.st, svec));
+    MCS_TRY(mcs_svmc_sweeps(g.st, A, B, S, mcsteps, temp, tf, seed, replica_offset, 0));
+    MCS_TRY(mcs_state_download_angles(g.st, svec));
+    return MCS_OK;
+}

@@ -1,0 +1,190 @@
+// mcs_common.cuh -- internal declarations shared by the translation units of libmcs_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mcs_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+void mcs_set_error(const char *fmt, ...);
+int mcs_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define MCS_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return mcs_cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define MCS_REQUIRE(cond, code, ...)    \
+    do {                                \
+        if (!(cond)) {                  \
+            mcs_set_error(__VA_ARGS__); \
+            return (code);              \
+        }                               \
+    } while (0)
+
+#define MCS_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != MCS_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// compiled instance (see mcs_instance.cu)
+// ------------------------------------------------------------------------------------------
+struct mcs_instance {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t N = 0, maxnb = 0;
+    int ncolors = 0;
+    int maxdeg = 0;      // max number of quadratic neighbours of a site (fields excluded)
+    int dpad = 1;        // row length of the ELL tables (>= 1)
+    bool has_field = false;
+    bool lut_ok = false; // (maxdeg + has_field + 2) <= 8 planes: the LUT kernels apply
+    int64_t launches = 0;
+
+    // host copies
+    std::vector<int32_t> color;       // [N]
+    std::vector<int32_t> order;       // [N] sites sorted by colour (stable in site index)
+    std::vector<int32_t> color_start; // [ncolors + 1] offsets into order
+
+    // device tables
+    int32_t *d_tab_idx = nullptr; // [N][maxnb]  reference table, neighbour index column (int(nbs[..,0]))
+    double *d_tab_J = nullptr;    // [N][maxnb]  reference table, coupling column (fp64, row order kept)
+    int32_t *d_ell_idx = nullptr; // [N][dpad]   quadratic neighbours, padded with the site itself
+    float *d_ell_J = nullptr;     // [N][dpad]   fp32 couplings, padded with 0
+    float *d_h = nullptr;         // [N]         fp32 local fields
+    int32_t *d_order = nullptr;   // [N]
+};
+
+struct mcs_state {
+    mcs_instance *inst = nullptr;
+    int kind = 0;
+    int64_t R = 0, P = 1;
+    int64_t Rpad = 0;        // PIQMC / SVMC: R rounded up to a multiple of 32 (lanes = replicas)
+    int64_t G = 0;           // SA: number of 32-replica words per site
+    uint64_t *d_W = nullptr; // PIQMC  [N][Rpad]  bit k = slice k, bit set <=> spin -1
+    uint32_t *d_V = nullptr; // SA     [N][G]     bit b of word g = replica 32 g + b, bit set <=> spin -1
+    float *d_theta = nullptr; // SVMC  [N][Rpad]
+    float *d_cosz = nullptr;  // SVMC  [N][Rpad]  cos(theta)
+    void *d_stage = nullptr;  // staging buffer for host <-> device conversion
+    size_t stage_bytes = 0;
+};
+
+int mcs_state_reserve_stage(mcs_state *st, size_t bytes);
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  Key = the user's 64-bit seed
+// (uniform over the launch); counter = (replica or word index, site, sweep, call tag), so a
+// replica's stream does not depend on launch geometry or on how replicas are sharded over GPUs.
+// ------------------------------------------------------------------------------------------
+#define MCS_PHILOX_M0 0xD2511F53u
+#define MCS_PHILOX_M1 0xCD9E8D57u
+#define MCS_PHILOX_W0 0x9E3779B9u
+#define MCS_PHILOX_W1 0xBB67AE85u
+
+__host__ __device__ __forceinline__ void mcs_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                           uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(MCS_PHILOX_M0, c0), lo0 = MCS_PHILOX_M0 * c0;
+        uint32_t hi1 = __umulhi(MCS_PHILOX_M1, c2), lo1 = MCS_PHILOX_M1 * c2;
+#else
+        uint64_t p0 = (uint64_t)MCS_PHILOX_M0 * c0, p1 = (uint64_t)MCS_PHILOX_M1 * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += MCS_PHILOX_W0;
+        k1 += MCS_PHILOX_W1;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// Same generator with the ten round keys precomputed on the host (rk[2r] = k0 + r W0,
+// rk[2r+1] = k1 + r W1).  The keys then sit in the kernel-parameter constant bank and feed the
+// 3-input XOR directly: 4 instructions per round (2 IMAD.WIDE + 2 LOP3) instead of 6.
+struct mcs_philox_keys {
+    uint32_t rk[20];
+};
+
+inline mcs_philox_keys mcs_philox_expand(uint64_t seed)
+{
+    mcs_philox_keys k;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        k.rk[2 * r] = k0;
+        k.rk[2 * r + 1] = k1;
+        k0 += MCS_PHILOX_W0;
+        k1 += MCS_PHILOX_W1;
+    }
+    return k;
+}
+
+__device__ __forceinline__ void mcs_philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     const mcs_philox_keys &k, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(MCS_PHILOX_M0, c0), lo0 = MCS_PHILOX_M0 * c0;
+        const uint32_t hi1 = __umulhi(MCS_PHILOX_M1, c2), lo1 = MCS_PHILOX_M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k.rk[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ k.rk[2 * r + 1];
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// call tags (counter word 3): which draw inside one (replica, site, sweep)
+enum {
+    MCS_TAG_GROUP0 = 0,      // 0..15: PIQMC slice groups / SA bit groups
+    MCS_TAG_LAST_SLICE = 16, // PIQMC odd-P closing slice
+    MCS_TAG_GLOBAL = 17,     // PIQMC world-line move
+    MCS_TAG_SVMC = 18,       // SVMC proposal + acceptance
+    MCS_TAG_INIT = 0x40000000u
+};
+
+// Metropolis acceptance threshold: the move is accepted iff a uniform 32-bit draw u satisfies
+// u <= T.  dE <= 0 -> always (qmc.pyx:140-141); otherwise P(accept) = ceil(p 2^32)/2^32 with
+// p = exp(-dE/teff) (qmc.pyx:142), floored at 2^-32 (the reference's own floor is 2^-31: it
+// compares exp(..) > rand()/RAND_MAX and rand() returns 0 once in 2^31 draws).
+// nl2e_over_t = -log2(e)/teff.  NaN dE (inf - inf at A = 0) -> never, like the reference.
+__device__ __forceinline__ uint32_t mcs_accept_threshold(float dE, float nl2e_over_t)
+{
+    if (dE <= 0.0f) return 0xFFFFFFFFu;
+    float t = ceilf(exp2f(dE * nl2e_over_t) * 4294967296.0f);
+    if (!(t >= 1.0f)) return 0u;
+    if (t >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)t - 1u;
+}
+
+// kernels launchers implemented in the other translation units
+int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
+                            int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset);
+int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcsteps, uint64_t seed,
+                         uint64_t replica_offset, uint64_t sweep_offset);
+int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
+                           int tf, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset);

@@ -1,0 +1,505 @@
+// mcs_piqmc.cu -- path-integral QMC sweeps on bit-packed world lines (sm_100a).
+//
+// Replaces the loop nest of qmc.QuantumAnneal (reference qmc.pyx:93-143) and
+// qmc.QuantumAnnealGlobal (qmc.pyx:358-438).
+//
+// Data layout in HBM:  W[site][replica] : uint64, bit k = Trotter slice k of that site's world
+// line in that replica, bit set <=> spin -1.  Replica is the fastest axis, so the 32 lanes of a
+// warp (= 32 consecutive replicas of ONE site) read and write 256 contiguous bytes, every
+// coupling of the site is warp-uniform, and the Trotter neighbours of slice k are bits k+-1 of
+// the same register (a rotate).
+//
+// One launch = one colour class of one sweep.  A warp owns (site, 32 replicas); each lane
+//   1. XORs its word with its <= 6 neighbour words: plane j bit k = "slice k is anti-aligned with
+//      neighbour j" (+ the word itself as the field plane, + two rotated XORs for slices k-1, k+1);
+//   2. the warp has precomputed, for its site and this schedule step, the Metropolis acceptance
+//      threshold of every one of the 2^(planes) sign patterns into shared memory (all lanes of a
+//      warp share it -- that is why replicas, not sites, sit on the lanes);
+//   3. even slices, then odd slices (then slice P-1 alone when P is odd -- the ring is not
+//      2-colourable): a PRMT sign-replicate transposes the planes into one byte-wide pattern index
+//      per slice, one LDS fetches the threshold, one Philox4x32-10 call decides four slices.
+// In-plane neighbours belong to other colour classes and are frozen during the launch, so every
+// attempt sees exactly the state a sequential sweep would (detailed balance per attempt).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "mcs_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 4; // warps per CTA
+
+struct PiqmcPass {
+    uint64_t *W;
+    const int32_t *ell_idx;
+    const float *ell_J;
+    const float *h;
+    const int32_t *sites; // the colour class
+    int nsites;
+    int dpad;
+    int nq;      // quadratic planes in use (= maxdeg)
+    int field;   // 1 if the field plane is in use
+    int G;       // warps per site = Rpad / 32
+    long long Rpad;
+    int P;
+    float bcoef;       // -2 B         (qmc.pyx:96)
+    float jperp2;      // 2 J_perp     (qmc.pyx:95,137-138)
+    float nl2e_over_t; // -log2(e)/teff
+    mcs_philox_keys keys; // ten Philox round keys, read straight from the parameter constant bank
+    uint32_t sweep_lo, sweep_hi;
+    uint32_t replica_offset;
+    int global_moves;
+};
+
+__device__ __forceinline__ uint32_t prmt_sign_bytes(uint32_t v)
+{
+    // byte i of the result = 0xFF if bit 8i+7 of v is set else 0x00 (PRMT with sign replication)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0xBA98u));
+    return r;
+}
+
+__device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
+{
+    return ((w << 1) | (w >> (P - 1))) & mask; // bit k <- bit k-1 (ring of P slices)
+}
+__device__ __forceinline__ uint64_t rotr_ring(uint64_t w, int P, uint64_t mask)
+{
+    return ((w >> 1) | (w << (P - 1))) & mask; // bit k <- bit k+1
+}
+
+__device__ __forceinline__ uint32_t prmt_byte(uint32_t v, int i)
+{
+    // byte i of v, zero extended (one PRMT; the second operand supplies the zero bytes)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0x4440u | (uint32_t)i));
+    return r;
+}
+
+// Pattern-index bits live at byte positions SH .. SH+NPL+1.  With at most 6 planes the index is
+// stored pre-multiplied by 4 (SH = 2) so that the extracted byte IS the shared-memory byte offset.
+template <int NPL>
+struct LutGeom {
+    static constexpr int SH = (NPL + 2 <= 6) ? 2 : 0;
+    static constexpr int ENT = 1 << (NPL + 2);
+};
+
+// One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in
+// `allowed`, against thresholds in lut[].  Returns the flip mask.
+template <int NPL, int PARITY>
+__device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w, int P, uint64_t pmask,
+                                          uint64_t allowed, const uint32_t *lut, uint32_t c0, uint32_t c1,
+                                          uint32_t c2, uint32_t c3hi, const mcs_philox_keys &keys)
+{
+    constexpr int SH = LutGeom<NPL>::SH;
+    const uint64_t tl = w ^ rotl_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k-1
+    const uint64_t tr = w ^ rotr_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k+1
+    uint32_t flip[2] = {0u, 0u};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int g = 1 - PARITY; g < 8; g += 2) { // slices 32*half + 8i + 7 - g, parity of 7-g == PARITY
+            if (32 * half + 7 - g >= P) continue;   // whole group beyond the last slice (warp-uniform)
+            uint32_t acc = 0;
+#pragma unroll
+            for (int p = 0; p < NPL + 2; ++p) {
+                const uint64_t plane = p < NPL ? pl[p < NPL ? p : 0] : (p == NPL ? tl : tr);
+                const uint32_t v = (uint32_t)(plane >> (32 * half)) << g;
+                acc |= prmt_sign_bytes(v) & (0x01010101u << (p + SH));
+            }
+            uint32_t rnd[4];
+            mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(half * 8 + g), keys, rnd);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t off = prmt_byte(acc, i); // = 4 * idx when SH == 2, idx otherwise
+                const uint32_t T = SH == 2 ? *(const uint32_t *)((const char *)lut + off) : lut[off];
+                if (rnd[i] <= T) flip[half] |= 1u << (8 * i + 7 - g);
+            }
+        }
+    }
+    return (((uint64_t)flip[1] << 32) | flip[0]) & allowed;
+}
+
+// WARPS warps per CTA, all working on the SAME site (WARPS*32 consecutive replicas), so the
+// threshold table is built once per CTA at a compile-time shared-memory address.
+template <int NPL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
+{
+    constexpr int ENT = LutGeom<NPL>::ENT;
+    __shared__ uint32_t s_lut[ENT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpg = a.G / WARPS; // CTAs per site
+    const int site = __ldg(&a.sites[blockIdx.x / cpg]);
+    const long long r = ((long long)(blockIdx.x % cpg) * WARPS + warp) * 32 + lane;
+
+    // ---- per-site coefficients (CTA-uniform) and the acceptance-threshold table ---------------
+    float c[NPL];
+    int nb[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        if (j < a.nq) {
+            nb[j] = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+            c[j] = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+        } else {
+            nb[j] = site;
+            c[j] = (a.field && j == a.nq) ? a.bcoef * __ldg(&a.h[site]) : 0.0f;
+        }
+    }
+    for (int e = threadIdx.x; e < ENT; e += WARPS * 32) {
+        float dE = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) dE += ((e >> j) & 1) ? -c[j] : c[j];
+        const int anti = ((e >> NPL) & 1) + ((e >> (NPL + 1)) & 1); // anti-aligned Trotter neighbours
+        dE += a.jperp2 * (float)(2 - 2 * anti);
+        s_lut[e] = mcs_accept_threshold(dE, a.nl2e_over_t);
+    }
+
+    // ---- this lane's world line and its in-plane anti-alignment planes ------------------------
+    const int P = a.P;
+    const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
+    uint64_t w = a.W[(long long)site * a.Rpad + r];
+    uint64_t pl[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        if (j < a.nq)
+            pl[j] = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
+        else
+            pl[j] = (a.field && j == a.nq) ? w : 0ull; // field plane: bit set <=> s = -1
+    }
+    if (WARPS == 1)
+        __syncwarp();
+    else
+        __syncthreads();
+    const uint32_t *lut = s_lut;
+
+    const uint32_t c0 = a.replica_offset + (uint32_t)r, c1 = (uint32_t)site, c2 = a.sweep_lo;
+    const uint32_t c3hi = a.sweep_hi << 8;
+    const bool oddP = (P & 1) != 0;
+    uint64_t even_allowed = 0x5555555555555555ull & pmask;
+    if (oddP) even_allowed &= ~(1ull << (P - 1)); // slice P-1 neighbours slice 0: handled alone below
+    const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
+
+    w ^= phase<NPL, 0>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys);
+    w ^= phase<NPL, 1>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys);
+    if (oddP) {
+        const int k = P - 1;
+        const uint64_t tl = w ^ rotl_ring(w, P, pmask), tr = w ^ rotr_ring(w, P, pmask);
+        uint32_t idx = 0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) idx |= (uint32_t)((pl[j] >> k) & 1ull) << j;
+        idx |= (uint32_t)((tl >> k) & 1ull) << NPL;
+        idx |= (uint32_t)((tr >> k) & 1ull) << (NPL + 1);
+        uint32_t rnd[4];
+        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
+        if (rnd[0] <= lut[idx]) w ^= 1ull << k;
+    }
+
+    // ---- world-line move: flip all P slices of this site (qmc.pyx:405-438) ---------------------
+    if (a.global_moves) {
+        float dE = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            uint64_t x;
+            if (j < a.nq)
+                x = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
+            else
+                x = (a.field && j == a.nq) ? w : 0ull;
+            dE += c[j] * (float)(P - 2 * __popcll(x));
+        }
+        uint32_t rnd[4];
+        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
+        if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
+    }
+    a.W[(long long)site * a.Rpad + r] = w;
+}
+
+// ------------------------------------------------------------------------------------------
+// General-degree pass (any sparse graph): same layout and phases, but the energy difference of
+// each slice is accumulated directly over the ELL row instead of looked up.  Used when a site has
+// more sign patterns than the 256-entry table (maxdeg + field > 6).
+// ------------------------------------------------------------------------------------------
+template <int PARITY>
+__device__ __forceinline__ uint64_t phase_direct(const PiqmcPass &a, int site, long long r, uint64_t w, int P,
+                                                 uint64_t pmask, uint64_t allowed, uint32_t c0, uint32_t c1,
+                                                 uint32_t c2, uint32_t c3hi)
+{
+    const uint64_t tl = w ^ rotl_ring(w, P, pmask);
+    const uint64_t tr = w ^ rotr_ring(w, P, pmask);
+    const float hc = a.field ? a.bcoef * __ldg(&a.h[site]) : 0.0f;
+    float e[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const int k = 2 * q + PARITY;
+        const int anti = (int)((tl >> k) & 1ull) + (int)((tr >> k) & 1ull);
+        e[q] = a.jperp2 * (float)(2 - 2 * anti) + (((w >> k) & 1ull) ? -hc : hc);
+    }
+    for (int j = 0; j < a.dpad; ++j) {
+        const float cj = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+        if (cj == 0.0f) continue; // padding (warp-uniform: same site on every lane)
+        const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+        const uint64_t x = w ^ a.W[(long long)nbj * a.Rpad + r];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const int k = 2 * q + PARITY;
+            const uint32_t sgn = (uint32_t)((x >> k) & 1ull) << 31;
+            e[q] += __uint_as_float(__float_as_uint(cj) ^ sgn);
+        }
+    }
+    uint64_t flip = 0;
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+        if (8 * q4 + PARITY >= P) continue;
+        uint32_t rnd[4];
+        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(PARITY * 8 + q4), a.keys, rnd);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = 4 * q4 + i;
+            if (rnd[i] <= mcs_accept_threshold(e[q], a.nl2e_over_t)) flip |= 1ull << (2 * q + PARITY);
+        }
+    }
+    return flip & allowed;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) piqmc_direct_pass_kernel(const __grid_constant__ PiqmcPass a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kWarps + warp;
+    if (item >= (long long)a.nsites * a.G) return;
+    const int site = a.sites[item / a.G];
+    const long long r = (item % a.G) * 32 + lane;
+    const int P = a.P;
+    const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
+    uint64_t w = a.W[(long long)site * a.Rpad + r];
+    const uint32_t c0 = a.replica_offset + (uint32_t)r, c1 = (uint32_t)site, c2 = a.sweep_lo;
+    const uint32_t c3hi = a.sweep_hi << 8;
+    const bool oddP = (P & 1) != 0;
+    uint64_t even_allowed = 0x5555555555555555ull & pmask;
+    if (oddP) even_allowed &= ~(1ull << (P - 1));
+    const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
+    w ^= phase_direct<0>(a, site, r, w, P, pmask, even_allowed, c0, c1, c2, c3hi);
+    w ^= phase_direct<1>(a, site, r, w, P, pmask, odd_allowed, c0, c1, c2, c3hi);
+    const float hc = a.field ? a.bcoef * __ldg(&a.h[site]) : 0.0f;
+    if (oddP) {
+        const int k = P - 1;
+        const uint64_t tl = w ^ rotl_ring(w, P, pmask), tr = w ^ rotr_ring(w, P, pmask);
+        const int anti = (int)((tl >> k) & 1ull) + (int)((tr >> k) & 1ull);
+        float dE = a.jperp2 * (float)(2 - 2 * anti) + (((w >> k) & 1ull) ? -hc : hc);
+        for (int j = 0; j < a.dpad; ++j) {
+            const float cj = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+            const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+            const uint64_t x = w ^ a.W[(long long)nbj * a.Rpad + r];
+            dE += ((x >> k) & 1ull) ? -cj : cj;
+        }
+        uint32_t rnd[4];
+        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
+        if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= 1ull << k;
+    }
+    if (a.global_moves) {
+        float dE = hc * (float)(P - 2 * __popcll(w & pmask));
+        for (int j = 0; j < a.dpad; ++j) {
+            const float cj = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+            const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+            const uint64_t x = (w ^ a.W[(long long)nbj * a.Rpad + r]) & pmask;
+            dE += cj * (float)(P - 2 * __popcll(x));
+        }
+        uint32_t rnd[4];
+        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
+        if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
+    }
+    a.W[(long long)site * a.Rpad + r] = w;
+}
+
+// ------------------------------------------------------------------------------------------
+// host <-> packed conversion, initialisation, energies
+// ------------------------------------------------------------------------------------------
+// in: int8 [R][N][P] (site fastest over threads -> contiguous reads); out: W[N][Rpad]
+__global__ void piqmc_pack_kernel(const int8_t *__restrict__ in, uint64_t *__restrict__ W, long long N,
+                                  long long R, long long Rpad, int P)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * R) return;
+    const long long r = t / N, i = t % N;
+    const int8_t *src = in + (r * N + i) * P;
+    uint64_t w = 0;
+    for (int k = 0; k < P; ++k) w |= (uint64_t)(src[k] < 0) << k;
+    W[i * Rpad + r] = w;
+}
+
+__global__ void piqmc_unpack_kernel(const uint64_t *__restrict__ W, int8_t *__restrict__ out, long long N,
+                                    long long R, long long Rpad, int P)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * R) return;
+    const long long r = t / N, i = t % N;
+    const uint64_t w = W[i * Rpad + r];
+    int8_t *dst = out + (r * N + i) * P;
+    for (int k = 0; k < P; ++k) dst[k] = ((w >> k) & 1ull) ? -1 : 1;
+}
+
+__global__ void piqmc_init_kernel(uint64_t *W, long long N, long long R, long long Rpad, int P, uint32_t key0,
+                                  uint32_t key1, uint32_t replica_offset)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * Rpad) return;
+    const long long i = t / Rpad, r = t % Rpad;
+    uint32_t rnd[4];
+    mcs_philox4x32_10(replica_offset + (uint32_t)r, (uint32_t)i, 0u, MCS_TAG_INIT, key0, key1, rnd);
+    const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
+    W[i * Rpad + r] = (r < R && (rnd[0] & 1u)) ? pmask : 0ull;
+}
+
+// Fixed-order fp64 classical energy per (replica, slice), bit-identical to the oracle's
+// mcs_oracle_ising_energy (definition of tools.ClassicalIsingEnergy, tools.pyx:99-118, with the
+// BLAS-order ambiguity removed): rows in site order, entries in table order, no FMA.
+__global__ void piqmc_energy_kernel(const uint64_t *__restrict__ W, const int32_t *__restrict__ tab_idx,
+                                    const double *__restrict__ tab_J, double *__restrict__ out, long long N,
+                                    int maxnb, long long R, long long Rpad, int P)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (r >= R) return;
+    double e = 0.0;
+    for (long long i = 0; i < N; ++i) {
+        double pair = 0.0, field = 0.0;
+        for (int s = 0; s < maxnb; ++s) {
+            const int j = tab_idx[i * maxnb + s];
+            const double jv = tab_J[i * maxnb + s];
+            if (j == i) {
+                field = __dadd_rn(field, jv);
+            } else {
+                const double sj = ((W[(long long)j * Rpad + r] >> k) & 1ull) ? -1.0 : 1.0;
+                pair = __dadd_rn(pair, __dmul_rn(jv, sj));
+            }
+        }
+        const double si = ((W[i * Rpad + r] >> k) & 1ull) ? -1.0 : 1.0;
+        e = __dadd_rn(e, __dmul_rn(si, __dadd_rn(__dmul_rn(0.5, pair), field)));
+    }
+    out[r * P + k] = e;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+template <int NPL>
+static void launch_lut_w(int warps, long long items, cudaStream_t s, const PiqmcPass &a)
+{
+    // items = nsites * G warps of work; `warps` divides G, so a CTA never straddles two sites
+    const unsigned grid = (unsigned)(items / warps);
+    if (warps == 4)
+        piqmc_lut_pass_kernel<NPL, 4><<<grid, 128, 0, s>>>(a);
+    else if (warps == 2)
+        piqmc_lut_pass_kernel<NPL, 2><<<grid, 64, 0, s>>>(a);
+    else
+        piqmc_lut_pass_kernel<NPL, 1><<<grid, 32, 0, s>>>(a);
+}
+
+static void launch_lut(int npl, int warps, long long items, cudaStream_t s, const PiqmcPass &a)
+{
+    switch (npl) {
+    case 1: launch_lut_w<1>(warps, items, s, a); break;
+    case 2: launch_lut_w<2>(warps, items, s, a); break;
+    case 3: launch_lut_w<3>(warps, items, s, a); break;
+    case 4: launch_lut_w<4>(warps, items, s, a); break;
+    case 5: launch_lut_w<5>(warps, items, s, a); break;
+    default: launch_lut_w<6>(warps, items, s, a); break;
+    }
+}
+
+int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
+                            int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
+{
+    mcs_instance *inst = st->inst;
+    const int P = (int)st->P;
+    const double teff = (double)temp * (double)P; // qmc.pyx:85: temp is a C float
+    MCS_REQUIRE(teff != 0.0 || S == 0, MCS_EZERODIV, "float division");
+    MCS_CUDA(cudaSetDevice(inst->device));
+    PiqmcPass a;
+    a.W = st->d_W;
+    a.ell_idx = inst->d_ell_idx;
+    a.ell_J = inst->d_ell_J;
+    a.h = inst->d_h;
+    a.dpad = inst->dpad;
+    a.nq = inst->maxdeg;
+    a.field = inst->has_field ? 1 : 0;
+    a.G = (int)(st->Rpad / 32);
+    a.Rpad = st->Rpad;
+    a.P = P;
+    a.keys = mcs_philox_expand(seed);
+    a.replica_offset = (uint32_t)replica_offset;
+    a.global_moves = global_moves ? 1 : 0;
+    const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
+    const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
+    uint64_t sweep = sweep_offset;
+    for (int64_t f = 0; f < S; ++f) {
+        const double jperp = -0.5 * teff * log(tanh(A[f] / teff)); // qmc.pyx:95
+        a.bcoef = (float)(-2.0 * B[f]);                            // qmc.pyx:96
+        a.jperp2 = (float)(2.0 * jperp);
+        a.nl2e_over_t = (float)(-1.4426950408889634 / teff);
+        for (int step = 0; step < mcsteps; ++step, ++sweep) {
+            a.sweep_lo = (uint32_t)sweep;
+            a.sweep_hi = (uint32_t)(sweep >> 32);
+            for (int c = 0; c < inst->ncolors; ++c) {
+                a.sites = inst->d_order + inst->color_start[c];
+                a.nsites = inst->color_start[c + 1] - inst->color_start[c];
+                if (a.nsites == 0) continue;
+                const long long items = (long long)a.nsites * a.G;
+                if (inst->lut_ok)
+                    launch_lut(npl, warps, items, inst->stream, a);
+                else
+                    piqmc_direct_pass_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kWarps * 32, 0,
+                                               inst->stream>>>(a);
+                inst->launches++;
+            }
+        }
+    }
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_piqmc_pack(mcs_state *st, const int8_t *d_in)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->R;
+    piqmc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(d_in, st->d_W, inst->N, st->R,
+                                                                            st->Rpad, (int)st->P);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_piqmc_unpack(mcs_state *st, int8_t *d_out)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->R;
+    piqmc_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(st->d_W, d_out, inst->N, st->R,
+                                                                              st->Rpad, (int)st->P);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_piqmc_init(mcs_state *st, uint64_t seed, uint64_t replica_offset)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->Rpad;
+    piqmc_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(
+        st->d_W, inst->N, st->R, st->Rpad, (int)st->P, (uint32_t)seed, (uint32_t)(seed >> 32),
+        (uint32_t)replica_offset);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_piqmc_energy(mcs_state *st, double *d_out)
+{
+    mcs_instance *inst = st->inst;
+    dim3 grid((unsigned)((st->R + 63) / 64), (unsigned)st->P);
+    piqmc_energy_kernel<<<grid, 64, 0, inst->stream>>>(st->d_W, inst->d_tab_idx, inst->d_tab_J, d_out, inst->N,
+                                                      (int)inst->maxnb, st->R, st->Rpad, (int)st->P);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}

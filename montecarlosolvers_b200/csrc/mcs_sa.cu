@@ -1,0 +1,341 @@
+// mcs_sa.cu -- classical simulated-annealing sweeps, multi-spin coded over restarts (sm_100a).
+//
+// Replaces the loop nest of sa.Anneal (reference sa.pyx:66-101).
+//
+// Data layout in HBM:  V[site][word] : uint32, bit b of word g = restart 32 g + b, bit set <=>
+// spin -1.  A warp owns (site, 32 consecutive words) = up to 1024 restarts of one site, so the
+// couplings and the 2^deg-entry acceptance-threshold table of the site are warp-uniform and the
+// 32 lanes read/write 128 contiguous bytes.  All 32 bits of a word are attempted in one launch
+// (same site, different restarts); neighbours are in other colour classes and frozen.
+#include <algorithm>
+#include <cmath>
+
+#include "mcs_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+
+struct SaPass {
+    uint32_t *V;
+    const int32_t *ell_idx;
+    const float *ell_J;
+    const float *h;
+    const int32_t *sites;
+    int nsites;
+    int dpad;
+    int nq;
+    int field;
+    int chunks; // ceil(G / 32) warps per site
+    long long G;
+    float nl2e_over_t; // -log2(e)/T
+    mcs_philox_keys keys;
+    uint32_t sweep_lo, sweep_hi;
+    uint32_t word_offset; // replica_offset / 32
+};
+
+__device__ __forceinline__ uint32_t prmt_sign_bytes(uint32_t v)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0xBA98u));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t prmt_byte(uint32_t v, int i)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0x4440u | (uint32_t)i));
+    return r;
+}
+
+// WARPS warps per CTA, all on the same site; the table sits at a compile-time shared address and,
+// for up to 6 planes, the pattern index is kept pre-multiplied by 4 (= the LDS byte offset).
+template <int NPL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) sa_lut_pass_kernel(const __grid_constant__ SaPass a)
+{
+    constexpr int ENT = 1 << NPL;
+    constexpr int SH = NPL <= 6 ? 2 : 0;
+    __shared__ uint32_t s_lut[ENT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cps = a.chunks / WARPS; // CTAs per site
+    const int site = __ldg(&a.sites[blockIdx.x / cps]);
+    const long long g = ((long long)(blockIdx.x % cps) * WARPS + warp) * 32 + lane;
+
+    float c[NPL];
+    int nb[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        if (j < a.nq) {
+            nb[j] = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+            c[j] = -2.0f * __ldg(&a.ell_J[(long long)site * a.dpad + j]); // sa.pyx:91-94
+        } else {
+            nb[j] = site;
+            c[j] = (a.field && j == a.nq) ? -2.0f * __ldg(&a.h[site]) : 0.0f;
+        }
+    }
+    for (int e = threadIdx.x; e < ENT; e += WARPS * 32) {
+        float dE = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) dE += ((e >> j) & 1) ? -c[j] : c[j];
+        s_lut[e] = mcs_accept_threshold(dE, a.nl2e_over_t);
+    }
+    if (WARPS == 1)
+        __syncwarp();
+    else
+        __syncthreads();
+    if (g >= a.G) return;
+
+    uint32_t v = a.V[(long long)site * a.G + g];
+    uint32_t pl[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        if (j < a.nq)
+            pl[j] = v ^ a.V[(long long)nb[j] * a.G + g];
+        else
+            pl[j] = (a.field && j == a.nq) ? v : 0u;
+    }
+    const uint32_t c0 = a.word_offset + (uint32_t)g, c1 = (uint32_t)site;
+    uint32_t flip = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { // restarts 8 i + 7 - q of this word
+        uint32_t acc = 0;
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) acc |= prmt_sign_bytes(pl[p] << q) & (0x01010101u << (p + SH));
+        uint32_t rnd[4];
+        mcs_philox4x32_10_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)q, a.keys, rnd);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t off = prmt_byte(acc, i);
+            const uint32_t T = SH == 2 ? *(const uint32_t *)((const char *)s_lut + off) : s_lut[off];
+            if (rnd[i] <= T) flip |= 1u << (8 * i + 7 - q);
+        }
+    }
+    a.V[(long long)site * a.G + g] = v ^ flip;
+}
+
+// general-degree pass: energy differences accumulated over the ELL row, one register per restart
+__global__ void __launch_bounds__(kWarps * 32) sa_direct_pass_kernel(const __grid_constant__ SaPass a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kWarps + warp;
+    if (item >= (long long)a.nsites * a.chunks) return;
+    const int site = a.sites[item / a.chunks];
+    const long long g = (item % a.chunks) * 32 + lane;
+    if (g >= a.G) return;
+    uint32_t v = a.V[(long long)site * a.G + g];
+    const float hc = a.field ? -2.0f * __ldg(&a.h[site]) : 0.0f;
+    float e[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) e[b] = ((v >> b) & 1u) ? -hc : hc;
+    for (int j = 0; j < a.dpad; ++j) {
+        const float cj = -2.0f * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+        if (cj == 0.0f) continue;
+        const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+        const uint32_t x = v ^ a.V[(long long)nbj * a.G + g];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) e[b] += __uint_as_float(__float_as_uint(cj) ^ (((x >> b) & 1u) << 31));
+    }
+    const uint32_t c0 = a.word_offset + (uint32_t)g, c1 = (uint32_t)site;
+    uint32_t flip = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        uint32_t rnd[4];
+        mcs_philox4x32_10_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)q, a.keys, rnd);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = 8 * i + 7 - q;
+            if (rnd[i] <= mcs_accept_threshold(e[b], a.nl2e_over_t)) flip |= 1u << b;
+        }
+    }
+    a.V[(long long)site * a.G + g] = v ^ flip;
+}
+
+// in: int8 [R][N]; thread per (site, word)
+__global__ void sa_pack_kernel(const int8_t *__restrict__ in, uint32_t *__restrict__ V, long long N, long long R,
+                               long long G)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * G) return;
+    const long long g = t / N, i = t % N;
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+        const long long r = g * 32 + b;
+        if (r < R) v |= (uint32_t)(in[r * N + i] < 0) << b;
+    }
+    V[i * G + g] = v;
+}
+
+__global__ void sa_unpack_kernel(const uint32_t *__restrict__ V, int8_t *__restrict__ out, long long N,
+                                 long long R, long long G)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * G) return;
+    const long long g = t / N, i = t % N;
+    const uint32_t v = V[i * G + g];
+    for (int b = 0; b < 32; ++b) {
+        const long long r = g * 32 + b;
+        if (r < R) out[r * N + i] = ((v >> b) & 1u) ? -1 : 1;
+    }
+}
+
+__global__ void sa_init_kernel(uint32_t *V, long long N, long long R, long long G, uint32_t key0, uint32_t key1,
+                               uint32_t replica_offset)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * G) return;
+    const long long i = t / G, g = t % G;
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+        const long long r = g * 32 + b;
+        if (r >= R) break;
+        uint32_t rnd[4];
+        // same draw as piqmc_init_kernel: replica r starts from the same spins in both solvers
+        mcs_philox4x32_10(replica_offset + (uint32_t)r, (uint32_t)i, 0u, MCS_TAG_INIT, key0, key1, rnd);
+        v |= (rnd[0] & 1u) << b;
+    }
+    V[i * G + g] = v;
+}
+
+// fixed-order fp64 energy per restart (see piqmc_energy_kernel)
+__global__ void sa_energy_kernel(const uint32_t *__restrict__ V, const int32_t *__restrict__ tab_idx,
+                                 const double *__restrict__ tab_J, double *__restrict__ out, long long N,
+                                 int maxnb, long long R, long long G)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const long long g = r >> 5;
+    const int b = (int)(r & 31);
+    double e = 0.0;
+    for (long long i = 0; i < N; ++i) {
+        double pair = 0.0, field = 0.0;
+        for (int s = 0; s < maxnb; ++s) {
+            const int j = tab_idx[i * maxnb + s];
+            const double jv = tab_J[i * maxnb + s];
+            if (j == i) {
+                field = __dadd_rn(field, jv);
+            } else {
+                const double sj = ((V[(long long)j * G + g] >> b) & 1u) ? -1.0 : 1.0;
+                pair = __dadd_rn(pair, __dmul_rn(jv, sj));
+            }
+        }
+        const double si = ((V[i * G + g] >> b) & 1u) ? -1.0 : 1.0;
+        e = __dadd_rn(e, __dmul_rn(si, __dadd_rn(__dmul_rn(0.5, pair), field)));
+    }
+    out[r] = e;
+}
+
+template <int NPL>
+void launch_lut_w(int warps, long long items, cudaStream_t s, const SaPass &a)
+{
+    const unsigned grid = (unsigned)(items / warps);
+    if (warps == 4)
+        sa_lut_pass_kernel<NPL, 4><<<grid, 128, 0, s>>>(a);
+    else if (warps == 2)
+        sa_lut_pass_kernel<NPL, 2><<<grid, 64, 0, s>>>(a);
+    else
+        sa_lut_pass_kernel<NPL, 1><<<grid, 32, 0, s>>>(a);
+}
+
+void launch_lut(int npl, int warps, long long items, cudaStream_t s, const SaPass &a)
+{
+    switch (npl) {
+    case 1: launch_lut_w<1>(warps, items, s, a); break;
+    case 2: launch_lut_w<2>(warps, items, s, a); break;
+    case 3: launch_lut_w<3>(warps, items, s, a); break;
+    case 4: launch_lut_w<4>(warps, items, s, a); break;
+    case 5: launch_lut_w<5>(warps, items, s, a); break;
+    case 6: launch_lut_w<6>(warps, items, s, a); break;
+    case 7: launch_lut_w<7>(warps, items, s, a); break;
+    default: launch_lut_w<8>(warps, items, s, a); break;
+    }
+}
+
+} // namespace
+
+int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcsteps, uint64_t seed,
+                         uint64_t replica_offset, uint64_t sweep_offset)
+{
+    mcs_instance *inst = st->inst;
+    MCS_REQUIRE((replica_offset & 31) == 0, MCS_EINVAL,
+                "mcs_sa_sweeps: replica_offset must be a multiple of 32 (restarts are packed 32 per word)");
+    MCS_CUDA(cudaSetDevice(inst->device));
+    SaPass a;
+    a.V = st->d_V;
+    a.ell_idx = inst->d_ell_idx;
+    a.ell_J = inst->d_ell_J;
+    a.h = inst->d_h;
+    a.dpad = inst->dpad;
+    a.nq = inst->maxdeg;
+    a.field = inst->has_field ? 1 : 0;
+    a.G = st->G;
+    a.chunks = (int)((st->G + 31) / 32);
+    a.keys = mcs_philox_expand(seed);
+    a.word_offset = (uint32_t)(replica_offset >> 5);
+    const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
+    const bool lut = npl <= 8;
+    const int warps = (a.chunks % 4 == 0) ? 4 : (a.chunks % 2 == 0) ? 2 : 1;
+    uint64_t sweep = sweep_offset;
+    for (int64_t t = 0; t < S; ++t) {
+        // exp(-ediff/temp), sa.pyx:98; temp == 0 gives -inf here -> threshold "never" for ediff > 0
+        a.nl2e_over_t = (float)(-1.4426950408889634 / sched[t]);
+        for (int step = 0; step < mcsteps; ++step, ++sweep) {
+            a.sweep_lo = (uint32_t)sweep;
+            a.sweep_hi = (uint32_t)(sweep >> 32);
+            for (int c = 0; c < inst->ncolors; ++c) {
+                a.sites = inst->d_order + inst->color_start[c];
+                a.nsites = inst->color_start[c + 1] - inst->color_start[c];
+                if (a.nsites == 0) continue;
+                const long long items = (long long)a.nsites * a.chunks;
+                if (lut)
+                    launch_lut(npl, warps, items, inst->stream, a);
+                else
+                    sa_direct_pass_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kWarps * 32, 0,
+                                            inst->stream>>>(a);
+                inst->launches++;
+            }
+        }
+    }
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_sa_pack(mcs_state *st, const int8_t *d_in)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->G;
+    sa_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(d_in, st->d_V, inst->N, st->R, st->G);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_sa_unpack(mcs_state *st, int8_t *d_out)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->G;
+    sa_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(st->d_V, d_out, inst->N, st->R, st->G);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_sa_init(mcs_state *st, uint64_t seed, uint64_t replica_offset)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->G;
+    sa_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(
+        st->d_V, inst->N, st->R, st->G, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)replica_offset);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_sa_energy(mcs_state *st, double *d_out)
+{
+    mcs_instance *inst = st->inst;
+    sa_energy_kernel<<<(unsigned)((st->R + 63) / 64), 64, 0, inst->stream>>>(
+        st->d_V, inst->d_tab_idx, inst->d_tab_J, d_out, inst->N, (int)inst->maxnb, st->R, st->G);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}

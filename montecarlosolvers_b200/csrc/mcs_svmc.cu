@@ -1,0 +1,218 @@
+// mcs_svmc.cu -- spin-vector Monte Carlo (O(2) rotors, theta in [0, pi]) sweeps (sm_100a).
+//
+// Replaces the loop nest of svmc.SpinVectorMonteCarlo (reference svmc.pyx:78-117) and of
+// svmc.SpinVectorMonteCarloTF (svmc.pyx:181-229); the batched forms (svmc.pyx:455-674) are the
+// replica axis.
+//
+// Data layout in HBM: theta[site][replica], cosz[site][replica] fp32, replica fastest: a warp owns
+// (site, 32 replicas), couplings are warp-uniform, every neighbour read is one coalesced 128-byte
+// line of cos(theta_j).  Colour classes are launched one after another; neighbours are frozen.
+#include <algorithm>
+#include <cmath>
+
+#include "mcs_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+
+struct SvmcPass {
+    float *theta;
+    float *cosz;
+    const int32_t *ell_idx;
+    const float *ell_J;
+    const float *h;
+    const int32_t *sites;
+    int nsites;
+    int dpad;
+    int field;
+    int G; // Rpad / 32
+    long long Rpad;
+    float a_coef, b_coef;
+    float nl2e_over_t;
+    int tf;
+    float tf_scale; // min(1, A/B) as the reference evaluates it (svmc.pyx:198-202)
+    mcs_philox_keys keys;
+    uint32_t sweep_lo, sweep_hi;
+    uint32_t replica_offset;
+};
+
+__global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_constant__ SvmcPass a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kWarps + warp;
+    if (item >= (long long)a.nsites * a.G) return;
+    const int site = a.sites[item / a.G];
+    const long long r = (item % a.G) * 32 + lane;
+    const float kPi = 3.14159265358979323846f;
+
+    const float th = a.theta[(long long)site * a.Rpad + r];
+    const float ci = a.cosz[(long long)site * a.Rpad + r];
+    float zfield = a.field ? __ldg(&a.h[site]) : 0.0f; // sum_j J_ij cos(theta_j) + h_i
+    for (int j = 0; j < a.dpad; ++j) {
+        const float jv = __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+        if (jv == 0.0f) continue;
+        const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+        zfield = fmaf(jv, a.cosz[(long long)nbj * a.Rpad + r], zfield);
+    }
+    uint32_t rnd[4];
+    mcs_philox4x32_10_rk(a.replica_offset + (uint32_t)r, (uint32_t)site, a.sweep_lo,
+                         (a.sweep_hi << 8) | MCS_TAG_SVMC, a.keys, rnd);
+    const float u0 = (float)(rnd[0] >> 8) * (1.0f / 16777216.0f); // [0, 1)
+    float thp;
+    if (!a.tf) {
+        thp = kPi * u0; // svmc.pyx:95
+    } else {            // svmc.pyx:198-207
+        thp = th + a.tf_scale * (2.0f * kPi * u0 - kPi);
+        thp = fminf(fmaxf(thp, 0.0f), kPi);
+    }
+    float sp, cp;
+    __sincosf(thp, &sp, &cp);
+    const float si = __sinf(th);
+    // svmc.pyx:96-110
+    const float dE = a.b_coef * (cp - ci) * zfield + a.a_coef * (si - sp);
+    if (rnd[1] <= mcs_accept_threshold(dE, a.nl2e_over_t)) { // svmc.pyx:112-115
+        a.theta[(long long)site * a.Rpad + r] = thp;
+        a.cosz[(long long)site * a.Rpad + r] = cp;
+    }
+}
+
+// host float64 [R][N] -> theta/cos [N][Rpad]
+__global__ void svmc_pack_kernel(const double *__restrict__ in, float *__restrict__ theta,
+                                 float *__restrict__ cosz, long long N, long long R, long long Rpad)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * R) return;
+    const long long r = t / N, i = t % N;
+    const double th = in[r * N + i];
+    theta[i * Rpad + r] = (float)th;
+    cosz[i * Rpad + r] = (float)cos(th);
+}
+
+__global__ void svmc_unpack_kernel(const float *__restrict__ theta, double *__restrict__ out, long long N,
+                                   long long R, long long Rpad)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * R) return;
+    const long long r = t / N, i = t % N;
+    out[r * N + i] = (double)theta[i * Rpad + r];
+}
+
+__global__ void svmc_init_kernel(float *theta, float *cosz, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    theta[t] = 1.57079632679489661923f; // pi/2: all rotors along x, the transverse-field ground state
+    cosz[t] = 0.0f;
+}
+
+// H = B (sum_bonds J cos cos + sum_i h cos) - A sum_i sin, fp64 from the stored angles
+__global__ void svmc_energy_kernel(const float *__restrict__ theta, const int32_t *__restrict__ tab_idx,
+                                   const double *__restrict__ tab_J, double *__restrict__ out, long long N,
+                                   int maxnb, long long R, long long Rpad, double a, double b)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double ez = 0.0, ex = 0.0;
+    for (long long i = 0; i < N; ++i) {
+        double pair = 0.0, field = 0.0;
+        for (int s = 0; s < maxnb; ++s) {
+            const int j = tab_idx[i * maxnb + s];
+            const double jv = tab_J[i * maxnb + s];
+            if (j == i)
+                field += jv;
+            else if (jv != 0.0)
+                pair += jv * cos((double)theta[(long long)j * Rpad + r]);
+        }
+        const double th = (double)theta[i * Rpad + r];
+        ez += cos(th) * (0.5 * pair + field);
+        ex += sin(th);
+    }
+    out[r] = b * ez - a * ex;
+}
+
+} // namespace
+
+int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
+                           int tf, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
+{
+    mcs_instance *inst = st->inst;
+    MCS_CUDA(cudaSetDevice(inst->device));
+    SvmcPass a;
+    a.theta = st->d_theta;
+    a.cosz = st->d_cosz;
+    a.ell_idx = inst->d_ell_idx;
+    a.ell_J = inst->d_ell_J;
+    a.h = inst->d_h;
+    a.dpad = inst->dpad;
+    a.field = inst->has_field ? 1 : 0;
+    a.G = (int)(st->Rpad / 32);
+    a.Rpad = st->Rpad;
+    a.tf = tf ? 1 : 0;
+    a.keys = mcs_philox_expand(seed);
+    a.replica_offset = (uint32_t)replica_offset;
+    a.nl2e_over_t = (float)(-1.4426950408889634 / (double)temp); // temp is a C float (svmc.pyx:24)
+    uint64_t sweep = sweep_offset;
+    for (int64_t f = 0; f < S; ++f) {
+        a.a_coef = (float)A[f];
+        a.b_coef = (float)B[f];
+        const double ab = A[f] / B[f]; // cdivision: inf / nan allowed (svmc.pyx:198)
+        a.tf_scale = (float)((ab > 1) ? 1.0 : ab);
+        for (int step = 0; step < mcsteps; ++step, ++sweep) {
+            a.sweep_lo = (uint32_t)sweep;
+            a.sweep_hi = (uint32_t)(sweep >> 32);
+            for (int c = 0; c < inst->ncolors; ++c) {
+                a.sites = inst->d_order + inst->color_start[c];
+                a.nsites = inst->color_start[c + 1] - inst->color_start[c];
+                if (a.nsites == 0) continue;
+                const long long items = (long long)a.nsites * a.G;
+                svmc_pass_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kWarps * 32, 0, inst->stream>>>(a);
+                inst->launches++;
+            }
+        }
+    }
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_svmc_pack(mcs_state *st, const double *d_in)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->R;
+    svmc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(d_in, st->d_theta, st->d_cosz, inst->N,
+                                                                           st->R, st->Rpad);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_svmc_unpack(mcs_state *st, double *d_out)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->R;
+    svmc_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(st->d_theta, d_out, inst->N, st->R,
+                                                                             st->Rpad);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_svmc_init(mcs_state *st)
+{
+    mcs_instance *inst = st->inst;
+    const long long n = inst->N * st->Rpad;
+    svmc_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(st->d_theta, st->d_cosz, n);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_svmc_energy(mcs_state *st, double a, double b, double *d_out)
+{
+    mcs_instance *inst = st->inst;
+    svmc_energy_kernel<<<(unsigned)((st->R + 63) / 64), 64, 0, inst->stream>>>(
+        st->d_theta, inst->d_tab_idx, inst->d_tab_J, d_out, inst->N, (int)inst->maxnb, st->R, st->Rpad, a, b);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}

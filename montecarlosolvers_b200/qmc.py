@@ -1,0 +1,127 @@
+"""Drop-in for the reference's `solvers.qmc` (path-integral quantum Monte Carlo sweeps).
+
+Same names and positional arguments as /root/reference/solvers/qmc.pyx; `confs` is mutated in place
+and the functions return None.  Extensions (keyword only): a leading replica axis on `confs`
+([R, N, P]: R independent anneals in one call), `seed=` for the counter-based RNG, `exact=True` +
+`libc_seed=` for the bit-exact sequential replay of the reference, `energies=True` to get the
+final per-slice classical energies back.
+"""
+import numpy as np
+
+from . import _common as C
+from . import _lib
+
+__all__ = ["QuantumAnneal", "QuantumAnnealGlobal", "DissipativeQuantumAnneal", "DissipativeQuantumAnnealGlobal"]
+
+
+def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable, seed, exact, libc_seed, device,
+         energies, replica_offset):
+    A = _lib.f64(A_sched)
+    B = _lib.f64(B_sched)
+    if A.ndim != 1 or B.ndim != 1:
+        raise ValueError("Buffer has wrong number of dimensions (expected 1)")
+    if B.size < A.size:
+        raise ValueError("B_sched is shorter than A_sched (undefined behaviour in the reference)")
+    nbs = C.check_nbs(nbs)
+    a8, batched, need_copy = C.spins_in(confs, 2, "confs")
+    R, N, P = a8.shape
+    inst = _lib.instance_for(nbs, device)
+    if inst.nspins != N:
+        raise ValueError("confs has %d spins but nbs describes %d" % (N, inst.nspins))
+    L = _lib.load()
+    temp = float(np.float32(temp))  # C float in the reference signature (qmc.pyx:28)
+    e_out = np.empty((R, P), dtype=np.float64) if energies else None
+    if exact or lookuptable is not None:
+        if not exact:
+            raise NotImplementedError(
+                "the Ohmic-bath term couples all Trotter slices of a site; only the exact sequential kernel "
+                "(exact=True, libc_seed=...) implements the Dissipative variants in this build")
+        lut = None
+        if lookuptable is not None:
+            lut = _lib.f64(lookuptable)
+            if lut.size < P - 1:
+                raise ValueError("lookuptable needs P-1 entries")
+        seeds = C.seeds_u32(libc_seed, R)
+        _lib.check(L.mcs_exact_qmc(inst._h, _lib.dptr(A), _lib.dptr(B), A.size, int(mcsteps), temp,
+                                   _lib.dptr(lut) if lut is not None else None, a8.ctypes.data, R, P,
+                                   int(bool(global_moves)), C.u32p(seeds), None, 0, None))
+        if energies:
+            st = _lib.State(inst, _lib.KIND_PIQMC, R, P) if P <= 64 else None
+            if st is None:
+                raise NotImplementedError("energies=True needs P <= 64")
+            st.upload_spins(a8)
+            e_out = st.energies()
+            st.close()
+    else:
+        _lib.check(L.mcs_piqmc_anneal(inst._h, _lib.dptr(A), _lib.dptr(B), A.size, int(mcsteps), temp,
+                                      a8.ctypes.data, R, P, int(bool(global_moves)), _lib.next_seed(seed),
+                                      int(replica_offset), _lib.dptr(e_out) if energies else None))
+    C.spins_out(confs, a8, batched, need_copy)
+    if energies:
+        return e_out if batched else e_out[0]
+    return None
+
+
+def QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, seed=None, exact=False,
+                  libc_seed=None, device=None, energies=False, replica_offset=0):
+    """QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads)
+
+    Path-integral QMC with single-spin flips (reference qmc.pyx:25-143).  H = sum_k (sum_ij J_ij
+    s_i^k s_j^k - J_perp sum_i s_i^k s_i^{k+1}), J_perp = -(PT/2) ln tanh(A/(PT)); for every value of
+    A_sched, `mcsteps` sweeps over all (spin, slice).  `nthreads` is accepted and ignored (it is
+    inert in the reference too: OpenMP is disabled in its setup.py:10-11).
+    Returns None; spins are flipped in place within `confs` ([N, P] or [R, N, P])."""
+    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, False, None, seed, exact, libc_seed, device, energies,
+                replica_offset)
+
+
+def QuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, seed=None, exact=False,
+                        libc_seed=None, device=None, energies=False, replica_offset=0):
+    """QuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads)
+
+    As QuantumAnneal plus one world-line move per spin per sweep (all P slices of a spin flipped
+    together, reference qmc.pyx:284-438)."""
+    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, None, seed, exact, libc_seed, device, energies,
+                replica_offset)
+
+
+def DissipativeQuantumAnneal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *, exact=True,
+                             libc_seed=None, device=None, energies=False):
+    """DissipativeQuantumAnneal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads)
+
+    PIQMC with the Ohmic-bath term (reference qmc.pyx:149-278); exact sequential kernel only."""
+    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, False, lookuptable, None, exact, libc_seed, device,
+                energies, 0)
+
+
+def DissipativeQuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *,
+                                   exact=True, libc_seed=None, device=None, energies=False):
+    """DissipativeQuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads)
+
+    Reference qmc.pyx:444-609; exact sequential kernel only."""
+    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, lookuptable, None, exact, libc_seed, device,
+                energies, 0)
+
+
+def delta_e(a, b, temp, confs, nbs, device=None):
+    """fp64 energy difference of every (spin, slice) visit for frozen configurations (qmc.pyx:112-138);
+    parity tier (a).  Returns float64 with the shape of `confs`."""
+    nbs = C.check_nbs(nbs)
+    a8, batched, _ = C.spins_in(confs, 2, "confs")
+    R, N, P = a8.shape
+    inst = _lib.instance_for(nbs, device)
+    out = np.empty((R, N, P), dtype=np.float64)
+    _lib.check(_lib.load().mcs_probe_qmc_delta_e(inst._h, float(a), float(b), float(np.float32(temp)),
+                                                 a8.ctypes.data, R, P, _lib.dptr(out)))
+    return out if batched else out[0]
+
+
+def delta_e_global(b, confs, nbs, device=None):
+    """fp64 world-line flip energy differences (qmc.pyx:416-431)."""
+    nbs = C.check_nbs(nbs)
+    a8, batched, _ = C.spins_in(confs, 2, "confs")
+    R, N, P = a8.shape
+    inst = _lib.instance_for(nbs, device)
+    out = np.empty((R, N), dtype=np.float64)
+    _lib.check(_lib.load().mcs_probe_qmc_delta_e_global(inst._h, float(b), a8.ctypes.data, R, P, _lib.dptr(out)))
+    return out if batched else out[0]

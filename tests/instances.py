@@ -47,3 +47,21 @@ def random_graph(n, nedges, seed=0, fields=True):
 
 def random_spins(n, seed):
     return (2 * np.random.RandomState(seed).randint(2, size=n) - 1).astype(np.int64)
+
+
+_SANTORO = {}
+
+
+def santoro():
+    """The reference's shipped 80x80 instance (tests/golden/santoro80.npz, made by make_golden.py),
+    with the example's sign flip isingJ[i,j] = -J_file (santoro80.py:242-244).
+    Returns (J dok, nbs[6400,4,2], ground_state int64[6400], E_gs)."""
+    if not _SANTORO:
+        import os
+        d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "santoro80.npz"))
+        J = sps.dok_matrix((6400, 6400))
+        for i, j, v in zip(d["i"], d["j"], d["J_file"]):
+            J[int(i), int(j)] = -1.0 * v
+        nbs = orc.GenerateNeighbors(6400, J, 4)
+        _SANTORO["v"] = (J, nbs, d["ground_state"].astype(np.int64), float(d["e_gs_per_spin"]) * 6400)
+    return _SANTORO["v"]

@@ -1,0 +1,158 @@
+"""Parity tiers (a) and (b) on the GPU, through the C ABI: fp64 probes and the sequential-order
+validation kernels must reproduce the oracle / the reference's golden trajectories BIT-EXACTLY."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import instances as inst
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def mcs():
+    import montecarlosolvers_b200 as m
+    m._lib.require_device()
+    return m
+
+
+def test_probe_delta_e_bit_exact(mcs):
+    for (_, nbs), P in ((inst.torus(6, seed=3, fields=True), 8), (inst.random_graph(40, 90, seed=2), 5),
+                        (inst.torus(4, seed=1), 2)):
+        n = nbs.shape[0]
+        R = 3
+        c = (2 * np.random.RandomState(7).randint(2, size=(R, n, P)) - 1).astype(np.int64)
+        got = mcs.qmc.delta_e(0.8, 0.7, 1.0 / P, c, nbs)
+        gotg = mcs.qmc.delta_e_global(0.7, c, nbs)
+        for r in range(R):
+            want = orc.qmc_delta_e(0.8, 0.7, 1.0 / P, c[r], nbs)
+            assert np.array_equal(got[r], want)
+            assert np.array_equal(gotg[r], orc.qmc_delta_e_global(0.7, c[r], nbs))
+        s = np.ascontiguousarray(c[:, :, 0])
+        gs = mcs.sa.delta_e(s, nbs)
+        for r in range(R):
+            assert np.array_equal(gs[r], orc.sa_delta_e(s[r], nbs))
+
+
+def test_state_energies_bit_exact_and_roundtrip(mcs):
+    _, nbs = inst.random_graph(50, 120, seed=5)
+    n = nbs.shape[0]
+    for P in (2, 7, 20, 33, 64):
+        R = 37
+        c = (2 * np.random.RandomState(P).randint(2, size=(R, n, P)) - 1).astype(np.int8)
+        I = mcs.Instance(nbs)
+        st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+        st.upload_spins(c)
+        assert np.array_equal(st.download_spins(), c)  # pack -> unpack round trip
+        e = st.energies()
+        for r in (0, 5, R - 1):
+            for k in (0, P - 1):
+                assert e[r, k] == orc.ising_energy(c[r, :, k].astype(np.int64), nbs)
+        st.close()
+    R = 70
+    s = (2 * np.random.RandomState(1).randint(2, size=(R, n)) - 1).astype(np.int8)
+    st = mcs.State(I, mcs._lib.KIND_SA, R, 1)
+    st.upload_spins(s)
+    assert np.array_equal(st.download_spins(), s)
+    e = st.energies()
+    for r in (0, 31, 32, R - 1):
+        assert e[r] == orc.ising_energy(s[r].astype(np.int64), nbs)
+
+
+def test_exact_qmc_golden(mcs):
+    d = np.load(os.path.join(G, "traj_qmc_torus6.npz"))
+    for P in (2, 3, 8, 20):
+        for glob in (0, 1):
+            c = np.asfortranarray(d["P%d_g%d_in" % (P, glob)].astype(np.int64))  # strided like the example
+            fn = mcs.qmc.QuantumAnnealGlobal if glob else mcs.qmc.QuantumAnneal
+            assert fn(d["A"], d["B"], int(d["mcsteps"]), 1.0 / P, c, d["nbs"], 1, exact=True,
+                      libc_seed=1000 + P) is None
+            assert np.array_equal(c, d["P%d_g%d_out" % (P, glob)])
+    d = np.load(os.path.join(G, "traj_qmc_graph40.npz"))
+    c = d["conf_in"].astype(np.int64)
+    e = mcs.qmc.QuantumAnnealGlobal(d["A"], d["B"], int(d["mcsteps"]), float(d["temp"]), c, d["nbs"], 1, exact=True,
+                                    libc_seed=int(d["seed"]), energies=True)
+    assert np.array_equal(c, d["conf_out"])
+    assert np.allclose(e, d["energies"], rtol=0, atol=1e-9)
+    c = d["conf_in"].astype(np.int64)
+    mcs.qmc.DissipativeQuantumAnnealGlobal(d["A"], d["B"], int(d["diss_mcsteps"]), float(d["temp"]), d["lut"], c,
+                                           d["nbs"], 1, libc_seed=int(d["diss_seed"]))
+    assert np.array_equal(c, d["diss_out"])
+
+
+def test_exact_qmc_batch_vs_oracle(mcs):
+    """R replicas at once, replica r seeded srand(50 + r): each equals its own oracle run."""
+    _, nbs = inst.torus(6, seed=11, fields=True)
+    n, P, R = 36, 6, 9
+    A = np.linspace(2.5, 0.05, 7)
+    B = np.ones(7)
+    c0 = (2 * np.random.RandomState(3).randint(2, size=(R, n, P)) - 1).astype(np.int8)
+    c = c0.copy()
+    mcs.qmc.QuantumAnnealGlobal(A, B, 2, 1.0 / P, c, nbs, 1, exact=True, libc_seed=50)
+    for r in range(R):
+        want = c0[r].astype(np.int64)
+        orc.QuantumAnnealGlobal(A, B, 2, 1.0 / P, want, nbs, 1, rng=50 + r)
+        assert np.array_equal(c[r], want)
+
+
+def test_exact_sa_golden(mcs):
+    d = np.load(os.path.join(G, "traj_sa_torus6.npz"))
+    s = d["s_in"].astype(np.int64)
+    mcs.sa.Anneal(d["sched"], int(d["mcsteps"]), s, d["nbs"], exact=True, libc_seed=int(d["seed"]))
+    assert np.array_equal(s, d["s_out"])
+    s = d["s_in"].astype(np.int64)
+    np.random.seed(int(d["ma_seed"]))
+    mcs.sa.AnnealMA(d["sched"], int(d["ma_mcsteps"]), s, d["nbs"], exact=True, libc_seed=int(d["ma_seed"]))
+    assert np.array_equal(s, d["ma_out"])
+    s = d["s_in"].astype(np.int64)
+    mcs.sa.Anneal_parallel(d["sched"], int(d["mcsteps"]), s, d["nbs"], 6, exact=True, libc_seed=int(d["seed"]))
+    assert np.array_equal(s, d["s_out"])
+
+
+def test_exact_svmc_golden(mcs):
+    d = np.load(os.path.join(G, "traj_svmc_torus5.npz"))
+    seed = int(d["seed"])
+    args = (d["A"], d["B"], int(d["mcsteps"]), float(d["temp"]))
+    for name in ("SpinVectorMonteCarlo", "SpinVectorMonteCarloTF"):
+        v = np.full(25, np.pi / 2)
+        np.random.seed(seed)
+        getattr(mcs.svmc, name)(*args, v, d["nbs"], exact=True, libc_seed=seed)
+        assert np.array_equal(v, d[name]), name
+    v = np.full((5, 25), np.pi / 2)
+    np.random.seed(seed)
+    mcs.svmc.SpinVectorMonteCarloCompact(*args, v, d["nbs"], exact=True, libc_seed=seed)
+    assert np.array_equal(v, d["SpinVectorMonteCarloCompact"])
+    v = np.full((4, 25), np.pi / 2)
+    mcs.svmc.SpinVectorMonteCarloTFCompact(*args, v, d["nbs"], exact=True, libc_seed=seed)
+    assert np.array_equal(v, d["SpinVectorMonteCarloTFCompact"])
+
+
+def test_exact_santoro_slice_of_reference_protocol(mcs):
+    """Full-size instance (80x80, P=20), a short QuantumAnnealGlobal segment: GPU replay == oracle."""
+    _, nbs, _, _ = inst.santoro()
+    P = 20
+    A = np.linspace(3.0, 2.5, 2)
+    s0 = inst.random_spins(6400, 0)
+    want = np.tile(s0, (P, 1)).T.copy()
+    got = want.copy()
+    orc.QuantumAnnealGlobal(A, np.ones(2), 1, 1.0 / P, want, nbs, 1, rng=2000)
+    mcs.qmc.QuantumAnnealGlobal(A, np.ones(2), 1, 1.0 / P, got, nbs, 1, exact=True, libc_seed=2000)
+    assert np.array_equal(got, want)
+
+
+def test_error_behaviour_matches_reference(mcs):
+    _, nbs = inst.torus(4, seed=1)
+    c = np.ones((16, 4), dtype=np.int64)
+    with pytest.raises(ZeroDivisionError):  # qmc.c:3030-3034
+        mcs.qmc.QuantumAnneal(np.ones(2), np.ones(2), 1, 0.0, c, nbs, 1)
+    with pytest.raises(ValueError):
+        mcs.qmc.QuantumAnneal(np.ones(2), np.ones(2), 1, 0.1, c.astype(np.float64), nbs, 1)
+    with pytest.raises(ValueError):
+        mcs.qmc.QuantumAnneal(np.ones(2), np.ones(2), 1, 0.1, c, nbs[0], 1)
+    with pytest.raises(ValueError):  # P = 1 reads out of bounds in the reference; refused here
+        mcs.qmc.QuantumAnneal(np.ones(2), np.ones(2), 1, 0.1, c[:, :1], nbs, 1)
+    with pytest.raises(ValueError):
+        mcs.sa.Anneal(np.ones(2, dtype=np.float32), 1, c[:, 0].copy(), nbs)

@@ -1,0 +1,302 @@
+"""Parity tier (c) and correctness of the production (coloured, Philox-driven) kernels, through the
+C ABI.  The coloured kernels do not follow the reference's visiting order, so they are checked
+  * against EXACT Boltzmann averages (full enumeration) on small instances -- detailed balance of
+    every code path: LUT and general-degree kernels, even / odd P, fields, non-bipartite colouring;
+  * against the reference's residual-energy statistics on the shipped 80x80 instance
+    (tests/golden/santoro_ref_stats.json, made by tests/golden/make_santoro_stats.py);
+  * for invariances: pack/unpack round trips, independence of sharding and of call splitting.
+Tolerances are stated in each test."""
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import instances as inst
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def mcs():
+    import montecarlosolvers_b200 as m
+    m._lib.require_device()
+    return m
+
+
+def _all_states(n):
+    return (1 - 2 * ((np.arange(2 ** n)[:, None] >> np.arange(n)[None, :]) & 1)).astype(np.int64)
+
+
+def _classical_energies(states, nbs):
+    """E(s) for every row of states [M, N] in the reference's convention (each mirrored bond half)."""
+    idx = nbs[:, :, 0].astype(int)
+    J = nbs[:, :, 1]
+    n = nbs.shape[0]
+    e = np.zeros(states.shape[0])
+    for i in range(n):
+        for s in range(nbs.shape[1]):
+            if idx[i, s] == i:
+                e += J[i, s] * states[:, i]
+            else:
+                e += 0.5 * J[i, s] * states[:, i] * states[:, idx[i, s]]
+    return e
+
+
+def _piqmc_exact(nbs, P, a, b, temp):
+    """Exact <E_cl of slice 0> and <s^k s^{k+1}> under exp(-S/teff), S = sum_k b E_cl(s^k) - jperp sum s s'."""
+    n = nbs.shape[0]
+    teff, jperp, _ = orc.qmc_coeffs(a, b, temp, P)
+    st = _all_states(n * P).reshape(-1, P, n)
+    S = np.zeros(st.shape[0])
+    ecl = []
+    for k in range(P):
+        ek = _classical_energies(st[:, k, :], nbs)
+        ecl.append(ek)
+        S += b * ek
+        S -= jperp * np.sum(st[:, k, :] * st[:, (k + 1) % P, :], axis=1)
+    w = np.exp(-(S - S.min()) / teff)
+    w /= w.sum()
+    link = np.mean([np.sum(st[:, k, :] * st[:, (k + 1) % P, :], axis=1) for k in range(P)], axis=0) / n
+    return float(np.dot(w, np.mean(ecl, axis=0))), float(np.dot(w, link))
+
+
+def _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, R=4096, burn=150, meas=40, global_moves=False, seed=5):
+    n = nbs.shape[0]
+    I = mcs.Instance(nbs)
+    st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+    st.init_random(seed)
+    A = np.full(burn, a)
+    st.piqmc_sweeps(A, np.full(burn, b), 1, temp, global_moves=global_moves, seed=seed)
+    es, ls = [], []
+    for t in range(meas):
+        st.piqmc_sweeps(np.full(3, a), np.full(3, b), 1, temp, global_moves=global_moves, seed=seed,
+                        sweep_offset=burn + 3 * t)
+        c = st.download_spins().astype(np.float64)  # [R, N, P]
+        es.append(st.energies().mean(axis=1))
+        ls.append((c * np.roll(c, -1, axis=2)).sum(axis=(1, 2)) / (n * P))
+    es, ls = np.array(es).mean(axis=0), np.array(ls).mean(axis=0)
+    st.close()
+    return es.mean(), es.std(ddof=1) / np.sqrt(R), ls.mean(), ls.std(ddof=1) / np.sqrt(R), I
+
+
+@pytest.mark.parametrize("case", ["ring4_P4", "tri5_fields_P3", "k8_direct_P2", "torus_P2_global"])
+def test_piqmc_samples_the_exact_boltzmann_distribution(mcs, case):
+    """Tolerance: |GPU mean - exact| <= 4.5 standard errors (over 4096 independent replicas)."""
+    if case == "ring4_P4":
+        J, nbs = inst.random_graph(4, 4, seed=1, fields=False)
+        P, glob = 4, False
+    elif case == "tri5_fields_P3":  # odd cycle -> greedy colouring (3 colours), fields, odd P
+        import scipy.sparse as sps
+        J = sps.dok_matrix((5, 5))
+        for (i, j, v) in ((0, 1, 0.9), (1, 2, -0.7), (0, 2, 0.5), (2, 3, 1.1), (3, 4, -0.6), (4, 0, 0.8)):
+            J[i, j] = v
+        J[1, 1] = 0.4
+        J[3, 3] = -0.3
+        nbs = orc.GenerateNeighbors(5, J, 4)
+        P, glob = 3, False
+    elif case == "k8_direct_P2":  # degree 7 -> 7 + 2 planes > 8: the general-degree kernel
+        import scipy.sparse as sps
+        rng = np.random.RandomState(3)
+        J = sps.dok_matrix((8, 8))
+        for i in range(8):
+            for j in range(i + 1, 8):
+                J[i, j] = rng.normal() * 0.5
+        nbs = orc.GenerateNeighbors(8, J, 7)
+        P, glob = 2, False
+    else:
+        J, nbs = inst.torus(2, seed=2, fields=True)
+        P, glob = 2, True
+    a, b, temp = 1.1, 0.8, 0.9 / P
+    e_exact, l_exact = _piqmc_exact(nbs, P, a, b, temp)
+    e, e_sem, l, l_sem, I = _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, global_moves=glob)
+    if case == "k8_direct_P2":
+        assert not I.lut_kernels
+    if case == "tri5_fields_P3":
+        assert I.ncolors == 3 and I.has_field
+    assert abs(e - e_exact) <= 4.5 * e_sem, (case, e, e_exact, e_sem)
+    assert abs(l - l_exact) <= 4.5 * l_sem, (case, l, l_exact, l_sem)
+
+
+@pytest.mark.parametrize("case", ["graph10_lut", "k10_direct"])
+def test_sa_samples_the_exact_boltzmann_distribution(mcs, case):
+    """Fixed temperature, 4096 restarts; tolerance 4.5 standard errors on <E>."""
+    if case == "graph10_lut":
+        _, nbs = inst.random_graph(10, 16, seed=4, fields=True)
+    else:
+        import scipy.sparse as sps
+        rng = np.random.RandomState(8)
+        J = sps.dok_matrix((10, 10))
+        for i in range(10):
+            for j in range(i + 1, 10):
+                J[i, j] = rng.normal() * 0.4
+        nbs = orc.GenerateNeighbors(10, J, 9)
+    T = 1.3
+    st_all = _all_states(10)
+    e_all = _classical_energies(st_all, nbs)
+    w = np.exp(-(e_all - e_all.min()) / T)
+    w /= w.sum()
+    e_exact = float(np.dot(w, e_all))
+    R = 4096
+    I = mcs.Instance(nbs)
+    st = mcs.State(I, mcs._lib.KIND_SA, R, 1)
+    st.init_random(9)
+    st.sa_sweeps(np.full(100, T), 1, seed=9)
+    es = []
+    for t in range(40):
+        st.sa_sweeps(np.full(3, T), 1, seed=9, sweep_offset=100 + 3 * t)
+        es.append(st.energies())
+    es = np.array(es).mean(axis=0)
+    assert abs(es.mean() - e_exact) <= 4.5 * es.std(ddof=1) / np.sqrt(R), (es.mean(), e_exact)
+
+
+def test_svmc_equilibrium_matches_oracle_dynamics(mcs):
+    """Continuous rotors: compare <H> at fixed (A, B, T) between the production kernel (2048 reads) and
+    the oracle's sequential dynamics (svmc.pyx:78-117).  Tolerance 4.5 combined standard errors."""
+    _, nbs = inst.torus(4, seed=6, fields=True)
+    n = 16
+    a, b, temp = 0.6, 1.0, 0.35
+    sweeps = 300
+    np.random.seed(0)
+    Ro = 96
+    vo = np.full((Ro, n), np.pi / 2)
+    for tf, name in ((False, "SpinVectorMonteCarloCompact"),):
+        orc.SpinVectorMonteCarloCompact(np.full(sweeps, a), np.full(sweeps, b), 1, temp, vo, nbs, rng=3)
+        eo = np.array([orc.svmc_energy(a, b, vo[r], nbs) for r in range(Ro)])
+        # reads of the oracle's Compact call share one randuni (svmc.pyx:506) -> decorrelate with more sweeps
+        R = 2048
+        v = np.full((R, n), np.pi / 2)
+        mcs.svmc.SpinVectorMonteCarloCompact(np.full(sweeps, a), np.full(sweeps, b), 1, temp, v, nbs, seed=11)
+        assert v.min() >= 0.0 and v.max() <= np.pi + 1e-6
+        eg = np.array([orc.svmc_energy(a, b, v[r], nbs) for r in range(R)])
+        sem = np.sqrt(eo.var(ddof=1) / Ro + eg.var(ddof=1) / R)
+        assert abs(eo.mean() - eg.mean()) <= 4.5 * sem, (eo.mean(), eg.mean(), sem)
+    # TF proposals stay in [0, pi] and lower the energy of a ferromagnet at low temperature
+    v = np.full((64, n), np.pi / 2)
+    s = np.linspace(0.05, 1.0, 200)
+    mcs.svmc.SpinVectorMonteCarloTFCompact(3 * (1 - s), s, 1, 0.05, v, nbs, seed=2)
+    assert v.min() >= 0.0 and v.max() <= np.pi + 1e-6
+    e_end = np.mean([orc.svmc_energy(0.0, 1.0, v[r], nbs) for r in range(64)])
+    e_start = orc.svmc_energy(0.0, 1.0, np.full(n, np.pi / 2), nbs)
+    assert e_end < e_start - 1.0
+
+
+def test_results_do_not_depend_on_sharding_or_call_splitting(mcs):
+    _, nbs = inst.torus(6, seed=3, fields=True)
+    n, P, R = 36, 8, 96
+    A = np.linspace(2.0, 0.1, 10)
+    B = np.ones(10)
+    c0 = (2 * np.random.RandomState(1).randint(2, size=(R, n, P)) - 1).astype(np.int8)
+    whole = c0.copy()
+    mcs.qmc.QuantumAnnealGlobal(A, B, 2, 1.0 / P, whole, nbs, 1, seed=77)
+    parts = c0.copy()
+    for lo, hi in ((0, 32), (32, 96)):  # two "GPUs"
+        sub = np.ascontiguousarray(parts[lo:hi])
+        mcs.qmc.QuantumAnnealGlobal(A, B, 2, 1.0 / P, sub, nbs, 1, seed=77, replica_offset=lo)
+        parts[lo:hi] = sub
+    assert np.array_equal(whole, parts)
+    assert not np.array_equal(whole, c0)
+    # a schedule split over two resident calls == one call (checkpoint / resume by slicing the schedule)
+    I = mcs.Instance(nbs)
+    st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+    st.upload_spins(c0)
+    st.piqmc_sweeps(A[:4], B[:4], 2, 1.0 / P, global_moves=True, seed=77)
+    st.piqmc_sweeps(A[4:], B[4:], 2, 1.0 / P, global_moves=True, seed=77, sweep_offset=8)
+    assert np.array_equal(st.download_spins(), whole)
+    # single reference-style [N, P] int64 call == replica 0 of the batch
+    one = c0[0].astype(np.int64)
+    assert mcs.qmc.QuantumAnnealGlobal(A, B, 2, 1.0 / P, one, nbs, 1, seed=77) is None
+    assert np.array_equal(one, whole[0])
+    s0 = np.ascontiguousarray(c0[:, :, 0])
+    s_whole = s0.copy()
+    mcs.sa.Anneal(np.linspace(3, 0, 12), 2, s_whole, nbs, seed=5)
+    s_parts = s0.copy()
+    for lo, hi in ((0, 64), (64, 96)):
+        sub = np.ascontiguousarray(s_parts[lo:hi])
+        mcs.sa.Anneal(np.linspace(3, 0, 12), 2, sub, nbs, seed=5, replica_offset=lo)
+        s_parts[lo:hi] = sub
+    assert np.array_equal(s_whole, s_parts)
+
+
+def _ref_stats():
+    with open(os.path.join(G, "santoro_ref_stats.json")) as f:
+        return json.load(f)
+
+
+def _two_sigma(name, got, ref_cell):
+    ref = np.asarray(ref_cell)
+    sem = np.sqrt(got.var(ddof=1) / got.size + ref.var(ddof=1) / ref.size)
+    return abs(got.mean() - ref.mean()), 2.0 * sem, "%s: gpu %.5f ref %.5f 2sigma %.5f" % (
+        name, got.mean(), ref.mean(), 2.0 * sem)
+
+
+@pytest.mark.parametrize("tau", [60, 146, 354])
+def test_santoro_sa_residual_energy_matches_reference(mcs, tau):
+    """Tier (c), CA protocol of santoro80.py:258-262: 256 anneals from the same initial states as the
+    reference run; mean residual energy per spin within 2 sigma (combined standard error)."""
+    _, nbs, _, e_gs = inst.santoro()
+    ref = _ref_stats()
+    R = 256
+    s = np.stack([inst.random_spins(6400, r) for r in range(R)]).astype(np.int8)
+    e = mcs.sa.Anneal(np.linspace(3.0, 0.0, tau), 1, s, nbs, seed=1234 + tau, energies=True)
+    got = (e - e_gs) / 6400
+    assert np.allclose(e[:3], [orc.ising_energy(s[r].astype(np.int64), nbs) for r in range(3)], rtol=0, atol=1e-9)
+    diff, tol, msg = _two_sigma("sa tau=%d" % tau, got, ref["cells"]["sa_tau%d" % tau])
+    print(msg)
+    assert diff <= tol, msg
+
+
+@pytest.mark.parametrize("glob", [1, 0])
+@pytest.mark.parametrize("tau", [60, 146, 354])
+def test_santoro_piqmc_residual_energy_matches_reference(mcs, tau, glob):
+    """Tier (c), PIQMC protocol of santoro80.py:279-298 (P = 20, PT = 1, Gamma 3 -> 1e-8 in tau steps, one
+    sweep each, best slice), started from the SAME 256 pre-annealed states as the reference run."""
+    _, nbs, _, e_gs = inst.santoro()
+    ref = _ref_stats()
+    P, R = 20, 256
+    pre = np.load(os.path.join(G, "santoro_preannealed.npz"))
+    s = np.where(np.unpackbits(pre["packed"], axis=1)[:, :6400] > 0, 1, -1).astype(np.int8)[:R]
+    confs = np.ascontiguousarray(np.repeat(s[:, :, None], P, axis=2))
+    fn = mcs.qmc.QuantumAnnealGlobal if glob else mcs.qmc.QuantumAnneal
+    e = fn(np.linspace(3.0, 1e-8, tau), np.ones(tau), 1, 1.0 / P, confs, nbs, 1, seed=99 + tau, energies=True)
+    got = (e.min(axis=1) - e_gs) / 6400
+    k = int(np.argmin(e[0]))
+    assert abs(e[0, k] - orc.ising_energy(confs[0, :, k].astype(np.int64), nbs)) < 1e-9
+    name = "qmc%s_P20_tau%d" % ("_global" if glob else "", tau)
+    diff, tol, msg = _two_sigma(name, got, ref["cells"][name])
+    print(msg)
+    assert diff <= tol, msg
+
+
+def test_full_size_properties_cfg3_shape(mcs):
+    """BASELINE cfg3 shape (80x80, P = 64) at reduced replica count: size-independent properties.
+    Energies never increase under a T -> 0, Gamma -> 0 quench; world lines align across slices;
+    pack/unpack is the identity; energies are bit-identical to the oracle's definition."""
+    _, nbs, _, e_gs = inst.santoro()
+    P, R = 64, 64
+    I = mcs.Instance(nbs)
+    assert I.ncolors == 2 and I.maxdeg == 4 and I.lut_kernels and not I.has_field
+    col = I.colors().reshape(80, 80)
+    assert np.array_equal(col ^ col[0, 0], (np.add.outer(np.arange(80), np.arange(80)) & 1))  # checkerboard
+    st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+    st.init_random(3)
+    c0 = st.download_spins()
+    assert np.all(c0 == c0[:, :, :1])  # identical across slices
+    assert abs(c0.astype(np.float64).mean()) < 0.01
+    e0 = st.energies()
+    st.piqmc_sweeps(np.linspace(3.0, 1e-8, 200), np.ones(200), 1, 1.0 / P, seed=4)
+    e1 = st.energies()
+    assert e1.min(axis=1).max() < e0.min(axis=1).min()
+    res = (e1.min(axis=1) - e_gs) / 6400
+    assert 0.0 < res.mean() < 0.05
+    c1 = st.download_spins()
+    assert e1[5, 7] == orc.ising_energy(c1[5, :, 7].astype(np.int64), nbs)
+    # at Gamma -> 0 the Trotter coupling is huge: slices of a world line agree almost everywhere
+    agree = (c1 == np.roll(c1, 1, axis=2)).mean()
+    assert agree > 0.99
+    st2 = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+    st2.upload_spins(c1)
+    assert np.array_equal(st2.download_spins(), c1)
