@@ -8,6 +8,7 @@ import ctypes
 import hashlib
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -188,6 +189,7 @@ class Instance(object):
         h = c_vp()
         check(load().mcs_instance_create(dptr(nbs), self.nspins, self.maxnb, self.device, ctypes.byref(h)))
         self._h = h
+        self._states = weakref.WeakSet()
         info = (c_i64 * 8)()
         check(load().mcs_instance_info(self._h, info))
         self.ncolors, self.maxdeg = int(info[2]), int(info[3])
@@ -215,6 +217,8 @@ class Instance(object):
 
     def close(self):
         if getattr(self, "_h", None):
+            for st in list(self._states):
+                st.close()
             load().mcs_instance_destroy(self._h)
             self._h = None
 
@@ -233,6 +237,7 @@ class State(object):
         h = c_vp()
         check(load().mcs_state_create(inst._h, kind, self.R, self.P, ctypes.byref(h)))
         self._h = h
+        inst._states.add(self)
 
     def _spin_shape(self):
         return (self.R, self.inst.nspins, self.P) if self.kind == KIND_PIQMC else (self.R, self.inst.nspins)

@@ -21,7 +21,7 @@ static size_t spin_bytes(const mcs_state *st) { return (size_t)st->R * st->inst-
 
 extern "C" int mcs_state_upload_spins(mcs_state *st, const int8_t *host)
 {
-    MCS_REQUIRE(st && host, MCS_EINVAL, "mcs_state_upload_spins: NULL argument");
+    MCS_REQUIRE(st && st->inst && host, MCS_EINVAL, "mcs_state_upload_spins: NULL argument");
     MCS_REQUIRE(st->kind == MCS_KIND_PIQMC || st->kind == MCS_KIND_SA, MCS_EINVAL,
                 "mcs_state_upload_spins: state holds angles, not spins");
     MCS_CUDA(cudaSetDevice(st->inst->device));
@@ -34,7 +34,7 @@ extern "C" int mcs_state_upload_spins(mcs_state *st, const int8_t *host)
 
 extern "C" int mcs_state_download_spins(mcs_state *st, int8_t *host)
 {
-    MCS_REQUIRE(st && host, MCS_EINVAL, "mcs_state_download_spins: NULL argument");
+    MCS_REQUIRE(st && st->inst && host, MCS_EINVAL, "mcs_state_download_spins: NULL argument");
     MCS_REQUIRE(st->kind == MCS_KIND_PIQMC || st->kind == MCS_KIND_SA, MCS_EINVAL,
                 "mcs_state_download_spins: state holds angles, not spins");
     MCS_CUDA(cudaSetDevice(st->inst->device));
@@ -49,7 +49,7 @@ extern "C" int mcs_state_download_spins(mcs_state *st, int8_t *host)
 
 extern "C" int mcs_state_upload_angles(mcs_state *st, const double *host)
 {
-    MCS_REQUIRE(st && host, MCS_EINVAL, "mcs_state_upload_angles: NULL argument");
+    MCS_REQUIRE(st && st->inst && host, MCS_EINVAL, "mcs_state_upload_angles: NULL argument");
     MCS_REQUIRE(st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_state_upload_angles: not an SVMC state");
     MCS_CUDA(cudaSetDevice(st->inst->device));
     const size_t bytes = (size_t)st->R * st->inst->N * sizeof(double);
@@ -60,7 +60,7 @@ extern "C" int mcs_state_upload_angles(mcs_state *st, const double *host)
 
 extern "C" int mcs_state_download_angles(mcs_state *st, double *host)
 {
-    MCS_REQUIRE(st && host, MCS_EINVAL, "mcs_state_download_angles: NULL argument");
+    MCS_REQUIRE(st && st->inst && host, MCS_EINVAL, "mcs_state_download_angles: NULL argument");
     MCS_REQUIRE(st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_state_download_angles: not an SVMC state");
     MCS_CUDA(cudaSetDevice(st->inst->device));
     const size_t bytes = (size_t)st->R * st->inst->N * sizeof(double);
@@ -73,7 +73,7 @@ extern "C" int mcs_state_download_angles(mcs_state *st, double *host)
 
 extern "C" int mcs_state_init_random(mcs_state *st, uint64_t seed, uint64_t replica_offset)
 {
-    MCS_REQUIRE(st, MCS_EINVAL, "mcs_state_init_random: NULL state");
+    MCS_REQUIRE(st && st->inst, MCS_EINVAL, "mcs_state_init_random: NULL or orphaned state");
     MCS_CUDA(cudaSetDevice(st->inst->device));
     if (st->kind == MCS_KIND_PIQMC) return mcs_piqmc_init(st, seed, replica_offset);
     if (st->kind == MCS_KIND_SA) return mcs_sa_init(st, seed, replica_offset);
@@ -82,7 +82,7 @@ extern "C" int mcs_state_init_random(mcs_state *st, uint64_t seed, uint64_t repl
 
 extern "C" int mcs_state_energies(mcs_state *st, double *host_out)
 {
-    MCS_REQUIRE(st && host_out, MCS_EINVAL, "mcs_state_energies: NULL argument");
+    MCS_REQUIRE(st && st->inst && host_out, MCS_EINVAL, "mcs_state_energies: NULL argument");
     MCS_REQUIRE(st->kind == MCS_KIND_PIQMC || st->kind == MCS_KIND_SA, MCS_EINVAL,
                 "mcs_state_energies: use mcs_state_svmc_energies for SVMC states");
     MCS_CUDA(cudaSetDevice(st->inst->device));
@@ -103,7 +103,7 @@ extern "C" int mcs_state_energies(mcs_state *st, double *host_out)
 
 extern "C" int mcs_state_svmc_energies(mcs_state *st, double a, double b, double *host_out)
 {
-    MCS_REQUIRE(st && host_out, MCS_EINVAL, "mcs_state_svmc_energies: NULL argument");
+    MCS_REQUIRE(st && st->inst && host_out, MCS_EINVAL, "mcs_state_svmc_energies: NULL argument");
     MCS_REQUIRE(st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_state_svmc_energies: not an SVMC state");
     MCS_CUDA(cudaSetDevice(st->inst->device));
     const size_t bytes = (size_t)st->R * sizeof(double);
@@ -124,7 +124,7 @@ extern "C" int mcs_state_svmc_energies(mcs_state *st, double a, double b, double
 extern "C" int mcs_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
                                 int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
 {
-    MCS_REQUIRE(st && st->kind == MCS_KIND_PIQMC, MCS_EINVAL, "mcs_piqmc_sweeps: not a PIQMC state");
+    MCS_REQUIRE(st && st->inst && st->kind == MCS_KIND_PIQMC, MCS_EINVAL, "mcs_piqmc_sweeps: not a PIQMC state");
     MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_piqmc_sweeps: bad schedule");
     return mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, sweep_offset);
 }
@@ -132,7 +132,7 @@ extern "C" int mcs_piqmc_sweeps(mcs_state *st, const double *A, const double *B,
 extern "C" int mcs_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcsteps, uint64_t seed,
                              uint64_t replica_offset, uint64_t sweep_offset)
 {
-    MCS_REQUIRE(st && st->kind == MCS_KIND_SA, MCS_EINVAL, "mcs_sa_sweeps: not an SA state");
+    MCS_REQUIRE(st && st->inst && st->kind == MCS_KIND_SA, MCS_EINVAL, "mcs_sa_sweeps: not an SA state");
     MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || sched), MCS_EINVAL, "mcs_sa_sweeps: bad schedule");
     return mcs_launch_sa_sweeps(st, sched, S, mcsteps, seed, replica_offset, sweep_offset);
 }
@@ -140,7 +140,7 @@ extern "C" int mcs_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int 
 extern "C" int mcs_svmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
                                int tf, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
 {
-    MCS_REQUIRE(st && st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_svmc_sweeps: not an SVMC state");
+    MCS_REQUIRE(st && st->inst && st->kind == MCS_KIND_SVMC, MCS_EINVAL, "mcs_svmc_sweeps: not an SVMC state");
     MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_svmc_sweeps: bad schedule");
     return mcs_launch_svmc_sweeps(st, A, B, S, mcsteps, temp, tf, seed, replica_offset, sweep_offset);
 }

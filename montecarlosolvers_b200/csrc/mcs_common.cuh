@@ -49,6 +49,7 @@ struct mcs_instance {
     bool has_field = false;
     bool lut_ok = false; // (maxdeg + has_field + 2) <= 8 planes: the LUT kernels apply
     int64_t launches = 0;
+    std::vector<struct mcs_state *> states; // live replica batches (orphaned if the instance dies first)
 
     // host copies
     std::vector<int32_t> color;       // [N]

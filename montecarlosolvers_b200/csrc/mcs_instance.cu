@@ -242,10 +242,30 @@ extern "C" int mcs_instance_create(const double *nbs, int64_t nspins, int64_t ma
     return MCS_OK;
 }
 
+static void state_release_device(mcs_state *st)
+{
+    cudaFree(st->d_W);
+    cudaFree(st->d_V);
+    cudaFree(st->d_theta);
+    cudaFree(st->d_cosz);
+    cudaFree(st->d_stage);
+    st->d_W = nullptr;
+    st->d_V = nullptr;
+    st->d_theta = st->d_cosz = nullptr;
+    st->d_stage = nullptr;
+    st->stage_bytes = 0;
+}
+
 extern "C" void mcs_instance_destroy(mcs_instance *inst)
 {
     if (!inst) return;
     cudaSetDevice(inst->device);
+    if (inst->stream) cudaStreamSynchronize(inst->stream);
+    for (mcs_state *st : inst->states) { // batches that outlive their instance become inert shells
+        state_release_device(st);
+        st->inst = nullptr;
+    }
+    inst->states.clear();
     cudaFree(inst->d_tab_idx);
     cudaFree(inst->d_tab_J);
     cudaFree(inst->d_ell_idx);
@@ -359,6 +379,7 @@ extern "C" int mcs_state_create(mcs_instance *inst, int kind, int64_t R, int64_t
         mcs_state_destroy(st);
         return rc;
     }
+    inst->states.push_back(st);
     *out = st;
     return MCS_OK;
 }
@@ -369,12 +390,10 @@ extern "C" void mcs_state_destroy(mcs_state *st)
     if (st->inst) {
         cudaSetDevice(st->inst->device);
         cudaStreamSynchronize(st->inst->stream);
+        auto &v = st->inst->states;
+        v.erase(std::remove(v.begin(), v.end(), st), v.end());
+        state_release_device(st);
     }
-    cudaFree(st->d_W);
-    cudaFree(st->d_V);
-    cudaFree(st->d_theta);
-    cudaFree(st->d_cosz);
-    cudaFree(st->d_stage);
     delete st;
 }
 
