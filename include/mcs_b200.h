@@ -74,6 +74,9 @@ int mcs_instance_colors(const mcs_instance *inst, int32_t *color /* [nspins] */)
 int mcs_timer_start(mcs_instance *inst);
 int mcs_timer_stop(mcs_instance *inst, double *ms);
 int mcs_synchronize(mcs_instance *inst);
+/* The one-shot host-buffer calls below keep their device batch + staging buffer cached in the
+ * instance between calls of the same shape; mcs_instance_trim releases that memory.          */
+int mcs_instance_trim(mcs_instance *inst);
 /* number of kernels this instance has launched so far (bench.py's gpu_launches)            */
 int64_t mcs_launch_count(const mcs_instance *inst);
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "mcs_timer_start": (ctypes.c_int, [c_vp]),
     "mcs_timer_stop": (ctypes.c_int, [c_vp, c_dp]),
     "mcs_synchronize": (ctypes.c_int, [c_vp]),
+    "mcs_instance_trim": (ctypes.c_int, [c_vp]),
     "mcs_launch_count": (c_i64, [c_vp]),
     "mcs_state_create": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64, c_i64, ctypes.POINTER(c_vp)]),
     "mcs_state_destroy": (None, [c_vp]),
@@ -210,6 +211,10 @@ class Instance(object):
 
     def synchronize(self):
         check(load().mcs_synchronize(self._h))
+
+    def trim(self):
+        """Release the device batch the one-shot calls keep cached between calls."""
+        check(load().mcs_instance_trim(self._h))
 
     @property
     def launches(self):

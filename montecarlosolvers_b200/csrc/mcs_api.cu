@@ -146,25 +146,20 @@ extern "C" int mcs_svmc_sweeps(mcs_state *st, const double *A, const double *B, 
 }
 
 // ---- one-shot host-buffer forms ----------------------------------------------------------------
-namespace {
-struct StateGuard {
-    mcs_state *st = nullptr;
-    ~StateGuard() { mcs_state_destroy(st); }
-};
-} // namespace
-
+// The device batch (and its staging buffer) lives in the instance and is reused by the next call of the
+// same shape: no cudaMalloc / cudaFree on the call path after the first call.
 extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const double *B, int64_t S, int mcsteps,
                                 float temp, int8_t *confs, int64_t R, int64_t P, int global_moves, uint64_t seed,
                                 uint64_t replica_offset, double *energies_out)
 {
     MCS_REQUIRE(inst && confs, MCS_EINVAL, "mcs_piqmc_anneal: NULL argument");
     MCS_REQUIRE((double)temp * (double)P != 0.0 || S == 0, MCS_EZERODIV, "float division");
-    StateGuard g;
-    MCS_TRY(mcs_state_create(inst, MCS_KIND_PIQMC, R, P, &g.st));
-    MCS_TRY(mcs_state_upload_spins(g.st, confs));
-    MCS_TRY(mcs_piqmc_sweeps(g.st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, 0));
-    MCS_TRY(mcs_state_download_spins(g.st, confs));
-    if (energies_out) MCS_TRY(mcs_state_energies(g.st, energies_out));
+    mcs_state *st = nullptr;
+    MCS_TRY(mcs_instance_scratch_state(inst, MCS_KIND_PIQMC, R, P, &st));
+    MCS_TRY(mcs_state_upload_spins(st, confs));
+    MCS_TRY(mcs_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, 0));
+    MCS_TRY(mcs_state_download_spins(st, confs));
+    if (energies_out) MCS_TRY(mcs_state_energies(st, energies_out));
     return MCS_OK;
 }
 
@@ -172,12 +167,12 @@ extern "C" int mcs_sa_anneal(mcs_instance *inst, const double *sched, int64_t S,
                              uint64_t seed, uint64_t replica_offset, double *energies_out)
 {
     MCS_REQUIRE(inst && svec, MCS_EINVAL, "mcs_sa_anneal: NULL argument");
-    StateGuard g;
-    MCS_TRY(mcs_state_create(inst, MCS_KIND_SA, R, 1, &g.st));
-    MCS_TRY(mcs_state_upload_spins(g.st, svec));
-    MCS_TRY(mcs_sa_sweeps(g.st, sched, S, mcsteps, seed, replica_offset, 0));
-    MCS_TRY(mcs_state_download_spins(g.st, svec));
-    if (energies_out) MCS_TRY(mcs_state_energies(g.st, energies_out));
+    mcs_state *st = nullptr;
+    MCS_TRY(mcs_instance_scratch_state(inst, MCS_KIND_SA, R, 1, &st));
+    MCS_TRY(mcs_state_upload_spins(st, svec));
+    MCS_TRY(mcs_sa_sweeps(st, sched, S, mcsteps, seed, replica_offset, 0));
+    MCS_TRY(mcs_state_download_spins(st, svec));
+    if (energies_out) MCS_TRY(mcs_state_energies(st, energies_out));
     return MCS_OK;
 }
 
@@ -185,10 +180,10 @@ extern "C" int mcs_svmc_anneal(mcs_instance *inst, const double *A, const double
                                float temp, double *svec, int64_t R, int tf, uint64_t seed, uint64_t replica_offset)
 {
     MCS_REQUIRE(inst && svec, MCS_EINVAL, "mcs_svmc_anneal: NULL argument");
-    StateGuard g;
-    MCS_TRY(mcs_state_create(inst, MCS_KIND_SVMC, R, 1, &g.st));
-    MCS_TRY(mcs_state_upload_angles(g.st, svec));
-    MCS_TRY(mcs_svmc_sweeps(g.st, A, B, S, mcsteps, temp, tf, seed, replica_offset, 0));
-    MCS_TRY(mcs_state_download_angles(g.st, svec));
+    mcs_state *st = nullptr;
+    MCS_TRY(mcs_instance_scratch_state(inst, MCS_KIND_SVMC, R, 1, &st));
+    MCS_TRY(mcs_state_upload_angles(st, svec));
+    MCS_TRY(mcs_svmc_sweeps(st, A, B, S, mcsteps, temp, tf, seed, replica_offset, 0));
+    MCS_TRY(mcs_state_download_angles(st, svec));
     return MCS_OK;
 }

@@ -50,6 +50,8 @@ struct mcs_instance {
     bool lut_ok = false; // (maxdeg + has_field + 2) <= 8 planes: the LUT kernels apply
     int64_t launches = 0;
     std::vector<struct mcs_state *> states; // live replica batches (orphaned if the instance dies first)
+    struct mcs_state *scratch[4] = {nullptr, nullptr, nullptr, nullptr}; // per-kind batch reused by the
+                                                                         // one-shot host-buffer calls
 
     // host copies
     std::vector<int32_t> color;       // [N]
@@ -80,6 +82,8 @@ struct mcs_state {
 };
 
 int mcs_state_reserve_stage(mcs_state *st, size_t bytes);
+// batch of the given shape owned by the instance and reused across one-shot calls (no cudaMalloc per call)
+int mcs_instance_scratch_state(mcs_instance *inst, int kind, int64_t R, int64_t P, mcs_state **out);
 
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  Key = the user's 64-bit seed
@@ -157,6 +161,34 @@ __device__ __forceinline__ void mcs_philox4x32_10_rk(uint32_t c0, uint32_t c1, u
     out[1] = c1;
     out[2] = c2;
     out[3] = c3;
+}
+
+// Powers of two kept in the kernel-parameter constant bank: shifts done as IMAD / IMAD.HI by a
+// multiplier ptxas cannot see through stay on the FMA pipe (an immediate 2^k would be strength-reduced to
+// SHF on the ALU pipe, which is the binding unit of the sweep kernels).
+//   left shift by s  (0 <= s <= 15):  x * up[s]
+//   right shift by r (1 <= r <= 8):   __umulhi(x, down[r])        down[r] = 2^(32 - r)
+struct mcs_pow2_table {
+    uint32_t up[16];
+    uint32_t down[9];
+};
+
+inline mcs_pow2_table mcs_pow2_make()
+{
+    mcs_pow2_table t;
+    for (int i = 0; i < 16; ++i) t.up[i] = 1u << i;
+    t.down[0] = 0;
+    for (int r = 1; r <= 8; ++r) t.down[r] = 1u << (32 - r);
+    return t;
+}
+
+// x shifted left by `delta` bits (right if negative) without touching the ALU pipe
+template <int DELTA>
+__device__ __forceinline__ uint32_t mcs_fma_shift(uint32_t x, const mcs_pow2_table &t)
+{
+    if (DELTA == 0) return x;
+    if (DELTA > 0) return x * t.up[DELTA > 0 ? DELTA : 0];
+    return __umulhi(x, t.down[DELTA < 0 ? -DELTA : 0]);
 }
 
 // call tags (counter word 3): which draw inside one (replica, site, sweep)

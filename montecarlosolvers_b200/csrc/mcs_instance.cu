@@ -261,6 +261,10 @@ extern "C" void mcs_instance_destroy(mcs_instance *inst)
     if (!inst) return;
     cudaSetDevice(inst->device);
     if (inst->stream) cudaStreamSynchronize(inst->stream);
+    for (int k = 0; k < 4; ++k) {
+        if (inst->scratch[k]) mcs_state_destroy(inst->scratch[k]);
+        inst->scratch[k] = nullptr;
+    }
     for (mcs_state *st : inst->states) { // batches that outlive their instance become inert shells
         state_release_device(st);
         st->inst = nullptr;
@@ -406,5 +410,31 @@ int mcs_state_reserve_stage(mcs_state *st, size_t bytes)
     st->stage_bytes = 0;
     MCS_CUDA(cudaMalloc(&st->d_stage, bytes));
     st->stage_bytes = bytes;
+    return MCS_OK;
+}
+
+int mcs_instance_scratch_state(mcs_instance *inst, int kind, int64_t R, int64_t P, mcs_state **out)
+{
+    MCS_REQUIRE(inst && out && kind >= 1 && kind <= 3, MCS_EINVAL, "mcs_instance_scratch_state: bad argument");
+    mcs_state *st = inst->scratch[kind];
+    if (st && (st->R != R || st->P != P)) {
+        mcs_state_destroy(st);
+        inst->scratch[kind] = st = nullptr;
+    }
+    if (!st) {
+        MCS_TRY(mcs_state_create(inst, kind, R, P, &st));
+        inst->scratch[kind] = st;
+    }
+    *out = st;
+    return MCS_OK;
+}
+
+extern "C" int mcs_instance_trim(mcs_instance *inst)
+{
+    MCS_REQUIRE(inst, MCS_EINVAL, "mcs_instance_trim: NULL instance");
+    for (int k = 0; k < 4; ++k) {
+        if (inst->scratch[k]) mcs_state_destroy(inst->scratch[k]);
+        inst->scratch[k] = nullptr;
+    }
     return MCS_OK;
 }

@@ -47,18 +47,11 @@ struct PiqmcPass {
     float jperp2;      // 2 J_perp     (qmc.pyx:95,137-138)
     float nl2e_over_t; // -log2(e)/teff
     mcs_philox_keys keys; // ten Philox round keys, read straight from the parameter constant bank
+    mcs_pow2_table pow2;  // 2^0 .. 2^15 (multipliers of the plane transposition, see phase())
     uint32_t sweep_lo, sweep_hi;
     uint32_t replica_offset;
     int global_moves;
 };
-
-__device__ __forceinline__ uint32_t prmt_sign_bytes(uint32_t v)
-{
-    // byte i of the result = 0xFF if bit 8i+7 of v is set else 0x00 (PRMT with sign replication)
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0xBA98u));
-    return r;
-}
 
 __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
 {
@@ -87,37 +80,66 @@ struct LutGeom {
 
 // One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in
 // `allowed`, against thresholds in lut[].  Returns the flip mask.
+//
+// Transposition of the planes into per-slice pattern indices: group g of a 32-bit half word holds
+// slices 8i + 7 - g (i = 0..3).  Plane p's bit of slice i must land at bit 8i + SH + p of the index
+// word, i.e. the half word is shifted by delta = SH + p - 7 + g (an IMAD / IMAD.HI by a power of two from
+// the constant bank: FMA pipe) and merged with one LOP3 (acc | (shifted & 0x01010101 << (SH+p)): ALU
+// pipe).  Byte i of the index word is then the pattern index of slice 8i + 7 - g (times 4 if SH == 2).
+template <int NPL, int G, int HALF>
+__device__ __forceinline__ uint32_t gather_index(const uint64_t (&pl)[NPL], uint64_t tl, uint64_t tr,
+                                                 const mcs_pow2_table &pow2)
+{
+    constexpr int SH = (NPL + 2 <= 6) ? 2 : 0;
+    uint32_t acc = 0;
+#define MCS_PLANE(p)                                                                              \
+    if (p < NPL + 2) {                                                                            \
+        const uint64_t plane = p < NPL ? pl[p < NPL ? p : 0] : (p == NPL ? tl : tr);              \
+        const uint32_t v = (uint32_t)(plane >> (32 * HALF));                                      \
+        acc |= mcs_fma_shift<SH + p - 7 + G>(v, pow2) & (0x01010101u << (SH + p));                \
+    }
+    MCS_PLANE(0) MCS_PLANE(1) MCS_PLANE(2) MCS_PLANE(3) MCS_PLANE(4) MCS_PLANE(5) MCS_PLANE(6) MCS_PLANE(7)
+#undef MCS_PLANE
+    return acc;
+}
+
+template <int NPL, int G, int HALF>
+__device__ __forceinline__ void attempt_group(uint32_t &flip, const uint64_t (&pl)[NPL], uint64_t tl, uint64_t tr,
+                                              const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2,
+                                              uint32_t c3hi, const mcs_philox_keys &keys,
+                                              const mcs_pow2_table &pow2)
+{
+    constexpr int SH = (NPL + 2 <= 6) ? 2 : 0;
+    const uint32_t acc = gather_index<NPL, G, HALF>(pl, tl, tr, pow2);
+    uint32_t rnd[4];
+    mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(HALF * 8 + G), keys, rnd);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t off = prmt_byte(acc, i); // = 4 * idx when SH == 2, idx otherwise
+        const uint32_t T = SH == 2 ? *(const uint32_t *)((const char *)lut + off) : lut[off];
+        if (rnd[i] <= T) flip += 1u << (8 * i + 7 - G); // each bit is added at most once: + == |
+    }
+}
+
+// One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in
+// `allowed`, against thresholds in lut[].  Returns the flip mask.
 template <int NPL, int PARITY>
 __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w, int P, uint64_t pmask,
                                           uint64_t allowed, const uint32_t *lut, uint32_t c0, uint32_t c1,
-                                          uint32_t c2, uint32_t c3hi, const mcs_philox_keys &keys)
+                                          uint32_t c2, uint32_t c3hi, const mcs_philox_keys &keys,
+                                          const mcs_pow2_table &pow2)
 {
-    constexpr int SH = LutGeom<NPL>::SH;
     const uint64_t tl = w ^ rotl_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k-1
     const uint64_t tr = w ^ rotr_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k+1
     uint32_t flip[2] = {0u, 0u};
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int g = 1 - PARITY; g < 8; g += 2) { // slices 32*half + 8i + 7 - g, parity of 7-g == PARITY
-            if (32 * half + 7 - g >= P) continue;   // whole group beyond the last slice (warp-uniform)
-            uint32_t acc = 0;
-#pragma unroll
-            for (int p = 0; p < NPL + 2; ++p) {
-                const uint64_t plane = p < NPL ? pl[p < NPL ? p : 0] : (p == NPL ? tl : tr);
-                const uint32_t v = (uint32_t)(plane >> (32 * half)) << g;
-                acc |= prmt_sign_bytes(v) & (0x01010101u << (p + SH));
-            }
-            uint32_t rnd[4];
-            mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(half * 8 + g), keys, rnd);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t off = prmt_byte(acc, i); // = 4 * idx when SH == 2, idx otherwise
-                const uint32_t T = SH == 2 ? *(const uint32_t *)((const char *)lut + off) : lut[off];
-                if (rnd[i] <= T) flip[half] |= 1u << (8 * i + 7 - g);
-            }
-        }
-    }
+    // group G of half H holds slices 32 H + 8 i + 7 - G; parity of 7 - G == PARITY  <=>  G = 1-PARITY, 3-PARITY, ...
+    // a whole group beyond the last slice is skipped (warp-uniform branch)
+#define MCS_GROUP(H, G)                                                                                      \
+    if (32 * H + 7 - (G) < P)                                                                                \
+        attempt_group<NPL, (G), H>(flip[H], pl, tl, tr, lut, c0, c1, c2, c3hi, keys, pow2);
+    MCS_GROUP(0, 1 - PARITY) MCS_GROUP(0, 3 - PARITY) MCS_GROUP(0, 5 - PARITY) MCS_GROUP(0, 7 - PARITY)
+    MCS_GROUP(1, 1 - PARITY) MCS_GROUP(1, 3 - PARITY) MCS_GROUP(1, 5 - PARITY) MCS_GROUP(1, 7 - PARITY)
+#undef MCS_GROUP
     return (((uint64_t)flip[1] << 32) | flip[0]) & allowed;
 }
 
@@ -180,8 +202,8 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
     if (oddP) even_allowed &= ~(1ull << (P - 1)); // slice P-1 neighbours slice 0: handled alone below
     const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
 
-    w ^= phase<NPL, 0>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys);
-    w ^= phase<NPL, 1>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys);
+    w ^= phase<NPL, 0>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2);
+    w ^= phase<NPL, 1>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2);
     if (oddP) {
         const int k = P - 1;
         const uint64_t tl = w ^ rotl_ring(w, P, pmask), tr = w ^ rotr_ring(w, P, pmask);
@@ -313,28 +335,83 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_direct_pass_kernel(const __
 // ------------------------------------------------------------------------------------------
 // host <-> packed conversion, initialisation, energies
 // ------------------------------------------------------------------------------------------
-// in: int8 [R][N][P] (site fastest over threads -> contiguous reads); out: W[N][Rpad]
-__global__ void piqmc_pack_kernel(const int8_t *__restrict__ in, uint64_t *__restrict__ W, long long N,
-                                  long long R, long long Rpad, int P)
+// int8 [R][N][P] (host order) <-> W[N][Rpad].  A 32x32 tile of (replica, site) is transposed through
+// shared memory so that both sides are coalesced: the spin side reads/writes 32 sites * P contiguous
+// bytes per warp, the packed side 32 replicas * 8 contiguous bytes per warp.
+// sign bits of 4 spin bytes -> 4-bit nibble: bits 7,15,23,31 are moved to 28..31 by one multiply.
+__device__ __forceinline__ uint32_t sign_nibble(uint32_t x) { return ((x & 0x80808080u) * 0x00204081u) >> 28; }
+// 4-bit nibble -> 4 spin bytes (+1 = 0x01, -1 = 0xFF)
+__device__ __forceinline__ uint32_t nibble_spins(uint32_t n)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= N * R) return;
-    const long long r = t / N, i = t % N;
-    const int8_t *src = in + (r * N + i) * P;
-    uint64_t w = 0;
-    for (int k = 0; k < P; ++k) w |= (uint64_t)(src[k] < 0) << k;
-    W[i * Rpad + r] = w;
+    const uint32_t b = (n * 0x00204081u) & 0x01010101u;
+    return 0x01010101u | (b * 0xFEu);
 }
 
-__global__ void piqmc_unpack_kernel(const uint64_t *__restrict__ W, int8_t *__restrict__ out, long long N,
-                                    long long R, long long Rpad, int P)
+__global__ void __launch_bounds__(1024) piqmc_pack_kernel(const int8_t *__restrict__ in, uint64_t *__restrict__ W,
+                                                          long long N, long long R, long long Rpad, int P)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= N * R) return;
-    const long long r = t / N, i = t % N;
-    const uint64_t w = W[i * Rpad + r];
+    __shared__ uint64_t tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long i0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+    {
+        const long long r = r0 + ty, i = i0 + tx;
+        uint64_t w = 0;
+        if (r < R && i < N) {
+            const int8_t *src = in + (r * N + i) * P;
+            if ((P & 15) == 0) {
+                for (int q = 0; q < P / 16; ++q) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(src) + q);
+                    const uint32_t nib = sign_nibble(x.x) | (sign_nibble(x.y) << 4) | (sign_nibble(x.z) << 8) |
+                                         (sign_nibble(x.w) << 12);
+                    w |= (uint64_t)nib << (16 * q);
+                }
+            } else if ((P & 3) == 0) {
+                for (int q = 0; q < P / 4; ++q)
+                    w |= (uint64_t)sign_nibble(__ldg(reinterpret_cast<const uint32_t *>(src) + q)) << (4 * q);
+            } else {
+                for (int k = 0; k < P; ++k) w |= (uint64_t)(src[k] < 0) << k;
+            }
+        }
+        tile[ty][tx] = w;
+    }
+    __syncthreads();
+    {
+        const long long i = i0 + ty, r = r0 + tx;
+        if (i < N && r < Rpad) W[i * Rpad + r] = tile[tx][ty];
+    }
+}
+
+__global__ void __launch_bounds__(1024) piqmc_unpack_kernel(const uint64_t *__restrict__ W, int8_t *__restrict__ out,
+                                                            long long N, long long R, long long Rpad, int P)
+{
+    __shared__ uint64_t tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long i0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+    {
+        const long long i = i0 + ty, r = r0 + tx;
+        tile[ty][tx] = (i < N && r < Rpad) ? W[i * Rpad + r] : 0ull;
+    }
+    __syncthreads();
+    const long long r = r0 + ty, i = i0 + tx;
+    if (r >= R || i >= N) return;
+    const uint64_t w = tile[tx][ty];
     int8_t *dst = out + (r * N + i) * P;
-    for (int k = 0; k < P; ++k) dst[k] = ((w >> k) & 1ull) ? -1 : 1;
+    if ((P & 15) == 0) {
+        for (int q = 0; q < P / 16; ++q) {
+            const uint32_t h = (uint32_t)(w >> (16 * q));
+            uint4 x;
+            x.x = nibble_spins(h & 0xFu);
+            x.y = nibble_spins((h >> 4) & 0xFu);
+            x.z = nibble_spins((h >> 8) & 0xFu);
+            x.w = nibble_spins((h >> 12) & 0xFu);
+            reinterpret_cast<uint4 *>(dst)[q] = x;
+        }
+    } else if ((P & 3) == 0) {
+        for (int q = 0; q < P / 4; ++q)
+            reinterpret_cast<uint32_t *>(dst)[q] = nibble_spins((uint32_t)(w >> (4 * q)) & 0xFu);
+    } else {
+        for (int k = 0; k < P; ++k) dst[k] = ((w >> k) & 1ull) ? -1 : 1;
+    }
 }
 
 __global__ void piqmc_init_kernel(uint64_t *W, long long N, long long R, long long Rpad, int P, uint32_t key0,
@@ -357,14 +434,14 @@ __global__ void piqmc_energy_kernel(const uint64_t *__restrict__ W, const int32_
                                     int maxnb, long long R, long long Rpad, int P)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y;
-    if (r >= R) return;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y;
+    if (r >= R || k >= P) return;
     double e = 0.0;
     for (long long i = 0; i < N; ++i) {
         double pair = 0.0, field = 0.0;
         for (int s = 0; s < maxnb; ++s) {
-            const int j = tab_idx[i * maxnb + s];
-            const double jv = tab_J[i * maxnb + s];
+            const int j = __ldg(&tab_idx[i * maxnb + s]);
+            const double jv = __ldg(&tab_J[i * maxnb + s]);
             if (j == i) {
                 field = __dadd_rn(field, jv);
             } else {
@@ -428,6 +505,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     a.Rpad = st->Rpad;
     a.P = P;
     a.keys = mcs_philox_expand(seed);
+    a.pow2 = mcs_pow2_make();
     a.replica_offset = (uint32_t)replica_offset;
     a.global_moves = global_moves ? 1 : 0;
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
@@ -462,9 +540,8 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
 int mcs_piqmc_pack(mcs_state *st, const int8_t *d_in)
 {
     mcs_instance *inst = st->inst;
-    const long long n = inst->N * st->R;
-    piqmc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(d_in, st->d_W, inst->N, st->R,
-                                                                            st->Rpad, (int)st->P);
+    dim3 grid((unsigned)((inst->N + 31) / 32), (unsigned)(st->Rpad / 32));
+    piqmc_pack_kernel<<<grid, dim3(32, 32), 0, inst->stream>>>(d_in, st->d_W, inst->N, st->R, st->Rpad, (int)st->P);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
@@ -473,9 +550,9 @@ int mcs_piqmc_pack(mcs_state *st, const int8_t *d_in)
 int mcs_piqmc_unpack(mcs_state *st, int8_t *d_out)
 {
     mcs_instance *inst = st->inst;
-    const long long n = inst->N * st->R;
-    piqmc_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(st->d_W, d_out, inst->N, st->R,
-                                                                              st->Rpad, (int)st->P);
+    dim3 grid((unsigned)((inst->N + 31) / 32), (unsigned)(st->Rpad / 32));
+    piqmc_unpack_kernel<<<grid, dim3(32, 32), 0, inst->stream>>>(st->d_W, d_out, inst->N, st->R, st->Rpad,
+                                                                 (int)st->P);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
@@ -496,8 +573,8 @@ int mcs_piqmc_init(mcs_state *st, uint64_t seed, uint64_t replica_offset)
 int mcs_piqmc_energy(mcs_state *st, double *d_out)
 {
     mcs_instance *inst = st->inst;
-    dim3 grid((unsigned)((st->R + 63) / 64), (unsigned)st->P);
-    piqmc_energy_kernel<<<grid, 64, 0, inst->stream>>>(st->d_W, inst->d_tab_idx, inst->d_tab_J, d_out, inst->N,
+    dim3 grid((unsigned)((st->R + 31) / 32), (unsigned)((st->P + 7) / 8));
+    piqmc_energy_kernel<<<grid, dim3(32, 8), 0, inst->stream>>>(st->d_W, inst->d_tab_idx, inst->d_tab_J, d_out, inst->N,
                                                       (int)inst->maxnb, st->R, st->Rpad, (int)st->P);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());

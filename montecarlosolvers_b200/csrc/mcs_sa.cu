@@ -30,16 +30,10 @@ struct SaPass {
     long long G;
     float nl2e_over_t; // -log2(e)/T
     mcs_philox_keys keys;
+    mcs_pow2_table pow2;
     uint32_t sweep_lo, sweep_hi;
     uint32_t word_offset; // replica_offset / 32
 };
-
-__device__ __forceinline__ uint32_t prmt_sign_bytes(uint32_t v)
-{
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0xBA98u));
-    return r;
-}
 
 __device__ __forceinline__ uint32_t prmt_byte(uint32_t v, int i)
 {
@@ -96,20 +90,28 @@ __global__ void __launch_bounds__(WARPS * 32) sa_lut_pass_kernel(const __grid_co
     }
     const uint32_t c0 = a.word_offset + (uint32_t)g, c1 = (uint32_t)site;
     uint32_t flip = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { // restarts 8 i + 7 - q of this word
-        uint32_t acc = 0;
-#pragma unroll
-        for (int p = 0; p < NPL; ++p) acc |= prmt_sign_bytes(pl[p] << q) & (0x01010101u << (p + SH));
-        uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)q, a.keys, rnd);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t off = prmt_byte(acc, i);
-            const uint32_t T = SH == 2 ? *(const uint32_t *)((const char *)s_lut + off) : s_lut[off];
-            if (rnd[i] <= T) flip |= 1u << (8 * i + 7 - q);
-        }
+    // group Q holds restarts 8 i + 7 - Q; plane p's bit of restart i goes to bit 8i + SH + p of the index word:
+    // shift by SH + p - 7 + Q as IMAD / IMAD.HI (FMA pipe) + one merging LOP3 (ALU pipe)
+#define MCS_SA_PLANE(Q, p)                                                                                    \
+    if (p < NPL) acc |= mcs_fma_shift<SH + p - 7 + Q>(pl[p < NPL ? p : 0], a.pow2) & (0x01010101u << (SH + p));
+#define MCS_SA_GROUP(Q)                                                                                       \
+    {                                                                                                         \
+        uint32_t acc = 0;                                                                                     \
+        MCS_SA_PLANE(Q, 0) MCS_SA_PLANE(Q, 1) MCS_SA_PLANE(Q, 2) MCS_SA_PLANE(Q, 3)                           \
+        MCS_SA_PLANE(Q, 4) MCS_SA_PLANE(Q, 5) MCS_SA_PLANE(Q, 6) MCS_SA_PLANE(Q, 7)                           \
+        uint32_t rnd[4];                                                                                      \
+        mcs_philox4x32_10_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(Q), a.keys, rnd);             \
+        _Pragma("unroll") for (int i = 0; i < 4; ++i)                                                         \
+        {                                                                                                     \
+            const uint32_t off = prmt_byte(acc, i);                                                           \
+            const uint32_t T = SH == 2 ? *(const uint32_t *)((const char *)s_lut + off) : s_lut[off];         \
+            if (rnd[i] <= T) flip |= 1u << (8 * i + 7 - (Q));                                                 \
+        }                                                                                                     \
     }
+    MCS_SA_GROUP(0) MCS_SA_GROUP(1) MCS_SA_GROUP(2) MCS_SA_GROUP(3)
+    MCS_SA_GROUP(4) MCS_SA_GROUP(5) MCS_SA_GROUP(6) MCS_SA_GROUP(7)
+#undef MCS_SA_GROUP
+#undef MCS_SA_PLANE
     a.V[(long long)site * a.G + g] = v ^ flip;
 }
 
@@ -270,6 +272,7 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
     a.G = st->G;
     a.chunks = (int)((st->G + 31) / 32);
     a.keys = mcs_philox_expand(seed);
+    a.pow2 = mcs_pow2_make();
     a.word_offset = (uint32_t)(replica_offset >> 5);
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const bool lut = npl <= 8;
