@@ -123,7 +123,7 @@ __device__ __forceinline__ void attempt_group(uint32_t &flip, const uint64_t (&p
 
 // One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in
 // `allowed`, against thresholds in lut[].  Returns the flip mask.
-template <int NPL, int PARITY>
+template <int NPL, int PARITY, bool FULL>
 __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w, int P, uint64_t pmask,
                                           uint64_t allowed, const uint32_t *lut, uint32_t c0, uint32_t c1,
                                           uint32_t c2, uint32_t c3hi, const mcs_philox_keys &keys,
@@ -135,7 +135,7 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
     // group G of half H holds slices 32 H + 8 i + 7 - G; parity of 7 - G == PARITY  <=>  G = 1-PARITY, 3-PARITY, ...
     // a whole group beyond the last slice is skipped (warp-uniform branch)
 #define MCS_GROUP(H, G)                                                                                      \
-    if (32 * H + 7 - (G) < P)                                                                                \
+    if (FULL || 32 * H + 7 - (G) < P)                                                                        \
         attempt_group<NPL, (G), H>(flip[H], pl, tl, tr, lut, c0, c1, c2, c3hi, keys, pow2);
     MCS_GROUP(0, 1 - PARITY) MCS_GROUP(0, 3 - PARITY) MCS_GROUP(0, 5 - PARITY) MCS_GROUP(0, 7 - PARITY)
     MCS_GROUP(1, 1 - PARITY) MCS_GROUP(1, 3 - PARITY) MCS_GROUP(1, 5 - PARITY) MCS_GROUP(1, 7 - PARITY)
@@ -145,7 +145,8 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
 
 // WARPS warps per CTA, all working on the SAME site (WARPS*32 consecutive replicas), so the
 // threshold table is built once per CTA at a compile-time shared-memory address.
-template <int NPL, int WARPS>
+// FULL: P == 64 (every group of four slices exists: no per-group branch, one basic block).
+template <int NPL, int WARPS, bool FULL>
 __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
     constexpr int ENT = LutGeom<NPL>::ENT;
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
     }
 
     // ---- this lane's world line and its in-plane anti-alignment planes ------------------------
-    const int P = a.P;
-    const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
+    const int P = FULL ? 64 : a.P;
+    const uint64_t pmask = (FULL || P == 64) ? ~0ull : ((1ull << P) - 1ull);
     uint64_t w = a.W[(long long)site * a.Rpad + r];
     uint64_t pl[NPL];
 #pragma unroll
@@ -194,16 +195,15 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
     else
         __syncthreads();
     const uint32_t *lut = s_lut;
-
     const uint32_t c0 = a.replica_offset + (uint32_t)r, c1 = (uint32_t)site, c2 = a.sweep_lo;
     const uint32_t c3hi = a.sweep_hi << 8;
-    const bool oddP = (P & 1) != 0;
+    const bool oddP = !FULL && (P & 1) != 0;
     uint64_t even_allowed = 0x5555555555555555ull & pmask;
     if (oddP) even_allowed &= ~(1ull << (P - 1)); // slice P-1 neighbours slice 0: handled alone below
     const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
 
-    w ^= phase<NPL, 0>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2);
-    w ^= phase<NPL, 1>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2);
+    w ^= phase<NPL, 0, FULL>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2);
+    w ^= phase<NPL, 1, FULL>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2);
     if (oddP) {
         const int k = P - 1;
         const uint64_t tl = w ^ rotl_ring(w, P, pmask), tr = w ^ rotr_ring(w, P, pmask);
@@ -465,12 +465,14 @@ static void launch_lut_w(int warps, long long items, cudaStream_t s, const Piqmc
 {
     // items = nsites * G warps of work; `warps` divides G, so a CTA never straddles two sites
     const unsigned grid = (unsigned)(items / warps);
-    if (warps == 4)
-        piqmc_lut_pass_kernel<NPL, 4><<<grid, 128, 0, s>>>(a);
+    if (a.P == 64 && warps == 4)
+        piqmc_lut_pass_kernel<NPL, 4, true><<<grid, 128, 0, s>>>(a);
+    else if (warps == 4)
+        piqmc_lut_pass_kernel<NPL, 4, false><<<grid, 128, 0, s>>>(a);
     else if (warps == 2)
-        piqmc_lut_pass_kernel<NPL, 2><<<grid, 64, 0, s>>>(a);
+        piqmc_lut_pass_kernel<NPL, 2, false><<<grid, 64, 0, s>>>(a);
     else
-        piqmc_lut_pass_kernel<NPL, 1><<<grid, 32, 0, s>>>(a);
+        piqmc_lut_pass_kernel<NPL, 1, false><<<grid, 32, 0, s>>>(a);
 }
 
 static void launch_lut(int npl, int warps, long long items, cudaStream_t s, const PiqmcPass &a)
