@@ -110,6 +110,14 @@ int mcs_state_svmc_energies(mcs_state *st, double a, double b, double *host_out)
 int mcs_piqmc_sweeps(mcs_state *st, const double *A_sched, const double *B_sched, int64_t schedsize,
                      int mcsteps, float temp, int global_moves, uint64_t seed,
                      uint64_t replica_offset, uint64_t sweep_offset);
+/* qmc.DissipativeQuantumAnneal[Global] (qmc.pyx:223-278, 523-609): as above plus the Ohmic-bath
+ * term sum_{d=1}^{P-1} 2 teff s_k s_{k+d} lookuptable[d-1] (qmc.pyx:268-273), lookuptable float64
+ * [P-1].  The bath couples all slices of a world line, so slices are visited in order inside a
+ * word; colour classes and replicas stay parallel.  Needs degree + field <= 6.               */
+int mcs_piqmc_sweeps_dissipative(mcs_state *st, const double *A_sched, const double *B_sched,
+                                 int64_t schedsize, int mcsteps, float temp, const double *lookuptable,
+                                 int global_moves, uint64_t seed, uint64_t replica_offset,
+                                 uint64_t sweep_offset);
 /* sa.Anneal (sa.pyx:66-101): Metropolis sweeps at temperature sched[itemp]                 */
 int mcs_sa_sweeps(mcs_state *st, const double *sched, int64_t schedsize, int mcsteps, uint64_t seed,
                   uint64_t replica_offset, uint64_t sweep_offset);

@@ -54,6 +54,8 @@ SIGNATURES = {
     "mcs_state_svmc_energies": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, c_dp]),
     "mcs_piqmc_sweeps": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                         c_u64, c_u64, c_u64]),
+    "mcs_piqmc_sweeps_dissipative": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_dp,
+                                                    ctypes.c_int, c_u64, c_u64, c_u64]),
     "mcs_sa_sweeps": (ctypes.c_int, [c_vp, c_dp, c_i64, ctypes.c_int, c_u64, c_u64, c_u64]),
     "mcs_svmc_sweeps": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                        c_u64, c_u64, c_u64]),
@@ -290,6 +292,17 @@ class State(object):
         check(load().mcs_piqmc_sweeps(self._h, dptr(A), dptr(B), A.size, int(mcsteps), float(temp),
                                       int(bool(global_moves)), int(seed) & (2 ** 64 - 1), int(replica_offset),
                                       int(sweep_offset)))
+
+    def piqmc_sweeps_dissipative(self, A, B, mcsteps, temp, lookuptable, global_moves=False, seed=0,
+                                 replica_offset=0, sweep_offset=0):
+        A, B, lut = f64(A), f64(B), f64(lookuptable)
+        if B.size < A.size:
+            raise ValueError("B_sched shorter than A_sched")
+        if lut.size < self.P - 1:
+            raise ValueError("lookuptable needs P-1 entries")
+        check(load().mcs_piqmc_sweeps_dissipative(self._h, dptr(A), dptr(B), A.size, int(mcsteps), float(temp),
+                                                  dptr(lut), int(bool(global_moves)), int(seed) & (2 ** 64 - 1),
+                                                  int(replica_offset), int(sweep_offset)))
 
     def sa_sweeps(self, sched, mcsteps, seed=0, replica_offset=0, sweep_offset=0):
         sched = f64(sched)

@@ -126,7 +126,20 @@ extern "C" int mcs_piqmc_sweeps(mcs_state *st, const double *A, const double *B,
 {
     MCS_REQUIRE(st && st->inst && st->kind == MCS_KIND_PIQMC, MCS_EINVAL, "mcs_piqmc_sweeps: not a PIQMC state");
     MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_piqmc_sweeps: bad schedule");
-    return mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, sweep_offset);
+    return mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, sweep_offset,
+                                   nullptr);
+}
+
+extern "C" int mcs_piqmc_sweeps_dissipative(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps,
+                                            float temp, const double *lookuptable, int global_moves, uint64_t seed,
+                                            uint64_t replica_offset, uint64_t sweep_offset)
+{
+    MCS_REQUIRE(st && st->inst && st->kind == MCS_KIND_PIQMC, MCS_EINVAL,
+                "mcs_piqmc_sweeps_dissipative: not a PIQMC state");
+    MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)) && lookuptable, MCS_EINVAL,
+                "mcs_piqmc_sweeps_dissipative: bad schedule or NULL lookuptable");
+    return mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, sweep_offset,
+                                   lookuptable);
 }
 
 extern "C" int mcs_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcsteps, uint64_t seed,

@@ -216,7 +216,8 @@ __device__ __forceinline__ uint32_t mcs_accept_threshold(float dE, float nl2e_ov
 
 // kernels launchers implemented in the other translation units
 int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
-                            int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset);
+                            int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset,
+                            const double *lookuptable /* nullptr: no Ohmic bath */);
 int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcsteps, uint64_t seed,
                          uint64_t replica_offset, uint64_t sweep_offset);
 int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,

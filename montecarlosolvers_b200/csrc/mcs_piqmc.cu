@@ -333,6 +333,101 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_direct_pass_kernel(const __
 }
 
 // ------------------------------------------------------------------------------------------
+// Ohmic-bath pass (qmc.DissipativeQuantumAnneal[Global], reference qmc.pyx:223-278, 523-609).
+// The bath couples slice k to EVERY other slice of the same world line,
+//     dE_bath(k) = sum_{d=1}^{P-1} 2 teff (s_k s_{k+d}) lookuptable[d-1]                (qmc.pyx:268-273),
+// so the slices of a word are visited one after another (no Trotter parity classes); sites of a colour
+// class and replicas stay parallel.  With y = rotr_ring(w, k) ^ (s_k ? ~0 : 0), bit d of y says
+// "slice k+d is anti-aligned with slice k", and the sum is C0 - sum_d 4 teff lut[d-1] y_d: a weighted
+// popcount evaluated byte by byte from a shared-memory table (8 x 256 floats, built once per CTA).
+// ------------------------------------------------------------------------------------------
+struct BathArgs {
+    const float *lut4; // [64]: 4 teff lookuptable[d-1] at index d (0 for d = 0 and d >= P)
+    float c0;          // 2 teff sum_d lookuptable[d-1]
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __grid_constant__ PiqmcPass a,
+                                                                      const BathArgs bath)
+{
+    __shared__ float s_tab[8][256];
+    for (int e = threadIdx.x; e < 8 * 256; e += kWarps * 32) {
+        const int b = e >> 8, v = e & 255;
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if ((v >> j) & 1) acc += __ldg(&bath.lut4[8 * b + j]);
+        s_tab[b][v] = acc;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kWarps + warp;
+    if (item >= (long long)a.nsites * a.G) return;
+    const int site = a.sites[item / a.G];
+    const long long r = (item % a.G) * 32 + lane;
+
+    float c[NPL];
+    int nb[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        if (j < a.nq) {
+            nb[j] = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+            c[j] = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+        } else {
+            nb[j] = site;
+            c[j] = (a.field && j == a.nq) ? a.bcoef * __ldg(&a.h[site]) : 0.0f;
+        }
+    }
+    const int P = a.P;
+    const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
+    uint64_t w = a.W[(long long)site * a.Rpad + r];
+    uint64_t pl[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        if (j < a.nq)
+            pl[j] = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
+        else
+            pl[j] = (a.field && j == a.nq) ? w : 0ull;
+    }
+    const uint32_t c0 = a.replica_offset + (uint32_t)r, c1 = (uint32_t)site, c2 = a.sweep_lo;
+    const uint32_t c3hi = a.sweep_hi << 8;
+    const int nbytes = (P + 7) >> 3;
+    uint32_t rnd[4];
+    for (int k = 0; k < P; ++k) {
+        if ((k & 3) == 0) mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(k >> 2), a.keys, rnd);
+        const uint32_t sk = (uint32_t)(w >> k) & 1u;
+        float dE = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) dE += ((pl[j] >> k) & 1ull) ? -c[j] : c[j];
+        const int kl = k == 0 ? P - 1 : k - 1, kr = k == P - 1 ? 0 : k + 1;
+        const int anti = (int)(((uint32_t)(w >> kl) & 1u) ^ sk) + (int)(((uint32_t)(w >> kr) & 1u) ^ sk);
+        dE += a.jperp2 * (float)(2 - 2 * anti);
+        uint64_t y = k == 0 ? w : (((w >> k) | (w << (P - k))) & pmask);
+        if (sk) y ^= pmask; // bit 0 becomes 0 either way: lut4[0] == 0
+        float wsum = 0.0f;
+        for (int b = 0; b < nbytes; ++b) wsum += s_tab[b][(uint32_t)(y >> (8 * b)) & 255u];
+        dE += bath.c0 - wsum;
+        const uint32_t u = (k & 3) == 0 ? rnd[0] : (k & 3) == 1 ? rnd[1] : (k & 3) == 2 ? rnd[2] : rnd[3];
+        if (u <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= 1ull << k;
+    }
+    if (a.global_moves) { // a world-line flip leaves every s_k s_k' invariant: no bath term (qmc.pyx:575-609)
+        float dE = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            uint64_t x;
+            if (j < a.nq)
+                x = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
+            else
+                x = (a.field && j == a.nq) ? w : 0ull;
+            dE += c[j] * (float)(P - 2 * __popcll(x));
+        }
+        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
+        if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
+    }
+    a.W[(long long)site * a.Rpad + r] = w;
+}
+
+// ------------------------------------------------------------------------------------------
 // host <-> packed conversion, initialisation, energies
 // ------------------------------------------------------------------------------------------
 // int8 [R][N][P] (host order) <-> W[N][Rpad].  A 32x32 tile of (replica, site) is transposed through
@@ -487,14 +582,48 @@ static void launch_lut(int npl, int warps, long long items, cudaStream_t s, cons
     }
 }
 
+static void launch_bath(int npl, unsigned grid, cudaStream_t s, const PiqmcPass &a, const BathArgs &b)
+{
+    switch (npl) {
+    case 1: piqmc_bath_pass_kernel<1><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    case 2: piqmc_bath_pass_kernel<2><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    case 3: piqmc_bath_pass_kernel<3><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    case 4: piqmc_bath_pass_kernel<4><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    case 5: piqmc_bath_pass_kernel<5><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    default: piqmc_bath_pass_kernel<6><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    }
+}
+
 int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
-                            int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
+                            int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset,
+                            const double *lookuptable)
 {
     mcs_instance *inst = st->inst;
     const int P = (int)st->P;
     const double teff = (double)temp * (double)P; // qmc.pyx:85: temp is a C float
     MCS_REQUIRE(teff != 0.0 || S == 0, MCS_EZERODIV, "float division");
     MCS_CUDA(cudaSetDevice(inst->device));
+    BathArgs bath;
+    bath.lut4 = nullptr;
+    bath.c0 = 0.0f;
+    float *d_lut4 = nullptr;
+    if (lookuptable) {
+        MCS_REQUIRE(inst->lut_ok, MCS_EUNSUPPORTED,
+                    "dissipative sweeps: the production kernel keeps a site's neighbour planes in registers "
+                    "(degree + field <= 6); use the exact kernel for this instance");
+        float h4[64];
+        double sum = 0.0;
+        for (int d = 0; d < 64; ++d) h4[d] = 0.0f;
+        for (int d = 1; d < P; ++d) {
+            h4[d] = (float)(4.0 * teff * lookuptable[d - 1]);
+            sum += lookuptable[d - 1];
+        }
+        bath.c0 = (float)(2.0 * teff * sum);
+        MCS_CUDA(cudaMallocAsync((void **)&d_lut4, sizeof(h4), inst->stream));
+        MCS_CUDA(cudaMemcpyAsync(d_lut4, h4, sizeof(h4), cudaMemcpyHostToDevice, inst->stream));
+        MCS_CUDA(cudaStreamSynchronize(inst->stream)); // h4 is on this stack frame
+        bath.lut4 = d_lut4;
+    }
     PiqmcPass a;
     a.W = st->d_W;
     a.ell_idx = inst->d_ell_idx;
@@ -526,7 +655,9 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
                 a.nsites = inst->color_start[c + 1] - inst->color_start[c];
                 if (a.nsites == 0) continue;
                 const long long items = (long long)a.nsites * a.G;
-                if (inst->lut_ok)
+                if (lookuptable)
+                    launch_bath(npl, (unsigned)((items + kWarps - 1) / kWarps), inst->stream, a, bath);
+                else if (inst->lut_ok)
                     launch_lut(npl, warps, items, inst->stream, a);
                 else
                     piqmc_direct_pass_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kWarps * 32, 0,
@@ -535,6 +666,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
             }
         }
     }
+    if (d_lut4) MCS_CUDA(cudaFreeAsync(d_lut4, inst->stream));
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
 }

@@ -39,11 +39,16 @@ struct SvmcPass {
 
 __global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_constant__ SvmcPass a)
 {
+    // The kWarps warps of a CTA take kWarps CONSECUTIVE SITES of the colour class for the same 32 replicas:
+    // neighbouring sites of one colour usually share neighbours (the 4 qubits on one side of a Chimera cell
+    // all couple to the same 4 on the other side), so their cos(theta_j) lines are fetched once into L1.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * kWarps + warp;
-    if (item >= (long long)a.nsites * a.G) return;
-    const int site = a.sites[item / a.G];
-    const long long r = (item % a.G) * 32 + lane;
+    const long long sblocks = (a.nsites + kWarps - 1) / kWarps;
+    const long long grp = blockIdx.x / sblocks;
+    const long long srank = (blockIdx.x % sblocks) * kWarps + warp;
+    if (srank >= a.nsites) return;
+    const int site = a.sites[srank];
+    const long long r = grp * 32 + lane;
     const float kPi = 3.14159265358979323846f;
 
     const float th = a.theta[(long long)site * a.Rpad + r];
@@ -165,8 +170,8 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
                 a.sites = inst->d_order + inst->color_start[c];
                 a.nsites = inst->color_start[c + 1] - inst->color_start[c];
                 if (a.nsites == 0) continue;
-                const long long items = (long long)a.nsites * a.G;
-                svmc_pass_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kWarps * 32, 0, inst->stream>>>(a);
+                const long long ctas = (long long)((a.nsites + kWarps - 1) / kWarps) * a.G;
+                svmc_pass_kernel<<<(unsigned)ctas, kWarps * 32, 0, inst->stream>>>(a);
                 inst->launches++;
             }
         }

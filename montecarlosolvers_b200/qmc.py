@@ -31,11 +31,21 @@ def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable,
     L = _lib.load()
     temp = float(np.float32(temp))  # C float in the reference signature (qmc.pyx:28)
     e_out = np.empty((R, P), dtype=np.float64) if energies else None
-    if exact or lookuptable is not None:
-        if not exact:
-            raise NotImplementedError(
-                "the Ohmic-bath term couples all Trotter slices of a site; only the exact sequential kernel "
-                "(exact=True, libc_seed=...) implements the Dissipative variants in this build")
+    if lookuptable is not None and not exact:
+        lut = _lib.f64(lookuptable)
+        if lut.size < P - 1:
+            raise ValueError("lookuptable needs P-1 entries")
+        st = _lib.State(inst, _lib.KIND_PIQMC, R, P)
+        try:
+            st.upload_spins(a8)
+            st.piqmc_sweeps_dissipative(A, B, mcsteps, temp, lut, global_moves=global_moves,
+                                        seed=_lib.next_seed(seed), replica_offset=replica_offset)
+            st.download_spins(a8)
+            if energies:
+                e_out = st.energies()
+        finally:
+            st.close()
+    elif exact:
         lut = None
         if lookuptable is not None:
             lut = _lib.f64(lookuptable)
@@ -85,22 +95,25 @@ def QuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1,
                 replica_offset)
 
 
-def DissipativeQuantumAnneal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *, exact=True,
-                             libc_seed=None, device=None, energies=False):
+def DissipativeQuantumAnneal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *, seed=None,
+                             exact=False, libc_seed=None, device=None, energies=False, replica_offset=0):
     """DissipativeQuantumAnneal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads)
 
-    PIQMC with the Ohmic-bath term (reference qmc.pyx:149-278); exact sequential kernel only."""
-    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, False, lookuptable, None, exact, libc_seed, device,
-                energies, 0)
+    PIQMC with the Ohmic-bath term sum_{d=1}^{P-1} 2 teff s_k s_{k+d} lookuptable[d-1] (reference
+    qmc.pyx:149-278).  The bath couples all slices of a world line, so the production kernel visits the
+    slices of a word in order (colour classes and replicas in parallel)."""
+    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, False, lookuptable, seed, exact, libc_seed, device,
+                energies, replica_offset)
 
 
 def DissipativeQuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *,
-                                   exact=True, libc_seed=None, device=None, energies=False):
+                                   seed=None, exact=False, libc_seed=None, device=None, energies=False,
+                                   replica_offset=0):
     """DissipativeQuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads)
 
-    Reference qmc.pyx:444-609; exact sequential kernel only."""
-    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, lookuptable, None, exact, libc_seed, device,
-                energies, 0)
+    Reference qmc.pyx:444-609: bath term + one world-line move per spin per sweep."""
+    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, lookuptable, seed, exact, libc_seed, device,
+                energies, replica_offset)
 
 
 def delta_e(a, b, temp, confs, nbs, device=None):

@@ -79,7 +79,7 @@ def test_exact_qmc_golden(mcs):
     assert np.allclose(e, d["energies"], rtol=0, atol=1e-9)
     c = d["conf_in"].astype(np.int64)
     mcs.qmc.DissipativeQuantumAnnealGlobal(d["A"], d["B"], int(d["diss_mcsteps"]), float(d["temp"]), d["lut"], c,
-                                           d["nbs"], 1, libc_seed=int(d["diss_seed"]))
+                                           d["nbs"], 1, exact=True, libc_seed=int(d["diss_seed"]))
     assert np.array_equal(c, d["diss_out"])
 
 

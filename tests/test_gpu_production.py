@@ -46,13 +46,19 @@ def _classical_energies(states, nbs):
     return e
 
 
-def _piqmc_exact(nbs, P, a, b, temp):
-    """Exact <E_cl of slice 0> and <s^k s^{k+1}> under exp(-S/teff), S = sum_k b E_cl(s^k) - jperp sum s s'."""
+def _piqmc_exact(nbs, P, a, b, temp, lut=None):
+    """Exact <E_cl of slice 0> and <s^k s^{k+1}> under exp(-S/teff), S = sum_k b E_cl(s^k) - jperp sum s s'
+    [- teff sum_{k<k'} lut[k'-k-1] s^k s^k' for the Ohmic bath: flipping s^k changes that by
+    2 teff sum_d s^k s^{k+d} lut[d-1] (qmc.pyx:268-273) when lut is symmetric, lut[d-1] == lut[P-d-1]]."""
     n = nbs.shape[0]
     teff, jperp, _ = orc.qmc_coeffs(a, b, temp, P)
     st = _all_states(n * P).reshape(-1, P, n)
     S = np.zeros(st.shape[0])
     ecl = []
+    if lut is not None:
+        for k in range(P):
+            for k2 in range(k + 1, P):
+                S -= teff * lut[k2 - k - 1] * np.sum(st[:, k, :] * st[:, k2, :], axis=1)
     for k in range(P):
         ek = _classical_energies(st[:, k, :], nbs)
         ecl.append(ek)
@@ -64,17 +70,25 @@ def _piqmc_exact(nbs, P, a, b, temp):
     return float(np.dot(w, np.mean(ecl, axis=0))), float(np.dot(w, link))
 
 
-def _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, R=4096, burn=150, meas=40, global_moves=False, seed=5):
+def _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, R=4096, burn=150, meas=40, global_moves=False, seed=5,
+                           lut=None):
     n = nbs.shape[0]
     I = mcs.Instance(nbs)
     st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
     st.init_random(seed)
-    A = np.full(burn, a)
-    st.piqmc_sweeps(A, np.full(burn, b), 1, temp, global_moves=global_moves, seed=seed)
+
+    def sweeps(nsw, off):
+        if lut is None:
+            st.piqmc_sweeps(np.full(nsw, a), np.full(nsw, b), 1, temp, global_moves=global_moves, seed=seed,
+                            sweep_offset=off)
+        else:
+            st.piqmc_sweeps_dissipative(np.full(nsw, a), np.full(nsw, b), 1, temp, lut, global_moves=global_moves,
+                                        seed=seed, sweep_offset=off)
+
+    sweeps(burn, 0)
     es, ls = [], []
     for t in range(meas):
-        st.piqmc_sweeps(np.full(3, a), np.full(3, b), 1, temp, global_moves=global_moves, seed=seed,
-                        sweep_offset=burn + 3 * t)
+        sweeps(3, burn + 3 * t)
         c = st.download_spins().astype(np.float64)  # [R, N, P]
         es.append(st.energies().mean(axis=1))
         ls.append((c * np.roll(c, -1, axis=2)).sum(axis=(1, 2)) / (n * P))
@@ -119,6 +133,32 @@ def test_piqmc_samples_the_exact_boltzmann_distribution(mcs, case):
         assert I.ncolors == 3 and I.has_field
     assert abs(e - e_exact) <= 4.5 * e_sem, (case, e, e_exact, e_sem)
     assert abs(l - l_exact) <= 4.5 * l_sem, (case, l, l_exact, l_sem)
+
+
+@pytest.mark.parametrize("P,glob", [(4, False), (5, True)])
+def test_dissipative_piqmc_samples_the_exact_boltzmann_distribution(mcs, P, glob):
+    """Ohmic-bath production kernel (qmc.pyx:149-278 / 444-609 semantics) against full enumeration of the
+    action including the long-range Trotter coupling; tolerance 4.5 standard errors over 4096 replicas."""
+    J, nbs = inst.random_graph(3, 3, seed=2, fields=True)
+    k = np.arange(1, P)
+    lut = 0.15 * (np.pi / (P * np.sin(np.pi * k / P))) ** 2  # docstring kernel (qmc.pyx:162-163), symmetric
+    a, b, temp = 0.9, 0.7, 1.1 / P
+    e_exact, l_exact = _piqmc_exact(nbs, P, a, b, temp, lut=lut)
+    e0, l0 = _piqmc_exact(nbs, P, a, b, temp)
+    assert abs(l_exact - l0) > 0.02  # the bath visibly stiffens the world lines: the test is sensitive to it
+    # stiff world lines equilibrate slowly under local moves (the oracle's own dynamics needs ~600 sweeps
+    # here): long burn-in
+    e, e_sem, l, l_sem, _ = _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, global_moves=glob, lut=lut, burn=3000)
+    print("dissipative P=%d glob=%s: E %.4f +- %.4f (exact %.4f), link %.4f +- %.4f (exact %.4f)" % (
+        P, glob, e, e_sem, e_exact, l, l_sem, l_exact))
+    assert abs(e - e_exact) <= 4.5 * e_sem, (e, e_exact, e_sem)
+    assert abs(l - l_exact) <= 4.5 * l_sem, (l, l_exact, l_sem)
+    # drop-in entry point, batched
+    c = (2 * np.random.RandomState(0).randint(2, size=(64, 3, P)) - 1).astype(np.int8)
+    c0 = c.copy()
+    fn = mcs.qmc.DissipativeQuantumAnnealGlobal if glob else mcs.qmc.DissipativeQuantumAnneal
+    assert fn(np.full(5, a), np.full(5, b), 1, temp, lut, c, nbs, 1, seed=3) is None
+    assert not np.array_equal(c, c0)
 
 
 @pytest.mark.parametrize("case", ["graph10_lut", "k10_direct"])
