@@ -65,9 +65,15 @@ void mcs_host_free(void *p);
  * the reference's row order (exact / probe kernels).                                        */
 int mcs_instance_create(const double *nbs, int64_t nspins, int64_t maxnb, int device,
                         mcs_instance **out);
+/* Time-dependent couplings, sa.NoisyAnneal / svmc.NoisySVMC[TF] (sa.pyx:291-378, svmc.pyx:236-448):
+ * nbs is float64 [nsteps][N][maxnb][2]; schedule step f of a later *_sweeps / exact call uses table f
+ * (the schedule may not be longer than nsteps).  Energies are evaluated with the LAST table.      */
+int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int64_t nspins, int64_t maxnb, int device,
+                              mcs_instance **out);
 void mcs_instance_destroy(mcs_instance *inst);
 /* info[0]=nspins info[1]=maxnb info[2]=ncolors info[3]=max degree (fields excluded)
- * info[4]=1 if any local field  info[5]=device  info[6]=1 if the LUT kernels apply        */
+ * info[4]=1 if any local field  info[5]=device  info[6]=1 if the LUT kernels apply
+ * info[7]=number of tables (1 unless created by mcs_instance_create_steps)                 */
 int mcs_instance_info(const mcs_instance *inst, int64_t info[8]);
 int mcs_instance_colors(const mcs_instance *inst, int32_t *color /* [nspins] */);
 /* CUDA-event stopwatch on the instance's stream: start ... stop returns milliseconds.      */

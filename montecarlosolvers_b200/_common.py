@@ -17,6 +17,8 @@ def check_nbs(nbs, ndim=3):
         raise ValueError("Buffer dtype mismatch, expected 'float64_t' but got '%s'" % nbs.dtype)
     if nbs.ndim != ndim:
         raise ValueError("Buffer has wrong number of dimensions (expected %d, got %d)" % (ndim, nbs.ndim))
+    if nbs.shape[-1] != 2:
+        raise ValueError("nbs must end in (neighbour index, coupling) pairs")
     return nbs
 
 

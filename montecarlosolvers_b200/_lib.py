@@ -35,6 +35,7 @@ SIGNATURES = {
     "mcs_host_alloc": (c_vp, [ctypes.c_size_t]),
     "mcs_host_free": (None, [c_vp]),
     "mcs_instance_create": (ctypes.c_int, [c_dp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "mcs_instance_create_steps": (ctypes.c_int, [c_dp, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "mcs_instance_destroy": (None, [c_vp]),
     "mcs_instance_info": (ctypes.c_int, [c_vp, c_i64p]),
     "mcs_instance_colors": (ctypes.c_int, [c_vp, c_i32p]),
@@ -183,14 +184,16 @@ class Instance(object):
 
     def __init__(self, nbs, device=0):
         nbs = np.ascontiguousarray(np.asarray(nbs), dtype=np.float64)
-        if nbs.ndim != 3:
+        if nbs.ndim not in (3, 4):
             raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % nbs.ndim)
-        if nbs.shape[2] != 2:
-            raise ValueError("nbs must be [nspins, maxnb, 2]")
-        self.nspins, self.maxnb = int(nbs.shape[0]), int(nbs.shape[1])
+        if nbs.shape[-1] != 2:
+            raise ValueError("nbs must be [nspins, maxnb, 2] (or [nsteps, nspins, maxnb, 2] for the Noisy solvers)")
+        self.nsteps = int(nbs.shape[0]) if nbs.ndim == 4 else 1
+        self.nspins, self.maxnb = int(nbs.shape[-3]), int(nbs.shape[-2])
         self.device = int(device)
         h = c_vp()
-        check(load().mcs_instance_create(dptr(nbs), self.nspins, self.maxnb, self.device, ctypes.byref(h)))
+        check(load().mcs_instance_create_steps(dptr(nbs), self.nsteps, self.nspins, self.maxnb, self.device,
+                                               ctypes.byref(h)))
         self._h = h
         self._states = weakref.WeakSet()
         info = (c_i64 * 8)()

@@ -43,6 +43,7 @@ struct mcs_instance {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t N = 0, maxnb = 0;
+    int64_t nsteps = 1;  // > 1: time-dependent couplings, one table per schedule step (Noisy* functions)
     int ncolors = 0;
     int maxdeg = 0;      // max number of quadratic neighbours of a site (fields excluded)
     int dpad = 1;        // row length of the ELL tables (>= 1)
@@ -59,11 +60,17 @@ struct mcs_instance {
     std::vector<int32_t> color_start; // [ncolors + 1] offsets into order
 
     // device tables
-    int32_t *d_tab_idx = nullptr; // [N][maxnb]  reference table, neighbour index column (int(nbs[..,0]))
-    double *d_tab_J = nullptr;    // [N][maxnb]  reference table, coupling column (fp64, row order kept)
-    int32_t *d_ell_idx = nullptr; // [N][dpad]   quadratic neighbours, padded with the site itself
-    float *d_ell_J = nullptr;     // [N][dpad]   fp32 couplings, padded with 0
-    float *d_h = nullptr;         // [N]         fp32 local fields
+    int32_t *d_tab_idx = nullptr; // [nsteps][N][maxnb]  reference table, neighbour index column (int(nbs[..,0]))
+    double *d_tab_J = nullptr;    // [nsteps][N][maxnb]  reference table, coupling column (fp64, row order kept)
+    int32_t *d_ell_idx = nullptr; // [N][dpad]           quadratic neighbours, padded with the site itself
+    float *d_ell_J = nullptr;     // [nsteps][N][dpad]   fp32 couplings, padded with 0
+    float *d_h = nullptr;         // [nsteps][N]         fp32 local fields
+
+    // tables of schedule step f (step 0 for static instances)
+    const float *ell_J_at(int64_t f) const { return d_ell_J + (nsteps > 1 ? (size_t)f * N * dpad : 0); }
+    const float *h_at(int64_t f) const { return d_h + (nsteps > 1 ? (size_t)f * N : 0); }
+    const int32_t *tab_idx_at(int64_t f) const { return d_tab_idx + (nsteps > 1 ? (size_t)f * N * maxnb : 0); }
+    const double *tab_J_at(int64_t f) const { return d_tab_J + (nsteps > 1 ? (size_t)f * N * maxnb : 0); }
     int32_t *d_order = nullptr;   // [N]
 };
 

@@ -204,6 +204,7 @@ struct ExactSaArgs {
     const int32_t *tab_idx;
     const double *tab_J;
     long long R;
+    long long tab_stride; // elements between the tables of consecutive schedule steps (0: static table)
     int N, maxnb, S, mcsteps;
 };
 
@@ -220,6 +221,8 @@ __global__ void exact_sa_kernel(const ExactSaArgs a)
     rng.len = 0;
     for (int t = 0; t < a.S; ++t) {
         const double temp = a.sched[t];
+        const int32_t *tab_idx = a.tab_idx + t * a.tab_stride; // NoisyAnneal: nbs[itemp] (sa.pyx:363-365)
+        const double *tab_J = a.tab_J + t * a.tab_stride;
         for (int step = 0; step < a.mcsteps; ++step) {
             shuffle(rng, perm, a.N);
             for (int ispin = 0; ispin < a.N; ++ispin) {
@@ -227,8 +230,8 @@ __global__ void exact_sa_kernel(const ExactSaArgs a)
                 const double m2s = __dmul_rn(-2.0, (double)sv[sidx]);
                 double e = 0.0;
                 for (int si = 0; si < a.maxnb; ++si) { // sa.pyx:84-94
-                    const int spinidx = a.tab_idx[(long long)sidx * a.maxnb + si];
-                    const double jval = a.tab_J[(long long)sidx * a.maxnb + si];
+                    const int spinidx = tab_idx[(long long)sidx * a.maxnb + si];
+                    const double jval = tab_J[(long long)sidx * a.maxnb + si];
                     if (spinidx == sidx)
                         e = __dadd_rn(e, __dmul_rn(m2s, jval));
                     else
@@ -256,6 +259,7 @@ struct ExactSvmcArgs {
     const int32_t *tab_idx;
     const double *tab_J;
     long long R;
+    long long tab_stride; // elements between the tables of consecutive schedule steps (0: static table)
     int N, maxnb, S, mcsteps, tf;
     int serial; // 1: a single thread walks all reads with ONE stream (svmc.pyx:624-674)
     double temp;
@@ -266,6 +270,8 @@ __device__ void exact_svmc_read(const ExactSvmcArgs &a, double *sv, int32_t *per
     const double pi = 3.141592653589793;
     for (int f = 0; f < a.S; ++f) {
         const double a_coeff = a.A[f], b_coeff = a.B[f];
+        const int32_t *tab_idx = a.tab_idx + f * a.tab_stride; // NoisySVMC: nbs[ifield] (svmc.pyx:317-319)
+        const double *tab_J = a.tab_J + f * a.tab_stride;
         for (int step = 0; step < a.mcsteps; ++step) {
             shuffle(rng, perm, a.N);
             for (int ispin = 0; ispin < a.N; ++ispin) {
@@ -292,8 +298,8 @@ __device__ void exact_svmc_read(const ExactSvmcArgs &a, double *sv, int32_t *per
                 const double zmagdiff = __dadd_rn(cos(theta_prop), -cos(sv[sidx]));
                 double e = 0.0;
                 for (int si = 0; si < a.maxnb; ++si) { // svmc.pyx:98-108
-                    const int spinidx = a.tab_idx[(long long)sidx * a.maxnb + si];
-                    const double jval = a.tab_J[(long long)sidx * a.maxnb + si];
+                    const int spinidx = tab_idx[(long long)sidx * a.maxnb + si];
+                    const double jval = tab_J[(long long)sidx * a.maxnb + si];
                     const double bjz = __dmul_rn(__dmul_rn(b_coeff, jval), zmagdiff);
                     if (spinidx == sidx)
                         e = __dadd_rn(e, bjz);
@@ -420,6 +426,7 @@ extern "C" int mcs_exact_qmc(mcs_instance *inst, const double *A, const double *
     MCS_REQUIRE(inst && confs && R > 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_exact_qmc: bad argument");
     MCS_REQUIRE(P >= 2, MCS_EINVAL, "mcs_exact_qmc: P >= 2 required (P=1 reads out of bounds in the reference)");
     MCS_REQUIRE(libc_seeds || rand_stream, MCS_EINVAL, "mcs_exact_qmc: need libc_seeds or rand_stream");
+    MCS_REQUIRE(inst->nsteps == 1, MCS_EUNSUPPORTED, "mcs_exact_qmc: time-dependent tables are an SA / SVMC feature");
     const double teff = (double)temp * (double)P;
     MCS_REQUIRE(teff != 0.0 || S == 0, MCS_EZERODIV, "float division");
     MCS_CUDA(cudaSetDevice(inst->device));
@@ -478,6 +485,7 @@ extern "C" int mcs_exact_sa(mcs_instance *inst, const double *sched, int64_t S, 
                             const uint32_t *libc_seeds, const double *randuni, int64_t *consumed)
 {
     MCS_REQUIRE(inst && svec && R > 0 && libc_seeds && (S == 0 || sched), MCS_EINVAL, "mcs_exact_sa: bad argument");
+    MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL, "mcs_exact_sa: schedule longer than the tables");
     MCS_CUDA(cudaSetDevice(inst->device));
     cudaStream_t s = inst->stream;
     std::vector<LibcState> states;
@@ -500,6 +508,7 @@ extern "C" int mcs_exact_sa(mcs_instance *inst, const double *sched, int64_t S, 
     a.tab_idx = inst->d_tab_idx;
     a.tab_J = inst->d_tab_J;
     a.R = R;
+    a.tab_stride = inst->nsteps > 1 ? inst->N * inst->maxnb : 0;
     a.N = (int)inst->N;
     a.maxnb = (int)inst->maxnb;
     a.S = (int)S;
@@ -520,6 +529,8 @@ extern "C" int mcs_exact_svmc(mcs_instance *inst, const double *A, const double 
 {
     MCS_REQUIRE(inst && svec && R > 0 && libc_seeds && (S == 0 || (A && B)), MCS_EINVAL,
                 "mcs_exact_svmc: bad argument");
+    MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
+                "mcs_exact_svmc: schedule longer than the tables");
     MCS_REQUIRE(randuni || tf, MCS_EINVAL,
                 "mcs_exact_svmc: randuni == NULL is only defined for the TF form (SpinVectorMonteCarloTFCompact)");
     MCS_CUDA(cudaSetDevice(inst->device));
@@ -560,6 +571,7 @@ extern "C" int mcs_exact_svmc(mcs_instance *inst, const double *A, const double 
     a.tab_idx = inst->d_tab_idx;
     a.tab_J = inst->d_tab_J;
     a.R = R;
+    a.tab_stride = inst->nsteps > 1 ? inst->N * inst->maxnb : 0;
     a.N = (int)inst->N;
     a.maxnb = (int)inst->maxnb;
     a.S = (int)S;

@@ -135,14 +135,18 @@ int upload(T **dst, const std::vector<T> &src)
 
 } // namespace
 
-extern "C" int mcs_instance_create(const double *nbs, int64_t nspins, int64_t maxnb, int device,
-                                   mcs_instance **out)
+// nsteps == 1: the static table nbs[N][maxnb][2].  nsteps > 1: the time-dependent table
+// nbs[nsteps][N][maxnb][2] of sa.NoisyAnneal / svmc.NoisySVMC[TF] (sa.pyx:291-378, svmc.pyx:236-448):
+// one colouring / ELL structure from the union of all steps' neighbours, one fp32 coupling row and field
+// per step (a neighbour absent at some step gets J = 0 there), the fp64 tables of every step verbatim.
+extern "C" int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int64_t nspins, int64_t maxnb,
+                                         int device, mcs_instance **out)
 {
     MCS_REQUIRE(out != nullptr, MCS_EINVAL, "mcs_instance_create: out is NULL");
     *out = nullptr;
-    MCS_REQUIRE(nbs != nullptr && nspins > 0 && maxnb > 0, MCS_EINVAL,
-                "mcs_instance_create: need nbs != NULL, nspins > 0, maxnb > 0 (got %lld, %lld)",
-                (long long)nspins, (long long)maxnb);
+    MCS_REQUIRE(nbs != nullptr && nspins > 0 && maxnb > 0 && nsteps > 0, MCS_EINVAL,
+                "mcs_instance_create: need nbs != NULL, nsteps > 0, nspins > 0, maxnb > 0 (got %lld, %lld, %lld)",
+                (long long)nsteps, (long long)nspins, (long long)maxnb);
     MCS_REQUIRE(nspins < (1ll << 31), MCS_EINVAL, "mcs_instance_create: nspins too large");
     int ndev = mcs_device_count();
     MCS_REQUIRE(ndev > 0, MCS_ENODEVICE,
@@ -150,50 +154,59 @@ extern "C" int mcs_instance_create(const double *nbs, int64_t nspins, int64_t ma
     MCS_REQUIRE(device >= 0 && device < ndev, MCS_EINVAL, "mcs_instance_create: device %d out of range [0,%d)",
                 device, ndev);
 
-    // ---- parse the reference table ---------------------------------------------------------
-    std::vector<int32_t> tab_idx((size_t)nspins * maxnb);
-    std::vector<double> tab_J((size_t)nspins * maxnb);
-    std::vector<std::map<int32_t, double>> quad(nspins);
-    std::vector<double> h(nspins, 0.0);
+    // ---- parse the reference table(s) ------------------------------------------------------
+    const size_t tab_n = (size_t)nspins * maxnb;
+    std::vector<int32_t> tab_idx(tab_n * nsteps);
+    std::vector<double> tab_J(tab_n * nsteps);
+    std::vector<std::vector<std::map<int32_t, double>>> quad(nsteps, std::vector<std::map<int32_t, double>>(nspins));
+    std::vector<double> h((size_t)nspins * nsteps, 0.0);
     bool has_field = false;
-    for (int64_t i = 0; i < nspins; ++i) {
-        for (int64_t s = 0; s < maxnb; ++s) {
-            double fi = nbs[(i * maxnb + s) * 2];
-            double jv = nbs[(i * maxnb + s) * 2 + 1];
-            MCS_REQUIRE(fi >= 0.0 && fi < (double)nspins, MCS_EINVAL,
-                        "mcs_instance_create: neighbour index %g of spin %lld out of range", fi, (long long)i);
-            int32_t j = (int32_t)fi; // int(nbs[i, si, 0]), qmc.pyx:116
-            tab_idx[i * maxnb + s] = j;
-            tab_J[i * maxnb + s] = jv;
-            if (jv == 0.0) continue; // zero padding (tools.pyx:52-59) or a null coupling: contributes +-0
-            if (j == (int32_t)i) {
-                h[i] += jv;
-                has_field = true;
-            } else {
-                quad[i][j] += jv;
+    for (int64_t t = 0; t < nsteps; ++t) {
+        const double *tab = nbs + (size_t)t * tab_n * 2;
+        for (int64_t i = 0; i < nspins; ++i) {
+            for (int64_t s = 0; s < maxnb; ++s) {
+                double fi = tab[(i * maxnb + s) * 2];
+                double jv = tab[(i * maxnb + s) * 2 + 1];
+                MCS_REQUIRE(fi >= 0.0 && fi < (double)nspins, MCS_EINVAL,
+                            "mcs_instance_create: neighbour index %g of spin %lld out of range", fi, (long long)i);
+                int32_t j = (int32_t)fi; // int(nbs[i, si, 0]), qmc.pyx:116
+                tab_idx[t * tab_n + i * maxnb + s] = j;
+                tab_J[t * tab_n + i * maxnb + s] = jv;
+                if (jv == 0.0) continue; // zero padding (tools.pyx:52-59) or a null coupling: contributes +-0
+                if (j == (int32_t)i) {
+                    h[t * nspins + i] += jv;
+                    has_field = true;
+                } else {
+                    quad[t][i][j] += jv;
+                }
             }
         }
     }
-    // symmetrised adjacency for colouring (a one-sided table entry still makes the two sites conflict)
-    std::vector<std::vector<int32_t>> adj(nspins);
-    for (int64_t i = 0; i < nspins; ++i)
-        for (auto &kv : quad[i]) {
-            adj[i].push_back(kv.first);
-            if (!quad[kv.first].count((int32_t)i)) adj[kv.first].push_back((int32_t)i);
+    // union structure over the steps; symmetrised adjacency for colouring (a one-sided table entry still
+    // makes the two sites conflict)
+    std::vector<std::vector<int32_t>> nbr(nspins), adj(nspins);
+    for (int64_t t = 0; t < nsteps; ++t)
+        for (int64_t i = 0; i < nspins; ++i)
+            for (auto &kv : quad[t][i]) {
+                nbr[i].push_back(kv.first);
+                adj[i].push_back(kv.first);
+                adj[kv.first].push_back((int32_t)i);
+            }
+    for (auto *v : {&nbr, &adj})
+        for (auto &a : *v) {
+            std::sort(a.begin(), a.end());
+            a.erase(std::unique(a.begin(), a.end()), a.end());
         }
-    for (auto &a : adj) {
-        std::sort(a.begin(), a.end());
-        a.erase(std::unique(a.begin(), a.end()), a.end());
-    }
 
     mcs_instance *inst = new mcs_instance();
     inst->device = device;
     inst->N = nspins;
     inst->maxnb = maxnb;
+    inst->nsteps = nsteps;
     inst->has_field = has_field;
     inst->ncolors = color_graph(adj, inst->color);
     int maxdeg = 0;
-    for (int64_t i = 0; i < nspins; ++i) maxdeg = std::max<int>(maxdeg, (int)quad[i].size());
+    for (int64_t i = 0; i < nspins; ++i) maxdeg = std::max<int>(maxdeg, (int)nbr[i].size());
     inst->maxdeg = maxdeg;
     inst->dpad = std::max(maxdeg, 1);
     inst->lut_ok = (maxdeg + (has_field ? 1 : 0) + 2) <= 8;
@@ -206,18 +219,22 @@ extern "C" int mcs_instance_create(const double *nbs, int64_t nspins, int64_t ma
     for (int64_t i = 0; i < nspins; ++i) inst->color_start[inst->color[i] + 1]++;
     for (int c = 0; c < inst->ncolors; ++c) inst->color_start[c + 1] += inst->color_start[c];
 
-    std::vector<int32_t> ell_idx((size_t)nspins * inst->dpad);
-    std::vector<float> ell_J((size_t)nspins * inst->dpad, 0.0f);
-    std::vector<float> hf(nspins);
+    const size_t ell_n = (size_t)nspins * inst->dpad;
+    std::vector<int32_t> ell_idx(ell_n);
+    std::vector<float> ell_J(ell_n * nsteps, 0.0f);
+    std::vector<float> hf((size_t)nspins * nsteps);
     for (int64_t i = 0; i < nspins; ++i) {
         int s = 0;
-        for (auto &kv : quad[i]) {
-            ell_idx[i * inst->dpad + s] = kv.first;
-            ell_J[i * inst->dpad + s] = (float)kv.second;
+        for (int32_t j : nbr[i]) {
+            ell_idx[i * inst->dpad + s] = j;
+            for (int64_t t = 0; t < nsteps; ++t) {
+                auto it = quad[t][i].find(j);
+                if (it != quad[t][i].end()) ell_J[t * ell_n + i * inst->dpad + s] = (float)it->second;
+            }
             ++s;
         }
         for (; s < inst->dpad; ++s) ell_idx[i * inst->dpad + s] = (int32_t)i;
-        hf[i] = (float)h[i];
+        for (int64_t t = 0; t < nsteps; ++t) hf[t * nspins + i] = (float)h[t * nspins + i];
     }
 
     int rc = MCS_OK;
@@ -240,6 +257,12 @@ extern "C" int mcs_instance_create(const double *nbs, int64_t nspins, int64_t ma
         return fail(rc);
     *out = inst;
     return MCS_OK;
+}
+
+extern "C" int mcs_instance_create(const double *nbs, int64_t nspins, int64_t maxnb, int device,
+                                   mcs_instance **out)
+{
+    return mcs_instance_create_steps(nbs, 1, nspins, maxnb, device, out);
 }
 
 static void state_release_device(mcs_state *st)
@@ -292,7 +315,7 @@ extern "C" int mcs_instance_info(const mcs_instance *inst, int64_t info[8])
     info[4] = inst->has_field ? 1 : 0;
     info[5] = inst->device;
     info[6] = inst->lut_ok ? 1 : 0;
-    info[7] = 0;
+    info[7] = inst->nsteps;
     return MCS_OK;
 }
 

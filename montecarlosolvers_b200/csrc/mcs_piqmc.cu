@@ -642,7 +642,12 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;
+    MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
+                "time-dependent instance has %lld tables but the schedule has %lld steps", (long long)inst->nsteps,
+                (long long)S);
     for (int64_t f = 0; f < S; ++f) {
+        a.ell_J = inst->ell_J_at(f);
+        a.h = inst->h_at(f);
         const double jperp = -0.5 * teff * log(tanh(A[f] / teff)); // qmc.pyx:95
         a.bcoef = (float)(-2.0 * B[f]);                            // qmc.pyx:96
         a.jperp2 = (float)(2.0 * jperp);
@@ -708,7 +713,7 @@ int mcs_piqmc_energy(mcs_state *st, double *d_out)
 {
     mcs_instance *inst = st->inst;
     dim3 grid((unsigned)((st->R + 31) / 32), (unsigned)((st->P + 7) / 8));
-    piqmc_energy_kernel<<<grid, dim3(32, 8), 0, inst->stream>>>(st->d_W, inst->d_tab_idx, inst->d_tab_J, d_out, inst->N,
+    piqmc_energy_kernel<<<grid, dim3(32, 8), 0, inst->stream>>>(st->d_W, inst->tab_idx_at(inst->nsteps - 1), inst->tab_J_at(inst->nsteps - 1), d_out, inst->N,
                                                       (int)inst->maxnb, st->R, st->Rpad, (int)st->P);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());

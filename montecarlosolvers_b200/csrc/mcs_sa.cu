@@ -278,7 +278,12 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
     const bool lut = npl <= 8;
     const int warps = (a.chunks % 4 == 0) ? 4 : (a.chunks % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;
+    MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
+                "time-dependent instance has %lld tables but the schedule has %lld steps", (long long)inst->nsteps,
+                (long long)S);
     for (int64_t t = 0; t < S; ++t) {
+        a.ell_J = inst->ell_J_at(t); // sa.NoisyAnneal: nbs[itemp] (sa.pyx:363-365)
+        a.h = inst->h_at(t);
         // exp(-ediff/temp), sa.pyx:98; temp == 0 gives -inf here -> threshold "never" for ediff > 0
         a.nl2e_over_t = (float)(-1.4426950408889634 / sched[t]);
         for (int step = 0; step < mcsteps; ++step, ++sweep) {
@@ -337,7 +342,7 @@ int mcs_sa_energy(mcs_state *st, double *d_out)
 {
     mcs_instance *inst = st->inst;
     sa_energy_kernel<<<(unsigned)((st->R + 63) / 64), 64, 0, inst->stream>>>(
-        st->d_V, inst->d_tab_idx, inst->d_tab_J, d_out, inst->N, (int)inst->maxnb, st->R, st->G);
+        st->d_V, inst->tab_idx_at(inst->nsteps - 1), inst->tab_J_at(inst->nsteps - 1), d_out, inst->N, (int)inst->maxnb, st->R, st->G);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;

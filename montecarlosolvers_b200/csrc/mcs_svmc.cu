@@ -158,7 +158,12 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
     a.replica_offset = (uint32_t)replica_offset;
     a.nl2e_over_t = (float)(-1.4426950408889634 / (double)temp); // temp is a C float (svmc.pyx:24)
     uint64_t sweep = sweep_offset;
+    MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
+                "time-dependent instance has %lld tables but the schedule has %lld steps", (long long)inst->nsteps,
+                (long long)S);
     for (int64_t f = 0; f < S; ++f) {
+        a.ell_J = inst->ell_J_at(f); // svmc.NoisySVMC: nbs[ifield] (svmc.pyx:317-319)
+        a.h = inst->h_at(f);
         a.a_coef = (float)A[f];
         a.b_coef = (float)B[f];
         const double ab = A[f] / B[f]; // cdivision: inf / nan allowed (svmc.pyx:198)
@@ -216,7 +221,7 @@ int mcs_svmc_energy(mcs_state *st, double a, double b, double *d_out)
 {
     mcs_instance *inst = st->inst;
     svmc_energy_kernel<<<(unsigned)((st->R + 63) / 64), 64, 0, inst->stream>>>(
-        st->d_theta, inst->d_tab_idx, inst->d_tab_J, d_out, inst->N, (int)inst->maxnb, st->R, st->Rpad, a, b);
+        st->d_theta, inst->tab_idx_at(inst->nsteps - 1), inst->tab_J_at(inst->nsteps - 1), d_out, inst->N, (int)inst->maxnb, st->R, st->Rpad, a, b);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;

@@ -12,14 +12,17 @@ from . import _lib
 __all__ = ["Anneal", "AnnealMA", "Anneal_parallel", "NoisyAnneal"]
 
 
-def _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset, randuni=None):
+def _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset, randuni=None,
+         nbs_ndim=3):
     sched = np.asarray(sched)
     if sched.dtype != np.float64:
         raise ValueError("Buffer dtype mismatch, expected 'float64_t' but got '%s'" % sched.dtype)
     if sched.ndim != 1:
         raise ValueError("Buffer has wrong number of dimensions (expected 1, got %d)" % sched.ndim)
     sched = np.ascontiguousarray(sched)
-    nbs = C.check_nbs(nbs)
+    nbs = C.check_nbs(nbs, nbs_ndim)
+    if nbs_ndim == 4 and not isinstance(nbs, _lib.Instance) and nbs.shape[0] < sched.size:
+        raise ValueError("nbs needs one table per schedule step")
     a8, batched, need_copy = C.spins_in(svec, 1, "svec")
     R, N = a8.shape
     inst = _lib.instance_for(nbs, device)
@@ -81,35 +84,20 @@ def Anneal_parallel(sched, mcsteps, svec, nbs, nthreads=1, *, seed=None, exact=F
     return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset)
 
 
-def NoisyAnneal(sched, mcsteps, svec, nbs, **kw):
-    """NoisyAnneal(sched, mcsteps, svec, nbs) -- time-dependent table nbs[sched, nspins, maxnb, 2]
-    (reference sa.pyx:291-378): every temperature step is its own compiled instance."""
-    sched = np.ascontiguousarray(sched, dtype=np.float64)
-    nbs = C.check_nbs(nbs, 4)
-    if nbs.shape[0] < sched.size:
-        raise ValueError("nbs needs one table per schedule step")
-    if kw.get("exact"):
-        raise NotImplementedError("NoisyAnneal: exact replay is not implemented in this build")
-    seed = _lib.next_seed(kw.pop("seed", None))
-    a8, batched, need_copy = C.spins_in(svec, 1, "svec")
-    R = a8.shape[0]
-    inst0 = _lib.Instance(nbs[0], kw.get("device") or _lib.default_device())
-    st = _lib.State(inst0, _lib.KIND_SA, R, 1)
-    st.upload_spins(a8)
-    cur = a8
-    st.close()
-    inst0.close()
-    for t in range(sched.size):  # one compiled table per step; state round-trips through the host
-        inst = _lib.Instance(nbs[t], kw.get("device") or _lib.default_device())
-        s = _lib.State(inst, _lib.KIND_SA, R, 1)
-        s.upload_spins(cur)
-        s.sa_sweeps(sched[t:t + 1], mcsteps, seed=seed, sweep_offset=t * int(mcsteps))
-        cur = s.download_spins()
-        s.close()
-        inst.close()
-    a8[...] = cur
-    C.spins_out(svec, a8, batched, need_copy)
-    return None
+def NoisyAnneal(sched, mcsteps, svec, nbs, *, seed=None, exact=False, libc_seed=None, device=None, energies=False,
+                replica_offset=0):
+    """NoisyAnneal(sched, mcsteps, svec, nbs)
+
+    Annealing with time-dependent couplings, `nbs` is [len(sched), nspins, maxnb, 2] and temperature step
+    `itemp` uses nbs[itemp] (reference sa.pyx:291-378).  All tables are compiled into one device instance
+    (one colouring from the union of the steps' graphs, one fp32 coupling row per step).  With exact=True
+    the acceptance uniforms are drawn from np.random as the reference does (:336).  energies=True evaluates
+    the LAST table."""
+    ru = None
+    if exact:
+        ru = np.random.uniform(size=(np.asarray(sched).size, int(mcsteps), svec.shape[-1], 1))
+    return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset, randuni=ru,
+                nbs_ndim=4)
 
 
 def delta_e(svec, nbs, device=None):

@@ -15,7 +15,7 @@ __all__ = ["SpinVectorMonteCarlo", "SpinVectorMonteCarloTF", "SpinVectorMonteCar
 
 
 def _run(A_sched, B_sched, mcsteps, temp, svec, nbs, tf, ndim, seed, exact, libc_seed, device, replica_offset,
-         rand_driven=False, randuni=None):
+         rand_driven=False, randuni=None, nbs_ndim=3):
     A = np.asarray(A_sched)
     B = np.asarray(B_sched)
     for s in (A, B):
@@ -26,7 +26,9 @@ def _run(A_sched, B_sched, mcsteps, temp, svec, nbs, tf, ndim, seed, exact, libc
     A, B = np.ascontiguousarray(A), np.ascontiguousarray(B)
     if B.size < A.size:
         raise ValueError("B_sched is shorter than A_sched")
-    nbs = C.check_nbs(nbs)
+    nbs = C.check_nbs(nbs, nbs_ndim)
+    if nbs_ndim == 4 and not isinstance(nbs, _lib.Instance) and nbs.shape[0] < A.size:
+        raise ValueError("nbs needs one table per schedule step")
     a, need_copy = C.angles_in(svec, ndim, "svec")
     R, N = a.shape
     inst = _lib.instance_for(nbs, device)
@@ -92,37 +94,20 @@ def SpinVectorMonteCarloTFCompact(A_sched, B_sched, mcsteps, temp, svec, nbs, *,
                 replica_offset, rand_driven=True)
 
 
-def NoisySVMC(A_sched, B_sched, mcsteps, temp, svec, nbs, **kw):
-    """NoisySVMC(A_sched, B_sched, mcsteps, temp, svec, nbs) with nbs[sched, nspins, maxnb, 2]
-    (reference svmc.pyx:236-334)."""
-    return _noisy(A_sched, B_sched, mcsteps, temp, svec, nbs, False, **kw)
+def NoisySVMC(A_sched, B_sched, mcsteps, temp, svec, nbs, *, seed=None, exact=False, libc_seed=None, device=None,
+              randuni=None):
+    """NoisySVMC(A_sched, B_sched, mcsteps, temp, svec, nbs)
+
+    SpinVectorMonteCarlo with time-dependent couplings nbs[len(A_sched), nspins, maxnb, 2]: schedule step
+    `ifield` uses nbs[ifield] (reference svmc.pyx:236-334)."""
+    return _run(A_sched, B_sched, mcsteps, temp, svec, nbs, False, 1, seed, exact, libc_seed, device, 0,
+                randuni=randuni, nbs_ndim=4)
 
 
-def NoisySVMCTF(A_sched, B_sched, mcsteps, temp, svec, nbs, **kw):
-    """NoisySVMCTF (reference svmc.pyx:340-448)."""
-    return _noisy(A_sched, B_sched, mcsteps, temp, svec, nbs, True, **kw)
+def NoisySVMCTF(A_sched, B_sched, mcsteps, temp, svec, nbs, *, seed=None, exact=False, libc_seed=None, device=None,
+                randuni=None):
+    """NoisySVMCTF(A_sched, B_sched, mcsteps, temp, svec, nbs)
 
-
-def _noisy(A_sched, B_sched, mcsteps, temp, svec, nbs, tf, seed=None, device=None, exact=False, **_):
-    if exact:
-        raise NotImplementedError("Noisy SVMC: exact replay is not implemented in this build")
-    A = np.ascontiguousarray(A_sched, dtype=np.float64)
-    B = np.ascontiguousarray(B_sched, dtype=np.float64)
-    nbs = C.check_nbs(nbs, 4)
-    if nbs.shape[0] < A.size:
-        raise ValueError("nbs needs one table per schedule step")
-    a, need_copy = C.angles_in(svec, 1, "svec")
-    seed = _lib.next_seed(seed)
-    dev = device if device is not None else _lib.default_device()
-    cur = a
-    for t in range(A.size):  # one compiled table per schedule step
-        inst = _lib.Instance(nbs[t], dev)
-        st = _lib.State(inst, _lib.KIND_SVMC, cur.shape[0], 1)
-        st.upload_angles(cur)
-        st.svmc_sweeps(A[t:t + 1], B[t:t + 1], mcsteps, float(np.float32(temp)), tf=tf, seed=seed,
-                       sweep_offset=t * int(mcsteps))
-        cur = st.download_angles()
-        st.close()
-        inst.close()
-    svec[...] = cur[0]
-    return None
+    TF-restricted proposals with time-dependent couplings (reference svmc.pyx:340-448)."""
+    return _run(A_sched, B_sched, mcsteps, temp, svec, nbs, True, 1, seed, exact, libc_seed, device, 0,
+                randuni=randuni, nbs_ndim=4)

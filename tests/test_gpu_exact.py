@@ -156,3 +156,30 @@ def test_error_behaviour_matches_reference(mcs):
         mcs.qmc.QuantumAnneal(np.ones(2), np.ones(2), 1, 0.1, c[:, :1], nbs, 1)
     with pytest.raises(ValueError):
         mcs.sa.Anneal(np.ones(2, dtype=np.float32), 1, c[:, 0].copy(), nbs)
+
+
+def test_exact_noisy_time_dependent_tables_vs_oracle(mcs):
+    """sa.NoisyAnneal (sa.pyx:291-378) and svmc.NoisySVMC[TF] (svmc.pyx:236-448): nbs[step] per schedule step."""
+    _, nbs = inst.random_graph(30, 60, seed=6)
+    S = 10
+    nbs4 = np.stack([nbs * np.array([1.0, 1.0 + 0.1 * t]) for t in range(S)])
+    sched = np.linspace(2.0, 0.1, S)
+    want = inst.random_spins(30, 3)
+    got = want.copy()
+    np.random.seed(4)
+    orc.NoisyAnneal(sched, 2, want, nbs4, rng=4)
+    np.random.seed(4)
+    assert mcs.sa.NoisyAnneal(sched, 2, got, nbs4, exact=True, libc_seed=4) is None
+    assert np.array_equal(got, want)
+    _, nbs = inst.torus(4, seed=7, fields=True)
+    s = np.linspace(1e-2, 1.0, 8)
+    A, B = 3.0 * (1 - s), s
+    nbs4 = np.stack([nbs * np.array([1.0, 1.0 + 0.05 * t]) for t in range(8)])
+    for name in ("NoisySVMC", "NoisySVMCTF"):
+        want = np.full(16, np.pi / 2)
+        got = want.copy()
+        np.random.seed(2)
+        getattr(orc, name)(A, B, 2, 0.1, want, nbs4, rng=2)
+        np.random.seed(2)
+        getattr(mcs.svmc, name)(A, B, 2, 0.1, got, nbs4, exact=True, libc_seed=2)
+        assert np.array_equal(got, want), name

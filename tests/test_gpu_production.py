@@ -261,6 +261,41 @@ def test_results_do_not_depend_on_sharding_or_call_splitting(mcs):
     assert np.array_equal(s_whole, s_parts)
 
 
+def test_time_dependent_tables_production(mcs):
+    """Noisy* production path: constant tables == the static instance bit for bit (same Philox stream);
+    a table that switches the couplings on over time is honoured step by step."""
+    _, nbs = inst.torus(6, seed=3, fields=True)
+    S, R = 12, 64
+    sched = np.linspace(2.5, 0.05, S)
+    s0 = (2 * np.random.RandomState(1).randint(2, size=(R, 36)) - 1).astype(np.int8)
+    a = s0.copy()
+    mcs.sa.Anneal(sched, 2, a, nbs, seed=9)
+    b = s0.copy()
+    mcs.sa.NoisyAnneal(sched, 2, b, np.stack([nbs] * S), seed=9)
+    assert np.array_equal(a, b)
+    # couplings scaled by 0 for the first half of the schedule: spins stay a random walk (no energy gain),
+    # then the real couplings anneal them
+    scale = np.array([0.0] * 6 + [1.0] * 6)
+    nbs4 = np.stack([nbs * np.array([1.0, sc]) for sc in scale])
+    I4 = mcs.Instance(nbs4)
+    assert I4.nsteps == S
+    st = mcs.State(I4, mcs._lib.KIND_SA, R, 1)
+    st.upload_spins(s0)
+    st.sa_sweeps(sched[:6], 2, seed=3)
+    e_mid = st.energies().mean()  # evaluated with the last (real) table
+    st.sa_sweeps(sched, 2, seed=3)
+    e_end = st.energies().mean()
+    e_rand = np.mean([orc.ising_energy(s0[r].astype(np.int64), nbs) for r in range(R)])
+    assert abs(e_mid - e_rand) < 6.0 and e_end < e_rand - 20.0, (e_rand, e_mid, e_end)
+    v = np.full((36,), np.pi / 2)
+    g = np.linspace(0.05, 1.0, S)
+    assert mcs.svmc.NoisySVMC(3 * (1 - g), g, 2, 0.1, v, np.stack([nbs] * S), seed=4) is None
+    w = np.full((16,), np.pi / 2)
+    _, nbs16 = inst.torus(4, seed=3, fields=True)
+    mcs.svmc.NoisySVMCTF(3 * (1 - g), g, 2, 0.1, w, np.stack([nbs16] * S), seed=4)
+    assert 0.0 <= w.min() and w.max() <= np.pi + 1e-6 and np.abs(w - np.pi / 2).max() > 0.1
+
+
 def _ref_stats():
     with open(os.path.join(G, "santoro_ref_stats.json")) as f:
         return json.load(f)
