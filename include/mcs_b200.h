@@ -73,9 +73,14 @@ int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int64_t nspins,
 void mcs_instance_destroy(mcs_instance *inst);
 /* info[0]=nspins info[1]=maxnb info[2]=ncolors info[3]=max degree (fields excluded)
  * info[4]=1 if any local field  info[5]=device  info[6]=1 if the LUT kernels apply
- * info[7]=number of tables (1 unless created by mcs_instance_create_steps)                 */
+ * info[7]=number of tables (1 unless created by mcs_instance_create_steps); bit 32 set when
+ *         the instance is dense (max degree >= 48): sweeps then run as blocked tensor-core GEMM
+ *         + in-block sequential updates instead of one colour class per site                */
 int mcs_instance_info(const mcs_instance *inst, int64_t info[8]);
 int mcs_instance_colors(const mcs_instance *inst, int32_t *color /* [nspins] */);
+/* dense instances only: enable = 0 routes sweeps through the general coloured kernels instead of the
+ * blocked tensor-core path (used to cross-check the two)                                      */
+int mcs_instance_set_dense(mcs_instance *inst, int enable);
 /* CUDA-event stopwatch on the instance's stream: start ... stop returns milliseconds.      */
 int mcs_timer_start(mcs_instance *inst);
 int mcs_timer_stop(mcs_instance *inst, double *ms);

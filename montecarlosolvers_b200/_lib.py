@@ -39,6 +39,7 @@ SIGNATURES = {
     "mcs_instance_destroy": (None, [c_vp]),
     "mcs_instance_info": (ctypes.c_int, [c_vp, c_i64p]),
     "mcs_instance_colors": (ctypes.c_int, [c_vp, c_i32p]),
+    "mcs_instance_set_dense": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "mcs_timer_start": (ctypes.c_int, [c_vp]),
     "mcs_timer_stop": (ctypes.c_int, [c_vp, c_dp]),
     "mcs_synchronize": (ctypes.c_int, [c_vp]),
@@ -200,11 +201,17 @@ class Instance(object):
         check(load().mcs_instance_info(self._h, info))
         self.ncolors, self.maxdeg = int(info[2]), int(info[3])
         self.has_field, self.lut_kernels = bool(info[4]), bool(info[6])
+        self.dense = bool(int(info[7]) >> 32)
 
     def colors(self):
         out = np.empty(self.nspins, dtype=np.int32)
         check(load().mcs_instance_colors(self._h, out.ctypes.data_as(c_i32p)))
         return out
+
+    def use_dense(self, enable=True):
+        """Dense instances: switch between the blocked tensor-core sweeps and the general coloured kernels."""
+        check(load().mcs_instance_set_dense(self._h, int(bool(enable))))
+        self.dense = bool(enable)
 
     def timer_start(self):
         check(load().mcs_timer_start(self._h))

@@ -49,6 +49,8 @@ struct mcs_instance {
     int dpad = 1;        // row length of the ELL tables (>= 1)
     bool has_field = false;
     bool lut_ok = false; // (maxdeg + has_field + 2) <= 8 planes: the LUT kernels apply
+    bool dense = false;  // near-complete graph: blocked tensor-core sweeps (mcs_dense.cu)
+    int64_t Npad = 0;    // N rounded up to the dense block size (128)
     int64_t launches = 0;
     std::vector<struct mcs_state *> states; // live replica batches (orphaned if the instance dies first)
     struct mcs_state *scratch[4] = {nullptr, nullptr, nullptr, nullptr}; // per-kind batch reused by the
@@ -72,6 +74,9 @@ struct mcs_instance {
     const int32_t *tab_idx_at(int64_t f) const { return d_tab_idx + (nsteps > 1 ? (size_t)f * N * maxnb : 0); }
     const double *tab_J_at(int64_t f) const { return d_tab_J + (nsteps > 1 ? (size_t)f * N * maxnb : 0); }
     int32_t *d_order = nullptr;   // [N]
+    void *d_Jhi = nullptr, *d_Jlo = nullptr; // dense only: [Npad][Npad] bf16 split J = hi + lo
+    float *d_Jf = nullptr;                   // dense only: [Npad][Npad] fp32
+    float *d_hpad = nullptr;                 // dense only: [Npad]
 };
 
 struct mcs_state {
@@ -86,6 +91,8 @@ struct mcs_state {
     float *d_cosz = nullptr;  // SVMC  [N][Rpad]  cos(theta)
     void *d_stage = nullptr;  // staging buffer for host <-> device conversion
     size_t stage_bytes = 0;
+    void *d_S16 = nullptr;    // dense sweeps: spins as bf16 +-1, [Cpad][Npad], column = (replica, slice)
+    long long S16_cols = 0;
 };
 
 int mcs_state_reserve_stage(mcs_state *st, size_t bytes);
@@ -225,6 +232,10 @@ __device__ __forceinline__ uint32_t mcs_accept_threshold(float dE, float nl2e_ov
 int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
                             int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset,
                             const double *lookuptable /* nullptr: no Ohmic bath */);
+bool mcs_dense_supported(const mcs_instance *inst, int P);
+int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const double *B, int64_t S, int mcsteps,
+                            float temp, int global_moves, uint64_t seed, uint64_t replica_offset,
+                            uint64_t sweep_offset);
 int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcsteps, uint64_t seed,
                          uint64_t replica_offset, uint64_t sweep_offset);
 int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,

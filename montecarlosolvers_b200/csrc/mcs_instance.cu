@@ -12,6 +12,8 @@
 #include <numeric>
 #include <queue>
 
+#include <cuda_bf16.h>
+
 #include "mcs_common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -255,6 +257,32 @@ extern "C" int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int6
         (rc = upload(&inst->d_ell_idx, ell_idx)) || (rc = upload(&inst->d_ell_J, ell_J)) ||
         (rc = upload(&inst->d_h, hf)) || (rc = upload(&inst->d_order, inst->order)))
         return fail(rc);
+    // dense instances (SK-like): the coupling matrix itself, fp32 and split into two bf16 halves
+    inst->dense = nsteps == 1 && maxdeg >= 48 && nspins <= 32768;
+    if (inst->dense) {
+        const int64_t Np = (nspins + 127) / 128 * 128;
+        inst->Npad = Np;
+        std::vector<float> Jf((size_t)Np * Np, 0.0f), hp((size_t)Np, 0.0f);
+        std::vector<__nv_bfloat16> Jhi((size_t)Np * Np), Jlo((size_t)Np * Np);
+        for (int64_t i = 0; i < nspins; ++i) {
+            for (auto &kv : quad[0][i]) Jf[(size_t)i * Np + kv.first] = (float)kv.second;
+            hp[i] = (float)h[i];
+        }
+        for (size_t e = 0; e < Jf.size(); ++e) {
+            const __nv_bfloat16 hi = __float2bfloat16(Jf[e]);
+            Jhi[e] = hi;
+            Jlo[e] = __float2bfloat16(Jf[e] - __bfloat162float(hi));
+        }
+        __nv_bfloat16 *dhi = nullptr, *dlo = nullptr;
+        if ((rc = upload(&dhi, Jhi)) || (rc = upload(&dlo, Jlo)) || (rc = upload(&inst->d_Jf, Jf)) ||
+            (rc = upload(&inst->d_hpad, hp))) {
+            cudaFree(dhi);
+            cudaFree(dlo);
+            return fail(rc);
+        }
+        inst->d_Jhi = dhi;
+        inst->d_Jlo = dlo;
+    }
     *out = inst;
     return MCS_OK;
 }
@@ -272,6 +300,9 @@ static void state_release_device(mcs_state *st)
     cudaFree(st->d_theta);
     cudaFree(st->d_cosz);
     cudaFree(st->d_stage);
+    cudaFree(st->d_S16);
+    st->d_S16 = nullptr;
+    st->S16_cols = 0;
     st->d_W = nullptr;
     st->d_V = nullptr;
     st->d_theta = st->d_cosz = nullptr;
@@ -299,6 +330,10 @@ extern "C" void mcs_instance_destroy(mcs_instance *inst)
     cudaFree(inst->d_ell_J);
     cudaFree(inst->d_h);
     cudaFree(inst->d_order);
+    cudaFree(inst->d_Jhi);
+    cudaFree(inst->d_Jlo);
+    cudaFree(inst->d_Jf);
+    cudaFree(inst->d_hpad);
     if (inst->ev0) cudaEventDestroy(inst->ev0);
     if (inst->ev1) cudaEventDestroy(inst->ev1);
     if (inst->stream) cudaStreamDestroy(inst->stream);
@@ -315,7 +350,15 @@ extern "C" int mcs_instance_info(const mcs_instance *inst, int64_t info[8])
     info[4] = inst->has_field ? 1 : 0;
     info[5] = inst->device;
     info[6] = inst->lut_ok ? 1 : 0;
-    info[7] = inst->nsteps;
+    info[7] = inst->nsteps + (inst->dense ? (1ll << 32) : 0); // bit 32: dense (blocked tensor-core sweeps)
+    return MCS_OK;
+}
+
+extern "C" int mcs_instance_set_dense(mcs_instance *inst, int enable)
+{
+    MCS_REQUIRE(inst, MCS_EINVAL, "mcs_instance_set_dense: NULL instance");
+    MCS_REQUIRE(!enable || inst->d_Jf, MCS_EINVAL, "mcs_instance_set_dense: instance was not compiled as dense");
+    inst->dense = enable != 0;
     return MCS_OK;
 }
 

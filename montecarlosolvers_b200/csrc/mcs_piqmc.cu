@@ -74,7 +74,6 @@ __device__ __forceinline__ uint32_t prmt_byte(uint32_t v, int i)
 // stored pre-multiplied by 4 (SH = 2) so that the extracted byte IS the shared-memory byte offset.
 template <int NPL>
 struct LutGeom {
-    static constexpr int SH = (NPL + 2 <= 6) ? 2 : 0;
     static constexpr int ENT = 1 << (NPL + 2);
 };
 
@@ -603,6 +602,9 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     const double teff = (double)temp * (double)P; // qmc.pyx:85: temp is a C float
     MCS_REQUIRE(teff != 0.0 || S == 0, MCS_EZERODIV, "float division");
     MCS_CUDA(cudaSetDevice(inst->device));
+    if (!lookuptable && mcs_dense_supported(inst, P))
+        return mcs_launch_dense_sweeps(st, MCS_KIND_PIQMC, A, B, S, mcsteps, temp, global_moves, seed, replica_offset,
+                                       sweep_offset);
     BathArgs bath;
     bath.lut4 = nullptr;
     bath.c0 = 0.0f;

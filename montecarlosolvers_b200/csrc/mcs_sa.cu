@@ -261,6 +261,9 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
     MCS_REQUIRE((replica_offset & 31) == 0, MCS_EINVAL,
                 "mcs_sa_sweeps: replica_offset must be a multiple of 32 (restarts are packed 32 per word)");
     MCS_CUDA(cudaSetDevice(inst->device));
+    if (mcs_dense_supported(inst, 1))
+        return mcs_launch_dense_sweeps(st, MCS_KIND_SA, sched, nullptr, S, mcsteps, 0.0f, 0, seed, replica_offset,
+                                       sweep_offset);
     SaPass a;
     a.V = st->d_V;
     a.ell_idx = inst->d_ell_idx;
