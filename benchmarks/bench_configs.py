@@ -97,6 +97,35 @@ def main():
         out.append({"config": "cfg4 SVMC%s Chimera C16 (N=2048, %d colours), 2048 reads, 1000 sweeps" % (
             "-TF" if tf else "", ci.ncolors), "ms": ms, "attempts_per_s": 2048 * 1000 * 2048 / (ms * 1e-3)})
         st.close()
+    # ---- cfg5: dense SK N = 2048, P = 32, R replicas (R P columns), local fields on the tensor cores
+    n = 2048
+    rng = np.random.default_rng(0)
+    Jm = np.triu(rng.normal(size=(n, n)) / np.sqrt(n), 1)
+    nb5 = np.zeros((n, n - 1, 2))
+    full = Jm + Jm.T
+    for i in range(n):
+        idx = np.delete(np.arange(n), i)
+        nb5[i, :, 0] = idx
+        nb5[i, :, 1] = full[i, idx]
+    di = mcs.Instance(nb5)
+    P5 = 32
+    A5, B5 = np.linspace(3.0, 1e-8, 20), np.ones(20)
+    for R5 in (128, 512):
+        st = mcs.State(di, mcs._lib.KIND_PIQMC, R5, P5)
+        st.init_random(1)
+        ms = timed(di, lambda: st.piqmc_sweeps(A5, B5, 1, 1.0 / P5, global_moves=True, seed=2), reps=2)
+        cols = R5 * P5
+        out.append({"config": "cfg5 dense SK N=2048 P=32 PIQMC-global, blocked tensor-core sweeps, 20 sweeps",
+                    "replicas": R5, "columns": cols, "ms": ms, "ms_per_sweep": ms / 20,
+                    "attempts_per_s": 20.0 * n * cols / (ms * 1e-3),
+                    "field_gemm_tflops_bf16x2": 20 * 2 * 2.0 * n * n * cols / (ms * 1e-3) / 1e12})
+        st.close()
+    di.use_dense(False)
+    st = mcs.State(di, mcs._lib.KIND_PIQMC, 128, P5)
+    st.init_random(1)
+    ms = timed(di, lambda: st.piqmc_sweeps(A5[:2], B5[:2], 1, 1.0 / P5, global_moves=True, seed=2), reps=1)
+    out.append({"config": "cfg5 same instance through the general coloured kernel (one colour class per site), 2 sweeps",
+                "replicas": 128, "ms": ms, "attempts_per_s": 2.0 * n * 128 * P5 / (ms * 1e-3)})
     for o in out:
         print(json.dumps(o))
 

@@ -17,11 +17,13 @@
 //
 // Spins live as S[column][site] bf16 (+1 / -1) between blocks; the bit-packed W / V arrays of the state
 // are expanded on entry and re-packed on exit of a sweeps call.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <mma.h>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "mcs_common.cuh"
 
@@ -50,57 +52,14 @@ struct DensePass {
 
 __device__ __forceinline__ void bar_decide() { asm volatile("bar.sync 1, %0;" ::"n"(kTC)); }
 
-__global__ void __launch_bounds__(kThreads) dense_block_kernel(const __grid_constant__ DensePass a)
+// ---- phase B: the block's sites one after another, fields in shared memory -----------------------
+// Hb [kBS][kHld] holds the fields from phase A; Jd / delta / gterm / sb are scratch of the sizes below.
+__device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, float *Jd, float *delta, float *gterm,
+                                              signed char *sb, int col0)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *Hb = reinterpret_cast<float *>(smem_raw);               // [kBS][kHld]
-    float *Jd = Hb + kBS * kHld;                                   // [kBS][kJld]
-    float *delta = Jd + kBS * kJld;                                // [kTC]
-    float *gterm = delta + kTC;                                    // [kTC]
-    signed char *sb = reinterpret_cast<signed char *>(gterm + kTC); // [kBS][kTC]
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int col0 = blockIdx.x * kTC;
+    const int tid = threadIdx.x;
     const int i0 = a.i0;
     const long long ld = a.Npad;
-
-    // ---- A. Hb = (Jhi + Jlo)[i0:i0+128, :] * S[:, col0:col0+64]  (tensor cores, fp32 accumulate) ----
-    {
-        using namespace nvcuda;
-        const int row0 = (warp >> 1) * 32, c0w = (warp & 1) * 32;
-        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][2];
-#pragma unroll
-        for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-            for (int ci = 0; ci < 2; ++ci) wmma::fill_fragment(acc[ri][ci], 0.0f);
-        const __nv_bfloat16 *Ahi = a.Jhi + (long long)(i0 + row0) * ld;
-        const __nv_bfloat16 *Alo = a.Jlo + (long long)(i0 + row0) * ld;
-        const __nv_bfloat16 *Bp = a.S + (long long)(col0 + c0w) * ld;
-#pragma unroll 2
-        for (int k0 = 0; k0 < a.Npad; k0 += 16) {
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fhi[2], flo[2];
-            wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> fb[2];
-#pragma unroll
-            for (int ri = 0; ri < 2; ++ri) {
-                wmma::load_matrix_sync(fhi[ri], Ahi + (long long)(16 * ri) * ld + k0, (unsigned)ld);
-                wmma::load_matrix_sync(flo[ri], Alo + (long long)(16 * ri) * ld + k0, (unsigned)ld);
-            }
-#pragma unroll
-            for (int ci = 0; ci < 2; ++ci) wmma::load_matrix_sync(fb[ci], Bp + (long long)(16 * ci) * ld + k0, (unsigned)ld);
-#pragma unroll
-            for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                for (int ci = 0; ci < 2; ++ci) {
-                    wmma::mma_sync(acc[ri][ci], fhi[ri], fb[ci], acc[ri][ci]);
-                    wmma::mma_sync(acc[ri][ci], flo[ri], fb[ci], acc[ri][ci]);
-                }
-        }
-#pragma unroll
-        for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-            for (int ci = 0; ci < 2; ++ci)
-                wmma::store_matrix_sync(Hb + (row0 + 16 * ri) * kHld + c0w + 16 * ci, acc[ri][ci], kHld,
-                                        wmma::mem_row_major);
-    }
     // diagonal block of J (fp32) and the block's spins of this CTA's columns
     for (int e = tid; e < kBS * kBS; e += kThreads) {
         const int r = e / kBS, c = e % kBS;
@@ -112,7 +71,6 @@ __global__ void __launch_bounds__(kThreads) dense_block_kernel(const __grid_cons
     }
     __syncthreads();
 
-    // ---- B. site after site ------------------------------------------------------------------
     const int c = tid;                 // decision threads: tid < kTC
     const int col = col0 + c;
     const int P = a.P;
@@ -179,6 +137,246 @@ __global__ void __launch_bounds__(kThreads) dense_block_kernel(const __grid_cons
     }
 }
 
+// ---- variant 1: phase A on the legacy tensor path (mma.sync through WMMA), operands read from L2 ----
+__global__ void __launch_bounds__(kThreads) dense_block_kernel(const __grid_constant__ DensePass a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *Hb = reinterpret_cast<float *>(smem_raw);               // [kBS][kHld]
+    float *Jd = Hb + kBS * kHld;                                   // [kBS][kJld]
+    float *delta = Jd + kBS * kJld;                                // [kTC]
+    float *gterm = delta + kTC;                                    // [kTC]
+    signed char *sb = reinterpret_cast<signed char *>(gterm + kTC); // [kBS][kTC]
+    const int warp = threadIdx.x >> 5;
+    const int col0 = blockIdx.x * kTC;
+    const int i0 = a.i0;
+    const long long ld = a.Npad;
+    {
+        using namespace nvcuda;
+        const int row0 = (warp >> 1) * 32, c0w = (warp & 1) * 32;
+        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][2];
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) wmma::fill_fragment(acc[ri][ci], 0.0f);
+        const __nv_bfloat16 *Ahi = a.Jhi + (long long)(i0 + row0) * ld;
+        const __nv_bfloat16 *Alo = a.Jlo + (long long)(i0 + row0) * ld;
+        const __nv_bfloat16 *Bp = a.S + (long long)(col0 + c0w) * ld;
+#pragma unroll 2
+        for (int k0 = 0; k0 < a.Npad; k0 += 16) {
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fhi[2], flo[2];
+            wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> fb[2];
+#pragma unroll
+            for (int ri = 0; ri < 2; ++ri) {
+                wmma::load_matrix_sync(fhi[ri], Ahi + (long long)(16 * ri) * ld + k0, (unsigned)ld);
+                wmma::load_matrix_sync(flo[ri], Alo + (long long)(16 * ri) * ld + k0, (unsigned)ld);
+            }
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) wmma::load_matrix_sync(fb[ci], Bp + (long long)(16 * ci) * ld + k0, (unsigned)ld);
+#pragma unroll
+            for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci) {
+                    wmma::mma_sync(acc[ri][ci], fhi[ri], fb[ci], acc[ri][ci]);
+                    wmma::mma_sync(acc[ri][ci], flo[ri], fb[ci], acc[ri][ci]);
+                }
+        }
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci)
+                wmma::store_matrix_sync(Hb + (row0 + 16 * ri) * kHld + c0w + 16 * ci, acc[ri][ci], kHld,
+                                        wmma::mem_row_major);
+    }
+    __syncthreads();
+    dense_phase_b(a, Hb, Jd, delta, gterm, sb, col0);
+}
+
+// ---- variant 2 (default): phase A on tcgen05 -------------------------------------------------------
+// TMA (cp.async.bulk.tensor, 128-byte swizzle) streams [128 x 64] tiles of Jhi / Jlo and a [64 x 64] tile of
+// S per stage into a 3-stage shared-memory ring; one thread issues tcgen05.mma (M = 128, N = 64, K = 16,
+// kind::f16, bf16 inputs) for the hi and the lo tile into ONE fp32 accumulator in tensor memory (64
+// columns); tcgen05.commit hands stages back to the producer and finally signals the epilogue warps, which
+// read the accumulator with tcgen05.ld (lane = block row) into the shared field tile Hb.  Phase B then
+// reuses the ring's shared memory.
+constexpr int kStages = 3;
+constexpr int kBK = 64;                                   // K elements per stage = one 128-byte swizzle row
+constexpr int kStageA = kBS * kBK * 2;                    // 16 KB
+constexpr int kStageB = kTC * kBK * 2;                    //  8 KB
+constexpr int kStageBytes = 2 * kStageA + kStageB;        // 40 KB
+constexpr int kRingBytes = kStages * kStageBytes;         // 120 KB
+constexpr int kHbBytes = kBS * kHld * 4;
+constexpr int kTmemCols = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (= 1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct DenseMaps {
+    alignas(64) unsigned char jhi[128];
+    alignas(64) unsigned char jlo[128];
+    alignas(64) unsigned char s[128];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+    dense_block_kernel_tc(const __grid_constant__ DensePass a, const __grid_constant__ DenseMaps maps)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // carve: [ring 120 KB | Hb 34 KB | barriers], ring 1024-byte aligned (128-byte swizzle atoms are 1024 B);
+    // phase B scratch aliases the ring
+    unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float *Hb = reinterpret_cast<float *>(ring + kRingBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kRingBytes + kHbBytes);
+    uint64_t *empty = full + kStages;
+    uint64_t *accum_full = empty + kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col0 = blockIdx.x * kTC;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int nkb = a.Npad / kBK;
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kStages;
+            mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
+            unsigned char *st = ring + s * kStageBytes;
+            mbar_expect_tx(&full[s], kStageBytes);
+            tma_load_2d(st, maps.jhi, kb * kBK, a.i0, &full[s]);
+            tma_load_2d(st + kStageA, maps.jlo, kb * kBK, a.i0, &full[s]);
+            tma_load_2d(st + 2 * kStageA, maps.s, kb * kBK, col0, &full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer: D[128 x 64] (+)= Ahi . B^T + Alo . B^T
+        // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 64, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTC >> 3) << 17) |
+                               ((uint32_t)(kBS >> 4) << 24);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kStages;
+            mbar_wait(&full[s], (kb / kStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(ring + s * kStageBytes);
+            const uint64_t dhi = umma_desc_sw128(sa), dlo = umma_desc_sw128(sa + kStageA),
+                           db = umma_desc_sw128(sa + 2 * kStageA);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) // 16 bf16 = 32 bytes = 2 descriptor units along K
+                umma_f16(tmem_base, dhi + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) umma_f16(tmem_base, dlo + 2 * k, db + 2 * k, idesc, 1u);
+            umma_commit(&empty[s]); // stage reusable once these MMAs have read it
+        }
+        umma_commit(accum_full);
+    }
+    __syncwarp();
+    if (warp < 4) {
+        // ---- epilogue: TMEM lane = block row, 64 fp32 columns -> Hb
+        mbar_wait(accum_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+            "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+            "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+              "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+              "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+              "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+              "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float *hrow = Hb + (warp * 32 + lane) * kHld;
+#pragma unroll
+        for (int q = 0; q < 64; ++q) hrow[q] = __uint_as_float(v[q]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+    // phase B scratch lives in the (now idle) ring
+    float *Jd = reinterpret_cast<float *>(ring);
+    float *delta = Jd + kBS * kJld;
+    float *gterm = delta + kTC;
+    signed char *sb = reinterpret_cast<signed char *>(gterm + kTC);
+    dense_phase_b(a, Hb, Jd, delta, gterm, sb, col0);
+}
+
 // W[N][Rpad] (bit k = slice k) -> S[(r P + k)][site]
 __global__ void dense_expand_piqmc_kernel(const uint64_t *__restrict__ W, __nv_bfloat16 *__restrict__ S, int N,
                                           int Npad, long long R, long long Rpad, int P, long long Cpad)
@@ -236,6 +434,36 @@ __global__ void dense_compress_sa_kernel(const __nv_bfloat16 *__restrict__ S, ui
 }
 
 constexpr size_t kSmemBytes = sizeof(float) * (kBS * kHld + kBS * kJld + 2 * kTC) + kBS * kTC;
+constexpr size_t kSmemBytesTc = kRingBytes + kHbBytes + 128 + 1024; // + barriers + slack for 1024-byte alignment
+static_assert(sizeof(float) * (kBS * kJld + 2 * kTC) + kBS * kTC <= kRingBytes, "phase B scratch must fit the ring");
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map_bf16_2d(void *out128, const void *base, uint64_t inner, uint64_t rows, uint32_t box_inner,
+                     uint32_t box_rows)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        void *p = nullptr;
+        MCS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        MCS_REQUIRE(p && q == cudaDriverEntryPointSuccess, MCS_ENODEVICE, "cuTensorMapEncodeTiled not available");
+        fn = (EncodeTiledFn)p;
+    }
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {inner * 2};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn((CUtensorMap *)out128, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MCS_REQUIRE(r == CUDA_SUCCESS, MCS_ENODEVICE, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return MCS_OK;
+}
 
 } // namespace
 
@@ -267,7 +495,18 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     if (!attr_set) {
         MCS_CUDA(cudaFuncSetAttribute(dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemBytes));
+        MCS_CUDA(cudaFuncSetAttribute(dense_block_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemBytesTc));
         attr_set = true;
+    }
+    // MCS_DENSE_IMPL=wmma selects the legacy-tensor-path variant (cross-check); default: tcgen05 + TMA
+    const char *impl = getenv("MCS_DENSE_IMPL");
+    const bool use_tc = !(impl && impl[0] == 'w');
+    DenseMaps maps;
+    if (use_tc) {
+        MCS_TRY(make_map_bf16_2d(maps.jhi, inst->d_Jhi, (uint64_t)Npad, (uint64_t)Npad, kBK, kBS));
+        MCS_TRY(make_map_bf16_2d(maps.jlo, inst->d_Jlo, (uint64_t)Npad, (uint64_t)Npad, kBK, kBS));
+        MCS_TRY(make_map_bf16_2d(maps.s, S16, (uint64_t)Npad, (uint64_t)Cpad, kBK, kTC));
     }
     const long long nexp = Cpad * Npad;
     if (kind == MCS_KIND_PIQMC)
@@ -310,7 +549,10 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
             a.sweep_hi = (uint32_t)(sweep >> 32);
             for (int i0 = 0; i0 < (int)inst->N; i0 += kBS) {
                 a.i0 = i0;
-                dense_block_kernel<<<(unsigned)(Cpad / kTC), kThreads, kSmemBytes, inst->stream>>>(a);
+                if (use_tc)
+                    dense_block_kernel_tc<<<(unsigned)(Cpad / kTC), kThreads, kSmemBytesTc, inst->stream>>>(a, maps);
+                else
+                    dense_block_kernel<<<(unsigned)(Cpad / kTC), kThreads, kSmemBytes, inst->stream>>>(a);
                 inst->launches++;
             }
         }
