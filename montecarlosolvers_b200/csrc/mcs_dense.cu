@@ -52,15 +52,52 @@ struct DensePass {
 
 __device__ __forceinline__ void bar_decide() { asm volatile("bar.sync 1, %0;" ::"n"(kTC)); }
 
-// ---- phase B: the block's sites one after another, fields in shared memory -----------------------
-// Hb [kBS][kHld] holds the fields from phase A; Jd / delta / gterm / sb are scratch of the sizes below.
-__device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, float *Jd, float *delta, float *gterm,
-                                              signed char *sb, int col0)
+// ---- phase B: the block's sites one after another -------------------------------------------------
+// Critical path per site: decide (64 threads) -> barrier -> rank-1 update -> barrier.  To keep it short,
+//   * every uniform the block will need is drawn up front, in parallel (the Philox counters do not depend
+//     on the state) and stored as lu = log2((u+1) 2^-32): the Metropolis test  u/2^32 < exp(-dE/teff)
+//     (qmc.pyx:140-143) becomes  dE <= 0  or  dE * (-log2 e / teff) >= lu  -- one multiply and a compare
+//     on the critical path instead of an exponential;
+//   * the field tile lives in REGISTERS during the block: thread t owns row t/2, columns 32 (t%2) .. +32, so
+//     the rank-1 update is 32 register FMAs; the owners of row m+1 publish it to shared memory for the
+//     next decision;
+//   * for P <= 32 a replica's slices are lanes of one warp: Trotter neighbours and the world-line sum go
+//     through shuffles, no shared memory or barrier between the parity phases.
+constexpr int kScrJd = 0;                                   // float [kBS][kJld]
+constexpr int kScrUloc = kScrJd + kBS * kJld * 4;           // float [kBS][kTC]: log2 of the local uniforms
+constexpr int kScrSb = kScrUloc + kBS * kTC * 4;            // int8 [kBS][kTC]
+constexpr int kScrFrow = kScrSb + kBS * kTC;                // float [kTC]
+constexpr int kScrDelta = kScrFrow + kTC * 4;               // float [kTC]
+constexpr int kScrGterm = kScrDelta + kTC * 4;              // float [kTC]
+constexpr int kScrHblk = kScrGterm + kTC * 4;               // float [kBS]: local fields h_i of the block
+constexpr int kScrBytes = kScrHblk + kBS * 4;
+static_assert(kBS * (kTC / 2) * 4 <= kBS * kHld * 4, "uglob must fit the (consumed) field tile");
+
+template <bool INWARP> // INWARP: P <= 32 (or SA): a replica's slices sit in one warp
+__device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, unsigned char *scr, int col0)
 {
-    const int tid = threadIdx.x;
+    float *Jd = reinterpret_cast<float *>(scr + kScrJd);
+    float *uloc = reinterpret_cast<float *>(scr + kScrUloc);
+    float *hblk = reinterpret_cast<float *>(scr + kScrHblk);
+    signed char *sb = reinterpret_cast<signed char *>(scr + kScrSb);
+    float *frow = reinterpret_cast<float *>(scr + kScrFrow);
+    float *delta = reinterpret_cast<float *>(scr + kScrDelta);
+    float *gterm = reinterpret_cast<float *>(scr + kScrGterm);
+    const int tid = threadIdx.x, lane = tid & 31;
     const int i0 = a.i0;
     const long long ld = a.Npad;
-    // diagonal block of J (fp32) and the block's spins of this CTA's columns
+    const int P = a.P;
+    const int mend = min(kBS, a.N - i0);
+
+    // field strip of this thread -> registers; the tile's shared memory then holds the world-line uniforms
+    const int row = tid >> 1, cbase = (tid & 1) * (kTC / 2);
+    float hreg[kTC / 2];
+#pragma unroll
+    for (int q = 0; q < kTC / 2; ++q) hreg[q] = Hb[row * kHld + cbase + q];
+    __syncthreads();
+    float *uglob = Hb; // [kBS][kTC/2], indexed by the CTA-local replica
+    if (tid < kBS) hblk[tid] = __ldg(&a.h[i0 + tid]);
+
     for (int e = tid; e < kBS * kBS; e += kThreads) {
         const int r = e / kBS, c = e % kBS;
         Jd[r * kJld + c] = __ldg(&a.Jf[(long long)(i0 + r) * ld + i0 + c]);
@@ -69,83 +106,127 @@ __device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, flo
         const int c = e / kBS, m = e % kBS; // consecutive threads -> consecutive sites of one column
         sb[m * kTC + c] = __bfloat162float(a.S[(long long)(col0 + c) * ld + i0 + m]) < 0.0f ? -1 : 1;
     }
+    for (int e = tid; e < kBS * kTC; e += kThreads) { // all uniforms of the block
+        const int m = e / kTC, c = e % kTC;
+        const int col = col0 + c, k = col % P;
+        const uint32_t rep = a.replica_offset + (uint32_t)(col / P);
+        if ((k & 3) == 0) {
+            uint32_t rnd[4];
+            mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(k >> 2), a.keys, rnd);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k + j < P) uloc[m * kTC + c + j] = __log2f((float)rnd[j] + 1.0f) - 32.0f;
+        }
+        if (a.global_moves && k == 0) {
+            uint32_t rnd[4];
+            mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
+            uglob[m * (kTC / 2) + c / P] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
+        }
+    }
+    if (row == 0) {
+#pragma unroll
+        for (int q = 0; q < kTC / 2; ++q) frow[cbase + q] = hreg[q];
+    }
     __syncthreads();
 
-    const int c = tid;                 // decision threads: tid < kTC
+    const int c = tid; // decision threads: tid < kTC
     const int col = col0 + c;
-    const int P = a.P;
-    const int k = col % P;             // slice
+    const int k = col % P; // slice
     const int cl = c - k + (k == 0 ? P - 1 : k - 1), cr = c - k + (k == P - 1 ? 0 : k + 1);
-    const uint32_t rep = a.replica_offset + (uint32_t)(col / P);
-    const int mend = min(kBS, a.N - i0);
     for (int m = 0; m < mend; ++m) {
-        int flipped = 0;
         if (tid < kTC) {
-            const int site = i0 + m;
-            const float field = Hb[m * kHld + c] + __ldg(&a.h[site]);
+            const float field = frow[c] + hblk[m];
             const int s_init = sb[m * kTC + c];
-            uint32_t rnd[4];
-            mcs_philox4x32_10_rk(rep, (uint32_t)site, a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(k >> 2), a.keys, rnd);
-            const uint32_t u = (k & 3) == 0 ? rnd[0] : (k & 3) == 1 ? rnd[1] : (k & 3) == 2 ? rnd[2] : rnd[3];
+            const float lu = uloc[m * kTC + c];
+            const float sc = a.nl2e_over_t;
+#define MCS_ACCEPT(dE, lg) (col < a.C && ((dE) <= 0.0f || (dE) * sc >= (lg)))
             int s = s_init;
-#pragma unroll 1
-            for (int parity = 0; parity < 2; ++parity) { // even slices, then odd slices (P is even or 1)
-                if ((k & 1) == parity) {
-                    float dE = a.bcoef * (float)s * field;
-                    if (a.trotter) dE += a.jperp2 * (float)(s * (sb[m * kTC + cl] + sb[m * kTC + cr]));
-                    if (col < a.C && u <= mcs_accept_threshold(dE, a.nl2e_over_t)) {
-                        s = -s;
-                        sb[m * kTC + c] = (signed char)s;
+            if (INWARP) {
+                if (a.trotter) {
+#pragma unroll
+                    for (int parity = 0; parity < 2; ++parity) { // even slices, then odd slices (P is even)
+                        const int sl = __shfl_sync(0xffffffffu, s, cl & 31), sr = __shfl_sync(0xffffffffu, s, cr & 31);
+                        if ((k & 1) == parity) {
+                            const float dE = a.bcoef * (float)s * field + a.jperp2 * (float)(s * (sl + sr));
+                            if (MCS_ACCEPT(dE, lu)) s = -s;
+                        }
                     }
+                } else {
+                    const float dE = a.bcoef * (float)s * field;
+                    if (MCS_ACCEPT(dE, lu)) s = -s;
                 }
-                if (!a.trotter) break;
-                bar_decide();
-            }
-            if (a.global_moves) { // world-line move: all P slices of the replica (qmc.pyx:405-438)
-                gterm[c] = a.bcoef * (float)s * field;
-                bar_decide();
-                float dE = 0.0f;
-                for (int q = 0; q < P; ++q) dE += gterm[c - k + q];
-                mcs_philox4x32_10_rk(rep, (uint32_t)site, a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
-                if (col < a.C && rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) {
-                    s = -s;
-                    sb[m * kTC + c] = (signed char)s;
+                if (a.global_moves) { // world-line move: all P slices of the replica (qmc.pyx:405-438)
+                    float dE = a.bcoef * (float)s * field;
+                    for (int off = 1; off < P; off <<= 1) dE += __shfl_xor_sync(0xffffffffu, dE, off);
+                    if (MCS_ACCEPT(dE, uglob[m * (kTC / 2) + c / P])) s = -s;
+                }
+            } else { // P == 64: the replica spans both decision warps -> shared memory + a 64-thread barrier
+#pragma unroll 1
+                for (int parity = 0; parity < 2; ++parity) {
+                    if ((k & 1) == parity) {
+                        const float dE = a.bcoef * (float)s * field +
+                                         a.jperp2 * (float)(s * (sb[m * kTC + cl] + sb[m * kTC + cr]));
+                        if (MCS_ACCEPT(dE, lu)) {
+                            s = -s;
+                            sb[m * kTC + c] = (signed char)s;
+                        }
+                    }
+                    bar_decide();
+                }
+                if (a.global_moves) {
+                    gterm[c] = a.bcoef * (float)s * field;
+                    bar_decide();
+                    float dE = 0.0f;
+                    for (int q = 0; q < P; ++q) dE += gterm[c - k + q];
+                    if (MCS_ACCEPT(dE, uglob[m * (kTC / 2) + c / P])) s = -s;
                 }
             }
+#undef MCS_ACCEPT
+            sb[m * kTC + c] = (signed char)s;
             delta[c] = (float)(s - s_init);
-            flipped = s != s_init;
         }
-        if (!__syncthreads_or(flipped)) continue; // nobody flipped: fields unchanged
-        {
-            const int row = tid >> 1, cbase = (tid & 1) * (kTC / 2);
-            if (row > m) {
-                const float jv = Jd[row * kJld + m];
-                if (jv != 0.0f) {
-                    float *hrow = Hb + row * kHld + cbase;
-#pragma unroll 8
-                    for (int q = 0; q < kTC / 2; ++q) hrow[q] = fmaf(jv, delta[cbase + q], hrow[q]);
+        __syncthreads();
+        if (row > m) {
+            const float jv = Jd[row * kJld + m];
+            if (jv != 0.0f) {
+#pragma unroll
+                for (int q4 = 0; q4 < kTC / 8; ++q4) {
+                    const float4 d = *reinterpret_cast<const float4 *>(delta + cbase + 4 * q4);
+                    hreg[4 * q4 + 0] = fmaf(jv, d.x, hreg[4 * q4 + 0]);
+                    hreg[4 * q4 + 1] = fmaf(jv, d.y, hreg[4 * q4 + 1]);
+                    hreg[4 * q4 + 2] = fmaf(jv, d.z, hreg[4 * q4 + 2]);
+                    hreg[4 * q4 + 3] = fmaf(jv, d.w, hreg[4 * q4 + 3]);
                 }
+            }
+            if (row == m + 1) {
+#pragma unroll
+                for (int q = 0; q < kTC / 2; ++q) frow[cbase + q] = hreg[q];
             }
         }
         __syncthreads();
     }
-    __syncthreads();
     // write the block's spins back
     for (int e = tid; e < kBS * kTC; e += kThreads) {
         const int cc = e / kBS, m = e % kBS;
         a.S[(long long)(col0 + cc) * ld + i0 + m] = __float2bfloat16((float)sb[m * kTC + cc]);
     }
+    (void)lane;
+}
+
+__device__ __forceinline__ void dense_phase_b_dispatch(const DensePass &a, float *Hb, unsigned char *scr, int col0)
+{
+    if (a.P <= 32)
+        dense_phase_b<true>(a, Hb, scr, col0);
+    else
+        dense_phase_b<false>(a, Hb, scr, col0);
 }
 
 // ---- variant 1: phase A on the legacy tensor path (mma.sync through WMMA), operands read from L2 ----
 __global__ void __launch_bounds__(kThreads) dense_block_kernel(const __grid_constant__ DensePass a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *Hb = reinterpret_cast<float *>(smem_raw);               // [kBS][kHld]
-    float *Jd = Hb + kBS * kHld;                                   // [kBS][kJld]
-    float *delta = Jd + kBS * kJld;                                // [kTC]
-    float *gterm = delta + kTC;                                    // [kTC]
-    signed char *sb = reinterpret_cast<signed char *>(gterm + kTC); // [kBS][kTC]
+    float *Hb = reinterpret_cast<float *>(smem_raw); // [kBS][kHld]
+    unsigned char *scr = smem_raw + kBS * kHld * 4;
     const int warp = threadIdx.x >> 5;
     const int col0 = blockIdx.x * kTC;
     const int i0 = a.i0;
@@ -188,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) dense_block_kernel(const __grid_cons
                                         wmma::mem_row_major);
     }
     __syncthreads();
-    dense_phase_b(a, Hb, Jd, delta, gterm, sb, col0);
+    dense_phase_b_dispatch(a, Hb, scr, col0);
 }
 
 // ---- variant 2 (default): phase A on tcgen05 -------------------------------------------------------
@@ -370,11 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
     // phase B scratch lives in the (now idle) ring
-    float *Jd = reinterpret_cast<float *>(ring);
-    float *delta = Jd + kBS * kJld;
-    float *gterm = delta + kTC;
-    signed char *sb = reinterpret_cast<signed char *>(gterm + kTC);
-    dense_phase_b(a, Hb, Jd, delta, gterm, sb, col0);
+    dense_phase_b_dispatch(a, Hb, ring, col0);
 }
 
 // W[N][Rpad] (bit k = slice k) -> S[(r P + k)][site]
@@ -433,9 +510,9 @@ __global__ void dense_compress_sa_kernel(const __nv_bfloat16 *__restrict__ S, ui
     V[(long long)i * G + g] = v;
 }
 
-constexpr size_t kSmemBytes = sizeof(float) * (kBS * kHld + kBS * kJld + 2 * kTC) + kBS * kTC;
+constexpr size_t kSmemBytes = kBS * kHld * 4 + kScrBytes;
 constexpr size_t kSmemBytesTc = kRingBytes + kHbBytes + 128 + 1024; // + barriers + slack for 1024-byte alignment
-static_assert(sizeof(float) * (kBS * kJld + 2 * kTC) + kBS * kTC <= kRingBytes, "phase B scratch must fit the ring");
+static_assert(kScrBytes <= kRingBytes, "phase B scratch must fit the ring");
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
