@@ -137,6 +137,15 @@ int mcs_svmc_sweeps(mcs_state *st, const double *A_sched, const double *B_sched,
                     int mcsteps, float temp, int tf, uint64_t seed, uint64_t replica_offset,
                     uint64_t sweep_offset);
 
+/* Swendsen-Wang cluster moves on the (space x Trotter) lattice, GPU union-find labelling.  The reference
+ * advertises cluster updates (README.md:4) but ships only experimental Wolff variants (qmc.pyx:620-1621)
+ * that raise on Linux and no Swendsen-Wang: there is no trajectory oracle, parity is equilibrium
+ * statistics (tests/test_gpu_cluster.py).  PIQMC state: bonds -B J_ij/teff in every slice, J_perp/teff
+ * along the Trotter ring, fields as bonds to a fixed ghost spin; (a, b) = (Gamma, B) of qmc.pyx:95-96.
+ * SA state: a, b ignored, couplings -J/temp.  Needs a symmetric static table.                     */
+int mcs_cluster_moves(mcs_state *st, double a, double b, float temp, int nmoves, uint64_t seed,
+                      uint64_t replica_offset, uint64_t sweep_offset);
+
 /* one-shot host-buffer forms (upload, sweep, download [, energies]) -- what the Python
  * drop-ins call.  energies_out may be NULL.                                                 */
 int mcs_piqmc_anneal(mcs_instance *inst, const double *A_sched, const double *B_sched,

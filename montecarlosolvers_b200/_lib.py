@@ -61,6 +61,8 @@ SIGNATURES = {
     "mcs_sa_sweeps": (ctypes.c_int, [c_vp, c_dp, c_i64, ctypes.c_int, c_u64, c_u64, c_u64]),
     "mcs_svmc_sweeps": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                        c_u64, c_u64, c_u64]),
+    "mcs_cluster_moves": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_int, c_u64,
+                                         c_u64, c_u64]),
     "mcs_piqmc_anneal": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_vp, c_i64, c_i64,
                                         ctypes.c_int, c_u64, c_u64, c_dp]),
     "mcs_sa_anneal": (ctypes.c_int, [c_vp, c_dp, c_i64, ctypes.c_int, c_vp, c_i64, c_u64, c_u64, c_dp]),
@@ -313,6 +315,11 @@ class State(object):
         check(load().mcs_piqmc_sweeps_dissipative(self._h, dptr(A), dptr(B), A.size, int(mcsteps), float(temp),
                                                   dptr(lut), int(bool(global_moves)), int(seed) & (2 ** 64 - 1),
                                                   int(replica_offset), int(sweep_offset)))
+
+    def cluster_moves(self, a, b, temp, nmoves=1, seed=0, replica_offset=0, sweep_offset=0):
+        """Swendsen-Wang moves at transverse field a, longitudinal coefficient b, temperature temp (SA: a, b unused)."""
+        check(load().mcs_cluster_moves(self._h, float(a), float(b), float(temp), int(nmoves),
+                                       int(seed) & (2 ** 64 - 1), int(replica_offset), int(sweep_offset)))
 
     def sa_sweeps(self, sched, mcsteps, seed=0, replica_offset=0, sweep_offset=0):
         sched = f64(sched)

@@ -158,6 +158,15 @@ extern "C" int mcs_svmc_sweeps(mcs_state *st, const double *A, const double *B, 
     return mcs_launch_svmc_sweeps(st, A, B, S, mcsteps, temp, tf, seed, replica_offset, sweep_offset);
 }
 
+extern "C" int mcs_cluster_moves(mcs_state *st, double a, double b, float temp, int nmoves, uint64_t seed,
+                                 uint64_t replica_offset, uint64_t sweep_offset)
+{
+    MCS_REQUIRE(st && st->inst && (st->kind == MCS_KIND_PIQMC || st->kind == MCS_KIND_SA), MCS_EINVAL,
+                "mcs_cluster_moves: needs a PIQMC or SA state");
+    MCS_REQUIRE(nmoves >= 0, MCS_EINVAL, "mcs_cluster_moves: nmoves < 0");
+    return mcs_launch_cluster_moves(st, a, b, (double)temp, nmoves, seed, replica_offset, sweep_offset);
+}
+
 // ---- one-shot host-buffer forms ----------------------------------------------------------------
 // The device batch (and its staging buffer) lives in the instance and is reused by the next call of the
 // same shape: no cudaMalloc / cudaFree on the call path after the first call.

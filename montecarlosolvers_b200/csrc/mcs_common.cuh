@@ -93,6 +93,8 @@ struct mcs_state {
     size_t stage_bytes = 0;
     void *d_S16 = nullptr;    // dense sweeps: spins as bf16 +-1, [Cpad][Npad], column = (replica, slice)
     long long S16_cols = 0;
+    int32_t *d_labels = nullptr; // cluster moves: union-find parents [(N P + 1)][replicas]
+    size_t labels_bytes = 0;
 };
 
 int mcs_state_reserve_stage(mcs_state *st, size_t bytes);
@@ -232,6 +234,8 @@ __device__ __forceinline__ uint32_t mcs_accept_threshold(float dE, float nl2e_ov
 int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
                             int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset,
                             const double *lookuptable /* nullptr: no Ohmic bath */);
+int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double temp, int nmoves, uint64_t seed,
+                             uint64_t replica_offset, uint64_t sweep_offset);
 bool mcs_dense_supported(const mcs_instance *inst, int P);
 int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const double *B, int64_t S, int mcsteps,
                             float temp, int global_moves, uint64_t seed, uint64_t replica_offset,

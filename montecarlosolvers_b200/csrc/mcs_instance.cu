@@ -303,6 +303,9 @@ static void state_release_device(mcs_state *st)
     cudaFree(st->d_S16);
     st->d_S16 = nullptr;
     st->S16_cols = 0;
+    cudaFree(st->d_labels);
+    st->d_labels = nullptr;
+    st->labels_bytes = 0;
     st->d_W = nullptr;
     st->d_V = nullptr;
     st->d_theta = st->d_cosz = nullptr;

@@ -1,0 +1,105 @@
+"""Swendsen-Wang cluster moves (GPU union-find).  The reference has no working cluster code to compare with
+(parity unpinned), so correctness = the moves leave the exact Boltzmann distribution
+invariant AND are ergodic on their own: cluster-only dynamics must reproduce full-enumeration averages."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import instances as inst
+from tests.test_gpu_production import _piqmc_exact, _all_states, _classical_energies
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mcs():
+    import montecarlosolvers_b200 as m
+    m._lib.require_device()
+    return m
+
+
+@pytest.mark.parametrize("case", ["ferro_ring_P4", "glass_fields_P3", "torus_P2"])
+@pytest.mark.parametrize("mix", ["cluster_only", "cluster_plus_local"])
+def test_sw_moves_sample_the_exact_distribution(mcs, case, mix):
+    """4096 replicas, tolerance 4.5 standard errors on <E_cl> and the Trotter link correlation."""
+    if case == "ferro_ring_P4":
+        import scipy.sparse as sps
+        J = sps.dok_matrix((4, 4))
+        for i in range(4):
+            J[i, (i + 1) % 4] = -0.8  # J < 0: ferromagnetic in the reference's convention
+        nbs = orc.GenerateNeighbors(4, J, 2)
+        P = 4
+    elif case == "glass_fields_P3":
+        _, nbs = inst.random_graph(5, 7, seed=3, fields=True)
+        P = 3
+    else:
+        _, nbs = inst.torus(2, seed=2, fields=True)
+        P = 2
+    a, b, temp = 1.0, 0.9, 1.0 / P
+    e_exact, l_exact = _piqmc_exact(nbs, P, a, b, temp)
+    n = nbs.shape[0]
+    R = 4096
+    I = mcs.Instance(nbs)
+    st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+    st.init_random(3)
+
+    def step(t):
+        if mix == "cluster_plus_local":
+            st.piqmc_sweeps(np.array([a]), np.array([b]), 1, temp, seed=5, sweep_offset=t)
+        st.cluster_moves(a, b, temp, 1, seed=5, sweep_offset=t)
+
+    for t in range(200):
+        step(t)
+    es, ls = [], []
+    for t in range(200, 320):
+        step(t)
+        if t % 3 == 0:
+            c = st.download_spins().astype(np.float64)
+            es.append(st.energies().mean(axis=1))
+            ls.append((c * np.roll(c, -1, axis=2)).sum(axis=(1, 2)) / (n * P))
+    es, ls = np.array(es).mean(axis=0), np.array(ls).mean(axis=0)
+    assert abs(es.mean() - e_exact) <= 4.5 * es.std(ddof=1) / np.sqrt(R), (es.mean(), e_exact)
+    assert abs(ls.mean() - l_exact) <= 4.5 * ls.std(ddof=1) / np.sqrt(R), (ls.mean(), l_exact)
+
+
+def test_sw_moves_sa_state_and_critical_ferromagnet(mcs):
+    """Classical (P = 1) SW on an 8-site ferromagnetic ring with a field, against enumeration; and the
+    drop-in entry point QuantumAnnealSW / QuantumAnnealWCL anneals a ferromagnet into its ground state."""
+    import scipy.sparse as sps
+    J = sps.dok_matrix((8, 8))
+    for i in range(8):
+        J[i, (i + 1) % 8] = -1.0
+    J[0, 0] = 0.3
+    nbs = orc.GenerateNeighbors(8, J, 3)
+    T = 1.5
+    sts = _all_states(8)
+    e_all = _classical_energies(sts, nbs)
+    w = np.exp(-(e_all - e_all.min()) / T)
+    w /= w.sum()
+    e_exact = float(np.dot(w, e_all))
+    m_exact = float(np.dot(w, sts.mean(axis=1)))
+    R = 4096
+    I = mcs.Instance(nbs)
+    st = mcs.State(I, mcs._lib.KIND_SA, R, 1)
+    st.init_random(1)
+    st.cluster_moves(0.0, 1.0, T, 100, seed=2)
+    es, ms = [], []
+    for t in range(40):
+        st.cluster_moves(0.0, 1.0, T, 2, seed=2, sweep_offset=100 + 2 * t)
+        es.append(st.energies())
+        ms.append(st.download_spins().astype(np.float64).mean(axis=1))
+    es, ms = np.array(es).mean(axis=0), np.array(ms).mean(axis=0)
+    assert abs(es.mean() - e_exact) <= 4.5 * es.std(ddof=1) / np.sqrt(R), (es.mean(), e_exact)
+    assert abs(ms.mean() - m_exact) <= 4.5 * ms.std(ddof=1) / np.sqrt(R), (ms.mean(), m_exact)
+    # drop-in: 6x6 ferromagnetic torus, every replica ends in one of the two ground states
+    Jt = sps.dok_matrix((36, 36))
+    for r in range(6):
+        for c in range(6):
+            i = r * 6 + c
+            Jt[i, r * 6 + (c + 1) % 6] = -1.0
+            Jt[i, ((r + 1) % 6) * 6 + c] = -1.0
+    nt = orc.GenerateNeighbors(36, Jt, 4)
+    P = 8
+    conf = (2 * np.random.RandomState(0).randint(2, size=(32, 36, P)) - 1).astype(np.int8)
+    e = mcs.qmc.QuantumAnnealWCL(np.linspace(2.5, 1e-3, 60), np.ones(60), 1, 0.5 / P, conf, nt, seed=4, energies=True)
+    assert np.all(e.min(axis=1) == -72.0)
