@@ -429,7 +429,7 @@ extern "C" int mcs_state_create(mcs_instance *inst, int kind, int64_t R, int64_t
     st->kind = kind;
     st->R = R;
     st->P = P;
-    st->Rpad = (R + 31) / 32 * 32;
+    st->Rpad = kind == MCS_KIND_SVMC ? (R + 127) / 128 * 128 : (R + 31) / 32 * 32; // SVMC lanes own 4 replicas
     st->G = (R + 31) / 32;
     cudaError_t e = cudaSuccess;
     if (kind == MCS_KIND_PIQMC) {

@@ -37,49 +37,73 @@ struct SvmcPass {
     uint32_t replica_offset;
 };
 
-__global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_constant__ SvmcPass a)
+// Rotor attempt (svmc.pyx:92-115) given the z-field of the site; (u0, u1) are its two 32-bit uniforms.
+__device__ __forceinline__ void svmc_decide(const SvmcPass &a, float zfield, float &th, float &cz, uint32_t u0,
+                                            uint32_t u1)
 {
-    // The kWarps warps of a CTA take kWarps CONSECUTIVE SITES of the colour class for the same 32 replicas:
-    // neighbouring sites of one colour usually share neighbours (the 4 qubits on one side of a Chimera cell
-    // all couple to the same 4 on the other side), so their cos(theta_j) lines are fetched once into L1.
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long sblocks = (a.nsites + kWarps - 1) / kWarps;
-    const long long grp = blockIdx.x / sblocks;
-    const long long srank = (blockIdx.x % sblocks) * kWarps + warp;
-    if (srank >= a.nsites) return;
-    const int site = a.sites[srank];
-    const long long r = grp * 32 + lane;
     const float kPi = 3.14159265358979323846f;
-
-    const float th = a.theta[(long long)site * a.Rpad + r];
-    const float ci = a.cosz[(long long)site * a.Rpad + r];
-    float zfield = a.field ? __ldg(&a.h[site]) : 0.0f; // sum_j J_ij cos(theta_j) + h_i
-    for (int j = 0; j < a.dpad; ++j) {
-        const float jv = __ldg(&a.ell_J[(long long)site * a.dpad + j]);
-        if (jv == 0.0f) continue;
-        const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
-        zfield = fmaf(jv, a.cosz[(long long)nbj * a.Rpad + r], zfield);
-    }
-    uint32_t rnd[4];
-    mcs_philox4x32_10_rk(a.replica_offset + (uint32_t)r, (uint32_t)site, a.sweep_lo,
-                         (a.sweep_hi << 8) | MCS_TAG_SVMC, a.keys, rnd);
-    const float u0 = (float)(rnd[0] >> 8) * (1.0f / 16777216.0f); // [0, 1)
+    const float f0 = (float)(u0 >> 8) * (1.0f / 16777216.0f); // [0, 1)
     float thp;
     if (!a.tf) {
-        thp = kPi * u0; // svmc.pyx:95
+        thp = kPi * f0; // svmc.pyx:95
     } else {            // svmc.pyx:198-207
-        thp = th + a.tf_scale * (2.0f * kPi * u0 - kPi);
+        thp = th + a.tf_scale * (2.0f * kPi * f0 - kPi);
         thp = fminf(fmaxf(thp, 0.0f), kPi);
     }
     float sp, cp;
     __sincosf(thp, &sp, &cp);
     const float si = __sinf(th);
-    // svmc.pyx:96-110
-    const float dE = a.b_coef * (cp - ci) * zfield + a.a_coef * (si - sp);
-    if (rnd[1] <= mcs_accept_threshold(dE, a.nl2e_over_t)) { // svmc.pyx:112-115
-        a.theta[(long long)site * a.Rpad + r] = thp;
-        a.cosz[(long long)site * a.Rpad + r] = cp;
+    const float dE = a.b_coef * (cp - cz) * zfield + a.a_coef * (si - sp); // svmc.pyx:96-110
+    // Metropolis (svmc.pyx:112-115): dE <= 0 or exp(-dE/T) > u  <=>  dE * (-log2 e / T) > log2 u
+    const float lu = __log2f((float)u1 + 1.0f) - 32.0f;
+    if (dE <= 0.0f || dE * a.nl2e_over_t >= lu) {
+        th = thp;
+        cz = cp;
     }
+}
+
+// A lane owns FOUR consecutive replicas of one site (128-bit loads of theta, cos theta and of every
+// neighbour's cos theta; the coupling row is read once per four attempts); a warp = 128 replicas of one
+// site; the kWarps warps of a CTA take kWarps consecutive sites of the colour class, which on Chimera-like
+// graphs share most of their neighbours (their lines stay in L1).  Rpad is a multiple of 128.
+__global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_constant__ SvmcPass a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long sblocks = (a.nsites + kWarps - 1) / kWarps;
+    const long long grp = blockIdx.x / sblocks; // group of 128 replicas
+    const long long srank = (blockIdx.x % sblocks) * kWarps + warp;
+    if (srank >= a.nsites) return;
+    const int site = a.sites[srank];
+    const long long r = grp * 128 + 4 * lane;
+    float4 *th_ptr = reinterpret_cast<float4 *>(a.theta + (size_t)site * a.Rpad + r);
+    float4 *cz_ptr = reinterpret_cast<float4 *>(a.cosz + (size_t)site * a.Rpad + r);
+    float4 th = *th_ptr, cz = *cz_ptr;
+    const float h0 = a.field ? __ldg(&a.h[site]) : 0.0f;
+    float4 z = make_float4(h0, h0, h0, h0); // sum_j J_ij cos(theta_j) + h_i
+    const float *jrow = a.ell_J + (size_t)site * a.dpad;
+    const int *irow = a.ell_idx + (size_t)site * a.dpad;
+    const float *czr = a.cosz + r;
+#pragma unroll 2
+    for (int j = 0; j < a.dpad; ++j) { // padding entries have J = 0 and point at the site itself
+        const float jv = __ldg(&jrow[j]);
+        const float4 c = *reinterpret_cast<const float4 *>(czr + (size_t)__ldg(&irow[j]) * a.Rpad);
+        z.x = fmaf(jv, c.x, z.x);
+        z.y = fmaf(jv, c.y, z.y);
+        z.z = fmaf(jv, c.z, z.z);
+        z.w = fmaf(jv, c.w, z.w);
+    }
+    uint32_t ra[4], rb[4];
+    // one Philox call per pair of replicas; the counter is the GLOBAL pair index, so a shard starting at an
+    // even replica_offset reproduces the un-sharded run
+    const uint32_t c0 = (a.replica_offset >> 1) + (uint32_t)(r >> 1);
+    mcs_philox4x32_10_rk(c0, (uint32_t)site, a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_SVMC, a.keys, ra);
+    mcs_philox4x32_10_rk(c0 + 1u, (uint32_t)site, a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_SVMC, a.keys, rb);
+    svmc_decide(a, z.x, th.x, cz.x, ra[0], ra[1]);
+    svmc_decide(a, z.y, th.y, cz.y, ra[2], ra[3]);
+    svmc_decide(a, z.z, th.z, cz.z, rb[0], rb[1]);
+    svmc_decide(a, z.w, th.w, cz.w, rb[2], rb[3]);
+    *th_ptr = th;
+    *cz_ptr = cz;
 }
 
 // host float64 [R][N] -> theta/cos [N][Rpad]
@@ -142,6 +166,7 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
                            int tf, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
 {
     mcs_instance *inst = st->inst;
+    MCS_REQUIRE((replica_offset & 1) == 0, MCS_EINVAL, "mcs_svmc_sweeps: replica_offset must be even");
     MCS_CUDA(cudaSetDevice(inst->device));
     SvmcPass a;
     a.theta = st->d_theta;
@@ -175,7 +200,7 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
                 a.sites = inst->d_order + inst->color_start[c];
                 a.nsites = inst->color_start[c + 1] - inst->color_start[c];
                 if (a.nsites == 0) continue;
-                const long long ctas = (long long)((a.nsites + kWarps - 1) / kWarps) * a.G;
+                const long long ctas = (long long)((a.nsites + kWarps - 1) / kWarps) * (a.Rpad / 128);
                 svmc_pass_kernel<<<(unsigned)ctas, kWarps * 32, 0, inst->stream>>>(a);
                 inst->launches++;
             }
