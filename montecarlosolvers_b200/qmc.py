@@ -16,7 +16,8 @@ __all__ = ["QuantumAnneal", "QuantumAnnealGlobal", "DissipativeQuantumAnneal", "
 
 
 def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable, seed, exact, libc_seed, device,
-         energies, replica_offset):
+         energies, replica_offset, rand_stream=None):
+    _run.last_consumed = None
     A = _lib.f64(A_sched)
     B = _lib.f64(B_sched)
     if A.ndim != 1 or B.ndim != 1:
@@ -52,10 +53,23 @@ def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable,
             lut = _lib.f64(lookuptable)
             if lut.size < P - 1:
                 raise ValueError("lookuptable needs P-1 entries")
-        seeds = C.seeds_u32(libc_seed, R)
-        _lib.check(L.mcs_exact_qmc(inst._h, _lib.dptr(A), _lib.dptr(B), A.size, int(mcsteps), temp,
-                                   _lib.dptr(lut) if lut is not None else None, a8.ctypes.data, R, P,
-                                   int(bool(global_moves)), C.u32p(seeds), None, 0, None))
+        consumed = np.zeros(R, dtype=np.int64)
+        if rand_stream is not None:
+            # recorded libc rand() outputs, int32 [R, n] (or [n] for a single anneal): the reference's own numbers
+            rs = np.ascontiguousarray(np.asarray(rand_stream, dtype=np.int32).reshape(R, -1))
+            _lib.check(L.mcs_exact_qmc(inst._h, _lib.dptr(A), _lib.dptr(B), A.size, int(mcsteps), temp,
+                                       _lib.dptr(lut) if lut is not None else None, a8.ctypes.data, R, P,
+                                       int(bool(global_moves)), None, rs.ctypes.data_as(_lib.c_i32p), rs.shape[1],
+                                       consumed.ctypes.data_as(_lib.c_i64p)))
+            if consumed.max() > rs.shape[1]:
+                raise ValueError("rand_stream too short: the replay needed %d values" % consumed.max())
+        else:
+            seeds = C.seeds_u32(libc_seed, R)
+            _lib.check(L.mcs_exact_qmc(inst._h, _lib.dptr(A), _lib.dptr(B), A.size, int(mcsteps), temp,
+                                       _lib.dptr(lut) if lut is not None else None, a8.ctypes.data, R, P,
+                                       int(bool(global_moves)), C.u32p(seeds), None, 0,
+                                       consumed.ctypes.data_as(_lib.c_i64p)))
+        _run.last_consumed = consumed
         if energies:
             st = _lib.State(inst, _lib.KIND_PIQMC, R, P) if P <= 64 else None
             if st is None:
@@ -74,7 +88,7 @@ def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable,
 
 
 def QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, seed=None, exact=False,
-                  libc_seed=None, device=None, energies=False, replica_offset=0):
+                  libc_seed=None, device=None, energies=False, replica_offset=0, rand_stream=None):
     """QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads)
 
     Path-integral QMC with single-spin flips (reference qmc.pyx:25-143).  H = sum_k (sum_ij J_ij
@@ -82,18 +96,18 @@ def QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, se
     A_sched, `mcsteps` sweeps over all (spin, slice).  `nthreads` is accepted and ignored (it is
     inert in the reference too: OpenMP is disabled in its setup.py:10-11).
     Returns None; spins are flipped in place within `confs` ([N, P] or [R, N, P])."""
-    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, False, None, seed, exact, libc_seed, device, energies,
-                replica_offset)
+    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, False, None, seed, exact or rand_stream is not None,
+                libc_seed, device, energies, replica_offset, rand_stream=rand_stream)
 
 
 def QuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, seed=None, exact=False,
-                        libc_seed=None, device=None, energies=False, replica_offset=0):
+                        libc_seed=None, device=None, energies=False, replica_offset=0, rand_stream=None):
     """QuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads)
 
     As QuantumAnneal plus one world-line move per spin per sweep (all P slices of a spin flipped
     together, reference qmc.pyx:284-438)."""
-    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, None, seed, exact, libc_seed, device, energies,
-                replica_offset)
+    return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, None, seed, exact or rand_stream is not None,
+                libc_seed, device, energies, replica_offset, rand_stream=rand_stream)
 
 
 def DissipativeQuantumAnneal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *, seed=None,
@@ -115,6 +129,14 @@ def DissipativeQuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, lookuptable,
     Reference qmc.pyx:444-609: bath term + one world-line move per spin per sweep."""
     return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, lookuptable, seed, exact, libc_seed, device,
                 energies, replica_offset)
+
+
+def last_rand_consumed():
+    """Number of libc rand() values each replica of the last exact=True call consumed (int64 [R])."""
+    return _run.last_consumed
+
+
+_run.last_consumed = None
 
 
 def delta_e(a, b, temp, confs, nbs, device=None):

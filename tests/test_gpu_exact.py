@@ -183,3 +183,23 @@ def test_exact_noisy_time_dependent_tables_vs_oracle(mcs):
         np.random.seed(2)
         getattr(mcs.svmc, name)(A, B, 2, 0.1, got, nbs4, exact=True, libc_seed=2)
         assert np.array_equal(got, want), name
+
+
+def test_exact_replay_fed_the_references_own_random_numbers(mcs):
+    """North-star tier (b) verbatim: the sequential kernel is FED recorded rand() outputs (here the first
+    values of the stream after srand(77), which is what the compiled reference drew when the golden fixture
+    was made) and reproduces the reference trajectory, consuming exactly as many values as the reference."""
+    d = np.load(os.path.join(G, "traj_qmc_torus6.npz"))
+    P = 8
+    for glob in (0, 1):
+        rng = orc.LibcRand(1000 + P)
+        stream = rng.draw(200000)
+        c = d["P%d_g%d_in" % (P, glob)].astype(np.int64).copy()
+        fn = mcs.qmc.QuantumAnnealGlobal if glob else mcs.qmc.QuantumAnneal
+        fn(d["A"], d["B"], int(d["mcsteps"]), 1.0 / P, c, d["nbs"], 1, rand_stream=stream)
+        assert np.array_equal(c, d["P%d_g%d_out" % (P, glob)])
+        used = int(mcs.qmc.last_rand_consumed()[0])
+        # the next value of the stream is what the reference's rand() returned right after the call
+        assert stream[used] == int(d["P%d_g%d_next_rand" % (P, glob)])
+        with pytest.raises(ValueError):
+            fn(d["A"], d["B"], int(d["mcsteps"]), 1.0 / P, c.copy(), d["nbs"], 1, rand_stream=stream[:100])
