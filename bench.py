@@ -153,7 +153,7 @@ def cpu_arm(nbs, sweeps, cores=None, want="auto"):
                       "qmc.QuantumAnneal" % (cores, sweeps)}
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -177,14 +177,14 @@ def run_reference(args):
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    out["line"] = line
     return 0
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, out):
     import torch
     import montecarlosolvers_b200 as mcs
     from montecarlosolvers_b200 import parallel
@@ -314,8 +314,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": args.traffic,
-                         "kernel": "piqmc_lut_pass_kernel<4,4>", "ms_per_launch": ms_per_launch,
+                         "frac": achieved / peak,
+                         # ncu --set full (profiles/r01b_piqmc_lut_pass_full64_ncu.txt): 212.6 MB read + 74.6 MB
+                         # written per launch at 4096 replicas; scales linearly with the replicas per GPU
+                         "traffic": args.traffic if args.traffic is not None else 287.2e6 * R / 4096.0,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01b_*",
+                         "kernel": "piqmc_lut_pass_kernel<4,4,true>", "ms_per_launch": ms_per_launch,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "the sweep is instruction-issue bound (Philox + threshold lookup per attempt), "
@@ -330,11 +334,28 @@ def run_ours(args):
             line["result"]["best_residual_energy_per_spin"] = float(np.min(energies)) / NSPINS - egs
             line["result"]["mean_residual_energy_per_spin"] = float(np.mean(energies)) / NSPINS - egs
         line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        out["line"] = line
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+class _StdoutToStderr(object):
+    """Everything libraries print to fd 1 while the bench runs (e.g. NCCL's version banner) goes to stderr,
+    so that stdout carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -348,11 +369,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sweeps", type=int, default=40, help="sweeps per core for the CPU baseline sample")
     ap.add_argument("--traffic", type=float, default=None,
-                    help="ncu dram bytes per launch of the dominant kernel (from profiles/), if known")
+                    help="ncu dram__bytes_read+write per launch of the dominant kernel; default: the committed "
+                         "capture profiles/r01b_piqmc_lut_pass_full64_ncu.txt scaled to this run's replicas")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    out = {}
+    with _StdoutToStderr():
+        rc = run_reference(args, out) if args.impl == "reference" else run_ours(args, out)
+    if "line" in out:
+        print(json.dumps(out["line"]), flush=True)
+    return rc
 
 
 if __name__ == "__main__":
