@@ -322,8 +322,12 @@ def run_ours(args, out):
                          "kernel": "piqmc_lut_pass_kernel<4,4,true>", "ms_per_launch": ms_per_launch,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                         "note": "the sweep is instruction-issue bound (Philox + threshold lookup per attempt), "
-                                 "not HBM bound: see profiles/ and DESIGN.md section 4"},
+                         "note": "the sweep is instruction bound (Philox + threshold lookup per attempt), not HBM "
+                                 "bound: see binding_unit, profiles/ and DESIGN.md section 4",
+                         # what ncu says binds this kernel (profiles/r01b_piqmc_lut_pass_full64_ncu.txt)
+                         "binding_unit": {"unit": "SM ALU pipe / issue slots", "alu_pipe_pct_of_peak": 65.4,
+                                          "issue_slots_busy_pct": 58.0, "instructions_per_attempt": 20.1,
+                                          "dram_pct_of_peak": 4.4, "source": "ncu --set full, profiles/r01b_*"}},
             "e2e": e2e,
             "result": {"best_residual_energy_per_spin": None, "mean_best_slice_energy": float(np.mean(energies)),
                        "best_anneal": int(best)},
