@@ -539,3 +539,92 @@ int mcs_oracle_qmc_dissipative(const double *A, const double *B, int schedsize, 
     free(ispins);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Coloured-order variants (NOT in the reference): the same fp64 visit arithmetic and the same
+ * acceptance rule as mcs_oracle_qmc_anneal / mcs_oracle_sa_anneal, but sites are visited colour
+ * class by colour class and, inside a site, even Trotter slices before odd ones -- the order the
+ * B200 production kernels use (montecarlosolvers_b200/csrc/mcs_piqmc.cu, mcs_sa.cu).  They exist to
+ * separate "different visiting order" from "different arithmetic" in parity tier (c): the GPU
+ * kernels must agree with THESE at the standard-error level, while the gap between these and the
+ * reference order is a property of the dynamics.
+ * order[]: sites sorted by colour; color_start[c] .. color_start[c+1]: the sites of colour c.
+ * -------------------------------------------------------------------------------------- */
+static inline void qmc_visit(int64_t *confs, int64_t cs0, int64_t cs1, const double *nbs, int maxnb, int slices,
+                             int ispin, int islice, double b_coeff, double jperp, double teff, mcs_rand_t *rng)
+{
+    double e = qmc_ediff(confs, cs0, cs1, nbs, maxnb, slices, ispin, islice, b_coeff, jperp);
+    if (e <= 0.0)
+        confs[ispin * cs0 + islice * cs1] *= -1;
+    else if (exp(-1.0 * e / teff) > mcs_rand(rng) / (double)MCS_RAND_MAX)
+        confs[ispin * cs0 + islice * cs1] *= -1;
+}
+
+int mcs_oracle_qmc_anneal_colored(const double *A, const double *B, int schedsize, int mcsteps, float temp,
+                                  int64_t *confs, int64_t cs0, int64_t cs1, int nspins, int slices,
+                                  const double *nbs, int maxnb, int global_moves, const int32_t *order,
+                                  const int32_t *color_start, int ncolors, mcs_rand_t *rng)
+{
+    double teff = (double)temp * (double)slices;
+    int ifield, step, c, q, k, parity;
+    int last_alone = (slices & 1) ? slices - 1 : -1; /* odd ring: slice P-1 is visited after the two parities */
+    (void)nspins;
+    if (teff == 0.0 && schedsize > 0) return -1;
+    for (ifield = 0; ifield < schedsize; ++ifield) {
+        double jperp = -0.5 * teff * log(tanh(A[ifield] / teff));
+        double b_coeff = -2.0 * B[ifield];
+        for (step = 0; step < mcsteps; ++step) {
+            for (c = 0; c < ncolors; ++c) {
+                for (q = color_start[c]; q < color_start[c + 1]; ++q) {
+                    int ispin = order[q];
+                    for (parity = 0; parity < 2; ++parity)
+                        for (k = parity; k < slices; k += 2)
+                            if (k != last_alone)
+                                qmc_visit(confs, cs0, cs1, nbs, maxnb, slices, ispin, k, b_coeff, jperp, teff, rng);
+                    if (last_alone >= 0)
+                        qmc_visit(confs, cs0, cs1, nbs, maxnb, slices, ispin, last_alone, b_coeff, jperp, teff, rng);
+                    if (global_moves) {
+                        double e = 0.0;
+                        for (k = 0; k < slices; ++k)
+                            e = qmc_inplane(confs, cs0, cs1, nbs, maxnb, ispin, k, b_coeff, e);
+                        if (e <= 0.0 || exp(-1.0 * e / teff) > mcs_rand(rng) / (double)MCS_RAND_MAX)
+                            for (k = 0; k < slices; ++k) confs[ispin * cs0 + k * cs1] *= -1;
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+void mcs_oracle_sa_anneal_colored(const double *sched, int schedsize, int mcsteps, int64_t *svec, int64_t ss,
+                                  int nspins, const double *nbs, int maxnb, const int32_t *order,
+                                  const int32_t *color_start, int ncolors, mcs_rand_t *rng)
+{
+    int itemp, step, c, q, si;
+    (void)nspins;
+    for (itemp = 0; itemp < schedsize; ++itemp) {
+        double temp = sched[itemp];
+        for (step = 0; step < mcsteps; ++step) {
+            for (c = 0; c < ncolors; ++c) {
+                for (q = color_start[c]; q < color_start[c + 1]; ++q) {
+                    int sidx = order[q];
+                    double s = (double)svec[sidx * ss];
+                    double ediff = 0.0;
+                    for (si = 0; si < maxnb; ++si) {
+                        int spinidx = NB_IDX(nbs, maxnb, sidx, si);
+                        double jval = NB_J(nbs, maxnb, sidx, si);
+                        if (spinidx == sidx)
+                            ediff += -2.0 * s * jval;
+                        else
+                            ediff += -2.0 * s * (jval * (double)svec[spinidx * ss]);
+                    }
+                    if (ediff <= 0.0)
+                        svec[sidx * ss] *= -1;
+                    else if (exp(-1.0 * ediff / temp) > mcs_rand(rng) / (double)MCS_RAND_MAX)
+                        svec[sidx * ss] *= -1;
+                }
+            }
+        }
+    }
+}

@@ -368,3 +368,47 @@ def ClassicalIsingEnergy(spins, J):
     d = np.diag(np.diag(J))
     np.fill_diagonal(J, 0.0)
     return np.dot(spins, np.dot(J, spins)) + np.sum(np.dot(d, spins))
+
+
+# ----------------------------------------------------------------------------------------------
+# coloured-order variants (not in the reference; see the comment in mcs_oracle.c)
+# ----------------------------------------------------------------------------------------------
+def _color_args(colors):
+    colors = np.asarray(colors, dtype=np.int32)
+    order = np.argsort(colors, kind="stable").astype(np.int32)
+    nc = int(colors.max()) + 1
+    start = np.zeros(nc + 1, dtype=np.int32)
+    start[1:] = np.cumsum(np.bincount(colors, minlength=nc))
+    return order, start, nc
+
+
+def QuantumAnnealColored(A_sched, B_sched, mcsteps, temp, confs, nbs, colors, global_moves=False, rng=None):
+    """qmc.pyx:93-143 visit arithmetic in the B200 kernels' visiting order (colour classes, slice parity)."""
+    A = _f64(A_sched)
+    B = _f64(B_sched)
+    _check_spins(confs, 2)
+    nbs = _nbs(nbs)
+    order, start, nc = _color_args(colors)
+    L = lib()
+    L.mcs_oracle_qmc_anneal_colored.restype = ctypes.c_int
+    rc = L.mcs_oracle_qmc_anneal_colored(
+        A.ctypes.data_as(c_dp), B.ctypes.data_as(c_dp), ctypes.c_int(A.size), ctypes.c_int(int(mcsteps)),
+        ctypes.c_float(temp), confs.ctypes.data_as(c_lp), _estr(confs, 0), _estr(confs, 1),
+        ctypes.c_int(confs.shape[0]), ctypes.c_int(confs.shape[1]), nbs.ctypes.data_as(c_dp),
+        ctypes.c_int(nbs.shape[1]), ctypes.c_int(int(bool(global_moves))), order.ctypes.data_as(c_ip),
+        start.ctypes.data_as(c_ip), ctypes.c_int(nc), _rng(rng).ptr)
+    if rc == -1:
+        raise ZeroDivisionError("float division")
+
+
+def AnnealColored(sched, mcsteps, svec, nbs, colors, rng=None):
+    """sa.pyx:84-99 visit arithmetic in the B200 kernels' visiting order (colour class by colour class)."""
+    sched = _f64(sched)
+    _check_spins(svec, 1)
+    nbs = _nbs(nbs)
+    order, start, nc = _color_args(colors)
+    lib().mcs_oracle_sa_anneal_colored(
+        sched.ctypes.data_as(c_dp), ctypes.c_int(sched.size), ctypes.c_int(int(mcsteps)),
+        svec.ctypes.data_as(c_lp), _estr(svec, 0), ctypes.c_int(svec.shape[0]), nbs.ctypes.data_as(c_dp),
+        ctypes.c_int(nbs.shape[1]), order.ctypes.data_as(c_ip), start.ctypes.data_as(c_ip), ctypes.c_int(nc),
+        _rng(rng).ptr)

@@ -301,6 +301,24 @@ def _ref_stats():
         return json.load(f)
 
 
+def _colored_stats():
+    with open(os.path.join(G, "santoro_colored_stats.json")) as f:
+        return json.load(f)
+
+
+def _tier_c_same_order(name, got, col_cell):
+    """Two-sided, standard-error level: the GPU kernel against the fp64 sequential oracle run in the SAME
+    visiting order (tests/golden/make_santoro_colored_stats.py).  |mean_gpu - mean_oracle| <= 2 sigma, sigma =
+    the combined standard error of the two 256-anneal means -- the north star's tolerance."""
+    col = np.asarray(col_cell)
+    sem = np.sqrt(got.var(ddof=1) / got.size + col.var(ddof=1) / col.size)
+    msg = "%s: gpu %.5f  coloured-order oracle %.5f  diff %+.2f sem" % (
+        name, got.mean(), col.mean(), (got.mean() - col.mean()) / sem)
+    print(msg)
+    assert got.size >= 256 and col.size >= 256
+    assert abs(got.mean() - col.mean()) <= 2.0 * sem, msg
+
+
 def _tier_c(name, got, ref_cell):
     """Tier (c) acceptance for one (solver, tau) cell over >= 256 anneals.
 
@@ -337,6 +355,7 @@ def test_santoro_sa_residual_energy_matches_reference(mcs, tau):
     got = (e - e_gs) / 6400
     assert np.allclose(e[:3], [orc.ising_energy(s[r].astype(np.int64), nbs) for r in range(3)], rtol=0, atol=1e-9)
     _tier_c("sa tau=%d" % tau, got, ref["cells"]["sa_tau%d" % tau])
+    _tier_c_same_order("sa tau=%d" % tau, got, _colored_stats()["cells"]["sa_tau%d" % tau])
 
 
 @pytest.mark.parametrize("glob", [1, 0])
@@ -357,6 +376,7 @@ def test_santoro_piqmc_residual_energy_matches_reference(mcs, tau, glob):
     assert abs(e[0, k] - orc.ising_energy(confs[0, :, k].astype(np.int64), nbs)) < 1e-9
     name = "qmc%s_P20_tau%d" % ("_global" if glob else "", tau)
     _tier_c(name, got, ref["cells"][name])
+    _tier_c_same_order(name, got, _colored_stats()["cells"][name])
 
 
 def test_full_size_properties_cfg3_shape(mcs):

