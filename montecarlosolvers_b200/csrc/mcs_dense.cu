@@ -73,9 +73,12 @@ constexpr int kScrHblk = kScrGterm + kTC * 4;               // float [kBS]: loca
 constexpr int kScrBytes = kScrHblk + kBS * 4;
 static_assert(kBS * (kTC / 2) * 4 <= kBS * kHld * 4, "uglob must fit the (consumed) field tile");
 
-template <bool INWARP> // INWARP: P <= 32 (or SA): a replica's slices sit in one warp
+// PT: compile-time P for the in-warp cases (1, 2, 4, 8, 16, 32: a replica's slices sit in one warp);
+// PT == 0: P == 64, the replica spans both decision warps (shared memory + a 64-thread barrier).
+template <int PT>
 __device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, unsigned char *scr, int col0)
 {
+    constexpr bool INWARP = PT != 0;
     float *Jd = reinterpret_cast<float *>(scr + kScrJd);
     float *uloc = reinterpret_cast<float *>(scr + kScrUloc);
     float *hblk = reinterpret_cast<float *>(scr + kScrHblk);
@@ -83,10 +86,10 @@ __device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, uns
     float *frow = reinterpret_cast<float *>(scr + kScrFrow);
     float *delta = reinterpret_cast<float *>(scr + kScrDelta);
     float *gterm = reinterpret_cast<float *>(scr + kScrGterm);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int i0 = a.i0;
     const long long ld = a.Npad;
-    const int P = a.P;
+    const int P = INWARP ? PT : a.P;
     const int mend = min(kBS, a.N - i0);
 
     // field strip of this thread -> registers; the tile's shared memory then holds the world-line uniforms
@@ -133,39 +136,41 @@ __device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, uns
     const int col = col0 + c;
     const int k = col % P; // slice
     const int cl = c - k + (k == 0 ? P - 1 : k - 1), cr = c - k + (k == P - 1 ? 0 : k + 1);
+    const int crep = c / P;
+    const bool valid = col < a.C;
+    const bool odd = (k & 1) != 0;
+    const float sc = a.nl2e_over_t, bco = a.bcoef, jp2 = a.jperp2;
+    const bool trotter = a.trotter != 0, glob = a.global_moves != 0;
+#define MCS_ACCEPT(dE, lg) (valid && ((dE) <= 0.0f || (dE) * sc >= (lg)))
     for (int m = 0; m < mend; ++m) {
         if (tid < kTC) {
-            const float field = frow[c] + hblk[m];
-            const int s_init = sb[m * kTC + c];
+            const float bf = bco * (frow[c] + hblk[m]); // -2B * local field
             const float lu = uloc[m * kTC + c];
-            const float sc = a.nl2e_over_t;
-#define MCS_ACCEPT(dE, lg) (col < a.C && ((dE) <= 0.0f || (dE) * sc >= (lg)))
-            int s = s_init;
+            const float s_init = (float)sb[m * kTC + c];
+            float s = s_init;
             if (INWARP) {
-                if (a.trotter) {
-#pragma unroll
-                    for (int parity = 0; parity < 2; ++parity) { // even slices, then odd slices (P is even)
-                        const int sl = __shfl_sync(0xffffffffu, s, cl & 31), sr = __shfl_sync(0xffffffffu, s, cr & 31);
-                        if ((k & 1) == parity) {
-                            const float dE = a.bcoef * (float)s * field + a.jperp2 * (float)(s * (sl + sr));
-                            if (MCS_ACCEPT(dE, lu)) s = -s;
-                        }
-                    }
+                if (trotter) { // even slices, then odd slices (P is even); neighbours by shuffle
+                    float nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                    float dE = s * fmaf(jp2, nb, bf);
+                    if (!odd && MCS_ACCEPT(dE, lu)) s = -s;
+                    nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                    dE = s * fmaf(jp2, nb, bf);
+                    if (odd && MCS_ACCEPT(dE, lu)) s = -s;
                 } else {
-                    const float dE = a.bcoef * (float)s * field;
+                    const float dE = s * bf;
                     if (MCS_ACCEPT(dE, lu)) s = -s;
                 }
-                if (a.global_moves) { // world-line move: all P slices of the replica (qmc.pyx:405-438)
-                    float dE = a.bcoef * (float)s * field;
-                    for (int off = 1; off < P; off <<= 1) dE += __shfl_xor_sync(0xffffffffu, dE, off);
-                    if (MCS_ACCEPT(dE, uglob[m * (kTC / 2) + c / P])) s = -s;
+                if (glob) { // world-line move: all P slices of the replica (qmc.pyx:405-438)
+                    float dE = s * bf;
+#pragma unroll
+                    for (int off = 1; off < PT; off <<= 1) dE += __shfl_xor_sync(0xffffffffu, dE, off);
+                    if (MCS_ACCEPT(dE, uglob[m * (kTC / 2) + crep])) s = -s;
                 }
             } else { // P == 64: the replica spans both decision warps -> shared memory + a 64-thread barrier
 #pragma unroll 1
                 for (int parity = 0; parity < 2; ++parity) {
                     if ((k & 1) == parity) {
-                        const float dE = a.bcoef * (float)s * field +
-                                         a.jperp2 * (float)(s * (sb[m * kTC + cl] + sb[m * kTC + cr]));
+                        const float dE = s * fmaf(jp2, (float)(sb[m * kTC + cl] + sb[m * kTC + cr]), bf);
                         if (MCS_ACCEPT(dE, lu)) {
                             s = -s;
                             sb[m * kTC + c] = (signed char)s;
@@ -173,52 +178,56 @@ __device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, uns
                     }
                     bar_decide();
                 }
-                if (a.global_moves) {
-                    gterm[c] = a.bcoef * (float)s * field;
+                if (glob) {
+                    gterm[c] = s * bf;
                     bar_decide();
                     float dE = 0.0f;
                     for (int q = 0; q < P; ++q) dE += gterm[c - k + q];
-                    if (MCS_ACCEPT(dE, uglob[m * (kTC / 2) + c / P])) s = -s;
+                    if (MCS_ACCEPT(dE, uglob[m * (kTC / 2) + crep])) s = -s;
                 }
             }
-#undef MCS_ACCEPT
             sb[m * kTC + c] = (signed char)s;
-            delta[c] = (float)(s - s_init);
+            delta[c] = s - s_init;
         }
         __syncthreads();
         if (row > m) {
             const float jv = Jd[row * kJld + m];
-            if (jv != 0.0f) {
 #pragma unroll
-                for (int q4 = 0; q4 < kTC / 8; ++q4) {
-                    const float4 d = *reinterpret_cast<const float4 *>(delta + cbase + 4 * q4);
-                    hreg[4 * q4 + 0] = fmaf(jv, d.x, hreg[4 * q4 + 0]);
-                    hreg[4 * q4 + 1] = fmaf(jv, d.y, hreg[4 * q4 + 1]);
-                    hreg[4 * q4 + 2] = fmaf(jv, d.z, hreg[4 * q4 + 2]);
-                    hreg[4 * q4 + 3] = fmaf(jv, d.w, hreg[4 * q4 + 3]);
-                }
+            for (int q4 = 0; q4 < kTC / 8; ++q4) {
+                const float4 d = *reinterpret_cast<const float4 *>(delta + cbase + 4 * q4);
+                hreg[4 * q4 + 0] = fmaf(jv, d.x, hreg[4 * q4 + 0]);
+                hreg[4 * q4 + 1] = fmaf(jv, d.y, hreg[4 * q4 + 1]);
+                hreg[4 * q4 + 2] = fmaf(jv, d.z, hreg[4 * q4 + 2]);
+                hreg[4 * q4 + 3] = fmaf(jv, d.w, hreg[4 * q4 + 3]);
             }
             if (row == m + 1) {
 #pragma unroll
-                for (int q = 0; q < kTC / 2; ++q) frow[cbase + q] = hreg[q];
+                for (int q4 = 0; q4 < kTC / 8; ++q4)
+                    *reinterpret_cast<float4 *>(frow + cbase + 4 * q4) =
+                        make_float4(hreg[4 * q4], hreg[4 * q4 + 1], hreg[4 * q4 + 2], hreg[4 * q4 + 3]);
             }
         }
         __syncthreads();
     }
+#undef MCS_ACCEPT
     // write the block's spins back
     for (int e = tid; e < kBS * kTC; e += kThreads) {
         const int cc = e / kBS, m = e % kBS;
         a.S[(long long)(col0 + cc) * ld + i0 + m] = __float2bfloat16((float)sb[m * kTC + cc]);
     }
-    (void)lane;
 }
 
 __device__ __forceinline__ void dense_phase_b_dispatch(const DensePass &a, float *Hb, unsigned char *scr, int col0)
 {
-    if (a.P <= 32)
-        dense_phase_b<true>(a, Hb, scr, col0);
-    else
-        dense_phase_b<false>(a, Hb, scr, col0);
+    switch (a.P) {
+    case 1: dense_phase_b<1>(a, Hb, scr, col0); break;
+    case 2: dense_phase_b<2>(a, Hb, scr, col0); break;
+    case 4: dense_phase_b<4>(a, Hb, scr, col0); break;
+    case 8: dense_phase_b<8>(a, Hb, scr, col0); break;
+    case 16: dense_phase_b<16>(a, Hb, scr, col0); break;
+    case 32: dense_phase_b<32>(a, Hb, scr, col0); break;
+    default: dense_phase_b<0>(a, Hb, scr, col0); break;
+    }
 }
 
 // ---- variant 1: phase A on the legacy tensor path (mma.sync through WMMA), operands read from L2 ----
