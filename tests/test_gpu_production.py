@@ -408,3 +408,43 @@ def test_full_size_properties_cfg3_shape(mcs):
     st2 = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
     st2.upload_spins(c1)
     assert np.array_equal(st2.download_spins(), c1)
+
+
+def test_edge_cases_empty_schedule_single_replica_and_extreme_slices(mcs):
+    """Reference-tested corners: empty schedule and mcsteps = 0 are no-ops, a single
+    [N, P] call works for P = 2 (left and right Trotter neighbour are the same slice, both counted,
+    qmc.pyx:137-138) and P = 64 (word completely filled), odd P, zero-padded table rows, A -> 0 (J_perp = inf:
+    no flips across aligned slices, no NaN leaks), SA at T = 0 only moves downhill."""
+    _, nbs = inst.random_graph(24, 40, seed=5, fields=True)  # irregular: rows are zero padded
+    assert (nbs[:, :, 1] == 0).any()
+    s0 = inst.random_spins(24, 2)
+    for P in (2, 3, 33, 64):
+        c = np.tile(s0, (P, 1)).T.copy()
+        c0 = c.copy()
+        assert mcs.qmc.QuantumAnneal(np.zeros(0), np.zeros(0), 5, 0.1, c, nbs, 1, seed=1) is None
+        assert np.array_equal(c, c0)
+        mcs.qmc.QuantumAnnealGlobal(np.linspace(2, 0.1, 4), np.ones(4), 0, 0.1, c, nbs, 1, seed=1)
+        assert np.array_equal(c, c0)
+        mcs.qmc.QuantumAnnealGlobal(np.linspace(2, 0.1, 30), np.ones(30), 2, 1.0 / P, c, nbs, 1, seed=1)
+        assert set(np.unique(c)) <= {-1, 1} and not np.array_equal(c, c0)
+        e = [orc.ising_energy(np.ascontiguousarray(c[:, k]), nbs) for k in range(P)]
+        assert min(e) < orc.ising_energy(s0, nbs)
+    # A = 0: J_perp = +inf.  Aligned world lines can never break; the run must not produce garbage.
+    P = 8
+    c = np.tile(s0, (P, 1)).T.copy()
+    mcs.qmc.QuantumAnneal(np.zeros(3), np.ones(3), 2, 1.0 / P, c, nbs, 1, seed=4)
+    assert np.all(c == c[:, :1]) and set(np.unique(c)) <= {-1, 1}
+    # SA quench at T = 0 from a batch that is not a multiple of 32 restarts
+    s = (2 * np.random.RandomState(3).randint(2, size=(45, 24)) - 1).astype(np.int64)
+    e0 = np.array([orc.ising_energy(s[r], nbs) for r in range(45)])
+    mcs.sa.Anneal(np.zeros(6), 1, s, nbs, seed=2)
+    e1 = np.array([orc.ising_energy(s[r], nbs) for r in range(45)])
+    assert np.all(e1 <= e0 + 1e-12) and np.all(orc.sa_delta_e(s[7], nbs) >= -1e-6)
+    # int8 C-contiguous batches are updated in place without a copy; int32 input round-trips through a copy
+    b8 = (2 * np.random.RandomState(1).randint(2, size=(8, 24, 4)) - 1).astype(np.int8)
+    keep = b8
+    mcs.qmc.QuantumAnneal(np.linspace(2, 0.1, 5), np.ones(5), 1, 0.25, b8, nbs, 1, seed=3)
+    assert keep is b8 and set(np.unique(b8)) <= {-1, 1}
+    b32 = b8.astype(np.int32)
+    mcs.qmc.QuantumAnneal(np.linspace(2, 0.1, 5), np.ones(5), 1, 0.25, b32, nbs, 1, seed=3)
+    assert b32.dtype == np.int32 and set(np.unique(b32)) <= {-1, 1}
