@@ -1,4 +1,5 @@
 // mcs_api.cu -- extern "C" entry points over resident replica batches (see include/mcs_b200.h).
+#include <algorithm>
 #include <cmath>
 
 #include "mcs_common.cuh"
@@ -170,18 +171,70 @@ extern "C" int mcs_cluster_moves(mcs_state *st, double a, double b, float temp, 
 // ---- one-shot host-buffer forms ----------------------------------------------------------------
 // The device batch (and its staging buffer) lives in the instance and is reused by the next call of the
 // same shape: no cudaMalloc / cudaFree on the call path after the first call.
+// Replicas are independent, so a large batch is cut into chunks that flow through a three-stage pipeline:
+// H2D(c+1) on one copy stream and D2H(c-1) on another overlap pack + sweeps + unpack of chunk c on the
+// compute stream.  Only the first upload and the last download stay exposed.
 extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const double *B, int64_t S, int mcsteps,
                                 float temp, int8_t *confs, int64_t R, int64_t P, int global_moves, uint64_t seed,
                                 uint64_t replica_offset, double *energies_out)
 {
     MCS_REQUIRE(inst && confs, MCS_EINVAL, "mcs_piqmc_anneal: NULL argument");
     MCS_REQUIRE((double)temp * (double)P != 0.0 || S == 0, MCS_EZERODIV, "float division");
+    MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_piqmc_anneal: bad schedule");
     mcs_state *st = nullptr;
     MCS_TRY(mcs_instance_scratch_state(inst, MCS_KIND_PIQMC, R, P, &st));
-    MCS_TRY(mcs_state_upload_spins(st, confs));
-    MCS_TRY(mcs_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, 0));
-    MCS_TRY(mcs_state_download_spins(st, confs));
-    if (energies_out) MCS_TRY(mcs_state_energies(st, energies_out));
+    MCS_CUDA(cudaSetDevice(inst->device));
+    const size_t per_replica = (size_t)inst->N * P;
+    MCS_TRY(mcs_state_reserve_stage(st, (size_t)R * per_replica));
+    int8_t *stage = (int8_t *)st->d_stage;
+    // dense instances expand the whole batch per call: no chunking there
+    const int nchunks = (R >= 1024 && !mcs_dense_supported(inst, (int)P)) ? 4 : 1;
+    if (nchunks > 1 && !inst->s_in) {
+        MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_in, cudaStreamNonBlocking));
+        MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_out, cudaStreamNonBlocking));
+        for (int q = 0; q < 8; ++q) {
+            MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_up[q], cudaEventDisableTiming));
+            MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_done[q], cudaEventDisableTiming));
+        }
+    }
+    const long long chunk = nchunks == 1 ? st->Rpad : ((st->Rpad / nchunks + 127) / 128) * 128;
+    cudaStream_t s_in = nchunks == 1 ? inst->stream : inst->s_in;
+    cudaStream_t s_out = nchunks == 1 ? inst->stream : inst->s_out;
+    int used = 0;
+    for (long long r0 = 0; r0 < R; r0 += chunk, ++used) { // uploads, back to back on the H2D stream
+        const long long nvalid = std::min<long long>(chunk, R - r0);
+        MCS_CUDA(cudaMemcpyAsync(stage + r0 * per_replica, confs + r0 * per_replica, (size_t)nvalid * per_replica,
+                                 cudaMemcpyHostToDevice, s_in));
+        if (nchunks > 1) MCS_CUDA(cudaEventRecord(inst->ev_up[used], s_in));
+    }
+    int rc = MCS_OK;
+    int c = 0;
+    for (long long r0 = 0; r0 < R && rc == MCS_OK; r0 += chunk, ++c) {
+        const long long nvalid = std::min<long long>(chunk, R - r0);
+        st->v0 = r0;
+        st->vR = std::min<long long>(chunk, st->Rpad - r0);
+        if (nchunks > 1) MCS_CUDA(cudaStreamWaitEvent(inst->stream, inst->ev_up[c], 0));
+        rc = mcs_piqmc_pack(st, stage);
+        if (rc == MCS_OK)
+            rc = mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, 0, nullptr);
+        if (rc == MCS_OK) rc = mcs_piqmc_unpack(st, stage);
+        if (rc != MCS_OK) break;
+        if (nchunks > 1) {
+            MCS_CUDA(cudaEventRecord(inst->ev_done[c], inst->stream));
+            MCS_CUDA(cudaStreamWaitEvent(s_out, inst->ev_done[c], 0));
+        }
+        MCS_CUDA(cudaMemcpyAsync(confs + r0 * per_replica, stage + r0 * per_replica, (size_t)nvalid * per_replica,
+                                 cudaMemcpyDeviceToHost, s_out));
+    }
+    st->v0 = 0;
+    st->vR = -1;
+    if (rc != MCS_OK) {
+        cudaDeviceSynchronize();
+        return rc;
+    }
+    if (energies_out) MCS_TRY(mcs_state_energies(st, energies_out)); // overlaps the last download
+    if (nchunks > 1) MCS_CUDA(cudaStreamSynchronize(s_out));
+    MCS_CUDA(cudaStreamSynchronize(inst->stream));
     return MCS_OK;
 }
 

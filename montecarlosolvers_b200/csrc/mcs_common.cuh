@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,8 @@ struct mcs_instance {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr; // copy streams of the pipelined one-shot calls (lazy)
+    cudaEvent_t ev_up[8] = {}, ev_done[8] = {};
     int64_t N = 0, maxnb = 0;
     int64_t nsteps = 1;  // > 1: time-dependent couplings, one table per schedule step (Noisy* functions)
     int ncolors = 0;
@@ -95,6 +98,12 @@ struct mcs_state {
     long long S16_cols = 0;
     int32_t *d_labels = nullptr; // cluster moves: union-find parents [(N P + 1)][replicas]
     size_t labels_bytes = 0;
+    // active replica window [v0, v0 + vR) of a PIQMC batch (vR < 0: everything).  Replicas are independent, so
+    // the one-shot call pipelines chunks: upload(c+1) and download(c-1) overlap the sweeps of chunk c.
+    long long v0 = 0, vR = -1;
+    long long win_lo() const { return vR < 0 ? 0 : v0; }
+    long long win_pad() const { return vR < 0 ? Rpad : vR; }                  // multiple of 32
+    long long win_valid() const { return vR < 0 ? R : std::max(0ll, std::min(R - v0, vR)); }
 };
 
 int mcs_state_reserve_stage(mcs_state *st, size_t bytes);

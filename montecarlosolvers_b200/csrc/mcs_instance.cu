@@ -337,6 +337,12 @@ extern "C" void mcs_instance_destroy(mcs_instance *inst)
     cudaFree(inst->d_Jlo);
     cudaFree(inst->d_Jf);
     cudaFree(inst->d_hpad);
+    for (int q = 0; q < 8; ++q) {
+        if (inst->ev_up[q]) cudaEventDestroy(inst->ev_up[q]);
+        if (inst->ev_done[q]) cudaEventDestroy(inst->ev_done[q]);
+    }
+    if (inst->s_in) cudaStreamDestroy(inst->s_in);
+    if (inst->s_out) cudaStreamDestroy(inst->s_out);
     if (inst->ev0) cudaEventDestroy(inst->ev0);
     if (inst->ev1) cudaEventDestroy(inst->ev1);
     if (inst->stream) cudaStreamDestroy(inst->stream);

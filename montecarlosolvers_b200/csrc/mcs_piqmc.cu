@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(1024) piqmc_pack_kernel(const int8_t *__restri
     __syncthreads();
     {
         const long long i = i0 + ty, r = r0 + tx;
-        if (i < N && r < Rpad) W[i * Rpad + r] = tile[tx][ty];
+        if (i < N) W[i * Rpad + r] = tile[tx][ty]; // r < 32 gridDim.y = width of the replica window
     }
 }
 
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(1024) piqmc_unpack_kernel(const uint64_t *__re
     const long long i0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
     {
         const long long i = i0 + ty, r = r0 + tx;
-        tile[ty][tx] = (i < N && r < Rpad) ? W[i * Rpad + r] : 0ull;
+        tile[ty][tx] = i < N ? W[i * Rpad + r] : 0ull;
     }
     __syncthreads();
     const long long r = r0 + ty, i = i0 + tx;
@@ -527,26 +527,40 @@ __global__ void piqmc_energy_kernel(const uint64_t *__restrict__ W, const int32_
                                     const double *__restrict__ tab_J, double *__restrict__ out, long long N,
                                     int maxnb, long long R, long long Rpad, int P)
 {
+    // thread = (replica, group of 8 consecutive slices): every word is loaded once for 8 accumulators; each
+    // accumulator still adds the sites in order 0..N-1 with the row's entries in table order (bit-exactness)
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y * blockDim.y + threadIdx.y;
-    if (r >= R || k >= P) return;
-    double e = 0.0;
+    const int k0 = (blockIdx.y * blockDim.y + threadIdx.y) * 8;
+    if (r >= R || k0 >= P) return;
+    double e[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) e[q] = 0.0;
     for (long long i = 0; i < N; ++i) {
-        double pair = 0.0, field = 0.0;
+        double pair[8], field = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pair[q] = 0.0;
         for (int s = 0; s < maxnb; ++s) {
             const int j = __ldg(&tab_idx[i * maxnb + s]);
             const double jv = __ldg(&tab_J[i * maxnb + s]);
             if (j == i) {
                 field = __dadd_rn(field, jv);
             } else {
-                const double sj = ((W[(long long)j * Rpad + r] >> k) & 1ull) ? -1.0 : 1.0;
-                pair = __dadd_rn(pair, __dmul_rn(jv, sj));
+                const uint32_t bits = (uint32_t)(W[(long long)j * Rpad + r] >> k0);
+                const double njv = -jv;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pair[q] = __dadd_rn(pair[q], ((bits >> q) & 1u) ? njv : jv); // jv * s_j
             }
         }
-        const double si = ((W[i * Rpad + r] >> k) & 1ull) ? -1.0 : 1.0;
-        e = __dadd_rn(e, __dmul_rn(si, __dadd_rn(__dmul_rn(0.5, pair), field)));
+        const uint32_t wi = (uint32_t)(W[i * Rpad + r] >> k0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const double t = __dadd_rn(__dmul_rn(0.5, pair[q]), field);
+            e[q] = __dadd_rn(e[q], ((wi >> q) & 1u) ? -t : t); // s_i * (0.5 pair + field)
+        }
     }
-    out[r * P + k] = e;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (k0 + q < P) out[r * P + k0 + q] = e[q];
 }
 
 } // namespace
@@ -627,19 +641,19 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
         bath.lut4 = d_lut4;
     }
     PiqmcPass a;
-    a.W = st->d_W;
+    a.W = st->d_W + st->win_lo();
     a.ell_idx = inst->d_ell_idx;
     a.ell_J = inst->d_ell_J;
     a.h = inst->d_h;
     a.dpad = inst->dpad;
     a.nq = inst->maxdeg;
     a.field = inst->has_field ? 1 : 0;
-    a.G = (int)(st->Rpad / 32);
+    a.G = (int)(st->win_pad() / 32);
     a.Rpad = st->Rpad;
     a.P = P;
     a.keys = mcs_philox_expand(seed);
     a.pow2 = mcs_pow2_make();
-    a.replica_offset = (uint32_t)replica_offset;
+    a.replica_offset = (uint32_t)(replica_offset + (uint64_t)st->win_lo());
     a.global_moves = global_moves ? 1 : 0;
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
@@ -681,8 +695,10 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
 int mcs_piqmc_pack(mcs_state *st, const int8_t *d_in)
 {
     mcs_instance *inst = st->inst;
-    dim3 grid((unsigned)((inst->N + 31) / 32), (unsigned)(st->Rpad / 32));
-    piqmc_pack_kernel<<<grid, dim3(32, 32), 0, inst->stream>>>(d_in, st->d_W, inst->N, st->R, st->Rpad, (int)st->P);
+    dim3 grid((unsigned)((inst->N + 31) / 32), (unsigned)(st->win_pad() / 32));
+    piqmc_pack_kernel<<<grid, dim3(32, 32), 0, inst->stream>>>(d_in + st->win_lo() * inst->N * st->P,
+                                                               st->d_W + st->win_lo(), inst->N, st->win_valid(),
+                                                               st->Rpad, (int)st->P);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
@@ -691,9 +707,10 @@ int mcs_piqmc_pack(mcs_state *st, const int8_t *d_in)
 int mcs_piqmc_unpack(mcs_state *st, int8_t *d_out)
 {
     mcs_instance *inst = st->inst;
-    dim3 grid((unsigned)((inst->N + 31) / 32), (unsigned)(st->Rpad / 32));
-    piqmc_unpack_kernel<<<grid, dim3(32, 32), 0, inst->stream>>>(st->d_W, d_out, inst->N, st->R, st->Rpad,
-                                                                 (int)st->P);
+    dim3 grid((unsigned)((inst->N + 31) / 32), (unsigned)(st->win_pad() / 32));
+    piqmc_unpack_kernel<<<grid, dim3(32, 32), 0, inst->stream>>>(st->d_W + st->win_lo(),
+                                                                 d_out + st->win_lo() * inst->N * st->P, inst->N,
+                                                                 st->win_valid(), st->Rpad, (int)st->P);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
@@ -714,8 +731,9 @@ int mcs_piqmc_init(mcs_state *st, uint64_t seed, uint64_t replica_offset)
 int mcs_piqmc_energy(mcs_state *st, double *d_out)
 {
     mcs_instance *inst = st->inst;
-    dim3 grid((unsigned)((st->R + 31) / 32), (unsigned)((st->P + 7) / 8));
-    piqmc_energy_kernel<<<grid, dim3(32, 8), 0, inst->stream>>>(st->d_W, inst->tab_idx_at(inst->nsteps - 1), inst->tab_J_at(inst->nsteps - 1), d_out, inst->N,
+    const int kgroups = (int)((st->P + 7) / 8);
+    dim3 grid((unsigned)((st->R + 31) / 32), (unsigned)((kgroups + 3) / 4));
+    piqmc_energy_kernel<<<grid, dim3(32, 4), 0, inst->stream>>>(st->d_W, inst->tab_idx_at(inst->nsteps - 1), inst->tab_J_at(inst->nsteps - 1), d_out, inst->N,
                                                       (int)inst->maxnb, st->R, st->Rpad, (int)st->P);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
