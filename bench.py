@@ -315,19 +315,19 @@ def run_ours(args, out):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         # ncu --set full (profiles/r01b_piqmc_lut_pass_full64_ncu.txt): 212.6 MB read + 74.6 MB
+                         # ncu --set full (profiles/r01_piqmc_lut_pass_ncu_full.txt): 212.6 MB read + 74.6 MB
                          # written per launch at 4096 replicas; scales linearly with the replicas per GPU
                          "traffic": args.traffic if args.traffic is not None else 287.2e6 * R / 4096.0,
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01b_*",
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_piqmc_lut_pass_ncu_full.txt",
                          "kernel": "piqmc_lut_pass_kernel<4,4,true>", "ms_per_launch": ms_per_launch,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "the sweep is instruction bound (Philox + threshold lookup per attempt), not HBM "
                                  "bound: see binding_unit, profiles/ and DESIGN.md section 4",
-                         # what ncu says binds this kernel (profiles/r01b_piqmc_lut_pass_full64_ncu.txt)
+                         # what ncu says binds this kernel (profiles/r01_piqmc_lut_pass_ncu_full.txt)
                          "binding_unit": {"unit": "SM ALU pipe / issue slots", "alu_pipe_pct_of_peak": 65.4,
                                           "issue_slots_busy_pct": 58.0, "instructions_per_attempt": 20.1,
-                                          "dram_pct_of_peak": 4.4, "source": "ncu --set full, profiles/r01b_*"}},
+                                          "dram_pct_of_peak": 4.4, "source": "ncu --set full, profiles/r01_piqmc_lut_pass_ncu_full.txt"}},
             "e2e": e2e,
             "result": {"best_residual_energy_per_spin": None, "mean_best_slice_energy": float(np.mean(energies)),
                        "best_anneal": int(best)},
@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--cpu-sweeps", type=int, default=40, help="sweeps per core for the CPU baseline sample")
     ap.add_argument("--traffic", type=float, default=None,
                     help="ncu dram__bytes_read+write per launch of the dominant kernel; default: the committed "
-                         "capture profiles/r01b_piqmc_lut_pass_full64_ncu.txt scaled to this run's replicas")
+                         "capture profiles/r01_piqmc_lut_pass_ncu_full.txt scaled to this run's replicas")
     args = ap.parse_args()
     out = {}
     with _StdoutToStderr():
