@@ -191,17 +191,17 @@ __device__ __forceinline__ void mcs_philox4x32_10_rk(uint32_t c0, uint32_t c1, u
 // Powers of two kept in the kernel-parameter constant bank: shifts done as IMAD / IMAD.HI by a
 // multiplier ptxas cannot see through stay on the FMA pipe (an immediate 2^k would be strength-reduced to
 // SHF on the ALU pipe, which is the binding unit of the sweep kernels).
-//   left shift by s  (0 <= s <= 15):  x * up[s]
+//   left shift by s  (0 <= s <= 31):  x * up[s]
 //   right shift by r (1 <= r <= 8):   __umulhi(x, down[r])        down[r] = 2^(32 - r)
 struct mcs_pow2_table {
-    uint32_t up[16];
+    uint32_t up[32];
     uint32_t down[9];
 };
 
 inline mcs_pow2_table mcs_pow2_make()
 {
     mcs_pow2_table t;
-    for (int i = 0; i < 16; ++i) t.up[i] = 1u << i;
+    for (int i = 0; i < 32; ++i) t.up[i] = 1u << i;
     t.down[0] = 0;
     for (int r = 1; r <= 8; ++r) t.down[r] = 1u << (32 - r);
     return t;
@@ -222,6 +222,7 @@ enum {
     MCS_TAG_LAST_SLICE = 16, // PIQMC odd-P closing slice
     MCS_TAG_GLOBAL = 17,     // PIQMC world-line move
     MCS_TAG_SVMC = 18,       // SVMC proposal + acceptance
+    MCS_TAG_REFINE = 0x80,   // OR-ed into a group tag: second half of the lazily refined uniforms
     MCS_TAG_INIT = 0x40000000u
 };
 

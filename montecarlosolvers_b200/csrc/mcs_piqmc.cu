@@ -16,13 +16,14 @@
 //      threshold of every one of the 2^(planes) sign patterns into shared memory (all lanes of a
 //      warp share it -- that is why replicas, not sites, sit on the lanes);
 //   3. even slices, then odd slices (then slice P-1 alone when P is odd -- the ring is not
-//      2-colourable): a PRMT sign-replicate transposes the planes into one byte-wide pattern index
-//      per slice, one LDS fetches the threshold, one Philox4x32-10 call decides four slices.
+//      2-colourable): the planes are transposed into one byte-wide pattern index per slice, one LDS
+//      fetches the threshold, one Philox4x32-10 call decides eight slices (lazily refined uniforms).
 // In-plane neighbours belong to other colour classes and are frozen during the launch, so every
 // attempt sees exactly the state a sequential sweep would (detailed balance per attempt).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "mcs_common.cuh"
 
@@ -47,10 +48,11 @@ struct PiqmcPass {
     float jperp2;      // 2 J_perp     (qmc.pyx:95,137-138)
     float nl2e_over_t; // -log2(e)/teff
     mcs_philox_keys keys; // ten Philox round keys, read straight from the parameter constant bank
-    mcs_pow2_table pow2;  // 2^0 .. 2^15 (multipliers of the plane transposition, see phase())
+    mcs_pow2_table pow2;  // 2^0 .. 2^31 (multipliers of the plane transposition, see phase())
     uint32_t sweep_lo, sweep_hi;
     uint32_t replica_offset;
     int global_moves;
+    uint32_t tie_thr; // 0x1ffff; 0xffffffff evaluates the refinement call for every attempt (test hook)
 };
 
 __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
@@ -70,102 +72,213 @@ __device__ __forceinline__ uint32_t prmt_byte(uint32_t v, int i)
     return r;
 }
 
-// Pattern-index bits live at byte positions SH .. SH+NPL+1.  With at most 6 planes the index is
-// stored pre-multiplied by 4 (SH = 2) so that the extracted byte IS the shared-memory byte offset.
+// ---- instruction budget (measured on B200, benchmarks/micro/pipe_rates.cu) -----------------------
+// ALU-pipe instructions (LOP3, PRMT, IADD3, SHF, ISETP, VIADDMNMX) and FMA-pipe IMAD both take 2 issue cycles
+// per warp and overlap with each other; IMAD.WIDE / IMAD.HI hold the FMA pipe for 4 cycles AND the ALU pipe
+// for 2.  A Philox4x32-10 call is 20 IMAD.WIDE + 20 LOP3, i.e. both pipes saturated for ~65 cycles: it is
+// two thirds of the sweep.  Everything below is arranged around that: (1) one Philox call decides eight
+// attempts (lazily refined uniforms), (2) whatever can is moved from the ALU to the FMA pipe (shifts as IMAD
+// by a constant-bank power of two, the reject bit shifted in by IMAD.X), (3) right shifts stay SHF (IMAD.HI
+// would cost both pipes).
+
+// Pattern-index bits live at byte positions SH .. SH+NPL+1 of an index word (one byte per slice).  With at
+// most 6 planes the index is stored pre-multiplied by 4 (SH = 2) so that the extracted byte IS the
+// shared-memory byte offset of the threshold.
 template <int NPL>
 struct LutGeom {
-    static constexpr int ENT = 1 << (NPL + 2);
+    static constexpr int NPP = NPL + 2;          // in-plane planes + the two Trotter planes
+    static constexpr int ENT = 1 << NPP;         // sign patterns
+    static constexpr int SH = (NPP <= 6) ? 2 : 0;
+    static constexpr int NPAIR = (NPP + 1) / 2;
 };
 
-// One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in
-// `allowed`, against thresholds in lut[].  Returns the flip mask.
-//
-// Transposition of the planes into per-slice pattern indices: group g of a 32-bit half word holds
-// slices 8i + 7 - g (i = 0..3).  Plane p's bit of slice i must land at bit 8i + SH + p of the index
-// word, i.e. the half word is shifted by delta = SH + p - 7 + g (an IMAD / IMAD.HI by a power of two from
-// the constant bank: FMA pipe) and merged with one LOP3 (acc | (shifted & 0x01010101 << (SH+p)): ALU
-// pipe).  Byte i of the index word is then the pattern index of slice 8i + 7 - g (times 4 if SH == 2).
-template <int NPL, int G, int HALF>
-__device__ __forceinline__ uint32_t gather_index(const uint64_t (&pl)[NPL], uint64_t tl, uint64_t tr,
-                                                 const mcs_pow2_table &pow2)
+template <int SH>
+__device__ __forceinline__ uint32_t lut_at(const uint32_t *lut, uint32_t off)
 {
-    constexpr int SH = (NPL + 2 <= 6) ? 2 : 0;
+    return SH == 2 ? *(const uint32_t *)((const char *)lut + off) : lut[off];
+}
+
+// x shifted left by DELTA bits (right if negative): left on the FMA pipe, right on the ALU pipe
+template <int DELTA>
+__device__ __forceinline__ uint32_t plane_shift(uint32_t x, const mcs_pow2_table &t)
+{
+    if (DELTA == 0) return x;
+    if (DELTA > 0) return x * t.up[DELTA > 0 ? DELTA : 0];
+    return x >> (DELTA < 0 ? -DELTA : 0);
+}
+
+// Within one Trotter-parity phase only every other bit of a plane is used, so two planes are interleaved into
+// one word first (plane 2j lowered to / kept at the even bit, plane 2j+1 one above it): the per-group
+// transposition then moves TWO index bits with one shift + one LOP3.
+//   PARITY 0 (slices at even bits k): m = (a & 0x5555...) | ((b << 1) & 0xAAAA...)   a at k, b at k+1
+//   PARITY 1 (slices at odd  bits k): m = ((a >> 1) & 0x5555...) | (b & 0xAAAA...)   a at k-1, b at k
+// Both stay inside the slice's own byte (k+1 <= 7 for even k, k-1 >= 0 for odd k).
+template <int PARITY>
+__device__ __forceinline__ uint32_t interleave_pair(uint32_t a, uint32_t b, const mcs_pow2_table &pow2)
+{
+    if (PARITY == 0) return (a & 0x55555555u) | (plane_shift<1>(b, pow2) & 0xAAAAAAAAu);
+    return (plane_shift<-1>(a, pow2) & 0x55555555u) | (b & 0xAAAAAAAAu);
+}
+
+// Index word of group G (slices 8 i + 7 - G of this 32-bit half, i = 0..3; 7 - G has the phase's parity):
+// byte i = pattern index of slice 8 i + 7 - G (times 4 if SH == 2).  m[j] = interleaved planes 2j, 2j+1; a
+// trailing single plane is m[NPAIR-1] as is.
+template <int NPP, int G, int PARITY>
+__device__ __forceinline__ uint32_t gather_index(const uint32_t (&m)[(NPP + 1) / 2], const mcs_pow2_table &pow2)
+{
+    constexpr int SH = (NPP <= 6) ? 2 : 0;
+    constexpr int S = 7 - G;                     // bit of the slice inside its byte
+    constexpr int LOW = PARITY == 0 ? S : S - 1; // where plane 2j of a pair sits
     uint32_t acc = 0;
-#define MCS_PLANE(p)                                                                              \
-    if (p < NPL + 2) {                                                                            \
-        const uint64_t plane = p < NPL ? pl[p < NPL ? p : 0] : (p == NPL ? tl : tr);              \
-        const uint32_t v = (uint32_t)(plane >> (32 * HALF));                                      \
-        acc |= mcs_fma_shift<SH + p - 7 + G>(v, pow2) & (0x01010101u << (SH + p));                \
-    }
-    MCS_PLANE(0) MCS_PLANE(1) MCS_PLANE(2) MCS_PLANE(3) MCS_PLANE(4) MCS_PLANE(5) MCS_PLANE(6) MCS_PLANE(7)
-#undef MCS_PLANE
+#define MCS_PAIRWORD(j)                                                                                       \
+    if (2 * (j) + 1 < NPP)                                                                                    \
+        acc |= plane_shift<SH + 2 * (j) - LOW>(m[(j) < (NPP + 1) / 2 ? (j) : 0], pow2) & (0x03030303u << (SH + 2 * (j))); \
+    else if (2 * (j) < NPP)                                                                                   \
+        acc |= plane_shift<SH + 2 * (j) - S>(m[(j) < (NPP + 1) / 2 ? (j) : 0], pow2) & (0x01010101u << (SH + 2 * (j)));
+    MCS_PAIRWORD(0) MCS_PAIRWORD(1) MCS_PAIRWORD(2) MCS_PAIRWORD(3)
+#undef MCS_PAIRWORD
     return acc;
 }
 
-template <int NPL, int G, int HALF>
-__device__ __forceinline__ void attempt_group(uint32_t &flip, const uint64_t (&pl)[NPL], uint64_t tl, uint64_t tr,
-                                              const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2,
-                                              uint32_t c3hi, const mcs_philox_keys &keys,
-                                              const mcs_pow2_table &pow2)
+// ---- decisions -------------------------------------------------------------------------------------
+// The table holds ~T, so the carry of ~T + u is "u > T" = reject.  IMAD.X shifts it into a per-group Horner
+// accumulator (acc * 256 + carry: one FMA-pipe instruction; the multiplier comes from the constant bank so
+// that ptxas cannot turn it into an ALU shift-add).  Bytes are visited 3,2,1,0, so acc ends with the reject
+// bit of byte i at bit 8 i.
+//
+// Lazily refined uniforms.  The uniform of an attempt is the 32-bit number u = (v << 16) | r, v = 16 bits of
+// the group pair's Philox call, r = 16 bits of a SECOND call (tag | MCS_TAG_REFINE) that is evaluated only when
+// it can matter: u <= T is decided by v alone unless v == T >> 16 (probability 2^-16), so one call serves
+// eight attempts instead of four.  Fast path: group A compares the word x itself (v = x >> 16; the low half
+// of x stands in for r and cannot change a decided comparison), group B compares x << 16 (v = x & 0xffff,
+// r = 0).  The sum s = ~T + u lies within 2^16 of a wrap whenever a comparison is undecided (the test
+// s + 2^16 < 2^17 mod 2^32 is conservative; one VIADDMNMX per attempt keeps the minimum), and then the whole
+// call is redone with both halves in refine_pair (out of line, ~0.4 % of the calls).  The outcome is
+// bit-identical to always evaluating both calls; tie_thr = 0xffffffff does exactly that and
+// tests/test_gpu_production.py compares the two.
+__device__ __forceinline__ uint32_t horner_reject(uint32_t acc, uint32_t mul, uint32_t nT, uint32_t u, uint32_t &smin)
 {
-    constexpr int SH = (NPL + 2 <= 6) ? 2 : 0;
-    const uint32_t acc = gather_index<NPL, G, HALF>(pl, tl, tr, pow2);
-    uint32_t rnd[4];
-    mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(HALF * 8 + G), keys, rnd);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t off = prmt_byte(acc, i); // = 4 * idx when SH == 2, idx otherwise
-        const uint32_t T = SH == 2 ? *(const uint32_t *)((const char *)lut + off) : lut[off];
-        if (rnd[i] <= T) flip += 1u << (8 * i + 7 - G); // each bit is added at most once: + == |
-    }
+    uint32_t out, s;
+    asm("add.cc.u32 %1, %2, %3;\n\tmadc.lo.u32 %0, %4, %5, 0;"
+        : "=r"(out), "=r"(s)
+        : "r"(nT), "r"(u), "r"(acc), "r"(mul));
+    smin = min(smin, s + 0x10000u);
+    return out;
 }
 
-// One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in
-// `allowed`, against thresholds in lut[].  Returns the flip mask.
+template <int SH>
+__device__ __noinline__ uint2 refine_pair(uint32_t accA, uint32_t accB, uint32_t x0, uint32_t x1, uint32_t x2,
+                                          uint32_t x3, const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2,
+                                          uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    uint32_t f[4];
+    mcs_philox4x32_10(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
+    const uint32_t x[4] = {x0, x1, x2, x3};
+    uint32_t chA = 0, chB = 0;
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+        const uint32_t TA = ~lut_at<SH>(lut, (accA >> (8 * i)) & 0xFFu);
+        const uint32_t TB = ~lut_at<SH>(lut, (accB >> (8 * i)) & 0xFFu);
+        const uint32_t uA = (x[i] & 0xFFFF0000u) | (f[i] >> 16);
+        const uint32_t uB = (x[i] << 16) | (f[i] & 0xFFFFu);
+        chA = (chA << 8) | (uA > TA ? 1u : 0u);
+        chB = (chB << 8) | (uB > TB ? 1u : 0u);
+    }
+    return make_uint2(chA, chB);
+}
+
+// groups GA and GB (same half, same parity) share one Philox call; rej accumulates REJECT bits
+template <int NPL, int GA, int GB, int HALF>
+__device__ __forceinline__ void decide_pair(uint32_t &rej, uint32_t accA, uint32_t accB, const uint32_t *lut,
+                                            uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3hi,
+                                            const mcs_philox_keys &keys, const mcs_pow2_table &pow2,
+                                            uint32_t tie_thr)
+{
+    constexpr int SH = LutGeom<NPL>::SH;
+    const uint32_t c3 = c3hi | (uint32_t)(HALF * 8 + GA);
+    uint32_t x[4];
+    mcs_philox4x32_10_rk(c0, c1, c2, c3, keys, x);
+    uint32_t chA = 0, chB = 0, smin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+        const uint32_t nTA = lut_at<SH>(lut, prmt_byte(accA, i));
+        const uint32_t nTB = lut_at<SH>(lut, prmt_byte(accB, i));
+        chA = horner_reject(chA, pow2.up[8], nTA, x[i], smin);
+        chB = horner_reject(chB, pow2.up[8], nTB, x[i] * pow2.up[16], smin);
+    }
+    if (smin <= tie_thr) { // some comparison of this call needs the low 16 bits: redo all eight with both halves
+        const uint2 r = refine_pair<SH>(accA, accB, x[0], x[1], x[2], x[3], lut, c0, c1, c2, c3, keys.rk[0], keys.rk[1]);
+        chA = r.x;
+        chB = r.y;
+    }
+    rej = chA * pow2.up[7 - GA] + rej;
+    rej = chB * pow2.up[7 - GB] + rej;
+}
+
+// One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in `allowed`,
+// against the (complemented) thresholds in lut[].  Returns the flip mask.
 template <int NPL, int PARITY, bool FULL>
 __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w, int P, uint64_t pmask,
                                           uint64_t allowed, const uint32_t *lut, uint32_t c0, uint32_t c1,
                                           uint32_t c2, uint32_t c3hi, const mcs_philox_keys &keys,
-                                          const mcs_pow2_table &pow2)
+                                          const mcs_pow2_table &pow2, uint32_t tie_thr)
 {
+    constexpr int NPP = LutGeom<NPL>::NPP, NPAIR = LutGeom<NPL>::NPAIR;
     const uint64_t tl = w ^ rotl_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k-1
     const uint64_t tr = w ^ rotr_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k+1
-    uint32_t flip[2] = {0u, 0u};
+    uint32_t m[2][NPAIR];
+#pragma unroll
+    for (int H = 0; H < 2; ++H)
+#pragma unroll
+        for (int j = 0; j < NPAIR; ++j) {
+            const int pa = 2 * j, pb = 2 * j + 1;
+            const uint64_t A = pa < NPL ? pl[pa < NPL ? pa : 0] : (pa == NPL ? tl : tr);
+            const uint64_t B = pb < NPL ? pl[pb < NPL ? pb : 0] : (pb == NPL ? tl : tr);
+            const uint32_t a = (uint32_t)(A >> (32 * H)), b = (uint32_t)(B >> (32 * H));
+            m[H][j] = pb < NPP ? interleave_pair<PARITY>(a, b, pow2) : a;
+        }
+    uint32_t rej[2] = {0u, 0u};
     // group G of half H holds slices 32 H + 8 i + 7 - G; parity of 7 - G == PARITY  <=>  G = 1-PARITY, 3-PARITY, ...
-    // a whole group beyond the last slice is skipped (warp-uniform branch)
-#define MCS_GROUP(H, G)                                                                                      \
-    if (FULL || 32 * H + 7 - (G) < P)                                                                        \
-        attempt_group<NPL, (G), H>(flip[H], pl, tl, tr, lut, c0, c1, c2, c3hi, keys, pow2);
-    MCS_GROUP(0, 1 - PARITY) MCS_GROUP(0, 3 - PARITY) MCS_GROUP(0, 5 - PARITY) MCS_GROUP(0, 7 - PARITY)
-    MCS_GROUP(1, 1 - PARITY) MCS_GROUP(1, 3 - PARITY) MCS_GROUP(1, 5 - PARITY) MCS_GROUP(1, 7 - PARITY)
-#undef MCS_GROUP
-    return (((uint64_t)flip[1] << 32) | flip[0]) & allowed;
+    // a pair of groups entirely beyond the last slice is skipped (warp-uniform branch)
+#define MCS_PAIR(H, GA, GB)                                                                                  \
+    if (FULL || 32 * H + 7 - (GB) < P) {                                                                     \
+        const uint32_t accA = gather_index<NPP, (GA), PARITY>(m[H], pow2);                                   \
+        const uint32_t accB = gather_index<NPP, (GB), PARITY>(m[H], pow2);                                   \
+        decide_pair<NPL, (GA), (GB), H>(rej[H], accA, accB, lut, c0, c1, c2, c3hi, keys, pow2, tie_thr);     \
+    }
+    MCS_PAIR(0, 1 - PARITY, 3 - PARITY) MCS_PAIR(0, 5 - PARITY, 7 - PARITY)
+    MCS_PAIR(1, 1 - PARITY, 3 - PARITY) MCS_PAIR(1, 5 - PARITY, 7 - PARITY)
+#undef MCS_PAIR
+    return ~(((uint64_t)rej[1] << 32) | rej[0]) & allowed;
 }
 
-// WARPS warps per CTA, all working on the SAME site (WARPS*32 consecutive replicas), so the
-// threshold table is built once per CTA at a compile-time shared-memory address.
-// FULL: P == 64 (every group of four slices exists: no per-group branch, one basic block).
-template <int NPL, int WARPS, bool FULL>
+// WARPS warps per CTA, all working on the SAME site (WARPS*32 consecutive replicas), so the threshold table
+// is built once per CTA at a compile-time shared-memory address.  grid = (CTAs per site, sites of the colour).
+// FULL: P == 64 (every group exists: no per-pair branch, one basic block).
+// FLD:  the instance has (1) / has no (0) field plane; the in-plane planes are then j < NPL - FLD, all
+//       compile-time (rows shorter than maxdeg are padded with the site itself and J = 0: a zero plane).
+template <int NPL, int WARPS, bool FULL, int FLD>
 __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
-    constexpr int ENT = LutGeom<NPL>::ENT;
+    constexpr int ENT = LutGeom<NPL>::ENT, NQ = NPL - FLD;
     __shared__ uint32_t s_lut[ENT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cpg = a.G / WARPS; // CTAs per site
-    const int site = __ldg(&a.sites[blockIdx.x / cpg]);
-    const long long r = ((long long)(blockIdx.x % cpg) * WARPS + warp) * 32 + lane;
+    const unsigned si = blockIdx.y + 65535u * blockIdx.z;
+    if (si >= (unsigned)a.nsites) return; // only when the colour class has more than 65535 sites (CTA-uniform)
+    const int site = __ldg(&a.sites[si]);
+    const long long r = ((long long)blockIdx.x * WARPS + warp) * 32 + lane;
 
     // ---- per-site coefficients (CTA-uniform) and the acceptance-threshold table ---------------
     float c[NPL];
     int nb[NPL];
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
-        if (j < a.nq) {
+        if (j < NQ) {
             nb[j] = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
             c[j] = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
         } else {
             nb[j] = site;
-            c[j] = (a.field && j == a.nq) ? a.bcoef * __ldg(&a.h[site]) : 0.0f;
+            c[j] = a.bcoef * __ldg(&a.h[site]);
         }
     }
     for (int e = threadIdx.x; e < ENT; e += WARPS * 32) {
@@ -174,7 +287,7 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
         for (int j = 0; j < NPL; ++j) dE += ((e >> j) & 1) ? -c[j] : c[j];
         const int anti = ((e >> NPL) & 1) + ((e >> (NPL + 1)) & 1); // anti-aligned Trotter neighbours
         dE += a.jperp2 * (float)(2 - 2 * anti);
-        s_lut[e] = mcs_accept_threshold(dE, a.nl2e_over_t);
+        s_lut[e] = ~mcs_accept_threshold(dE, a.nl2e_over_t);
     }
 
     // ---- this lane's world line and its in-plane anti-alignment planes ------------------------
@@ -183,12 +296,8 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
     uint64_t w = a.W[(long long)site * a.Rpad + r];
     uint64_t pl[NPL];
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        if (j < a.nq)
-            pl[j] = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
-        else
-            pl[j] = (a.field && j == a.nq) ? w : 0ull; // field plane: bit set <=> s = -1
-    }
+    for (int j = 0; j < NPL; ++j)
+        pl[j] = j < NQ ? (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask : w; // field plane: bit set <=> s = -1
     if (WARPS == 1)
         __syncwarp();
     else
@@ -201,8 +310,8 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
     if (oddP) even_allowed &= ~(1ull << (P - 1)); // slice P-1 neighbours slice 0: handled alone below
     const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
 
-    w ^= phase<NPL, 0, FULL>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2);
-    w ^= phase<NPL, 1, FULL>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2);
+    w ^= phase<NPL, 0, FULL>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr);
+    w ^= phase<NPL, 1, FULL>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr);
     if (oddP) {
         const int k = P - 1;
         const uint64_t tl = w ^ rotl_ring(w, P, pmask), tr = w ^ rotr_ring(w, P, pmask);
@@ -213,7 +322,7 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
         idx |= (uint32_t)((tr >> k) & 1ull) << (NPL + 1);
         uint32_t rnd[4];
         mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
-        if (rnd[0] <= lut[idx]) w ^= 1ull << k;
+        if (rnd[0] <= ~lut[idx]) w ^= 1ull << k;
     }
 
     // ---- world-line move: flip all P slices of this site (qmc.pyx:405-438) ---------------------
@@ -221,11 +330,7 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
         float dE = 0.0f;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-            uint64_t x;
-            if (j < a.nq)
-                x = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
-            else
-                x = (a.field && j == a.nq) ? w : 0ull;
+            const uint64_t x = j < NQ ? (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask : w & pmask;
             dE += c[j] * (float)(P - 2 * __popcll(x));
         }
         uint32_t rnd[4];
@@ -568,30 +673,40 @@ __global__ void piqmc_energy_kernel(const uint64_t *__restrict__ W, const int32_
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-template <int NPL>
-static void launch_lut_w(int warps, long long items, cudaStream_t s, const PiqmcPass &a)
+template <int NPL, int FLD>
+static void launch_lut_wf(int warps, const PiqmcPass &a, cudaStream_t s)
 {
-    // items = nsites * G warps of work; `warps` divides G, so a CTA never straddles two sites
-    const unsigned grid = (unsigned)(items / warps);
+    // a.G = warps of work per site; `warps` divides it, so a CTA never straddles two sites
+    const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
+    const dim3 grid((unsigned)(a.G / warps), ny, nz);
     if (a.P == 64 && warps == 4)
-        piqmc_lut_pass_kernel<NPL, 4, true><<<grid, 128, 0, s>>>(a);
+        piqmc_lut_pass_kernel<NPL, 4, true, FLD><<<grid, 128, 0, s>>>(a);
     else if (warps == 4)
-        piqmc_lut_pass_kernel<NPL, 4, false><<<grid, 128, 0, s>>>(a);
+        piqmc_lut_pass_kernel<NPL, 4, false, FLD><<<grid, 128, 0, s>>>(a);
     else if (warps == 2)
-        piqmc_lut_pass_kernel<NPL, 2, false><<<grid, 64, 0, s>>>(a);
+        piqmc_lut_pass_kernel<NPL, 2, false, FLD><<<grid, 64, 0, s>>>(a);
     else
-        piqmc_lut_pass_kernel<NPL, 1, false><<<grid, 32, 0, s>>>(a);
+        piqmc_lut_pass_kernel<NPL, 1, false, FLD><<<grid, 32, 0, s>>>(a);
 }
 
-static void launch_lut(int npl, int warps, long long items, cudaStream_t s, const PiqmcPass &a)
+template <int NPL>
+static void launch_lut_w(int warps, const PiqmcPass &a, cudaStream_t s)
+{
+    if (a.field)
+        launch_lut_wf<NPL, 1>(warps, a, s);
+    else
+        launch_lut_wf<NPL, 0>(warps, a, s);
+}
+
+static void launch_lut(int npl, int warps, cudaStream_t s, const PiqmcPass &a)
 {
     switch (npl) {
-    case 1: launch_lut_w<1>(warps, items, s, a); break;
-    case 2: launch_lut_w<2>(warps, items, s, a); break;
-    case 3: launch_lut_w<3>(warps, items, s, a); break;
-    case 4: launch_lut_w<4>(warps, items, s, a); break;
-    case 5: launch_lut_w<5>(warps, items, s, a); break;
-    default: launch_lut_w<6>(warps, items, s, a); break;
+    case 1: launch_lut_w<1>(warps, a, s); break;
+    case 2: launch_lut_w<2>(warps, a, s); break;
+    case 3: launch_lut_w<3>(warps, a, s); break;
+    case 4: launch_lut_w<4>(warps, a, s); break;
+    case 5: launch_lut_w<5>(warps, a, s); break;
+    default: launch_lut_w<6>(warps, a, s); break;
     }
 }
 
@@ -655,6 +770,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     a.pow2 = mcs_pow2_make();
     a.replica_offset = (uint32_t)(replica_offset + (uint64_t)st->win_lo());
     a.global_moves = global_moves ? 1 : 0;
+    a.tie_thr = getenv("MCS_PIQMC_ALWAYS_REFINE") ? 0xFFFFFFFFu : 0x1FFFFu;
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;
@@ -679,7 +795,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
                 if (lookuptable)
                     launch_bath(npl, (unsigned)((items + kWarps - 1) / kWarps), inst->stream, a, bath);
                 else if (inst->lut_ok)
-                    launch_lut(npl, warps, items, inst->stream, a);
+                    launch_lut(npl, warps, inst->stream, a);
                 else
                     piqmc_direct_pass_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kWarps * 32, 0,
                                                inst->stream>>>(a);

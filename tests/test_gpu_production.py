@@ -261,6 +261,46 @@ def test_results_do_not_depend_on_sharding_or_call_splitting(mcs):
     assert np.array_equal(s_whole, s_parts)
 
 
+@pytest.mark.parametrize("case", ["torus_fields_P64", "torus_P20_global", "torus5_fields_P7", "santoro_rows_P64"])
+def test_lazily_refined_uniforms_equal_always_refined(mcs, case):
+    """The PIQMC pass decides eight attempts per Philox call from 16-bit halves and evaluates the second
+    (refinement) call only when a comparison is within 2^-16 of its threshold.  That must be invisible:
+    MCS_PIQMC_ALWAYS_REFINE=1 evaluates both calls for every attempt (the defining 32-bit-uniform algorithm)
+    and the trajectories must agree bit for bit -- including runs long / cold enough that refinements occur
+    (about one attempt in 2^15 takes the slow path)."""
+    if case == "torus_fields_P64":
+        (_, nbs), P, R, S, glob = inst.torus(8, seed=11, fields=True), 64, 256, 60, False
+    elif case == "torus_P20_global":
+        (_, nbs), P, R, S, glob = inst.torus(6, seed=12), 20, 128, 80, True
+    elif case == "torus5_fields_P7":
+        (_, nbs), P, R, S, glob = inst.torus(5, seed=4, fields=True), 7, 256, 160, False  # 7 planes, odd P, 3+ colours
+    else:
+        nbs, P, R, S, glob = inst.santoro()[1], 64, 128, 12, False
+    n = nbs.shape[0]
+    A, B = np.linspace(3.0, 1e-8, S), np.ones(S)
+    I = mcs.Instance(nbs)
+    if not I.lut_kernels:
+        pytest.skip("instance is served by the general-degree kernel")
+    c0 = (2 * np.random.RandomState(2).randint(2, size=(R, n, 1)) - 1).astype(np.int8).repeat(P, axis=2)
+    out = []
+    for always in (False, True):
+        if always:
+            os.environ["MCS_PIQMC_ALWAYS_REFINE"] = "1"
+        try:
+            st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+            st.upload_spins(np.ascontiguousarray(c0))
+            st.piqmc_sweeps(A, B, 1, 1.0 / P, global_moves=glob, seed=123)
+            out.append(st.download_spins())
+            st.close()
+        finally:
+            os.environ.pop("MCS_PIQMC_ALWAYS_REFINE", None)
+    assert not np.array_equal(out[0], c0)
+    assert np.array_equal(out[0], out[1])
+    # attempts made: R S P n; expected refinements ~ attempts / 2^15 (conservative test) -- make sure the case
+    # is large enough that the slow path was actually exercised
+    assert R * S * P * n / 2.0 ** 15 > 50
+
+
 def test_time_dependent_tables_production(mcs):
     """Noisy* production path: constant tables == the static instance bit for bit (same Philox stream);
     a table that switches the couplings on over time is honoured step by step."""
