@@ -13,7 +13,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmcs_b200.so")
+SO_PATH = os.environ.get("MCS_B200_LIB") or os.path.join(_HERE, "libmcs_b200.so")  # override: kernel experiments
 
 MCS_OK, MCS_EINVAL, MCS_ENODEVICE, MCS_EZERODIV, MCS_EUNSUPPORTED, MCS_ENOMEM = 0, -1, -2, -3, -4, -5
 KIND_PIQMC, KIND_SA, KIND_SVMC = 1, 2, 3

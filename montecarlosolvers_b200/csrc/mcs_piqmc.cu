@@ -52,7 +52,7 @@ struct PiqmcPass {
     uint32_t sweep_lo, sweep_hi;
     uint32_t replica_offset;
     int global_moves;
-    uint32_t tie_thr; // 0x1ffff; 0xffffffff evaluates the refinement call for every attempt (test hook)
+    uint32_t tie_thr; // 0x20000; 0xffffffff evaluates the refinement call for every attempt (test hook)
 };
 
 __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
@@ -153,7 +153,8 @@ __device__ __forceinline__ uint32_t gather_index(const uint32_t (&m)[(NPP + 1) /
 // of x stands in for r and cannot change a decided comparison), group B compares x << 16 (v = x & 0xffff,
 // r = 0).  The sum s = ~T + u lies within 2^16 of a wrap whenever a comparison is undecided (the test
 // s + 2^16 < 2^17 mod 2^32 is conservative; one VIADDMNMX per attempt keeps the minimum), and then the whole
-// call is redone with both halves in refine_pair (out of line, ~0.4 % of the calls).  The outcome is
+// call is flagged and redone with both halves at the end of the phase (refine_pair, cold code, ~0.4 % of
+// the calls -- slices of one parity do not interact, so the order does not matter).  The outcome is
 // bit-identical to always evaluating both calls; tie_thr = 0xffffffff does exactly that and
 // tests/test_gpu_production.py compares the two.
 __device__ __forceinline__ uint32_t horner_reject(uint32_t acc, uint32_t mul, uint32_t nT, uint32_t u, uint32_t &smin)
@@ -166,53 +167,74 @@ __device__ __forceinline__ uint32_t horner_reject(uint32_t acc, uint32_t mul, ui
     return out;
 }
 
+// Slow path of the lazily refined uniforms: redo one flagged call (groups GA, GB of one half) with both Philox
+// halves, u = (v << 16) | r, and replace its eight reject bits.  Runs at the end of the phase; the Philox
+// calls and comparisons sit in an out-of-line function so that this cold code costs the hot path no registers.
 template <int SH>
-__device__ __noinline__ uint2 refine_pair(uint32_t accA, uint32_t accB, uint32_t x0, uint32_t x1, uint32_t x2,
-                                          uint32_t x3, const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2,
-                                          uint32_t c3, uint32_t k0, uint32_t k1)
+__device__ __noinline__ uint2 refine_call(uint32_t accA, uint32_t accB, const uint32_t *lut, uint32_t c0, uint32_t c1,
+                                          uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
-    uint32_t f[4];
+    uint32_t x[4], f[4];
+    mcs_philox4x32_10(c0, c1, c2, c3, k0, k1, x);
     mcs_philox4x32_10(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
-    const uint32_t x[4] = {x0, x1, x2, x3};
-    uint32_t chA = 0, chB = 0;
+    uint32_t chA = 0, chB = 0; // reject bit of byte i at bit 8 i
 #pragma unroll
-    for (int i = 3; i >= 0; --i) {
+    for (int i = 0; i < 4; ++i) {
         const uint32_t TA = ~lut_at<SH>(lut, (accA >> (8 * i)) & 0xFFu);
         const uint32_t TB = ~lut_at<SH>(lut, (accB >> (8 * i)) & 0xFFu);
         const uint32_t uA = (x[i] & 0xFFFF0000u) | (f[i] >> 16);
         const uint32_t uB = (x[i] << 16) | (f[i] & 0xFFFFu);
-        chA = (chA << 8) | (uA > TA ? 1u : 0u);
-        chB = (chB << 8) | (uB > TB ? 1u : 0u);
+        chA |= (uA > TA ? 1u : 0u) << (8 * i);
+        chB |= (uB > TB ? 1u : 0u) << (8 * i);
     }
     return make_uint2(chA, chB);
 }
 
-// groups GA and GB (same half, same parity) share one Philox call; rej accumulates REJECT bits
+template <int NPL, int GA, int GB, int PARITY>
+__device__ __forceinline__ void refine_pair(uint32_t &rej, const uint32_t (&m)[LutGeom<NPL>::NPAIR],
+                                            const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            const mcs_philox_keys &keys, const mcs_pow2_table &pow2)
+{
+    constexpr int NPP = LutGeom<NPL>::NPP;
+    const uint32_t accA = gather_index<NPP, GA, PARITY>(m, pow2);
+    const uint32_t accB = gather_index<NPP, GB, PARITY>(m, pow2);
+    const uint2 ch = refine_call<LutGeom<NPL>::SH>(accA, accB, lut, c0, c1, c2, c3, keys.rk[0], keys.rk[1]);
+    rej = (rej & ~((0x01010101u << (7 - GA)) | (0x01010101u << (7 - GB)))) | (ch.x << (7 - GA)) | (ch.y << (7 - GB));
+}
+
+// groups GA and GB (same half, same parity) share one Philox call; rej accumulates REJECT bits, flags the
+// calls whose fast path was not conclusive (Horner again: flags * 2 + undecided)
 template <int NPL, int GA, int GB, int HALF>
-__device__ __forceinline__ void decide_pair(uint32_t &rej, uint32_t accA, uint32_t accB, const uint32_t *lut,
-                                            uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3hi,
-                                            const mcs_philox_keys &keys, const mcs_pow2_table &pow2,
-                                            uint32_t tie_thr)
+__device__ __forceinline__ void decide_pair(uint32_t &rej, uint32_t &flags, uint32_t accA, uint32_t accB,
+                                            const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2,
+                                            uint32_t c3hi, const mcs_philox_keys &keys, const mcs_pow2_table &pow2,
+                                            uint32_t tie_thr, uint2 *slot)
 {
     constexpr int SH = LutGeom<NPL>::SH;
-    const uint32_t c3 = c3hi | (uint32_t)(HALF * 8 + GA);
     uint32_t x[4];
-    mcs_philox4x32_10_rk(c0, c1, c2, c3, keys, x);
+    mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(HALF * 8 + GA), keys, x);
     uint32_t chA = 0, chB = 0, smin = 0xFFFFFFFFu;
+    // The eight index bytes are extracted by the LSU, not the ALU pipe (the binding unit): one 64-bit store of
+    // the two index words to this thread's private slot, eight byte loads (conflict-free: a warp's slots are
+    // 32 consecutive 8-byte words).  Inline PTX so that the compiler cannot forward the store into shifts.
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(slot);
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(accA), "r"(accB) : "memory");
 #pragma unroll
     for (int i = 3; i >= 0; --i) {
-        const uint32_t nTA = lut_at<SH>(lut, prmt_byte(accA, i));
-        const uint32_t nTB = lut_at<SH>(lut, prmt_byte(accB, i));
+        uint32_t oA, oB;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oA) : "r"(saddr + i) : "memory");
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oB) : "r"(saddr + 4 + i) : "memory");
+        const uint32_t nTA = lut_at<SH>(lut, oA);
+        const uint32_t nTB = lut_at<SH>(lut, oB);
         chA = horner_reject(chA, pow2.up[8], nTA, x[i], smin);
         chB = horner_reject(chB, pow2.up[8], nTB, x[i] * pow2.up[16], smin);
     }
-    if (smin <= tie_thr) { // some comparison of this call needs the low 16 bits: redo all eight with both halves
-        const uint2 r = refine_pair<SH>(accA, accB, x[0], x[1], x[2], x[3], lut, c0, c1, c2, c3, keys.rk[0], keys.rk[1]);
-        chA = r.x;
-        chB = r.y;
-    }
     rej = chA * pow2.up[7 - GA] + rej;
     rej = chB * pow2.up[7 - GB] + rej;
+    // undecided <=> smin < tie_thr <=> ~smin + tie_thr carries: IADD3 + IMAD.X like the decisions themselves
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\tmadc.lo.u32 %0, %0, %3, 0;\n\t}"
+        : "+r"(flags)
+        : "r"(~smin), "r"(tie_thr), "r"(pow2.up[1]));
 }
 
 // One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in `allowed`,
@@ -221,7 +243,7 @@ template <int NPL, int PARITY, bool FULL>
 __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w, int P, uint64_t pmask,
                                           uint64_t allowed, const uint32_t *lut, uint32_t c0, uint32_t c1,
                                           uint32_t c2, uint32_t c3hi, const mcs_philox_keys &keys,
-                                          const mcs_pow2_table &pow2, uint32_t tie_thr)
+                                          const mcs_pow2_table &pow2, uint32_t tie_thr, uint2 *bounce, int nthreads)
 {
     constexpr int NPP = LutGeom<NPL>::NPP, NPAIR = LutGeom<NPL>::NPAIR;
     const uint64_t tl = w ^ rotl_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k-1
@@ -237,18 +259,30 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
             const uint32_t a = (uint32_t)(A >> (32 * H)), b = (uint32_t)(B >> (32 * H));
             m[H][j] = pb < NPP ? interleave_pair<PARITY>(a, b, pow2) : a;
         }
-    uint32_t rej[2] = {0u, 0u};
+    uint32_t rej[2] = {0u, 0u}, flags = 0u;
     // group G of half H holds slices 32 H + 8 i + 7 - G; parity of 7 - G == PARITY  <=>  G = 1-PARITY, 3-PARITY, ...
-    // a pair of groups entirely beyond the last slice is skipped (warp-uniform branch)
+    // pair q = 2 H + (GA > 3) is flags bit 3 - q after the four Horner steps; a pair entirely beyond the last
+    // slice is skipped (warp-uniform branch) but still shifts the flags
 #define MCS_PAIR(H, GA, GB)                                                                                  \
     if (FULL || 32 * H + 7 - (GB) < P) {                                                                     \
         const uint32_t accA = gather_index<NPP, (GA), PARITY>(m[H], pow2);                                   \
         const uint32_t accB = gather_index<NPP, (GB), PARITY>(m[H], pow2);                                   \
-        decide_pair<NPL, (GA), (GB), H>(rej[H], accA, accB, lut, c0, c1, c2, c3hi, keys, pow2, tie_thr);     \
+        decide_pair<NPL, (GA), (GB), H>(rej[H], flags, accA, accB, lut, c0, c1, c2, c3hi, keys, pow2, tie_thr, \
+                                        bounce + (2 * H + (GA) / 4) * nthreads);                                    \
+    } else {                                                                                                 \
+        flags *= 2u;                                                                                         \
     }
     MCS_PAIR(0, 1 - PARITY, 3 - PARITY) MCS_PAIR(0, 5 - PARITY, 7 - PARITY)
     MCS_PAIR(1, 1 - PARITY, 3 - PARITY) MCS_PAIR(1, 5 - PARITY, 7 - PARITY)
 #undef MCS_PAIR
+    if (flags) { // rare (about 3 % of the warp-phases): Horner order, pair 0 ended at bit 3 ... pair 3 at bit 0
+#define MCS_REFINE(H, GA, GB, BIT)                                                                           \
+    if (flags & (BIT))                                                                                       \
+        refine_pair<NPL, (GA), (GB), PARITY>(rej[H], m[H], lut, c0, c1, c2, c3hi | (uint32_t)(H * 8 + (GA)), keys, pow2);
+        MCS_REFINE(0, 1 - PARITY, 3 - PARITY, 8u) MCS_REFINE(0, 5 - PARITY, 7 - PARITY, 4u)
+        MCS_REFINE(1, 1 - PARITY, 3 - PARITY, 2u) MCS_REFINE(1, 5 - PARITY, 7 - PARITY, 1u)
+#undef MCS_REFINE
+    }
     return ~(((uint64_t)rej[1] << 32) | rej[0]) & allowed;
 }
 
@@ -257,8 +291,11 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
 // FULL: P == 64 (every group exists: no per-pair branch, one basic block).
 // FLD:  the instance has (1) / has no (0) field plane; the in-plane planes are then j < NPL - FLD, all
 //       compile-time (rows shorter than maxdeg are padded with the site itself and J = 0: a zero plane).
+#ifndef MCS_LUT_MINBLOCKS
+#define MCS_LUT_MINBLOCKS 8 // <= 64 registers: the big basic blocks otherwise tempt ptxas into 80+ for no gain
+#endif
 template <int NPL, int WARPS, bool FULL, int FLD>
-__global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
+__global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
     constexpr int ENT = LutGeom<NPL>::ENT, NQ = NPL - FLD;
     __shared__ uint32_t s_lut[ENT];
@@ -274,8 +311,8 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
         if (j < NQ) {
-            nb[j] = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
-            c[j] = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+            nb[j] = __ldg(&a.ell_idx[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j]);
+            c[j] = a.bcoef * __ldg(&a.ell_J[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j]);
         } else {
             nb[j] = site;
             c[j] = a.bcoef * __ldg(&a.h[site]);
@@ -293,11 +330,14 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
     // ---- this lane's world line and its in-plane anti-alignment planes ------------------------
     const int P = FULL ? 64 : a.P;
     const uint64_t pmask = (FULL || P == 64) ? ~0ull : ((1ull << P) - 1ull);
-    uint64_t w = a.W[(long long)site * a.Rpad + r];
+    // row offsets as one IMAD.WIDE.U32 each (site indices and Rpad are below 2^32)
+    const uint32_t rpad = (uint32_t)a.Rpad;
+    const uint64_t *Wr = a.W + r;
+    uint64_t w = Wr[(uint64_t)(uint32_t)site * rpad];
     uint64_t pl[NPL];
 #pragma unroll
     for (int j = 0; j < NPL; ++j)
-        pl[j] = j < NQ ? (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask : w; // field plane: bit set <=> s = -1
+        pl[j] = j < NQ ? (w ^ Wr[(uint64_t)(uint32_t)nb[j] * rpad]) & pmask : w; // field plane: bit set <=> s = -1
     if (WARPS == 1)
         __syncwarp();
     else
@@ -310,8 +350,12 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
     if (oddP) even_allowed &= ~(1ull << (P - 1)); // slice P-1 neighbours slice 0: handled alone below
     const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
 
-    w ^= phase<NPL, 0, FULL>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr);
-    w ^= phase<NPL, 1, FULL>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr);
+    __shared__ uint2 s_bounce[8 * WARPS * 32]; // [phase][pair][thread]: private slots for the index bytes
+    uint2 *bounce = s_bounce + threadIdx.x;
+    w ^= phase<NPL, 0, FULL>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr, bounce,
+                             WARPS * 32);
+    w ^= phase<NPL, 1, FULL>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
+                             bounce + 4 * WARPS * 32, WARPS * 32);
     if (oddP) {
         const int k = P - 1;
         const uint64_t tl = w ^ rotl_ring(w, P, pmask), tr = w ^ rotr_ring(w, P, pmask);
@@ -330,14 +374,14 @@ __global__ void __launch_bounds__(WARPS * 32) piqmc_lut_pass_kernel(const __grid
         float dE = 0.0f;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-            const uint64_t x = j < NQ ? (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask : w & pmask;
+            const uint64_t x = j < NQ ? (w ^ Wr[(uint64_t)(uint32_t)nb[j] * rpad]) & pmask : w & pmask;
             dE += c[j] * (float)(P - 2 * __popcll(x));
         }
         uint32_t rnd[4];
         mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
         if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
     }
-    a.W[(long long)site * a.Rpad + r] = w;
+    a.W[(uint64_t)(uint32_t)site * rpad + r] = w;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -770,7 +814,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     a.pow2 = mcs_pow2_make();
     a.replica_offset = (uint32_t)(replica_offset + (uint64_t)st->win_lo());
     a.global_moves = global_moves ? 1 : 0;
-    a.tie_thr = getenv("MCS_PIQMC_ALWAYS_REFINE") ? 0xFFFFFFFFu : 0x1FFFFu;
+    a.tie_thr = getenv("MCS_PIQMC_ALWAYS_REFINE") ? 0xFFFFFFFFu : 0x20000u;
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;
