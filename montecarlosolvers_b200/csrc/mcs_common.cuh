@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -207,15 +208,6 @@ inline mcs_pow2_table mcs_pow2_make()
     return t;
 }
 
-// x shifted left by `delta` bits (right if negative) without touching the ALU pipe
-template <int DELTA>
-__device__ __forceinline__ uint32_t mcs_fma_shift(uint32_t x, const mcs_pow2_table &t)
-{
-    if (DELTA == 0) return x;
-    if (DELTA > 0) return x * t.up[DELTA > 0 ? DELTA : 0];
-    return __umulhi(x, t.down[DELTA < 0 ? -DELTA : 0]);
-}
-
 // call tags (counter word 3): which draw inside one (replica, site, sweep)
 enum {
     MCS_TAG_GROUP0 = 0,      // 0..15: PIQMC slice groups / SA bit groups
@@ -225,6 +217,127 @@ enum {
     MCS_TAG_REFINE = 0x80,   // OR-ed into a group tag: second half of the lazily refined uniforms
     MCS_TAG_INIT = 0x40000000u
 };
+
+// ---- building blocks shared by the bit-packed sweep kernels (mcs_piqmc.cu, mcs_sa.cu) ---------------
+// Instruction budget, measured on B200 (benchmarks/micro/pipe_rates.cu): ALU-pipe instructions (LOP3, PRMT,
+// IADD3, SHF, ISETP, VIADDMNMX) and FMA-pipe IMAD take 2 issue cycles per warp each and overlap with each
+// other; IMAD.WIDE / IMAD.HI hold the FMA pipe for 4 cycles AND the ALU pipe for 2.  A Philox4x32-10 call is
+// 20 IMAD.WIDE + 20 LOP3 -- both pipes saturated for ~65 cycles -- so (1) one call decides eight attempts
+// (lazily refined uniforms, below), (2) left shifts and the shifting-in of decision bits are IMAD / IMAD.X by
+// constant-bank powers of two (FMA pipe), (3) right shifts stay SHF (IMAD.HI would cost both pipes), (4) the
+// bytes of an index word are extracted by the LSU (shared-memory bounce) rather than by PRMT.
+
+// x shifted left by DELTA bits (right if negative): left on the FMA pipe, right on the ALU pipe
+template <int DELTA>
+__device__ __forceinline__ uint32_t mcs_plane_shift(uint32_t x, const mcs_pow2_table &t)
+{
+    if (DELTA == 0) return x;
+    if (DELTA > 0) return x * t.up[DELTA > 0 ? DELTA : 0];
+    return x >> (DELTA < 0 ? -DELTA : 0);
+}
+
+// byte i of v, zero extended (one PRMT; the second operand supplies the zero bytes)
+__device__ __forceinline__ uint32_t mcs_prmt_byte(uint32_t v, int i)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0x4440u | (uint32_t)i));
+    return r;
+}
+
+// threshold-table entry; with SH == 2 `off` already is the byte offset (pattern index * 4)
+template <int SH>
+__device__ __forceinline__ uint32_t mcs_lut_at(const uint32_t *lut, uint32_t off)
+{
+    return SH == 2 ? *(const uint32_t *)((const char *)lut + off) : lut[off];
+}
+
+// Decisions.  The tables hold ~T, so the carry of ~T + u is "u > T" = reject.  IMAD.X shifts it into a Horner
+// accumulator (acc * mul + carry, mul = 256 from the constant bank so that ptxas cannot turn it into an ALU
+// shift-add): visiting bytes 3,2,1,0 leaves the reject bit of byte i at bit 8 i.
+//
+// Lazily refined uniforms.  The uniform of an attempt is the 32-bit number u = (v << 16) | r, v = 16 bits of
+// the group pair's Philox call, r = 16 bits of a SECOND call (tag | MCS_TAG_REFINE) that is evaluated only when
+// it can matter: u <= T is decided by v alone unless v == T >> 16 (probability 2^-16), so one call serves
+// eight attempts instead of four.  Fast path: group A compares the word x itself (v = x >> 16; the low half
+// of x stands in for r and cannot change a decided comparison), group B compares x << 16 (v = x & 0xffff,
+// r = 0).  The sum s = ~T + u lies within 2^16 of a wrap whenever a comparison is undecided (the test
+// s + 2^16 < 2^17 mod 2^32 is conservative; one VIADDMNMX per attempt keeps the minimum in smin); the call is
+// then flagged and redone with both halves (mcs_refine_call) after the hot loop.  The outcome is bit-identical
+// to always evaluating both calls; tie_thr = 0xffffffff does exactly that (MCS_ALWAYS_REFINE=1, tested).
+__device__ __forceinline__ uint32_t mcs_horner_reject(uint32_t acc, uint32_t mul, uint32_t nT, uint32_t u,
+                                                      uint32_t &smin)
+{
+    uint32_t out, s;
+    asm("add.cc.u32 %1, %2, %3;\n\tmadc.lo.u32 %0, %4, %5, 0;"
+        : "=r"(out), "=r"(s)
+        : "r"(nT), "r"(u), "r"(acc), "r"(mul));
+    smin = min(smin, s + 0x10000u);
+    return out;
+}
+
+// flags = flags * 2 + (smin < tie_thr): the "call undecided" bit, again as carry + IMAD.X
+__device__ __forceinline__ void mcs_horner_flag(uint32_t &flags, uint32_t smin, uint32_t tie_thr, uint32_t two)
+{
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\tmadc.lo.u32 %0, %0, %3, 0;\n\t}"
+        : "+r"(flags)
+        : "r"(~smin), "r"(tie_thr), "r"(two));
+}
+
+// One Philox call decides the eight attempts whose pattern-index bytes are accA (group A) and accB (group B);
+// returns the Horner accumulators (reject bit of byte i at bit 8 i) and updates the undecided flags.  The index
+// bytes go through this thread's private 8-byte shared-memory slot (one 64-bit store, eight byte loads:
+// conflict-free, a warp's slots are consecutive) -- inline PTX so that the store is not forwarded into shifts.
+template <int SH>
+__device__ __forceinline__ void mcs_decide_call(uint32_t &chA, uint32_t &chB, uint32_t &flags, uint32_t accA,
+                                                uint32_t accB, const uint32_t *lut, uint32_t c0, uint32_t c1,
+                                                uint32_t c2, uint32_t c3, const mcs_philox_keys &keys,
+                                                const mcs_pow2_table &pow2, uint32_t tie_thr, uint2 *slot)
+{
+    uint32_t x[4];
+    mcs_philox4x32_10_rk(c0, c1, c2, c3, keys, x);
+    chA = 0;
+    chB = 0;
+    uint32_t smin = 0xFFFFFFFFu;
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(slot);
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(accA), "r"(accB) : "memory");
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+        uint32_t oA, oB;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oA) : "r"(saddr + i) : "memory");
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oB) : "r"(saddr + 4 + i) : "memory");
+        chA = mcs_horner_reject(chA, pow2.up[8], mcs_lut_at<SH>(lut, oA), x[i], smin);
+        chB = mcs_horner_reject(chB, pow2.up[8], mcs_lut_at<SH>(lut, oB), x[i] * pow2.up[16], smin);
+    }
+    mcs_horner_flag(flags, smin, tie_thr, pow2.up[1]);
+}
+
+// Slow path of the lazily refined uniforms: the same eight attempts with both Philox halves,
+// u = (v << 16) | r.  Out of line so that this cold code costs the hot path no registers.
+template <int SH>
+__device__ __noinline__ uint2 mcs_refine_call(uint32_t accA, uint32_t accB, const uint32_t *lut, uint32_t c0,
+                                              uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    uint32_t x[4], f[4];
+    mcs_philox4x32_10(c0, c1, c2, c3, k0, k1, x);
+    mcs_philox4x32_10(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
+    uint32_t chA = 0, chB = 0; // reject bit of byte i at bit 8 i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t TA = ~mcs_lut_at<SH>(lut, (accA >> (8 * i)) & 0xFFu);
+        const uint32_t TB = ~mcs_lut_at<SH>(lut, (accB >> (8 * i)) & 0xFFu);
+        const uint32_t uA = (x[i] & 0xFFFF0000u) | (f[i] >> 16);
+        const uint32_t uB = (x[i] << 16) | (f[i] & 0xFFFFu);
+        chA |= (uA > TA ? 1u : 0u) << (8 * i);
+        chB |= (uB > TB ? 1u : 0u) << (8 * i);
+    }
+    return make_uint2(chA, chB);
+}
+
+inline uint32_t mcs_tie_threshold()
+{
+    const char *e = getenv("MCS_ALWAYS_REFINE");
+    return (e && e[0] == '1') ? 0xFFFFFFFFu : 0x20000u;
+}
 
 // Metropolis acceptance threshold: the move is accepted iff a uniform 32-bit draw u satisfies
 // u <= T.  dE <= 0 -> always (qmc.pyx:140-141); otherwise P(accept) = ceil(p 2^32)/2^32 with

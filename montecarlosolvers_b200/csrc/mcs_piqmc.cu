@@ -64,23 +64,6 @@ __device__ __forceinline__ uint64_t rotr_ring(uint64_t w, int P, uint64_t mask)
     return ((w >> 1) | (w << (P - 1))) & mask; // bit k <- bit k+1
 }
 
-__device__ __forceinline__ uint32_t prmt_byte(uint32_t v, int i)
-{
-    // byte i of v, zero extended (one PRMT; the second operand supplies the zero bytes)
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0x4440u | (uint32_t)i));
-    return r;
-}
-
-// ---- instruction budget (measured on B200, benchmarks/micro/pipe_rates.cu) -----------------------
-// ALU-pipe instructions (LOP3, PRMT, IADD3, SHF, ISETP, VIADDMNMX) and FMA-pipe IMAD both take 2 issue cycles
-// per warp and overlap with each other; IMAD.WIDE / IMAD.HI hold the FMA pipe for 4 cycles AND the ALU pipe
-// for 2.  A Philox4x32-10 call is 20 IMAD.WIDE + 20 LOP3, i.e. both pipes saturated for ~65 cycles: it is
-// two thirds of the sweep.  Everything below is arranged around that: (1) one Philox call decides eight
-// attempts (lazily refined uniforms), (2) whatever can is moved from the ALU to the FMA pipe (shifts as IMAD
-// by a constant-bank power of two, the reject bit shifted in by IMAD.X), (3) right shifts stay SHF (IMAD.HI
-// would cost both pipes).
-
 // Pattern-index bits live at byte positions SH .. SH+NPL+1 of an index word (one byte per slice).  With at
 // most 6 planes the index is stored pre-multiplied by 4 (SH = 2) so that the extracted byte IS the
 // shared-memory byte offset of the threshold.
@@ -92,21 +75,6 @@ struct LutGeom {
     static constexpr int NPAIR = (NPP + 1) / 2;
 };
 
-template <int SH>
-__device__ __forceinline__ uint32_t lut_at(const uint32_t *lut, uint32_t off)
-{
-    return SH == 2 ? *(const uint32_t *)((const char *)lut + off) : lut[off];
-}
-
-// x shifted left by DELTA bits (right if negative): left on the FMA pipe, right on the ALU pipe
-template <int DELTA>
-__device__ __forceinline__ uint32_t plane_shift(uint32_t x, const mcs_pow2_table &t)
-{
-    if (DELTA == 0) return x;
-    if (DELTA > 0) return x * t.up[DELTA > 0 ? DELTA : 0];
-    return x >> (DELTA < 0 ? -DELTA : 0);
-}
-
 // Within one Trotter-parity phase only every other bit of a plane is used, so two planes are interleaved into
 // one word first (plane 2j lowered to / kept at the even bit, plane 2j+1 one above it): the per-group
 // transposition then moves TWO index bits with one shift + one LOP3.
@@ -116,8 +84,8 @@ __device__ __forceinline__ uint32_t plane_shift(uint32_t x, const mcs_pow2_table
 template <int PARITY>
 __device__ __forceinline__ uint32_t interleave_pair(uint32_t a, uint32_t b, const mcs_pow2_table &pow2)
 {
-    if (PARITY == 0) return (a & 0x55555555u) | (plane_shift<1>(b, pow2) & 0xAAAAAAAAu);
-    return (plane_shift<-1>(a, pow2) & 0x55555555u) | (b & 0xAAAAAAAAu);
+    if (PARITY == 0) return (a & 0x55555555u) | (mcs_plane_shift<1>(b, pow2) & 0xAAAAAAAAu);
+    return (mcs_plane_shift<-1>(a, pow2) & 0x55555555u) | (b & 0xAAAAAAAAu);
 }
 
 // Index word of group G (slices 8 i + 7 - G of this 32-bit half, i = 0..3; 7 - G has the phase's parity):
@@ -132,64 +100,16 @@ __device__ __forceinline__ uint32_t gather_index(const uint32_t (&m)[(NPP + 1) /
     uint32_t acc = 0;
 #define MCS_PAIRWORD(j)                                                                                       \
     if (2 * (j) + 1 < NPP)                                                                                    \
-        acc |= plane_shift<SH + 2 * (j) - LOW>(m[(j) < (NPP + 1) / 2 ? (j) : 0], pow2) & (0x03030303u << (SH + 2 * (j))); \
+        acc |= mcs_plane_shift<SH + 2 * (j) - LOW>(m[(j) < (NPP + 1) / 2 ? (j) : 0], pow2) & (0x03030303u << (SH + 2 * (j))); \
     else if (2 * (j) < NPP)                                                                                   \
-        acc |= plane_shift<SH + 2 * (j) - S>(m[(j) < (NPP + 1) / 2 ? (j) : 0], pow2) & (0x01010101u << (SH + 2 * (j)));
+        acc |= mcs_plane_shift<SH + 2 * (j) - S>(m[(j) < (NPP + 1) / 2 ? (j) : 0], pow2) & (0x01010101u << (SH + 2 * (j)));
     MCS_PAIRWORD(0) MCS_PAIRWORD(1) MCS_PAIRWORD(2) MCS_PAIRWORD(3)
 #undef MCS_PAIRWORD
     return acc;
 }
 
-// ---- decisions -------------------------------------------------------------------------------------
-// The table holds ~T, so the carry of ~T + u is "u > T" = reject.  IMAD.X shifts it into a per-group Horner
-// accumulator (acc * 256 + carry: one FMA-pipe instruction; the multiplier comes from the constant bank so
-// that ptxas cannot turn it into an ALU shift-add).  Bytes are visited 3,2,1,0, so acc ends with the reject
-// bit of byte i at bit 8 i.
-//
-// Lazily refined uniforms.  The uniform of an attempt is the 32-bit number u = (v << 16) | r, v = 16 bits of
-// the group pair's Philox call, r = 16 bits of a SECOND call (tag | MCS_TAG_REFINE) that is evaluated only when
-// it can matter: u <= T is decided by v alone unless v == T >> 16 (probability 2^-16), so one call serves
-// eight attempts instead of four.  Fast path: group A compares the word x itself (v = x >> 16; the low half
-// of x stands in for r and cannot change a decided comparison), group B compares x << 16 (v = x & 0xffff,
-// r = 0).  The sum s = ~T + u lies within 2^16 of a wrap whenever a comparison is undecided (the test
-// s + 2^16 < 2^17 mod 2^32 is conservative; one VIADDMNMX per attempt keeps the minimum), and then the whole
-// call is flagged and redone with both halves at the end of the phase (refine_pair, cold code, ~0.4 % of
-// the calls -- slices of one parity do not interact, so the order does not matter).  The outcome is
-// bit-identical to always evaluating both calls; tie_thr = 0xffffffff does exactly that and
-// tests/test_gpu_production.py compares the two.
-__device__ __forceinline__ uint32_t horner_reject(uint32_t acc, uint32_t mul, uint32_t nT, uint32_t u, uint32_t &smin)
-{
-    uint32_t out, s;
-    asm("add.cc.u32 %1, %2, %3;\n\tmadc.lo.u32 %0, %4, %5, 0;"
-        : "=r"(out), "=r"(s)
-        : "r"(nT), "r"(u), "r"(acc), "r"(mul));
-    smin = min(smin, s + 0x10000u);
-    return out;
-}
-
-// Slow path of the lazily refined uniforms: redo one flagged call (groups GA, GB of one half) with both Philox
-// halves, u = (v << 16) | r, and replace its eight reject bits.  Runs at the end of the phase; the Philox
-// calls and comparisons sit in an out-of-line function so that this cold code costs the hot path no registers.
-template <int SH>
-__device__ __noinline__ uint2 refine_call(uint32_t accA, uint32_t accB, const uint32_t *lut, uint32_t c0, uint32_t c1,
-                                          uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
-{
-    uint32_t x[4], f[4];
-    mcs_philox4x32_10(c0, c1, c2, c3, k0, k1, x);
-    mcs_philox4x32_10(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
-    uint32_t chA = 0, chB = 0; // reject bit of byte i at bit 8 i
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t TA = ~lut_at<SH>(lut, (accA >> (8 * i)) & 0xFFu);
-        const uint32_t TB = ~lut_at<SH>(lut, (accB >> (8 * i)) & 0xFFu);
-        const uint32_t uA = (x[i] & 0xFFFF0000u) | (f[i] >> 16);
-        const uint32_t uB = (x[i] << 16) | (f[i] & 0xFFFFu);
-        chA |= (uA > TA ? 1u : 0u) << (8 * i);
-        chB |= (uB > TB ? 1u : 0u) << (8 * i);
-    }
-    return make_uint2(chA, chB);
-}
-
+// Slow path (see mcs_common.cuh, "lazily refined uniforms"): redo one flagged call (groups GA, GB of one half)
+// with both Philox halves and replace its eight reject bits.  Runs at the end of the phase.
 template <int NPL, int GA, int GB, int PARITY>
 __device__ __forceinline__ void refine_pair(uint32_t &rej, const uint32_t (&m)[LutGeom<NPL>::NPAIR],
                                             const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -198,43 +118,22 @@ __device__ __forceinline__ void refine_pair(uint32_t &rej, const uint32_t (&m)[L
     constexpr int NPP = LutGeom<NPL>::NPP;
     const uint32_t accA = gather_index<NPP, GA, PARITY>(m, pow2);
     const uint32_t accB = gather_index<NPP, GB, PARITY>(m, pow2);
-    const uint2 ch = refine_call<LutGeom<NPL>::SH>(accA, accB, lut, c0, c1, c2, c3, keys.rk[0], keys.rk[1]);
+    const uint2 ch = mcs_refine_call<LutGeom<NPL>::SH>(accA, accB, lut, c0, c1, c2, c3, keys.rk[0], keys.rk[1]);
     rej = (rej & ~((0x01010101u << (7 - GA)) | (0x01010101u << (7 - GB)))) | (ch.x << (7 - GA)) | (ch.y << (7 - GB));
 }
 
-// groups GA and GB (same half, same parity) share one Philox call; rej accumulates REJECT bits, flags the
-// calls whose fast path was not conclusive (Horner again: flags * 2 + undecided)
+// groups GA and GB (same half, same parity) share one Philox call; rej accumulates REJECT bits
 template <int NPL, int GA, int GB, int HALF>
 __device__ __forceinline__ void decide_pair(uint32_t &rej, uint32_t &flags, uint32_t accA, uint32_t accB,
                                             const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2,
                                             uint32_t c3hi, const mcs_philox_keys &keys, const mcs_pow2_table &pow2,
                                             uint32_t tie_thr, uint2 *slot)
 {
-    constexpr int SH = LutGeom<NPL>::SH;
-    uint32_t x[4];
-    mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(HALF * 8 + GA), keys, x);
-    uint32_t chA = 0, chB = 0, smin = 0xFFFFFFFFu;
-    // The eight index bytes are extracted by the LSU, not the ALU pipe (the binding unit): one 64-bit store of
-    // the two index words to this thread's private slot, eight byte loads (conflict-free: a warp's slots are
-    // 32 consecutive 8-byte words).  Inline PTX so that the compiler cannot forward the store into shifts.
-    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(slot);
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(accA), "r"(accB) : "memory");
-#pragma unroll
-    for (int i = 3; i >= 0; --i) {
-        uint32_t oA, oB;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oA) : "r"(saddr + i) : "memory");
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oB) : "r"(saddr + 4 + i) : "memory");
-        const uint32_t nTA = lut_at<SH>(lut, oA);
-        const uint32_t nTB = lut_at<SH>(lut, oB);
-        chA = horner_reject(chA, pow2.up[8], nTA, x[i], smin);
-        chB = horner_reject(chB, pow2.up[8], nTB, x[i] * pow2.up[16], smin);
-    }
+    uint32_t chA, chB;
+    mcs_decide_call<LutGeom<NPL>::SH>(chA, chB, flags, accA, accB, lut, c0, c1, c2,
+                                      c3hi | (uint32_t)(HALF * 8 + GA), keys, pow2, tie_thr, slot);
     rej = chA * pow2.up[7 - GA] + rej;
     rej = chB * pow2.up[7 - GB] + rej;
-    // undecided <=> smin < tie_thr <=> ~smin + tie_thr carries: IADD3 + IMAD.X like the decisions themselves
-    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\tmadc.lo.u32 %0, %0, %3, 0;\n\t}"
-        : "+r"(flags)
-        : "r"(~smin), "r"(tie_thr), "r"(pow2.up[1]));
 }
 
 // One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in `allowed`,
@@ -814,7 +713,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     a.pow2 = mcs_pow2_make();
     a.replica_offset = (uint32_t)(replica_offset + (uint64_t)st->win_lo());
     a.global_moves = global_moves ? 1 : 0;
-    a.tie_thr = getenv("MCS_PIQMC_ALWAYS_REFINE") ? 0xFFFFFFFFu : 0x20000u;
+    a.tie_thr = mcs_tie_threshold();
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;

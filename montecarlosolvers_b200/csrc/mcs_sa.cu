@@ -33,45 +33,59 @@ struct SaPass {
     mcs_pow2_table pow2;
     uint32_t sweep_lo, sweep_hi;
     uint32_t word_offset; // replica_offset / 32
+    uint32_t tie_thr;     // lazily refined uniforms (mcs_common.cuh)
 };
 
-__device__ __forceinline__ uint32_t prmt_byte(uint32_t v, int i)
+// Index word of group Q (restarts 8 i + 7 - Q of the word, i = 0..3): plane p's bit of restart 8 i + 7 - Q goes
+// to bit 8 i + SH + p, i.e. the plane is shifted by SH + p - 7 + Q and merged with one LOP3.  Every bit of
+// every plane is used here (no Trotter parity), so planes cannot be interleaved first as in mcs_piqmc.cu.
+template <int NPL, int Q>
+__device__ __forceinline__ uint32_t sa_gather_index(const uint32_t (&pl)[NPL], const mcs_pow2_table &pow2)
 {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0x4440u | (uint32_t)i));
-    return r;
+    constexpr int SH = NPL <= 6 ? 2 : 0;
+    uint32_t acc = 0;
+#define MCS_SA_PLANE(p)                                                                                       \
+    if (p < NPL) acc |= mcs_plane_shift<SH + p - 7 + Q>(pl[p < NPL ? p : 0], pow2) & (0x01010101u << (SH + p));
+    MCS_SA_PLANE(0) MCS_SA_PLANE(1) MCS_SA_PLANE(2) MCS_SA_PLANE(3)
+    MCS_SA_PLANE(4) MCS_SA_PLANE(5) MCS_SA_PLANE(6) MCS_SA_PLANE(7)
+#undef MCS_SA_PLANE
+    return acc;
 }
 
-// WARPS warps per CTA, all on the same site; the table sits at a compile-time shared address and,
-// for up to 6 planes, the pattern index is kept pre-multiplied by 4 (= the LDS byte offset).
-template <int NPL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) sa_lut_pass_kernel(const __grid_constant__ SaPass a)
+// WARPS warps per CTA, all on the same site; grid = (CTAs per site, sites of the colour class).  The table
+// (complemented thresholds, see mcs_common.cuh) sits at a compile-time shared address and, for up to 6 planes,
+// the pattern index is kept pre-multiplied by 4 (= the LDS byte offset).  Groups 2q and 2q+1 share one Philox
+// call (lazily refined uniforms).  FLD: the instance has (1) / has no (0) field plane.
+template <int NPL, int WARPS, int FLD>
+__global__ void __launch_bounds__(WARPS * 32, 8) sa_lut_pass_kernel(const __grid_constant__ SaPass a)
 {
-    constexpr int ENT = 1 << NPL;
+    constexpr int ENT = 1 << NPL, NQ = NPL - FLD;
     constexpr int SH = NPL <= 6 ? 2 : 0;
     __shared__ uint32_t s_lut[ENT];
+    __shared__ uint2 s_bounce[4 * WARPS * 32]; // [call][thread]: private slots for the index bytes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cps = a.chunks / WARPS; // CTAs per site
-    const int site = __ldg(&a.sites[blockIdx.x / cps]);
-    const long long g = ((long long)(blockIdx.x % cps) * WARPS + warp) * 32 + lane;
+    const unsigned si = blockIdx.y + 65535u * blockIdx.z;
+    if (si >= (unsigned)a.nsites) return; // only when the colour class has more than 65535 sites (CTA-uniform)
+    const int site = __ldg(&a.sites[si]);
+    const uint32_t g = ((uint32_t)blockIdx.x * WARPS + warp) * 32 + lane;
 
     float c[NPL];
     int nb[NPL];
 #pragma unroll
     for (int j = 0; j < NPL; ++j) {
-        if (j < a.nq) {
-            nb[j] = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
-            c[j] = -2.0f * __ldg(&a.ell_J[(long long)site * a.dpad + j]); // sa.pyx:91-94
+        if (j < NQ) {
+            nb[j] = __ldg(&a.ell_idx[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j]);
+            c[j] = -2.0f * __ldg(&a.ell_J[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j]); // sa.pyx:91-94
         } else {
             nb[j] = site;
-            c[j] = (a.field && j == a.nq) ? -2.0f * __ldg(&a.h[site]) : 0.0f;
+            c[j] = -2.0f * __ldg(&a.h[site]);
         }
     }
     for (int e = threadIdx.x; e < ENT; e += WARPS * 32) {
         float dE = 0.0f;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) dE += ((e >> j) & 1) ? -c[j] : c[j];
-        s_lut[e] = mcs_accept_threshold(dE, a.nl2e_over_t);
+        s_lut[e] = ~mcs_accept_threshold(dE, a.nl2e_over_t);
     }
     if (WARPS == 1)
         __syncwarp();
@@ -79,40 +93,38 @@ __global__ void __launch_bounds__(WARPS * 32) sa_lut_pass_kernel(const __grid_co
         __syncthreads();
     if (g >= a.G) return;
 
-    uint32_t v = a.V[(long long)site * a.G + g];
+    const uint32_t G32 = (uint32_t)a.G;
+    uint32_t *Vg = a.V + g;
+    const uint32_t v = Vg[(uint64_t)(uint32_t)site * G32];
     uint32_t pl[NPL];
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        if (j < a.nq)
-            pl[j] = v ^ a.V[(long long)nb[j] * a.G + g];
-        else
-            pl[j] = (a.field && j == a.nq) ? v : 0u;
-    }
-    const uint32_t c0 = a.word_offset + (uint32_t)g, c1 = (uint32_t)site;
-    uint32_t flip = 0;
-    // group Q holds restarts 8 i + 7 - Q; plane p's bit of restart i goes to bit 8i + SH + p of the index word:
-    // shift by SH + p - 7 + Q as IMAD / IMAD.HI (FMA pipe) + one merging LOP3 (ALU pipe)
-#define MCS_SA_PLANE(Q, p)                                                                                    \
-    if (p < NPL) acc |= mcs_fma_shift<SH + p - 7 + Q>(pl[p < NPL ? p : 0], a.pow2) & (0x01010101u << (SH + p));
-#define MCS_SA_GROUP(Q)                                                                                       \
+    for (int j = 0; j < NPL; ++j) pl[j] = j < NQ ? v ^ Vg[(uint64_t)(uint32_t)nb[j] * G32] : v;
+    const uint32_t c0 = a.word_offset + g, c1 = (uint32_t)site, c2 = a.sweep_lo, c3hi = a.sweep_hi << 8;
+    uint2 *bounce = s_bounce + threadIdx.x;
+    uint32_t rej = 0, flags = 0;
+#define MCS_SA_CALL(q)                                                                                        \
     {                                                                                                         \
-        uint32_t acc = 0;                                                                                     \
-        MCS_SA_PLANE(Q, 0) MCS_SA_PLANE(Q, 1) MCS_SA_PLANE(Q, 2) MCS_SA_PLANE(Q, 3)                           \
-        MCS_SA_PLANE(Q, 4) MCS_SA_PLANE(Q, 5) MCS_SA_PLANE(Q, 6) MCS_SA_PLANE(Q, 7)                           \
-        uint32_t rnd[4];                                                                                      \
-        mcs_philox4x32_10_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(Q), a.keys, rnd);             \
-        _Pragma("unroll") for (int i = 0; i < 4; ++i)                                                         \
-        {                                                                                                     \
-            const uint32_t off = prmt_byte(acc, i);                                                           \
-            const uint32_t T = SH == 2 ? *(const uint32_t *)((const char *)s_lut + off) : s_lut[off];         \
-            if (rnd[i] <= T) flip |= 1u << (8 * i + 7 - (Q));                                                 \
-        }                                                                                                     \
+        uint32_t chA, chB;                                                                                    \
+        mcs_decide_call<SH>(chA, chB, flags, sa_gather_index<NPL, 2 * (q)>(pl, a.pow2),                       \
+                            sa_gather_index<NPL, 2 * (q) + 1>(pl, a.pow2), s_lut, c0, c1, c2,                 \
+                            c3hi | (uint32_t)(2 * (q)), a.keys, a.pow2, a.tie_thr, bounce + (q) * WARPS * 32);\
+        rej = chA * a.pow2.up[7 - 2 * (q)] + rej;                                                             \
+        rej = chB * a.pow2.up[6 - 2 * (q)] + rej;                                                             \
     }
-    MCS_SA_GROUP(0) MCS_SA_GROUP(1) MCS_SA_GROUP(2) MCS_SA_GROUP(3)
-    MCS_SA_GROUP(4) MCS_SA_GROUP(5) MCS_SA_GROUP(6) MCS_SA_GROUP(7)
-#undef MCS_SA_GROUP
-#undef MCS_SA_PLANE
-    a.V[(long long)site * a.G + g] = v ^ flip;
+    MCS_SA_CALL(0) MCS_SA_CALL(1) MCS_SA_CALL(2) MCS_SA_CALL(3)
+#undef MCS_SA_CALL
+    if (flags) { // rare: Horner order, call 0 ended at bit 3 ... call 3 at bit 0
+#define MCS_SA_REFINE(q)                                                                                      \
+    if (flags & (8u >> (q))) {                                                                                \
+        const uint2 ch = mcs_refine_call<SH>(sa_gather_index<NPL, 2 * (q)>(pl, a.pow2),                       \
+                                             sa_gather_index<NPL, 2 * (q) + 1>(pl, a.pow2), s_lut, c0, c1, c2,\
+                                             c3hi | (uint32_t)(2 * (q)), a.keys.rk[0], a.keys.rk[1]);         \
+        rej = (rej & ~(0x03030303u << (6 - 2 * (q)))) | (ch.x << (7 - 2 * (q))) | (ch.y << (6 - 2 * (q)));    \
+    }
+        MCS_SA_REFINE(0) MCS_SA_REFINE(1) MCS_SA_REFINE(2) MCS_SA_REFINE(3)
+#undef MCS_SA_REFINE
+    }
+    Vg[(uint64_t)(uint32_t)site * G32] = v ^ ~rej;
 }
 
 // general-degree pass: energy differences accumulated over the ELL row, one register per restart
@@ -226,29 +238,40 @@ __global__ void sa_energy_kernel(const uint32_t *__restrict__ V, const int32_t *
     out[r] = e;
 }
 
-template <int NPL>
-void launch_lut_w(int warps, long long items, cudaStream_t s, const SaPass &a)
+template <int NPL, int FLD>
+void launch_lut_wf(int warps, cudaStream_t s, const SaPass &a)
 {
-    const unsigned grid = (unsigned)(items / warps);
+    // a.chunks = warps of work per site; `warps` divides it, so a CTA never straddles two sites
+    const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
+    const dim3 grid((unsigned)(a.chunks / warps), ny, nz);
     if (warps == 4)
-        sa_lut_pass_kernel<NPL, 4><<<grid, 128, 0, s>>>(a);
+        sa_lut_pass_kernel<NPL, 4, FLD><<<grid, 128, 0, s>>>(a);
     else if (warps == 2)
-        sa_lut_pass_kernel<NPL, 2><<<grid, 64, 0, s>>>(a);
+        sa_lut_pass_kernel<NPL, 2, FLD><<<grid, 64, 0, s>>>(a);
     else
-        sa_lut_pass_kernel<NPL, 1><<<grid, 32, 0, s>>>(a);
+        sa_lut_pass_kernel<NPL, 1, FLD><<<grid, 32, 0, s>>>(a);
 }
 
-void launch_lut(int npl, int warps, long long items, cudaStream_t s, const SaPass &a)
+template <int NPL>
+void launch_lut_w(int warps, cudaStream_t s, const SaPass &a)
+{
+    if (a.field)
+        launch_lut_wf<NPL, 1>(warps, s, a);
+    else
+        launch_lut_wf<NPL, 0>(warps, s, a);
+}
+
+void launch_lut(int npl, int warps, cudaStream_t s, const SaPass &a)
 {
     switch (npl) {
-    case 1: launch_lut_w<1>(warps, items, s, a); break;
-    case 2: launch_lut_w<2>(warps, items, s, a); break;
-    case 3: launch_lut_w<3>(warps, items, s, a); break;
-    case 4: launch_lut_w<4>(warps, items, s, a); break;
-    case 5: launch_lut_w<5>(warps, items, s, a); break;
-    case 6: launch_lut_w<6>(warps, items, s, a); break;
-    case 7: launch_lut_w<7>(warps, items, s, a); break;
-    default: launch_lut_w<8>(warps, items, s, a); break;
+    case 1: launch_lut_w<1>(warps, s, a); break;
+    case 2: launch_lut_w<2>(warps, s, a); break;
+    case 3: launch_lut_w<3>(warps, s, a); break;
+    case 4: launch_lut_w<4>(warps, s, a); break;
+    case 5: launch_lut_w<5>(warps, s, a); break;
+    case 6: launch_lut_w<6>(warps, s, a); break;
+    case 7: launch_lut_w<7>(warps, s, a); break;
+    default: launch_lut_w<8>(warps, s, a); break;
     }
 }
 
@@ -277,6 +300,7 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
     a.keys = mcs_philox_expand(seed);
     a.pow2 = mcs_pow2_make();
     a.word_offset = (uint32_t)(replica_offset >> 5);
+    a.tie_thr = mcs_tie_threshold();
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const bool lut = npl <= 8;
     const int warps = (a.chunks % 4 == 0) ? 4 : (a.chunks % 2 == 0) ? 2 : 1;
@@ -298,7 +322,7 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
                 if (a.nsites == 0) continue;
                 const long long items = (long long)a.nsites * a.chunks;
                 if (lut)
-                    launch_lut(npl, warps, items, inst->stream, a);
+                    launch_lut(npl, warps, inst->stream, a);
                 else
                     sa_direct_pass_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kWarps * 32, 0,
                                             inst->stream>>>(a);

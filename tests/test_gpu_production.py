@@ -265,7 +265,7 @@ def test_results_do_not_depend_on_sharding_or_call_splitting(mcs):
 def test_lazily_refined_uniforms_equal_always_refined(mcs, case):
     """The PIQMC pass decides eight attempts per Philox call from 16-bit halves and evaluates the second
     (refinement) call only when a comparison is within 2^-16 of its threshold.  That must be invisible:
-    MCS_PIQMC_ALWAYS_REFINE=1 evaluates both calls for every attempt (the defining 32-bit-uniform algorithm)
+    MCS_ALWAYS_REFINE=1 evaluates both calls for every attempt (the defining 32-bit-uniform algorithm)
     and the trajectories must agree bit for bit -- including runs long / cold enough that refinements occur
     (about one attempt in 2^15 takes the slow path)."""
     if case == "torus_fields_P64":
@@ -285,7 +285,7 @@ def test_lazily_refined_uniforms_equal_always_refined(mcs, case):
     out = []
     for always in (False, True):
         if always:
-            os.environ["MCS_PIQMC_ALWAYS_REFINE"] = "1"
+            os.environ["MCS_ALWAYS_REFINE"] = "1"
         try:
             st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
             st.upload_spins(np.ascontiguousarray(c0))
@@ -293,12 +293,44 @@ def test_lazily_refined_uniforms_equal_always_refined(mcs, case):
             out.append(st.download_spins())
             st.close()
         finally:
-            os.environ.pop("MCS_PIQMC_ALWAYS_REFINE", None)
+            os.environ.pop("MCS_ALWAYS_REFINE", None)
     assert not np.array_equal(out[0], c0)
     assert np.array_equal(out[0], out[1])
     # attempts made: R S P n; expected refinements ~ attempts / 2^15 (conservative test) -- make sure the case
     # is large enough that the slow path was actually exercised
     assert R * S * P * n / 2.0 ** 15 > 50
+
+
+@pytest.mark.parametrize("case", ["torus_fields", "santoro", "graph_deg7"])
+def test_sa_lazily_refined_uniforms_equal_always_refined(mcs, case):
+    """Same invariance for the SA pass (mcs_sa.cu shares the decision code, mcs_common.cuh)."""
+    if case == "torus_fields":
+        nbs, R, S = inst.torus(8, seed=21, fields=True)[1], 4096, 300
+    elif case == "santoro":
+        nbs, R, S = inst.santoro()[1], 1024, 20
+    else:
+        nbs, R, S = inst.random_graph(60, 75, seed=7, fields=True)[1], 2048, 300
+    n = nbs.shape[0]
+    I = mcs.Instance(nbs)
+    if I.maxdeg + int(I.has_field) > 8:
+        pytest.skip("instance is served by the general-degree kernel")
+    sched = np.linspace(3.0, 0.05, S)
+    c0 = (2 * np.random.RandomState(3).randint(2, size=(R, n)) - 1).astype(np.int8)
+    out = []
+    for always in (False, True):
+        if always:
+            os.environ["MCS_ALWAYS_REFINE"] = "1"
+        try:
+            st = mcs.State(I, mcs._lib.KIND_SA, R, 1)
+            st.upload_spins(c0)
+            st.sa_sweeps(sched, 1, seed=99)
+            out.append(st.download_spins())
+            st.close()
+        finally:
+            os.environ.pop("MCS_ALWAYS_REFINE", None)
+    assert not np.array_equal(out[0], c0)
+    assert np.array_equal(out[0], out[1])
+    assert R * S * n / 2.0 ** 15 > 50
 
 
 def test_time_dependent_tables_production(mcs):
