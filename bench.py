@@ -56,6 +56,38 @@ def load_instance():
     return tools.GenerateNeighbors(NSPINS, J, 4), name
 
 
+def roofline(achieved, peak, have_peaks, R, ms_per_launch, bytes_per_launch, n_pass, args):
+    """The base contract's HBM roofline of the pass kernel, plus what ncu says actually binds it.  The ncu
+    numbers come from the committed capture profiles/r01_piqmc_lut_pass_ncu.json (profiles/capture.sh +
+    profiles/summarize_ncu.py), taken at 4096 replicas per GPU; traffic scales linearly with the replicas."""
+    prof, src = None, os.path.join("profiles", "r01_piqmc_lut_pass_ncu.json")
+    try:
+        prof = json.load(open(os.path.join(ROOT, src)))
+    except (OSError, ValueError):
+        pass
+    attempts_per_launch = bytes_per_launch / 0.25
+    out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "traffic": args.traffic, "kernel": "piqmc_lut_pass_kernel<4,4,true,0>", "ms_per_launch": ms_per_launch,
+           "algorithmic_bytes_per_launch": bytes_per_launch,
+           "algorithmic_bytes_per_attempt": 0.25,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if have_peaks else "fallback 6650 GB/s",
+           "note": "the sweep is instruction bound (Philox multiplies and the per-attempt threshold compare on the "
+                   "ALU / FMA pipes), not HBM bound: see binding_unit, profiles/ and DESIGN.md section 4"}
+    if prof:
+        scale = R / 4096.0
+        if args.traffic is None:
+            out["traffic"] = (prof["dram_bytes_read"] + prof["dram_bytes_write"]) * scale
+        out["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum, " + src
+        out["binding_unit"] = {
+            "unit": "SM ALU pipe (+ FMA pipe held by IMAD.WIDE): instruction issue",
+            "alu_pipe_inst_pct_of_peak": prof["alu_pipe_inst_pct_of_peak"],
+            "fma_pipe_cycles_active_pct": prof["fma_pipe_cycles_active_pct"],
+            "issue_slots_busy_pct": prof["issue_slots_busy_pct"],
+            "instructions_per_attempt": prof["warp_instructions"] * 32.0 / (attempts_per_launch / scale),
+            "dram_pct_of_peak": prof["dram_pct_of_peak"], "source": "ncu --set full, " + src}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
@@ -313,21 +345,7 @@ def run_ours(args, out):
                        "wall_s_timed_region": wall},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         # ncu --set full (profiles/r01_piqmc_lut_pass_ncu_full.txt): 212.6 MB read + 74.6 MB
-                         # written per launch at 4096 replicas; scales linearly with the replicas per GPU
-                         "traffic": args.traffic if args.traffic is not None else 287.2e6 * R / 4096.0,
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_piqmc_lut_pass_ncu_full.txt",
-                         "kernel": "piqmc_lut_pass_kernel<4,4,true>", "ms_per_launch": ms_per_launch,
-                         "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                         "note": "the sweep is instruction bound (Philox + threshold lookup per attempt), not HBM "
-                                 "bound: see binding_unit, profiles/ and DESIGN.md section 4",
-                         # what ncu says binds this kernel (profiles/r01_piqmc_lut_pass_ncu_full.txt)
-                         "binding_unit": {"unit": "SM ALU pipe / issue slots", "alu_pipe_pct_of_peak": 65.4,
-                                          "issue_slots_busy_pct": 58.0, "instructions_per_attempt": 20.1,
-                                          "dram_pct_of_peak": 4.4, "source": "ncu --set full, profiles/r01_piqmc_lut_pass_ncu_full.txt"}},
+            "roofline": roofline(achieved, peak, bool(peaks), R, ms_per_launch, bytes_per_launch, n_pass, args),
             "e2e": e2e,
             "result": {"best_residual_energy_per_spin": None, "mean_best_slice_energy": float(np.mean(energies)),
                        "best_anneal": int(best)},

@@ -187,9 +187,35 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
     const size_t per_replica = (size_t)inst->N * P;
     MCS_TRY(mcs_state_reserve_stage(st, (size_t)R * per_replica));
     int8_t *stage = (int8_t *)st->d_stage;
-    // dense instances expand the whole batch per call: no chunking there
-    const int nchunks = (R >= 1024 && !mcs_dense_supported(inst, (int)P)) ? 4 : 1;
-    if (nchunks > 1 && !inst->s_in) {
+    // Replicas are independent, so the batch is cut into windows and the H2D copy of window c+1 / the D2H copy of
+    // window c-1 overlap the sweeps of window c.  The first and the last window are small (their copies are the
+    // only exposed ones), the middle one large (every window costs a launch tail per pass); measured on the
+    // cfg3 workload: 3.5 % over the resident time (benchmarks/e2e_probe.py).
+    // Dense instances expand the whole batch per call: no windows there.
+    long long win[8];
+    int nwin = 0;
+    if (R >= 1024 && !mcs_dense_supported(inst, (int)P)) {
+        const long long edge = std::max<long long>(128, ((st->Rpad / 16 + 127) / 128) * 128);
+        win[nwin++] = edge;
+        win[nwin++] = st->Rpad - 2 * edge;
+        win[nwin++] = edge;
+        if (const char *e = getenv("MCS_WINDOWS")) { // experiments: comma-separated window sizes (multiples of 128)
+            nwin = 0;
+            long long tot = 0;
+            for (const char *q = e; *q && nwin < 7;) {
+                char *end;
+                const long long v = strtoll(q, &end, 10);
+                if (end == q || v <= 0 || v % 128) break;
+                win[nwin++] = v;
+                tot += v;
+                q = *end == ',' ? end + 1 : end;
+            }
+            if (tot < st->Rpad) win[nwin++] = st->Rpad - tot;
+        }
+    } else {
+        win[nwin++] = st->Rpad;
+    }
+    if (nwin > 1 && !inst->s_in) {
         MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_in, cudaStreamNonBlocking));
         MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_out, cudaStreamNonBlocking));
         for (int q = 0; q < 8; ++q) {
@@ -197,29 +223,30 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
             MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_done[q], cudaEventDisableTiming));
         }
     }
-    const long long chunk = nchunks == 1 ? st->Rpad : ((st->Rpad / nchunks + 127) / 128) * 128;
-    cudaStream_t s_in = nchunks == 1 ? inst->stream : inst->s_in;
-    cudaStream_t s_out = nchunks == 1 ? inst->stream : inst->s_out;
-    int used = 0;
-    for (long long r0 = 0; r0 < R; r0 += chunk, ++used) { // uploads, back to back on the H2D stream
-        const long long nvalid = std::min<long long>(chunk, R - r0);
-        MCS_CUDA(cudaMemcpyAsync(stage + r0 * per_replica, confs + r0 * per_replica, (size_t)nvalid * per_replica,
-                                 cudaMemcpyHostToDevice, s_in));
-        if (nchunks > 1) MCS_CUDA(cudaEventRecord(inst->ev_up[used], s_in));
+    cudaStream_t s_in = nwin == 1 ? inst->stream : inst->s_in;
+    cudaStream_t s_out = nwin == 1 ? inst->stream : inst->s_out;
+    {
+        long long r0 = 0;
+        for (int c = 0; c < nwin && r0 < R; r0 += win[c], ++c) { // uploads, back to back on the H2D stream
+            const long long nvalid = std::min<long long>(win[c], R - r0);
+            MCS_CUDA(cudaMemcpyAsync(stage + r0 * per_replica, confs + r0 * per_replica,
+                                     (size_t)nvalid * per_replica, cudaMemcpyHostToDevice, s_in));
+            if (nwin > 1) MCS_CUDA(cudaEventRecord(inst->ev_up[c], s_in));
+        }
     }
     int rc = MCS_OK;
-    int c = 0;
-    for (long long r0 = 0; r0 < R && rc == MCS_OK; r0 += chunk, ++c) {
-        const long long nvalid = std::min<long long>(chunk, R - r0);
+    long long r0 = 0;
+    for (int c = 0; c < nwin && r0 < R && rc == MCS_OK; r0 += win[c], ++c) {
+        const long long nvalid = std::min<long long>(win[c], R - r0);
         st->v0 = r0;
-        st->vR = std::min<long long>(chunk, st->Rpad - r0);
-        if (nchunks > 1) MCS_CUDA(cudaStreamWaitEvent(inst->stream, inst->ev_up[c], 0));
+        st->vR = std::min<long long>(win[c], st->Rpad - r0);
+        if (nwin > 1) MCS_CUDA(cudaStreamWaitEvent(inst->stream, inst->ev_up[c], 0));
         rc = mcs_piqmc_pack(st, stage);
         if (rc == MCS_OK)
             rc = mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, 0, nullptr);
         if (rc == MCS_OK) rc = mcs_piqmc_unpack(st, stage);
         if (rc != MCS_OK) break;
-        if (nchunks > 1) {
+        if (nwin > 1) {
             MCS_CUDA(cudaEventRecord(inst->ev_done[c], inst->stream));
             MCS_CUDA(cudaStreamWaitEvent(s_out, inst->ev_done[c], 0));
         }
@@ -233,7 +260,7 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
         return rc;
     }
     if (energies_out) MCS_TRY(mcs_state_energies(st, energies_out)); // overlaps the last download
-    if (nchunks > 1) MCS_CUDA(cudaStreamSynchronize(s_out));
+    if (nwin > 1) MCS_CUDA(cudaStreamSynchronize(s_out));
     MCS_CUDA(cudaStreamSynchronize(inst->stream));
     return MCS_OK;
 }
