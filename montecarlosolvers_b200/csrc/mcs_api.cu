@@ -1,6 +1,9 @@
 // mcs_api.cu -- extern "C" entry points over resident replica batches (see include/mcs_b200.h).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "mcs_common.cuh"
 
@@ -179,6 +182,8 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
                                 uint64_t replica_offset, double *energies_out)
 {
     MCS_REQUIRE(inst && confs, MCS_EINVAL, "mcs_piqmc_anneal: NULL argument");
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     MCS_REQUIRE((double)temp * (double)P != 0.0 || S == 0, MCS_EZERODIV, "float division");
     MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_piqmc_anneal: bad schedule");
     mcs_state *st = nullptr;
@@ -188,50 +193,91 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
     MCS_TRY(mcs_state_reserve_stage(st, (size_t)R * per_replica));
     int8_t *stage = (int8_t *)st->d_stage;
     // Replicas are independent, so the batch is cut into windows and the H2D copy of window c+1 / the D2H copy of
-    // window c-1 overlap the sweeps of window c.  The first and the last window are small (their copies are the
-    // only exposed ones), the middle one large (every window costs a launch tail per pass); measured on the
-    // cfg3 workload: 3.5 % over the resident time (benchmarks/e2e_probe.py).
+    // window c-1 overlap the sweeps of window c.  The first window is small (its upload is exposed in any case)
+    // and its upload is TIMED: the host link of the B200 boxes was seen anywhere between 1.5 and 55 GB/s from
+    // pinned memory (benchmarks/pcie_diag.py; the cfg3 anneal needs 1.6 GB/s each way).  On a fast link the rest
+    // is one large window and a small last one (every window costs a launch tail per colour pass: 128-replica
+    // windows sweep 34 % slower per replica than 2048-replica ones); on a slow link it is a ramp 2 : 4 : 4 ... 2 : 1
+    // so that every copy hides behind the sweeps of its neighbour.  cfg3, fast link: 3.5 % over the resident time.
     // Dense instances expand the whole batch per call: no windows there.
-    long long win[8];
+    constexpr int kMaxWin = 16;
+    long long win[kMaxWin];
     int nwin = 0;
-    if (R >= 1024 && !mcs_dense_supported(inst, (int)P)) {
-        const long long edge = std::max<long long>(128, ((st->Rpad / 16 + 127) / 128) * 128);
-        win[nwin++] = edge;
-        win[nwin++] = st->Rpad - 2 * edge;
-        win[nwin++] = edge;
-        if (const char *e = getenv("MCS_WINDOWS")) { // experiments: comma-separated window sizes (multiples of 128)
-            nwin = 0;
-            long long tot = 0;
-            for (const char *q = e; *q && nwin < 7;) {
-                char *end;
-                const long long v = strtoll(q, &end, 10);
-                if (end == q || v <= 0 || v % 128) break;
-                win[nwin++] = v;
-                tot += v;
-                q = *end == ',' ? end + 1 : end;
-            }
-            if (tot < st->Rpad) win[nwin++] = st->Rpad - tot;
-        }
-    } else {
-        win[nwin++] = st->Rpad;
-    }
-    if (nwin > 1 && !inst->s_in) {
+    const bool windows = R >= 1024 && !mcs_dense_supported(inst, (int)P);
+    if (windows && !inst->s_in) {
         MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_in, cudaStreamNonBlocking));
         MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_out, cudaStreamNonBlocking));
-        for (int q = 0; q < 8; ++q) {
-            MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_up[q], cudaEventDisableTiming));
+        MCS_CUDA(cudaEventCreate(&inst->ev_t0));
+        for (int q = 0; q < kMaxWin; ++q) {
+            MCS_CUDA(cudaEventCreate(&inst->ev_up[q]));
             MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_done[q], cudaEventDisableTiming));
         }
     }
-    cudaStream_t s_in = nwin == 1 ? inst->stream : inst->s_in;
-    cudaStream_t s_out = nwin == 1 ? inst->stream : inst->s_out;
-    {
-        long long r0 = 0;
-        for (int c = 0; c < nwin && r0 < R; r0 += win[c], ++c) { // uploads, back to back on the H2D stream
+    cudaStream_t s_in = windows ? inst->s_in : inst->stream;
+    cudaStream_t s_out = windows ? inst->s_out : inst->stream;
+    // MCS_TRACE_E2E=1: per-window timeline (upload done / sweeps start / sweeps done / download done), ms from call start
+    const bool trace = getenv("MCS_TRACE_E2E") != nullptr;
+    cudaEvent_t tr0 = nullptr, tr_up[kMaxWin], tr_c0[kMaxWin], tr_c1[kMaxWin], tr_dn[kMaxWin];
+    if (trace) {
+        cudaEventCreate(&tr0);
+        for (int q = 0; q < kMaxWin; ++q) {
+            cudaEventCreate(&tr_up[q]);
+            cudaEventCreate(&tr_c0[q]);
+            cudaEventCreate(&tr_c1[q]);
+            cudaEventCreate(&tr_dn[q]);
+        }
+        cudaEventRecord(tr0, inst->stream);
+    }
+    if (!windows) {
+        win[nwin++] = st->Rpad;
+        MCS_CUDA(cudaMemcpyAsync(stage, confs, (size_t)R * per_replica, cudaMemcpyHostToDevice, s_in));
+        if (trace) cudaEventRecord(tr_up[0], s_in);
+    } else {
+        const long long e = 128 * std::max<long long>(1, st->Rpad / 4096);
+        // window 0, timed
+        MCS_CUDA(cudaEventRecord(inst->ev_t0, s_in));
+        MCS_CUDA(cudaMemcpyAsync(stage, confs, (size_t)e * per_replica, cudaMemcpyHostToDevice, s_in));
+        MCS_CUDA(cudaEventRecord(inst->ev_up[0], s_in));
+        if (trace) cudaEventRecord(tr_up[0], s_in);
+        MCS_CUDA(cudaEventSynchronize(inst->ev_up[0]));
+        float ms0 = 0.0f;
+        MCS_CUDA(cudaEventElapsedTime(&ms0, inst->ev_t0, inst->ev_up[0]));
+        double gbs = (double)e * per_replica / (std::max(ms0, 1e-3f) * 1e6);
+        if (const char *g = getenv("MCS_ASSUME_LINK_GBS")) gbs = atof(g); // tests: force the slow- / fast-link plan
+        win[nwin++] = e;
+        long long left = st->Rpad - e;
+        if (const char *env = getenv("MCS_WINDOWS")) { // experiments: sizes of the windows after the first one
+            for (const char *q = env; *q && nwin < kMaxWin - 1;) {
+                char *end;
+                const long long v = strtoll(q, &end, 10);
+                if (end == q || v <= 0 || v % 128 || v >= left) break;
+                win[nwin++] = v;
+                left -= v;
+                q = *end == ',' ? end + 1 : end;
+            }
+            win[nwin++] = left;
+        } else if (gbs >= 16.0 || left < 12 * e) { // fast link: [e, big, 2e]
+            win[nwin++] = left - 2 * e;
+            win[nwin++] = 2 * e;
+        } else { // slow link: e, 2e, 4e, 4e, ..., 2e, e
+            win[nwin++] = 2 * e;
+            left -= 2 * e + 3 * e; // this one and the closing 2e + e
+            while (left > 0 && nwin < kMaxWin - 3) {
+                const long long v = (left <= 6 * e || nwin == kMaxWin - 4) ? left : 4 * e;
+                win[nwin++] = v;
+                left -= v;
+            }
+            win[nwin++] = 2 * e;
+            win[nwin++] = e;
+        }
+        if (trace) fprintf(stderr, "[mcs e2e] first upload %.1f GB/s -> %d windows (host %.1f ms)\n", gbs, nwin, host_ms());
+        long long r0 = e;
+        for (int c = 1; c < nwin && r0 < R; r0 += win[c], ++c) { // the other uploads, back to back on the H2D stream
             const long long nvalid = std::min<long long>(win[c], R - r0);
             MCS_CUDA(cudaMemcpyAsync(stage + r0 * per_replica, confs + r0 * per_replica,
                                      (size_t)nvalid * per_replica, cudaMemcpyHostToDevice, s_in));
-            if (nwin > 1) MCS_CUDA(cudaEventRecord(inst->ev_up[c], s_in));
+            MCS_CUDA(cudaEventRecord(inst->ev_up[c], s_in));
+            if (trace) cudaEventRecord(tr_up[c], s_in);
         }
     }
     int rc = MCS_OK;
@@ -240,18 +286,21 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
         const long long nvalid = std::min<long long>(win[c], R - r0);
         st->v0 = r0;
         st->vR = std::min<long long>(win[c], st->Rpad - r0);
-        if (nwin > 1) MCS_CUDA(cudaStreamWaitEvent(inst->stream, inst->ev_up[c], 0));
+        if (windows) MCS_CUDA(cudaStreamWaitEvent(inst->stream, inst->ev_up[c], 0));
+        if (trace) cudaEventRecord(tr_c0[c], inst->stream);
         rc = mcs_piqmc_pack(st, stage);
         if (rc == MCS_OK)
             rc = mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, 0, nullptr);
         if (rc == MCS_OK) rc = mcs_piqmc_unpack(st, stage);
         if (rc != MCS_OK) break;
-        if (nwin > 1) {
+        if (trace) cudaEventRecord(tr_c1[c], inst->stream);
+        if (windows) {
             MCS_CUDA(cudaEventRecord(inst->ev_done[c], inst->stream));
             MCS_CUDA(cudaStreamWaitEvent(s_out, inst->ev_done[c], 0));
         }
         MCS_CUDA(cudaMemcpyAsync(confs + r0 * per_replica, stage + r0 * per_replica, (size_t)nvalid * per_replica,
                                  cudaMemcpyDeviceToHost, s_out));
+        if (trace) cudaEventRecord(tr_dn[c], s_out);
     }
     st->v0 = 0;
     st->vR = -1;
@@ -259,9 +308,31 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
         cudaDeviceSynchronize();
         return rc;
     }
+    if (trace) fprintf(stderr, "[mcs e2e] host: everything enqueued at %.1f ms\n", host_ms());
     if (energies_out) MCS_TRY(mcs_state_energies(st, energies_out)); // overlaps the last download
-    if (nwin > 1) MCS_CUDA(cudaStreamSynchronize(s_out));
+    if (trace) fprintf(stderr, "[mcs e2e] host: energies back at %.1f ms\n", host_ms());
+    if (windows) MCS_CUDA(cudaStreamSynchronize(s_out));
     MCS_CUDA(cudaStreamSynchronize(inst->stream));
+    if (trace) {
+        fprintf(stderr, "[mcs e2e] host: streams drained at %.1f ms\n", host_ms());
+        cudaDeviceSynchronize();
+        for (int c = 0; c < nwin; ++c) {
+            float up = 0, c0 = 0, c1 = 0, dn = 0;
+            cudaEventElapsedTime(&up, tr0, tr_up[c]);
+            cudaEventElapsedTime(&c0, tr0, tr_c0[c]);
+            cudaEventElapsedTime(&c1, tr0, tr_c1[c]);
+            cudaEventElapsedTime(&dn, tr0, tr_dn[c]);
+            fprintf(stderr, "[mcs e2e] window %d (%lld replicas): uploaded %.1f, sweeps %.1f .. %.1f, downloaded %.1f ms\n",
+                    c, win[c], up, c0, c1, dn);
+        }
+        cudaEventDestroy(tr0);
+        for (int q = 0; q < kMaxWin; ++q) {
+            cudaEventDestroy(tr_up[q]);
+            cudaEventDestroy(tr_c0[q]);
+            cudaEventDestroy(tr_c1[q]);
+            cudaEventDestroy(tr_dn[q]);
+        }
+    }
     return MCS_OK;
 }
 

@@ -337,7 +337,7 @@ extern "C" void mcs_instance_destroy(mcs_instance *inst)
     cudaFree(inst->d_Jlo);
     cudaFree(inst->d_Jf);
     cudaFree(inst->d_hpad);
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 16; ++q) {
         if (inst->ev_up[q]) cudaEventDestroy(inst->ev_up[q]);
         if (inst->ev_done[q]) cudaEventDestroy(inst->ev_done[q]);
     }
