@@ -53,16 +53,22 @@ struct DensePass {
 __device__ __forceinline__ void bar_decide() { asm volatile("bar.sync 1, %0;" ::"n"(kTC)); }
 
 // ---- phase B: the block's sites one after another -------------------------------------------------
-// Critical path per site: decide (64 threads) -> barrier -> rank-1 update -> barrier.  To keep it short,
-//   * every uniform the block will need is drawn up front, in parallel (the Philox counters do not depend
-//     on the state) and stored as lu = log2((u+1) 2^-32): the Metropolis test  u/2^32 < exp(-dE/teff)
-//     (qmc.pyx:140-143) becomes  dE <= 0  or  dE * (-log2 e / teff) >= lu  -- one multiply and a compare
-//     on the critical path instead of an exponential;
-//   * the field tile lives in REGISTERS during the block: thread t owns row t/2, columns 32 (t%2) .. +32, so
-//     the rank-1 update is 32 register FMAs; the owners of row m+1 publish it to shared memory for the
-//     next decision;
+// The sequential chain (128 decisions per block, each followed by a rank-1 correction of the later rows) is
+// what bounds the dense sweep, so it is cut into STRIPS of 16 rows:
+//   * the two decision warps (lane = column) take the strip's 16 field values of their column into registers,
+//     decide the 16 sites one after another and apply each rank-1 correction to the REST OF THE STRIP
+//     themselves (<= 15 register FMAs, J broadcast from shared memory): no CTA barrier inside a strip;
+//   * after the strip one barrier, then all eight warps apply the strip's rank-16 correction
+//     Hb[row, :] += sum_j J[row, r0 + j] * delta_j[:] to the later rows of the block (shared memory tile), one
+//     barrier, next strip: 16 barriers per block instead of 256;
+//   * every uniform the block will need is drawn up front, in parallel (the Philox counters do not depend on
+//     the state) and stored as lu = log2((u+1) 2^-32): the Metropolis test  u/2^32 < exp(-dE/teff)
+//     (qmc.pyx:140-143) becomes  dE <= 0  or  dE * (-log2 e / teff) >= lu  -- one multiply and a compare on
+//     the critical path instead of an exponential;
 //   * for P <= 32 a replica's slices are lanes of one warp: Trotter neighbours and the world-line sum go
-//     through shuffles, no shared memory or barrier between the parity phases.
+//     through shuffles.  P == 64 (a replica spans both decision warps) keeps the older row-by-row scheme
+//     (dense_phase_b_rows) with shared memory + a 64-thread barrier between the parity phases.
+constexpr int kSB = 16;                                     // rows per strip
 constexpr int kScrJd = 0;                                   // float [kBS][kJld]
 constexpr int kScrUloc = kScrJd + kBS * kJld * 4;           // float [kBS][kTC]: log2 of the local uniforms
 constexpr int kScrSb = kScrUloc + kBS * kTC * 4;            // int8 [kBS][kTC]
@@ -70,13 +76,15 @@ constexpr int kScrFrow = kScrSb + kBS * kTC;                // float [kTC]
 constexpr int kScrDelta = kScrFrow + kTC * 4;               // float [kTC]
 constexpr int kScrGterm = kScrDelta + kTC * 4;              // float [kTC]
 constexpr int kScrHblk = kScrGterm + kTC * 4;               // float [kBS]: local fields h_i of the block
-constexpr int kScrBytes = kScrHblk + kBS * 4;
-static_assert(kBS * (kTC / 2) * 4 <= kBS * kHld * 4, "uglob must fit the (consumed) field tile");
+constexpr int kScrDstrip = kScrHblk + kBS * 4;              // float [kSB][kTC]: spin changes of the strip
+constexpr int kScrBytes = kScrDstrip + kSB * kTC * 4;
+constexpr int kUglobBytes = kBS * (kTC / 2) * 4;            // float [kBS][kTC/2]: log2 of the world-line uniforms
 
 // PT: compile-time P for the in-warp cases (1, 2, 4, 8, 16, 32: a replica's slices sit in one warp);
 // PT == 0: P == 64, the replica spans both decision warps (shared memory + a 64-thread barrier).
 template <int PT>
-__device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, unsigned char *scr, int col0)
+__device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb, unsigned char *scr, float *uglob,
+                                                   int col0)
 {
     constexpr bool INWARP = PT != 0;
     float *Jd = reinterpret_cast<float *>(scr + kScrJd);
@@ -98,7 +106,6 @@ __device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, uns
 #pragma unroll
     for (int q = 0; q < kTC / 2; ++q) hreg[q] = Hb[row * kHld + cbase + q];
     __syncthreads();
-    float *uglob = Hb; // [kBS][kTC/2], indexed by the CTA-local replica
     if (tid < kBS) hblk[tid] = __ldg(&a.h[i0 + tid]);
 
     for (int e = tid; e < kBS * kBS; e += kThreads) {
@@ -217,16 +224,139 @@ __device__ __forceinline__ void dense_phase_b(const DensePass &a, float *Hb, uns
     }
 }
 
-__device__ __forceinline__ void dense_phase_b_dispatch(const DensePass &a, float *Hb, unsigned char *scr, int col0)
+// Strip scheme (see above), P in {1, 2, 4, 8, 16, 32}.
+template <int PT>
+__device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *Hb, unsigned char *scr, float *uglob,
+                                                     int col0)
+{
+    float *Jd = reinterpret_cast<float *>(scr + kScrJd);
+    float *uloc = reinterpret_cast<float *>(scr + kScrUloc);
+    float *hblk = reinterpret_cast<float *>(scr + kScrHblk);
+    signed char *sb = reinterpret_cast<signed char *>(scr + kScrSb);
+    float *dstrip = reinterpret_cast<float *>(scr + kScrDstrip);
+    const int tid = threadIdx.x;
+    const int i0 = a.i0;
+    const long long ld = a.Npad;
+    constexpr int P = PT;
+    const int mend = min(kBS, a.N - i0);
+
+    if (tid < kBS) hblk[tid] = __ldg(&a.h[i0 + tid]);
+    for (int e = tid; e < kBS * kBS; e += kThreads) {
+        const int r = e / kBS, c = e % kBS;
+        Jd[r * kJld + c] = __ldg(&a.Jf[(long long)(i0 + r) * ld + i0 + c]);
+    }
+    for (int e = tid; e < kBS * kTC; e += kThreads) {
+        const int c = e / kBS, m = e % kBS; // consecutive threads -> consecutive sites of one column
+        sb[m * kTC + c] = __bfloat162float(a.S[(long long)(col0 + c) * ld + i0 + m]) < 0.0f ? -1 : 1;
+    }
+    for (int e = tid; e < kBS * kTC; e += kThreads) { // all uniforms of the block
+        const int m = e / kTC, c = e % kTC;
+        const int col = col0 + c, k = col % P;
+        const uint32_t rep = a.replica_offset + (uint32_t)(col / P);
+        if ((k & 3) == 0) {
+            uint32_t rnd[4];
+            mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(k >> 2), a.keys, rnd);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k + j < P) uloc[m * kTC + c + j] = __log2f((float)rnd[j] + 1.0f) - 32.0f;
+        }
+        if (a.global_moves && k == 0) {
+            uint32_t rnd[4];
+            mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
+            uglob[m * (kTC / 2) + c / P] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
+        }
+    }
+    __syncthreads();
+
+    const int c = tid & (kTC - 1); // column of a decision thread (tid < kTC)
+    const int col = col0 + c;
+    const int k = col % P; // slice
+    const int cl = c - k + (k == 0 ? P - 1 : k - 1), cr = c - k + (k == P - 1 ? 0 : k + 1);
+    const int crep = c / P;
+    const bool valid = col < a.C;
+    const bool odd = (k & 1) != 0;
+    const float sc = a.nl2e_over_t, bco = a.bcoef, jp2 = a.jperp2;
+    const bool trotter = a.trotter != 0 && P > 1, glob = a.global_moves != 0;
+#define MCS_ACCEPT(dE, lg) (valid && ((dE) <= 0.0f || (dE) * sc >= (lg)))
+    for (int r0 = 0; r0 < mend; r0 += kSB) {
+        if (tid < kTC) {
+            float f[kSB];
+#pragma unroll
+            for (int j = 0; j < kSB; ++j) f[j] = Hb[(r0 + j) * kHld + c];
+#pragma unroll
+            for (int j = 0; j < kSB; ++j) {
+                const int m = r0 + j;
+                float d = 0.0f;
+                if (m < mend) { // CTA-uniform
+                    const float bf = bco * (f[j] + hblk[m]); // -2B * local field
+                    const float lu = uloc[m * kTC + c];
+                    const float s_init = (float)sb[m * kTC + c];
+                    float s = s_init;
+                    if (trotter) { // even slices, then odd slices (P is even); neighbours by shuffle
+                        float nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                        float dE = s * fmaf(jp2, nb, bf);
+                        if (!odd && MCS_ACCEPT(dE, lu)) s = -s;
+                        nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                        dE = s * fmaf(jp2, nb, bf);
+                        if (odd && MCS_ACCEPT(dE, lu)) s = -s;
+                    } else {
+                        const float dE = s * bf;
+                        if (MCS_ACCEPT(dE, lu)) s = -s;
+                    }
+                    if (glob) { // world-line move: all P slices of the replica (qmc.pyx:405-438)
+                        float dE = s * bf;
+#pragma unroll
+                        for (int off = 1; off < PT; off <<= 1) dE += __shfl_xor_sync(0xffffffffu, dE, off);
+                        if (MCS_ACCEPT(dE, uglob[m * (kTC / 2) + crep])) s = -s;
+                    }
+                    sb[m * kTC + c] = (signed char)s;
+                    d = s - s_init;
+                    // rank-1 correction of the rest of the strip (this column only, registers)
+#pragma unroll
+                    for (int j2 = j + 1; j2 < kSB; ++j2) f[j2] = fmaf(Jd[(r0 + j2) * kJld + m], d, f[j2]);
+                }
+                dstrip[j * kTC + c] = d;
+            }
+        }
+        __syncthreads();
+        // rank-16 correction of the later rows of the block: item = (row, 4 columns)
+        const int nrows = mend - (r0 + kSB);
+        for (int it = tid; it < nrows * (kTC / 4); it += kThreads) {
+            const int row = r0 + kSB + it / (kTC / 4), c4 = (it % (kTC / 4)) * 4;
+            float4 h = *reinterpret_cast<const float4 *>(Hb + row * kHld + c4);
+            const float *jr = Jd + row * kJld + r0;
+#pragma unroll
+            for (int j = 0; j < kSB; ++j) {
+                const float jv = jr[j];
+                const float4 dd = *reinterpret_cast<const float4 *>(dstrip + j * kTC + c4);
+                h.x = fmaf(jv, dd.x, h.x);
+                h.y = fmaf(jv, dd.y, h.y);
+                h.z = fmaf(jv, dd.z, h.z);
+                h.w = fmaf(jv, dd.w, h.w);
+            }
+            *reinterpret_cast<float4 *>(Hb + row * kHld + c4) = h;
+        }
+        __syncthreads();
+    }
+#undef MCS_ACCEPT
+    // write the block's spins back
+    for (int e = tid; e < kBS * kTC; e += kThreads) {
+        const int cc = e / kBS, m = e % kBS;
+        a.S[(long long)(col0 + cc) * ld + i0 + m] = __float2bfloat16((float)sb[m * kTC + cc]);
+    }
+}
+
+__device__ __forceinline__ void dense_phase_b_dispatch(const DensePass &a, float *Hb, unsigned char *scr,
+                                                       float *uglob, int col0)
 {
     switch (a.P) {
-    case 1: dense_phase_b<1>(a, Hb, scr, col0); break;
-    case 2: dense_phase_b<2>(a, Hb, scr, col0); break;
-    case 4: dense_phase_b<4>(a, Hb, scr, col0); break;
-    case 8: dense_phase_b<8>(a, Hb, scr, col0); break;
-    case 16: dense_phase_b<16>(a, Hb, scr, col0); break;
-    case 32: dense_phase_b<32>(a, Hb, scr, col0); break;
-    default: dense_phase_b<0>(a, Hb, scr, col0); break;
+    case 1: dense_phase_b_strips<1>(a, Hb, scr, uglob, col0); break;
+    case 2: dense_phase_b_strips<2>(a, Hb, scr, uglob, col0); break;
+    case 4: dense_phase_b_strips<4>(a, Hb, scr, uglob, col0); break;
+    case 8: dense_phase_b_strips<8>(a, Hb, scr, uglob, col0); break;
+    case 16: dense_phase_b_strips<16>(a, Hb, scr, uglob, col0); break;
+    case 32: dense_phase_b_strips<32>(a, Hb, scr, uglob, col0); break;
+    default: dense_phase_b_rows<0>(a, Hb, scr, uglob, col0); break;
     }
 }
 
@@ -236,6 +366,7 @@ __global__ void __launch_bounds__(kThreads) dense_block_kernel(const __grid_cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *Hb = reinterpret_cast<float *>(smem_raw); // [kBS][kHld]
     unsigned char *scr = smem_raw + kBS * kHld * 4;
+    float *uglob = reinterpret_cast<float *>(scr + kScrBytes);
     const int warp = threadIdx.x >> 5;
     const int col0 = blockIdx.x * kTC;
     const int i0 = a.i0;
@@ -278,7 +409,7 @@ __global__ void __launch_bounds__(kThreads) dense_block_kernel(const __grid_cons
                                         wmma::mem_row_major);
     }
     __syncthreads();
-    dense_phase_b_dispatch(a, Hb, scr, col0);
+    dense_phase_b_dispatch(a, Hb, scr, uglob, col0);
 }
 
 // ---- variant 2 (default): phase A on tcgen05 -------------------------------------------------------
@@ -459,8 +590,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
-    // phase B scratch lives in the (now idle) ring
-    dense_phase_b_dispatch(a, Hb, ring, col0);
+    // phase B scratch lives in the (now idle) ring, the world-line uniforms behind the barriers
+    dense_phase_b_dispatch(a, Hb, ring, reinterpret_cast<float *>(ring + kRingBytes + kHbBytes + 128), col0);
 }
 
 // W[N][Rpad] (bit k = slice k) -> S[(r P + k)][site]
@@ -519,8 +650,9 @@ __global__ void dense_compress_sa_kernel(const __nv_bfloat16 *__restrict__ S, ui
     V[(long long)i * G + g] = v;
 }
 
-constexpr size_t kSmemBytes = kBS * kHld * 4 + kScrBytes;
-constexpr size_t kSmemBytesTc = kRingBytes + kHbBytes + 128 + 1024; // + barriers + slack for 1024-byte alignment
+constexpr size_t kSmemBytes = kBS * kHld * 4 + kScrBytes + kUglobBytes;
+constexpr size_t kSmemBytesTc = kRingBytes + kHbBytes + 128 + kUglobBytes + 1024; // + barriers + world-line uniforms
+                                                                                  // + slack for 1024-byte alignment
 static_assert(kScrBytes <= kRingBytes, "phase B scratch must fit the ring");
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
