@@ -218,6 +218,31 @@ enum {
     MCS_TAG_INIT = 0x40000000u
 };
 
+// ---- programmatic dependent launch (sm_90+) -----------------------------------------------------------
+// Consecutive colour passes depend on each other through the state only.  A pass kernel signals
+// launch_dependents at once (the next pass may start occupying SMs as soon as every CTA of this one is resident)
+// and executes griddepcontrol.wait right before its first read of the state: its launch latency, its parameter
+// / coupling loads and its threshold-table build overlap the tail of the previous pass.  Matters for small
+// batches, where a pass takes only a few microseconds.
+__device__ __forceinline__ void mcs_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void mcs_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename Kernel, typename Args>
+inline cudaError_t mcs_launch_pdl(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, const Args &args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
 // ---- building blocks shared by the bit-packed sweep kernels (mcs_piqmc.cu, mcs_sa.cu) ---------------
 // Instruction budget, measured on B200 (benchmarks/micro/pipe_rates.cu): ALU-pipe instructions (LOP3, PRMT,
 // IADD3, SHF, ISETP, VIADDMNMX) and FMA-pipe IMAD take 2 issue cycles per warp each and overlap with each

@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS) piqmc_lut_pass_
     constexpr int ENT = LutGeom<NPL>::ENT, NQ = NPL - FLD;
     __shared__ uint32_t s_lut[ENT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    mcs_pdl_launch_dependents();
     const unsigned si = blockIdx.y + 65535u * blockIdx.z;
     if (si >= (unsigned)a.nsites) return; // only when the colour class has more than 65535 sites (CTA-uniform)
     const int site = __ldg(&a.sites[si]);
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS) piqmc_lut_pass_
     // row offsets as one IMAD.WIDE.U32 each (site indices and Rpad are below 2^32)
     const uint32_t rpad = (uint32_t)a.Rpad;
     const uint64_t *Wr = a.W + r;
+    mcs_pdl_wait(); // everything above depends on the instance and the schedule only
     uint64_t w = Wr[(uint64_t)(uint32_t)site * rpad];
     uint64_t pl[NPL];
 #pragma unroll
@@ -623,13 +625,13 @@ static void launch_lut_wf(int warps, const PiqmcPass &a, cudaStream_t s)
     const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
     const dim3 grid((unsigned)(a.G / warps), ny, nz);
     if (a.P == 64 && warps == 4)
-        piqmc_lut_pass_kernel<NPL, 4, true, FLD><<<grid, 128, 0, s>>>(a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD>, grid, dim3(128), s, a);
     else if (warps == 4)
-        piqmc_lut_pass_kernel<NPL, 4, false, FLD><<<grid, 128, 0, s>>>(a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD>, grid, dim3(128), s, a);
     else if (warps == 2)
-        piqmc_lut_pass_kernel<NPL, 2, false, FLD><<<grid, 64, 0, s>>>(a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD>, grid, dim3(64), s, a);
     else
-        piqmc_lut_pass_kernel<NPL, 1, false, FLD><<<grid, 32, 0, s>>>(a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD>, grid, dim3(32), s, a);
 }
 
 template <int NPL>

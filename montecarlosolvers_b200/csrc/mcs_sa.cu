@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sa_lut_pass_kernel(const __grid
     __shared__ uint32_t s_lut[ENT];
     __shared__ uint2 s_bounce[4 * WARPS * 32]; // [call][thread]: private slots for the index bytes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    mcs_pdl_launch_dependents();
     const unsigned si = blockIdx.y + 65535u * blockIdx.z;
     if (si >= (unsigned)a.nsites) return; // only when the colour class has more than 65535 sites (CTA-uniform)
     const int site = __ldg(&a.sites[si]);
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sa_lut_pass_kernel(const __grid
 
     const uint32_t G32 = (uint32_t)a.G;
     uint32_t *Vg = a.V + g;
+    mcs_pdl_wait(); // everything above depends on the instance and the schedule only
     const uint32_t v = Vg[(uint64_t)(uint32_t)site * G32];
     uint32_t pl[NPL];
 #pragma unroll
@@ -245,11 +247,11 @@ void launch_lut_wf(int warps, cudaStream_t s, const SaPass &a)
     const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
     const dim3 grid((unsigned)(a.chunks / warps), ny, nz);
     if (warps == 4)
-        sa_lut_pass_kernel<NPL, 4, FLD><<<grid, 128, 0, s>>>(a);
+        mcs_launch_pdl(sa_lut_pass_kernel<NPL, 4, FLD>, grid, dim3(128), s, a);
     else if (warps == 2)
-        sa_lut_pass_kernel<NPL, 2, FLD><<<grid, 64, 0, s>>>(a);
+        mcs_launch_pdl(sa_lut_pass_kernel<NPL, 2, FLD>, grid, dim3(64), s, a);
     else
-        sa_lut_pass_kernel<NPL, 1, FLD><<<grid, 32, 0, s>>>(a);
+        mcs_launch_pdl(sa_lut_pass_kernel<NPL, 1, FLD>, grid, dim3(32), s, a);
 }
 
 template <int NPL>

@@ -68,6 +68,7 @@ __device__ __forceinline__ void svmc_decide(const SvmcPass &a, float zfield, flo
 // graphs share most of their neighbours (their lines stay in L1).  Rpad is a multiple of 128.
 __global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_constant__ SvmcPass a)
 {
+    mcs_pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long sblocks = (a.nsites + kWarps - 1) / kWarps;
     const long long grp = blockIdx.x / sblocks; // group of 128 replicas
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_con
     const long long r = grp * 128 + 4 * lane;
     float4 *th_ptr = reinterpret_cast<float4 *>(a.theta + (size_t)site * a.Rpad + r);
     float4 *cz_ptr = reinterpret_cast<float4 *>(a.cosz + (size_t)site * a.Rpad + r);
+    mcs_pdl_wait(); // the state is first read here
     float4 th = *th_ptr, cz = *cz_ptr;
     const float h0 = a.field ? __ldg(&a.h[site]) : 0.0f;
     float4 z = make_float4(h0, h0, h0, h0); // sum_j J_ij cos(theta_j) + h_i
@@ -201,7 +203,7 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
                 a.nsites = inst->color_start[c + 1] - inst->color_start[c];
                 if (a.nsites == 0) continue;
                 const long long ctas = (long long)((a.nsites + kWarps - 1) / kWarps) * (a.Rpad / 128);
-                svmc_pass_kernel<<<(unsigned)ctas, kWarps * 32, 0, inst->stream>>>(a);
+                mcs_launch_pdl(svmc_pass_kernel, dim3((unsigned)ctas), dim3(kWarps * 32), inst->stream, a);
                 inst->launches++;
             }
         }
