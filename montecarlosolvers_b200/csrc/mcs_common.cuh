@@ -81,6 +81,7 @@ struct mcs_instance {
     void *d_Jhi = nullptr, *d_Jlo = nullptr; // dense only: [Npad][Npad] bf16 split J = hi + lo
     float *d_Jf = nullptr;                   // dense only: [Npad][Npad] fp32
     float *d_hpad = nullptr;                 // dense only: [Npad]
+    double field_bound = 0.0;                // dense only: max_i (sum_j |J_ij| + |h_i|)
 };
 
 struct mcs_state {

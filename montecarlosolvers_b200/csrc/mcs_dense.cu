@@ -33,7 +33,7 @@ constexpr int kBS = 128;      // sites per block
 constexpr int kTC = 64;       // columns per CTA (a multiple of every supported P)
 constexpr int kThreads = 256; // 8 warps
 constexpr int kHld = kTC + 4; // leading dimension of the field tile (multiple of 4 floats for WMMA stores)
-constexpr int kJld = kBS + 1;
+constexpr int kJld = kBS + 4; // rows 16-byte aligned (cp.async); the decision warps read J by broadcast
 
 struct DensePass {
     const __nv_bfloat16 *Jhi, *Jlo; // [Npad][Npad] row i = couplings of site i (bf16 split of J)
@@ -48,7 +48,18 @@ struct DensePass {
     mcs_philox_keys keys;
     uint32_t sweep_lo, sweep_hi, replica_offset;
     int global_moves;
+    float gscale, ginv; // world-line sums in fixed point: 2^K and 2^-K, K such that P |dE|_max 2^K < 2^30
+    unsigned long long *trace; // MCS_DENSE_TRACE=1: phase timestamps of CTA 0 (ns), else nullptr
 };
+
+__device__ __forceinline__ void dense_stamp(const DensePass &a, int slot)
+{
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[slot] = t;
+    }
+}
 
 __device__ __forceinline__ void bar_decide() { asm volatile("bar.sync 1, %0;" ::"n"(kTC)); }
 
@@ -108,6 +119,7 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
     __syncthreads();
     if (tid < kBS) hblk[tid] = __ldg(&a.h[i0 + tid]);
 
+#pragma unroll 4
     for (int e = tid; e < kBS * kBS; e += kThreads) {
         const int r = e / kBS, c = e % kBS;
         Jd[r * kJld + c] = __ldg(&a.Jf[(long long)(i0 + r) * ld + i0 + c]);
@@ -116,6 +128,7 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
         const int c = e / kBS, m = e % kBS; // consecutive threads -> consecutive sites of one column
         sb[m * kTC + c] = __bfloat162float(a.S[(long long)(col0 + c) * ld + i0 + m]) < 0.0f ? -1 : 1;
     }
+#pragma unroll 1
     for (int e = tid; e < kBS * kTC; e += kThreads) { // all uniforms of the block
         const int m = e / kTC, c = e % kTC;
         const int col = col0 + c, k = col % P;
@@ -238,35 +251,59 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
     const int i0 = a.i0;
     const long long ld = a.Npad;
     constexpr int P = PT;
-    const int mend = min(kBS, a.N - i0);
 
+    // Prologue: everything phase B needs besides the fields, fetched with as many requests in flight as possible
+    // (it is pure latency: 64 KB of J, 16 KB of spins, 2304 Philox calls per CTA).
+    // J block: 128 rows x 512 B as 16-byte cp.async chunks, all issued before anything is waited for
+    for (int e = tid; e < kBS * (kBS / 4); e += kThreads) {
+        const int r = e / (kBS / 4), c4 = (e % (kBS / 4)) * 4;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Jd + r * kJld + c4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a.Jf + (long long)(i0 + r) * ld + i0 + c4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     if (tid < kBS) hblk[tid] = __ldg(&a.h[i0 + tid]);
-    for (int e = tid; e < kBS * kBS; e += kThreads) {
-        const int r = e / kBS, c = e % kBS;
-        Jd[r * kJld + c] = __ldg(&a.Jf[(long long)(i0 + r) * ld + i0 + c]);
-    }
-    for (int e = tid; e < kBS * kTC; e += kThreads) {
-        const int c = e / kBS, m = e % kBS; // consecutive threads -> consecutive sites of one column
-        sb[m * kTC + c] = __bfloat162float(a.S[(long long)(col0 + c) * ld + i0 + m]) < 0.0f ? -1 : 1;
-    }
-    for (int e = tid; e < kBS * kTC; e += kThreads) { // all uniforms of the block
-        const int m = e / kTC, c = e % kTC;
-        const int col = col0 + c, k = col % P;
-        const uint32_t rep = a.replica_offset + (uint32_t)(col / P);
-        if ((k & 3) == 0) {
-            uint32_t rnd[4];
-            mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(k >> 2), a.keys, rnd);
+    // spins: item = (column, 8 consecutive sites) = one 16-byte load of bf16, stored transposed as int8
+    {
+        uint4 v[kBS * kTC / 8 / kThreads];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (k + j < P) uloc[m * kTC + c + j] = __log2f((float)rnd[j] + 1.0f) - 32.0f;
+        for (int q = 0; q < kBS * kTC / 8 / kThreads; ++q) {
+            const int e = tid + q * kThreads, cc = e / (kBS / 8), m8 = (e % (kBS / 8)) * 8;
+            v[q] = __ldg(reinterpret_cast<const uint4 *>(a.S + (long long)(col0 + cc) * ld + i0 + m8));
         }
-        if (a.global_moves && k == 0) {
+#pragma unroll
+        for (int q = 0; q < kBS * kTC / 8 / kThreads; ++q) {
+            const int e = tid + q * kThreads, cc = e / (kBS / 8), m8 = (e % (kBS / 8)) * 8;
+            const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+            for (int t = 0; t < 8; ++t) // bf16 sign bit: bit 15 of each half word
+                sb[(m8 + t) * kTC + cc] = ((w[t >> 1] >> (16 * (t & 1) + 15)) & 1u) ? -1 : 1;
+        }
+    }
+    // uniforms: one Philox call = four consecutive slices of one (row, replica); calls spread evenly over the threads
+    constexpr int G4 = (P + 3) / 4;               // calls per (row, replica)
+    constexpr int NREP = kTC / P;                 // replicas of this CTA
+#pragma unroll 2
+    for (int e = tid; e < kBS * NREP * G4; e += kThreads) {
+        const int m = e / (NREP * G4), rr = (e / G4) % NREP, g = e % G4;
+        const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * P) / P);
+        uint32_t rnd[4];
+        mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)g, a.keys, rnd);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (4 * g + j < P) uloc[m * kTC + rr * P + 4 * g + j] = __log2f((float)rnd[j] + 1.0f) - 32.0f;
+    }
+    if (a.global_moves) {
+        for (int e = tid; e < kBS * NREP; e += kThreads) {
+            const int m = e / NREP, rr = e % NREP;
+            const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * P) / P);
             uint32_t rnd[4];
             mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
-            uglob[m * (kTC / 2) + c / P] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
+            uglob[m * (kTC / 2) + rr] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    dense_stamp(a, 2);
 
     const int c = tid & (kTC - 1); // column of a decision thread (tid < kTC)
     const int col = col0 + c;
@@ -277,50 +314,61 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
     const bool odd = (k & 1) != 0;
     const float sc = a.nl2e_over_t, bco = a.bcoef, jp2 = a.jperp2;
     const bool trotter = a.trotter != 0 && P > 1, glob = a.global_moves != 0;
-#define MCS_ACCEPT(dE, lg) (valid && ((dE) <= 0.0f || (dE) * sc >= (lg)))
-    for (int r0 = 0; r0 < mend; r0 += kSB) {
+    const unsigned segmask = PT >= 32 ? 0xffffffffu : (((1u << (PT & 31)) - 1u) << ((tid & 31) & ~(PT - 1)));
+// branch-free (bitwise, no short circuit): the decision chain is latency bound
+#define MCS_ACCEPT(dE, lg) (valid & (((dE) <= 0.0f) | ((dE) * sc >= (lg))))
+    // Rows beyond N (last block of an N that is not a multiple of 128) are decided like the others: their couplings
+    // and fields are zero padding and their spins are never read back, so the strip code has no per-row branch --
+    // one basic block per strip, every operand of the 16 steps prefetched into registers up front.
+#pragma unroll 1
+    for (int r0 = 0; r0 < kBS; r0 += kSB) {
         if (tid < kTC) {
-            float f[kSB];
+            float f[kSB], lu[kSB], hb[kSB], s0[kSB], ug[kSB];
 #pragma unroll
-            for (int j = 0; j < kSB; ++j) f[j] = Hb[(r0 + j) * kHld + c];
+            for (int j = 0; j < kSB; ++j) {
+                f[j] = Hb[(r0 + j) * kHld + c];
+                lu[j] = uloc[(r0 + j) * kTC + c];
+                hb[j] = hblk[r0 + j];
+                s0[j] = (float)sb[(r0 + j) * kTC + c];
+                ug[j] = glob ? uglob[(r0 + j) * (kTC / 2) + crep] : 0.0f;
+            }
 #pragma unroll
             for (int j = 0; j < kSB; ++j) {
                 const int m = r0 + j;
-                float d = 0.0f;
-                if (m < mend) { // CTA-uniform
-                    const float bf = bco * (f[j] + hblk[m]); // -2B * local field
-                    const float lu = uloc[m * kTC + c];
-                    const float s_init = (float)sb[m * kTC + c];
-                    float s = s_init;
-                    if (trotter) { // even slices, then odd slices (P is even); neighbours by shuffle
-                        float nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
-                        float dE = s * fmaf(jp2, nb, bf);
-                        if (!odd && MCS_ACCEPT(dE, lu)) s = -s;
-                        nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
-                        dE = s * fmaf(jp2, nb, bf);
-                        if (odd && MCS_ACCEPT(dE, lu)) s = -s;
-                    } else {
-                        const float dE = s * bf;
-                        if (MCS_ACCEPT(dE, lu)) s = -s;
-                    }
-                    if (glob) { // world-line move: all P slices of the replica (qmc.pyx:405-438)
-                        float dE = s * bf;
-#pragma unroll
-                        for (int off = 1; off < PT; off <<= 1) dE += __shfl_xor_sync(0xffffffffu, dE, off);
-                        if (MCS_ACCEPT(dE, uglob[m * (kTC / 2) + crep])) s = -s;
-                    }
-                    sb[m * kTC + c] = (signed char)s;
-                    d = s - s_init;
-                    // rank-1 correction of the rest of the strip (this column only, registers)
-#pragma unroll
-                    for (int j2 = j + 1; j2 < kSB; ++j2) f[j2] = fmaf(Jd[(r0 + j2) * kJld + m], d, f[j2]);
+                const float bf = bco * (f[j] + hb[j]); // -2B * local field
+                float s = s0[j];
+                if (trotter) { // even slices, then odd slices (P is even); neighbours by shuffle
+                    float nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                    float dE = s * fmaf(jp2, nb, bf);
+                    s = ((!odd) & MCS_ACCEPT(dE, lu[j])) ? -s : s;
+                    nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                    dE = s * fmaf(jp2, nb, bf);
+                    s = (odd & MCS_ACCEPT(dE, lu[j])) ? -s : s;
+                } else {
+                    const float dE = s * bf;
+                    s = MCS_ACCEPT(dE, lu[j]) ? -s : s;
                 }
+                if (glob) { // world-line move: all P slices of the replica (qmc.pyx:405-438)
+                    // sum over the replica's lanes in fixed point with one redux.sync instead of log2(P)
+                    // dependent shuffles (the scale is chosen per launch from the instance's largest possible
+                    // field: resolution P |dE|_max 2^-30, finer than the fp32 butterfly it replaces)
+                    const int part = __float2int_rn(s * bf * a.gscale);
+                    const float dE = (float)__reduce_add_sync(segmask, part) * a.ginv;
+                    s = MCS_ACCEPT(dE, ug[j]) ? -s : s;
+                }
+                sb[m * kTC + c] = (signed char)s;
+                const float d = s - s0[j];
+                // rank-1 correction of the rest of the strip (this column only, registers)
+#pragma unroll
+                for (int j2 = j + 1; j2 < kSB; ++j2) f[j2] = fmaf(Jd[(r0 + j2) * kJld + m], d, f[j2]);
                 dstrip[j * kTC + c] = d;
             }
         }
         __syncthreads();
+        if (r0 == 0) dense_stamp(a, 3);
         // rank-16 correction of the later rows of the block: item = (row, 4 columns)
-        const int nrows = mend - (r0 + kSB);
+        const int nrows = kBS - (r0 + kSB);
+#pragma unroll 1
         for (int it = tid; it < nrows * (kTC / 4); it += kThreads) {
             const int row = r0 + kSB + it / (kTC / 4), c4 = (it % (kTC / 4)) * 4;
             float4 h = *reinterpret_cast<const float4 *>(Hb + row * kHld + c4);
@@ -337,9 +385,12 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
             *reinterpret_cast<float4 *>(Hb + row * kHld + c4) = h;
         }
         __syncthreads();
+        if (r0 == 0) dense_stamp(a, 4);
     }
+    dense_stamp(a, 5);
 #undef MCS_ACCEPT
     // write the block's spins back
+#pragma unroll 4
     for (int e = tid; e < kBS * kTC; e += kThreads) {
         const int cc = e / kBS, m = e % kBS;
         a.S[(long long)(col0 + cc) * ld + i0 + m] = __float2bfloat16((float)sb[m * kTC + cc]);
@@ -493,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     dense_block_kernel_tc(const __grid_constant__ DensePass a, const __grid_constant__ DenseMaps maps)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    dense_stamp(a, 0);
     // carve: [ring 120 KB | Hb 34 KB | barriers], ring 1024-byte aligned (128-byte swizzle atoms are 1024 B);
     // phase B scratch aliases the ring
     unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -590,8 +642,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
+    dense_stamp(a, 1);
     // phase B scratch lives in the (now idle) ring, the world-line uniforms behind the barriers
     dense_phase_b_dispatch(a, Hb, ring, reinterpret_cast<float *>(ring + kRingBytes + kHbBytes + 128), col0);
+    dense_stamp(a, 6);
 }
 
 // W[N][Rpad] (bit k = slice k) -> S[(r P + k)][site]
@@ -749,6 +803,9 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     a.keys = mcs_philox_expand(seed);
     a.replica_offset = (uint32_t)replica_offset;
     a.global_moves = (kind == MCS_KIND_PIQMC && global_moves) ? 1 : 0;
+    a.gscale = a.ginv = 1.0f;
+    a.trace = nullptr;
+    if (getenv("MCS_DENSE_TRACE")) MCS_CUDA(cudaMalloc((void **)&a.trace, 8 * sizeof(unsigned long long)));
     const double teff = (double)temp * (double)P;
     uint64_t sweep = sweep_offset;
     for (int64_t f = 0; f < S; ++f) {
@@ -757,6 +814,10 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
             a.bcoef = (float)(-2.0 * B[f]);
             a.jperp2 = (float)(2.0 * jperp);
             a.nl2e_over_t = (float)(-1.4426950408889634 / teff);
+            const double dEmax = std::max(1e-30, std::fabs(2.0 * B[f]) * inst->field_bound * (double)P);
+            const int K = std::max(-60, std::min(60, (int)std::floor(std::log2(1073741824.0 / dEmax))));
+            a.gscale = (float)std::ldexp(1.0, K);
+            a.ginv = (float)std::ldexp(1.0, -K);
         } else {
             a.bcoef = -2.0f;
             a.jperp2 = 0.0f;
@@ -786,5 +847,16 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     }
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
+    if (a.trace) { // timestamps of the last block launch: start, GEMM done, prologue done, first strip decided,
+                   // first strip applied, all strips done, spins written back
+        unsigned long long t[8];
+        MCS_CUDA(cudaStreamSynchronize(inst->stream));
+        MCS_CUDA(cudaMemcpy(t, a.trace, sizeof(t), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[mcs dense] CTA 0 of the last block: GEMM %.1f us, prologue %.1f, strip 0 decisions %.1f, strip 0 "
+                        "update %.1f, all strips %.1f, write-back %.1f\n",
+                (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3,
+                (t[5] - t[2]) * 1e-3, (t[6] - t[5]) * 1e-3);
+        cudaFree(a.trace);
+    }
     return MCS_OK;
 }

@@ -264,9 +264,15 @@ extern "C" int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int6
         inst->Npad = Np;
         std::vector<float> Jf((size_t)Np * Np, 0.0f), hp((size_t)Np, 0.0f);
         std::vector<__nv_bfloat16> Jhi((size_t)Np * Np), Jlo((size_t)Np * Np);
+        inst->field_bound = 0.0;
         for (int64_t i = 0; i < nspins; ++i) {
-            for (auto &kv : quad[0][i]) Jf[(size_t)i * Np + kv.first] = (float)kv.second;
+            double rowsum = std::fabs(h[i]);
+            for (auto &kv : quad[0][i]) {
+                Jf[(size_t)i * Np + kv.first] = (float)kv.second;
+                rowsum += std::fabs(kv.second);
+            }
             hp[i] = (float)h[i];
+            inst->field_bound = std::max(inst->field_bound, rowsum);
         }
         for (size_t e = 0; e < Jf.size(); ++e) {
             const __nv_bfloat16 hi = __float2bfloat16(Jf[e]);
