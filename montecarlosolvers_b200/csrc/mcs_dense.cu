@@ -544,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     dense_block_kernel_tc(const __grid_constant__ DensePass a, const __grid_constant__ DenseMaps maps)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    mcs_pdl_launch_dependents(); // the next block's launch, barrier set-up and TMEM allocation overlap this block's tail
     dense_stamp(a, 0);
     // carve: [ring 120 KB | Hb 34 KB | barriers], ring 1024-byte aligned (128-byte swizzle atoms are 1024 B);
     // phase B scratch aliases the ring
@@ -576,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = a.Npad / kBK;
+    mcs_pdl_wait(); // S (and nothing else read from here on) is written by the previous block's kernel
 
     if (warp == 0 && lane == 0) {
         // ---- TMA producer
@@ -739,6 +741,21 @@ int make_map_bf16_2d(void *out128, const void *base, uint64_t inner, uint64_t ro
 
 } // namespace
 
+static void launch_dense_tc(unsigned grid, cudaStream_t stream, const DensePass &a, const DenseMaps &maps)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytesTc;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, dense_block_kernel_tc, a, maps);
+}
+
 bool mcs_dense_supported(const mcs_instance *inst, int P)
 {
     if (!inst->dense || inst->nsteps != 1) return false;
@@ -829,7 +846,7 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
             for (int i0 = 0; i0 < (int)inst->N; i0 += kBS) {
                 a.i0 = i0;
                 if (use_tc)
-                    dense_block_kernel_tc<<<(unsigned)(Cpad / kTC), kThreads, kSmemBytesTc, inst->stream>>>(a, maps);
+                    launch_dense_tc((unsigned)(Cpad / kTC), inst->stream, a, maps);
                 else
                     dense_block_kernel<<<(unsigned)(Cpad / kTC), kThreads, kSmemBytes, inst->stream>>>(a);
                 inst->launches++;
