@@ -45,6 +45,21 @@ def random_graph(n, nedges, seed=0, fields=True):
     return J, orc.GenerateNeighbors(n, J, maxnb)
 
 
+def circulant(n, offsets=(1, 2, 3), seed=0, fields=True):
+    """Ring with couplings to i +- o for every o in offsets (degree 2 len(offsets)), optional fields: a
+    high-degree sparse graph for the 7- and 8-plane threshold tables."""
+    rng = np.random.RandomState(seed)
+    J = sps.dok_matrix((n, n))
+    for i in range(n):
+        for o in offsets:
+            j = (i + o) % n
+            if (i, j) not in J and (j, i) not in J:
+                J[i, j] = rng.uniform(-1.5, 1.5)
+        if fields:
+            J[i, i] = rng.uniform(-1.0, 1.0)
+    return J, orc.GenerateNeighbors(n, J, 2 * len(offsets) + (1 if fields else 0))
+
+
 def random_spins(n, seed):
     return (2 * np.random.RandomState(seed).randint(2, size=n) - 1).astype(np.int64)
 

@@ -97,7 +97,8 @@ def _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, R=4096, burn=150, meas=40, g
     return es.mean(), es.std(ddof=1) / np.sqrt(R), ls.mean(), ls.std(ddof=1) / np.sqrt(R), I
 
 
-@pytest.mark.parametrize("case", ["ring4_P4", "tri5_fields_P3", "k8_direct_P2", "torus_P2_global"])
+@pytest.mark.parametrize("case", ["ring4_P4", "tri5_fields_P3", "k8_direct_P2", "torus_P2_global",
+                                  "circulant6_7planes_P3", "circulant7_8planes_P2_global"])
 def test_piqmc_samples_the_exact_boltzmann_distribution(mcs, case):
     """Tolerance: |GPU mean - exact| <= 4.5 standard errors (over 4096 independent replicas)."""
     if case == "ring4_P4":
@@ -121,6 +122,12 @@ def test_piqmc_samples_the_exact_boltzmann_distribution(mcs, case):
                 J[i, j] = rng.normal() * 0.5
         nbs = orc.GenerateNeighbors(8, J, 7)
         P, glob = 2, False
+    elif case == "circulant6_7planes_P3":  # degree 4 + field + 2 Trotter planes = 7: index not pre-multiplied, odd P
+        J, nbs = inst.circulant(6, (1, 2), seed=2, fields=True)
+        P, glob = 3, False
+    elif case == "circulant7_8planes_P2_global":  # degree 6 + 2 Trotter planes = 8: the 256-entry table
+        J, nbs = inst.circulant(7, (1, 2, 3), seed=3, fields=False)
+        P, glob = 2, True
     else:
         J, nbs = inst.torus(2, seed=2, fields=True)
         P, glob = 2, True
@@ -131,6 +138,8 @@ def test_piqmc_samples_the_exact_boltzmann_distribution(mcs, case):
         assert not I.lut_kernels
     if case == "tri5_fields_P3":
         assert I.ncolors == 3 and I.has_field
+    if case.startswith("circulant"):
+        assert I.lut_kernels and I.maxdeg + int(I.has_field) + 2 == (7 if "7planes" in case else 8)
     assert abs(e - e_exact) <= 4.5 * e_sem, (case, e, e_exact, e_sem)
     assert abs(l - l_exact) <= 4.5 * l_sem, (case, l, l_exact, l_sem)
 
@@ -161,11 +170,15 @@ def test_dissipative_piqmc_samples_the_exact_boltzmann_distribution(mcs, P, glob
     assert not np.array_equal(c, c0)
 
 
-@pytest.mark.parametrize("case", ["graph10_lut", "k10_direct"])
+@pytest.mark.parametrize("case", ["graph10_lut", "circulant10_7planes", "circulant10_8planes", "k10_direct"])
 def test_sa_samples_the_exact_boltzmann_distribution(mcs, case):
     """Fixed temperature, 4096 restarts; tolerance 4.5 standard errors on <E>."""
     if case == "graph10_lut":
         _, nbs = inst.random_graph(10, 16, seed=4, fields=True)
+    elif case == "circulant10_7planes":  # degree 6 + field
+        _, nbs = inst.circulant(10, (1, 2, 3), seed=4, fields=True)
+    elif case == "circulant10_8planes":  # degree 8
+        _, nbs = inst.circulant(10, (1, 2, 3, 4), seed=5, fields=False)
     else:
         import scipy.sparse as sps
         rng = np.random.RandomState(8)
@@ -261,7 +274,8 @@ def test_results_do_not_depend_on_sharding_or_call_splitting(mcs):
     assert np.array_equal(s_whole, s_parts)
 
 
-@pytest.mark.parametrize("case", ["torus_fields_P64", "torus_P20_global", "torus5_fields_P7", "santoro_rows_P64"])
+@pytest.mark.parametrize("case", ["torus_fields_P64", "torus_P20_global", "torus5_fields_P7", "santoro_rows_P64",
+                                  "circulant_8planes_P16"])
 def test_lazily_refined_uniforms_equal_always_refined(mcs, case):
     """The PIQMC pass decides eight attempts per Philox call from 16-bit halves and evaluates the second
     (refinement) call only when a comparison is within 2^-16 of its threshold.  That must be invisible:
@@ -274,6 +288,8 @@ def test_lazily_refined_uniforms_equal_always_refined(mcs, case):
         (_, nbs), P, R, S, glob = inst.torus(6, seed=12), 20, 128, 80, True
     elif case == "torus5_fields_P7":
         (_, nbs), P, R, S, glob = inst.torus(5, seed=4, fields=True), 7, 256, 160, False  # 7 planes, odd P, 3+ colours
+    elif case == "circulant_8planes_P16":  # degree 6: 6 in-plane + 2 Trotter planes, 256-entry table
+        (_, nbs), P, R, S, glob = inst.circulant(40, (1, 2, 3), seed=8, fields=False), 16, 256, 120, True
     else:
         nbs, P, R, S, glob = inst.santoro()[1], 64, 128, 12, False
     n = nbs.shape[0]
@@ -301,15 +317,19 @@ def test_lazily_refined_uniforms_equal_always_refined(mcs, case):
     assert R * S * P * n / 2.0 ** 15 > 50
 
 
-@pytest.mark.parametrize("case", ["torus_fields", "santoro", "graph_deg7"])
+@pytest.mark.parametrize("case", ["torus_fields", "santoro", "graph_deg6", "circulant_7planes", "circulant_8planes"])
 def test_sa_lazily_refined_uniforms_equal_always_refined(mcs, case):
     """Same invariance for the SA pass (mcs_sa.cu shares the decision code, mcs_common.cuh)."""
     if case == "torus_fields":
         nbs, R, S = inst.torus(8, seed=21, fields=True)[1], 4096, 300
     elif case == "santoro":
         nbs, R, S = inst.santoro()[1], 1024, 20
-    else:
+    elif case == "graph_deg6":
         nbs, R, S = inst.random_graph(60, 75, seed=7, fields=True)[1], 2048, 300
+    elif case == "circulant_7planes":  # degree 6 + field: the table index is no longer pre-multiplied (SH = 0)
+        nbs, R, S = inst.circulant(48, (1, 2, 3), seed=5, fields=True)[1], 2048, 300
+    else:
+        nbs, R, S = inst.circulant(48, (1, 2, 3, 4), seed=6, fields=False)[1], 2048, 300
     n = nbs.shape[0]
     I = mcs.Instance(nbs)
     if I.maxdeg + int(I.has_field) > 8:
