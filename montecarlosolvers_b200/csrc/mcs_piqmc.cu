@@ -190,11 +190,13 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
 // FULL: P == 64 (every group exists: no per-pair branch, one basic block).
 // FLD:  the instance has (1) / has no (0) field plane; the in-plane planes are then j < NPL - FLD, all
 //       compile-time (rows shorter than maxdeg are padded with the site itself and J = 0: a zero plane).
+// register cap: the big basic blocks otherwise tempt ptxas into 80+ registers for no gain (measured); 64 is
+// spill-free up to 4 in-plane planes, the 5- and 6-plane kernels get 80
 #ifndef MCS_LUT_MINBLOCKS
-#define MCS_LUT_MINBLOCKS 8 // <= 64 registers: the big basic blocks otherwise tempt ptxas into 80+ for no gain
+#define MCS_LUT_MINBLOCKS(NPL) ((NPL) >= 5 ? 6 : 8)
 #endif
 template <int NPL, int WARPS, bool FULL, int FLD>
-__global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
+__global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
     constexpr int ENT = LutGeom<NPL>::ENT, NQ = NPL - FLD;
     __shared__ uint32_t s_lut[ENT];
