@@ -52,7 +52,7 @@ struct mcs_instance {
     int maxdeg = 0;      // max number of quadratic neighbours of a site (fields excluded)
     int dpad = 1;        // row length of the ELL tables (>= 1)
     bool has_field = false;
-    bool lut_ok = false; // (maxdeg + has_field + 2) <= 8 planes: the LUT kernels apply
+    bool lut_ok = false; // (maxdeg + has_field + 2) <= 10 planes: the threshold-table PIQMC kernels apply
     bool dense = false;  // near-complete graph: blocked tensor-core sweeps (mcs_dense.cu)
     int64_t Npad = 0;    // N rounded up to the dense block size (128)
     int64_t launches = 0;
@@ -357,6 +357,58 @@ __device__ __noinline__ uint2 mcs_refine_call(uint32_t accA, uint32_t accB, cons
         chB |= (uB > TB ? 1u : 0u) << (8 * i);
     }
     return make_uint2(chA, chB);
+}
+
+// ---- wide index fields (9 or 10 planes: degree + field of 7 or 8 in the PIQMC kernel) --------------------
+// The pattern index no longer fits a byte, so an index word holds TWO 16-bit fields (index * 4) and one Philox
+// call serves four index words: A0, A1 (compare x[1], x[0] and x[3], x[2] themselves) and B0, B1 (the same words
+// shifted left by 16).  Otherwise identical to mcs_decide_call / mcs_refine_call: reject bit of field i ends at
+// bit 16 i of the Horner accumulator.
+__device__ __forceinline__ void mcs_decide_call16(uint32_t (&ch)[4], uint32_t &flags, const uint32_t (&acc)[4],
+                                                  const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                  uint32_t c3, const mcs_philox_keys &keys,
+                                                  const mcs_pow2_table &pow2, uint32_t tie_thr, uint4 *slot)
+{
+    uint32_t x[4];
+    mcs_philox4x32_10_rk(c0, c1, c2, c3, keys, x);
+    uint32_t smin = 0xFFFFFFFFu;
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(slot);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(acc[0]), "r"(acc[1]), "r"(acc[2]),
+                 "r"(acc[3])
+                 : "memory");
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        ch[w] = 0;
+#pragma unroll
+        for (int i = 1; i >= 0; --i) {
+            uint32_t off;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(off) : "r"(saddr + 4 * w + 2 * i) : "memory");
+            const uint32_t xi = x[2 * (w & 1) + i];
+            ch[w] = mcs_horner_reject(ch[w], pow2.up[16], mcs_lut_at<2>(lut, off), w < 2 ? xi : xi * pow2.up[16], smin);
+        }
+    }
+    mcs_horner_flag(flags, smin, tie_thr, pow2.up[1]);
+}
+
+static __device__ __noinline__ uint4 mcs_refine_call16(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, const uint32_t *lut,
+                                                uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                uint32_t k1)
+{
+    uint32_t x[4], f[4];
+    mcs_philox4x32_10(c0, c1, c2, c3, k0, k1, x);
+    mcs_philox4x32_10(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
+    const uint32_t acc[4] = {a0, a1, a2, a3};
+    uint32_t ch[4] = {0u, 0u, 0u, 0u}; // reject bit of field i at bit 16 i
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t T = ~mcs_lut_at<2>(lut, (acc[w] >> (16 * i)) & 0xFFFFu);
+            const uint32_t xi = x[2 * (w & 1) + i], fi = f[2 * (w & 1) + i];
+            const uint32_t u = w < 2 ? ((xi & 0xFFFF0000u) | (fi >> 16)) : ((xi << 16) | (fi & 0xFFFFu));
+            ch[w] |= (u > T ? 1u : 0u) << (16 * i);
+        }
+    return make_uint4(ch[0], ch[1], ch[2], ch[3]);
 }
 
 inline uint32_t mcs_tie_threshold()

@@ -211,7 +211,7 @@ extern "C" int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int6
     for (int64_t i = 0; i < nspins; ++i) maxdeg = std::max<int>(maxdeg, (int)nbr[i].size());
     inst->maxdeg = maxdeg;
     inst->dpad = std::max(maxdeg, 1);
-    inst->lut_ok = (maxdeg + (has_field ? 1 : 0) + 2) <= 8;
+    inst->lut_ok = (maxdeg + (has_field ? 1 : 0) + 2) <= 10; // threshold-table PIQMC kernels: up to 8 in-plane planes
 
     inst->order.resize(nspins);
     std::iota(inst->order.begin(), inst->order.end(), 0);

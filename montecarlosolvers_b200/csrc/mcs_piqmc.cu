@@ -64,14 +64,16 @@ __device__ __forceinline__ uint64_t rotr_ring(uint64_t w, int P, uint64_t mask)
     return ((w >> 1) | (w << (P - 1))) & mask; // bit k <- bit k+1
 }
 
-// Pattern-index bits live at byte positions SH .. SH+NPL+1 of an index word (one byte per slice).  With at
-// most 6 planes the index is stored pre-multiplied by 4 (SH = 2) so that the extracted byte IS the
+// Pattern-index bits live at bit positions SH .. SH+NPL+1 of a field of an index word: one BYTE per slice up to
+// 8 planes, one HALF WORD per slice for 9 and 10 planes (FW = field width).  Where it fits (up to 6 planes, and
+// always in half words) the index is stored pre-multiplied by 4 (SH = 2), so that the extracted field IS the
 // shared-memory byte offset of the threshold.
 template <int NPL>
 struct LutGeom {
     static constexpr int NPP = NPL + 2;          // in-plane planes + the two Trotter planes
     static constexpr int ENT = 1 << NPP;         // sign patterns
-    static constexpr int SH = (NPP <= 6) ? 2 : 0;
+    static constexpr int FW = NPP <= 8 ? 8 : 16;
+    static constexpr int SH = (NPP <= 6 || FW == 16) ? 2 : 0;
     static constexpr int NPAIR = (NPP + 1) / 2;
 };
 
@@ -106,6 +108,64 @@ __device__ __forceinline__ uint32_t gather_index(const uint32_t (&m)[(NPP + 1) /
     MCS_PAIRWORD(0) MCS_PAIRWORD(1) MCS_PAIRWORD(2) MCS_PAIRWORD(3)
 #undef MCS_PAIRWORD
     return acc;
+}
+
+// Half-word version (9, 10 planes): field i = pattern index * 4 of slice 16 i + S of this 32-bit half (i = 0, 1).
+template <int NPP, int S, int PARITY>
+__device__ __forceinline__ uint32_t gather_index16(const uint32_t (&m)[(NPP + 1) / 2], const mcs_pow2_table &pow2)
+{
+    constexpr int SH = 2;
+    constexpr int LOW = PARITY == 0 ? S : S - 1; // where plane 2j of a pair sits
+    uint32_t acc = 0;
+#define MCS_PAIRWORD(j)                                                                                       \
+    if (2 * (j) + 1 < NPP)                                                                                    \
+        acc |= mcs_plane_shift<SH + 2 * (j) - LOW>(m[(j) < (NPP + 1) / 2 ? (j) : 0], pow2) & (0x00030003u << (SH + 2 * (j))); \
+    else if (2 * (j) < NPP)                                                                                   \
+        acc |= mcs_plane_shift<SH + 2 * (j) - S>(m[(j) < (NPP + 1) / 2 ? (j) : 0], pow2) & (0x00010001u << (SH + 2 * (j)));
+    MCS_PAIRWORD(0) MCS_PAIRWORD(1) MCS_PAIRWORD(2) MCS_PAIRWORD(3) MCS_PAIRWORD(4)
+#undef MCS_PAIRWORD
+    return acc;
+}
+
+// One call of the half-word version: slices S0 > S1 > S2 > S3 (same parity) of both fields of half HALF;
+// S0, S1 are the "A" groups, S2, S3 the "B" groups of mcs_decide_call16.
+template <int NPL, int S0, int PARITY>
+__device__ __forceinline__ void gather_call16(uint32_t (&acc)[4], const uint32_t (&m)[LutGeom<NPL>::NPAIR],
+                                              const mcs_pow2_table &pow2)
+{
+    constexpr int NPP = LutGeom<NPL>::NPP;
+    acc[0] = gather_index16<NPP, S0, PARITY>(m, pow2);
+    acc[1] = gather_index16<NPP, S0 - 2, PARITY>(m, pow2);
+    acc[2] = gather_index16<NPP, S0 - 4, PARITY>(m, pow2);
+    acc[3] = gather_index16<NPP, S0 - 6, PARITY>(m, pow2);
+}
+
+template <int NPL, int S0, int PARITY>
+__device__ __forceinline__ void decide_call16(uint32_t &rej, uint32_t &flags, const uint32_t (&m)[LutGeom<NPL>::NPAIR],
+                                              const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const mcs_philox_keys &keys, const mcs_pow2_table &pow2,
+                                              uint32_t tie_thr, uint4 *slot)
+{
+    uint32_t acc[4], ch[4];
+    gather_call16<NPL, S0, PARITY>(acc, m, pow2);
+    mcs_decide_call16(ch, flags, acc, lut, c0, c1, c2, c3, keys, pow2, tie_thr, slot);
+    rej = ch[0] * pow2.up[S0] + rej;
+    rej = ch[1] * pow2.up[S0 - 2] + rej;
+    rej = ch[2] * pow2.up[S0 - 4] + rej;
+    rej = ch[3] * pow2.up[S0 - 6] + rej;
+}
+
+template <int NPL, int S0, int PARITY>
+__device__ __forceinline__ void refine_call16(uint32_t &rej, const uint32_t (&m)[LutGeom<NPL>::NPAIR],
+                                              const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const mcs_philox_keys &keys, const mcs_pow2_table &pow2)
+{
+    uint32_t acc[4];
+    gather_call16<NPL, S0, PARITY>(acc, m, pow2);
+    const uint4 ch = mcs_refine_call16(acc[0], acc[1], acc[2], acc[3], lut, c0, c1, c2, c3, keys.rk[0], keys.rk[1]);
+    const uint32_t mask = (0x00010001u << S0) | (0x00010001u << (S0 - 2)) | (0x00010001u << (S0 - 4)) |
+                          (0x00010001u << (S0 - 6));
+    rej = (rej & ~mask) | (ch.x << S0) | (ch.y << (S0 - 2)) | (ch.z << (S0 - 4)) | (ch.w << (S0 - 6));
 }
 
 // Slow path (see mcs_common.cuh, "lazily refined uniforms"): redo one flagged call (groups GA, GB of one half)
@@ -159,6 +219,32 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
             m[H][j] = pb < NPP ? interleave_pair<PARITY>(a, b, pow2) : a;
         }
     uint32_t rej[2] = {0u, 0u}, flags = 0u;
+    if (LutGeom<NPL>::FW == 16) {
+        // half-word index fields: call q of half H covers slices 32 H + 16 i + s, s = S0, S0-2, S0-4, S0-6,
+        // S0 = 14 + PARITY (q = 0) or 6 + PARITY (q = 1); tag = 8 H + 4 PARITY + q
+        uint4 *slot16 = reinterpret_cast<uint4 *>(bounce);
+#define MCS_CALL16(H, Q, S0)                                                                                 \
+    if (FULL || 32 * H + (S0) - 6 < P) {                                                                     \
+        decide_call16<NPL, (S0), PARITY>(rej[H], flags, m[H], lut, c0, c1, c2,                               \
+                                         c3hi | (uint32_t)(8 * H + 4 * PARITY + (Q)), keys, pow2, tie_thr,   \
+                                         slot16 + (2 * H + (Q)) * nthreads);                                 \
+    } else {                                                                                                 \
+        flags *= 2u;                                                                                         \
+    }
+        MCS_CALL16(0, 0, 14 + PARITY) MCS_CALL16(0, 1, 6 + PARITY)
+        MCS_CALL16(1, 0, 14 + PARITY) MCS_CALL16(1, 1, 6 + PARITY)
+#undef MCS_CALL16
+        if (flags) {
+#define MCS_REFINE16(H, Q, S0, BIT)                                                                          \
+    if (flags & (BIT))                                                                                       \
+        refine_call16<NPL, (S0), PARITY>(rej[H], m[H], lut, c0, c1, c2,                                      \
+                                         c3hi | (uint32_t)(8 * H + 4 * PARITY + (Q)), keys, pow2);
+            MCS_REFINE16(0, 0, 14 + PARITY, 8u) MCS_REFINE16(0, 1, 6 + PARITY, 4u)
+            MCS_REFINE16(1, 0, 14 + PARITY, 2u) MCS_REFINE16(1, 1, 6 + PARITY, 1u)
+#undef MCS_REFINE16
+        }
+        return ~(((uint64_t)rej[1] << 32) | rej[0]) & allowed;
+    }
     // group G of half H holds slices 32 H + 8 i + 7 - G; parity of 7 - G == PARITY  <=>  G = 1-PARITY, 3-PARITY, ...
     // pair q = 2 H + (GA > 3) is flags bit 3 - q after the four Horner steps; a pair entirely beyond the last
     // slice is skipped (warp-uniform branch) but still shifts the flags
@@ -191,9 +277,9 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
 // FLD:  the instance has (1) / has no (0) field plane; the in-plane planes are then j < NPL - FLD, all
 //       compile-time (rows shorter than maxdeg are padded with the site itself and J = 0: a zero plane).
 // register cap: the big basic blocks otherwise tempt ptxas into 80+ registers for no gain (measured); 64 is
-// spill-free up to 4 in-plane planes, the 5- and 6-plane kernels get 80
+// spill-free up to 4 in-plane planes, the 5- and 6-plane kernels get 80, the half-word-index kernels 128
 #ifndef MCS_LUT_MINBLOCKS
-#define MCS_LUT_MINBLOCKS(NPL) ((NPL) >= 5 ? 6 : 8)
+#define MCS_LUT_MINBLOCKS(NPL) ((NPL) >= 7 ? 4 : (NPL) >= 5 ? 6 : 8)
 #endif
 template <int NPL, int WARPS, bool FULL, int FLD>
 __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
@@ -253,12 +339,14 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     if (oddP) even_allowed &= ~(1ull << (P - 1)); // slice P-1 neighbours slice 0: handled alone below
     const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
 
-    __shared__ uint2 s_bounce[8 * WARPS * 32]; // [phase][pair][thread]: private slots for the index bytes
-    uint2 *bounce = s_bounce + threadIdx.x;
+    // [phase][call][thread]: private slots for the index fields (8 bytes per call, 16 with half-word fields)
+    __shared__ __align__(16) uint2 s_bounce[(LutGeom<NPL>::FW == 16 ? 16 : 8) * WARPS * 32];
+    constexpr int kSlot = LutGeom<NPL>::FW == 16 ? 2 : 1; // uint2 per thread and call
+    uint2 *bounce = s_bounce + kSlot * threadIdx.x;
     w ^= phase<NPL, 0, FULL>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr, bounce,
                              WARPS * 32);
     w ^= phase<NPL, 1, FULL>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
-                             bounce + 4 * WARPS * 32, WARPS * 32);
+                             bounce + 4 * kSlot * WARPS * 32, WARPS * 32);
     if (oddP) {
         const int k = P - 1;
         const uint64_t tl = w ^ rotl_ring(w, P, pmask), tr = w ^ rotr_ring(w, P, pmask);
@@ -653,7 +741,9 @@ static void launch_lut(int npl, int warps, cudaStream_t s, const PiqmcPass &a)
     case 3: launch_lut_w<3>(warps, a, s); break;
     case 4: launch_lut_w<4>(warps, a, s); break;
     case 5: launch_lut_w<5>(warps, a, s); break;
-    default: launch_lut_w<6>(warps, a, s); break;
+    case 6: launch_lut_w<6>(warps, a, s); break;
+    case 7: launch_lut_w<7>(warps, a, s); break;
+    default: launch_lut_w<8>(warps, a, s); break;
     }
 }
 
@@ -686,7 +776,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     bath.c0 = 0.0f;
     float *d_lut4 = nullptr;
     if (lookuptable) {
-        MCS_REQUIRE(inst->lut_ok, MCS_EUNSUPPORTED,
+        MCS_REQUIRE(inst->maxdeg + (inst->has_field ? 1 : 0) <= 6, MCS_EUNSUPPORTED,
                     "dissipative sweeps: the production kernel keeps a site's neighbour planes in registers "
                     "(degree + field <= 6); use the exact kernel for this instance");
         float h4[64];
@@ -721,6 +811,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;
+    const bool force_direct = getenv("MCS_FORCE_DIRECT") != nullptr; // tests: general-degree kernel on any instance
     MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
                 "time-dependent instance has %lld tables but the schedule has %lld steps", (long long)inst->nsteps,
                 (long long)S);
@@ -741,7 +832,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
                 const long long items = (long long)a.nsites * a.G;
                 if (lookuptable)
                     launch_bath(npl, (unsigned)((items + kWarps - 1) / kWarps), inst->stream, a, bath);
-                else if (inst->lut_ok)
+                else if (inst->lut_ok && !force_direct)
                     launch_lut(npl, warps, inst->stream, a);
                 else
                     piqmc_direct_pass_kernel<<<(unsigned)((items + kWarps - 1) / kWarps), kWarps * 32, 0,
