@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
 // ------------------------------------------------------------------------------------------
 // General-degree pass (any sparse graph): same layout and phases, but the energy difference of
 // each slice is accumulated directly over the ELL row instead of looked up.  Used when a site has
-// more sign patterns than the 256-entry table (maxdeg + field > 6).
+// more sign patterns than the 1024-entry table (maxdeg + field > 8).
 // ------------------------------------------------------------------------------------------
 template <int PARITY>
 __device__ __forceinline__ uint64_t phase_direct(const PiqmcPass &a, int site, long long r, uint64_t w, int P,
