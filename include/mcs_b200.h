@@ -72,7 +72,8 @@ int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int64_t nspins,
                               mcs_instance **out);
 void mcs_instance_destroy(mcs_instance *inst);
 /* info[0]=nspins info[1]=maxnb info[2]=ncolors info[3]=max degree (fields excluded)
- * info[4]=1 if any local field  info[5]=device  info[6]=1 if the LUT kernels apply
+ * info[4]=1 if any local field  info[5]=device  info[6]=1 if the threshold-table PIQMC
+ * kernels apply (degree + field <= 8)
  * info[7]=number of tables (1 unless created by mcs_instance_create_steps); bit 32 set when
  *         the instance is dense (max degree >= 48): sweeps then run as blocked tensor-core GEMM
  *         + in-block sequential updates instead of one colour class per site                */
@@ -147,7 +148,9 @@ int mcs_cluster_moves(mcs_state *st, double a, double b, float temp, int nmoves,
                       uint64_t replica_offset, uint64_t sweep_offset);
 
 /* one-shot host-buffer forms (upload, sweep, download [, energies]) -- what the Python
- * drop-ins call.  energies_out may be NULL.                                                 */
+ * drop-ins call.  energies_out may be NULL.  mcs_piqmc_anneal with R >= 1024 cuts the batch
+ * into replica windows and overlaps the H2D copy / sweeps / D2H copy of neighbouring windows;
+ * page-locked host buffers (mcs_host_alloc) are needed for the overlap, pageable ones work.  */
 int mcs_piqmc_anneal(mcs_instance *inst, const double *A_sched, const double *B_sched,
                      int64_t schedsize, int mcsteps, float temp, int8_t *confs /* [R][N][P] */,
                      int64_t R, int64_t P, int global_moves, uint64_t seed, uint64_t replica_offset,
