@@ -367,7 +367,8 @@ def run_ours(args, out):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u64 bit-packed spins / f32 thresholds / u32 Philox",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+            "dtype_detail": "bit-packed spins in u64 words (bit k = Trotter slice k); u32 acceptance thresholds from f32 energies; u32 Philox",
             "data": name + ", Philox-initialised spins",
             "config": {"workload": "80x80 PIQMC P=64, %d anneals total (%d per GPU), A=linspace(3,1e-8,%d), B=1, "
                                    "mcsteps=1, T=1/64 (BASELINE configs[2])" % (R_total, R, S),
