@@ -133,7 +133,8 @@ int mcs_piqmc_sweeps_dissipative(mcs_state *st, const double *A_sched, const dou
 /* sa.Anneal (sa.pyx:66-101): Metropolis sweeps at temperature sched[itemp]                 */
 int mcs_sa_sweeps(mcs_state *st, const double *sched, int64_t schedsize, int mcsteps, uint64_t seed,
                   uint64_t replica_offset, uint64_t sweep_offset);
-/* svmc.SpinVectorMonteCarlo (svmc.pyx:78-117); tf != 0: SpinVectorMonteCarloTF (:181-229)  */
+/* svmc.SpinVectorMonteCarlo (svmc.pyx:78-117); tf != 0: SpinVectorMonteCarloTF (:181-229).
+ * replica_offset must be a multiple of 4 (one Philox call serves four consecutive replicas). */
 int mcs_svmc_sweeps(mcs_state *st, const double *A_sched, const double *B_sched, int64_t schedsize,
                     int mcsteps, float temp, int tf, uint64_t seed, uint64_t replica_offset,
                     uint64_t sweep_offset);

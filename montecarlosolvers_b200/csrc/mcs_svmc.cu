@@ -35,14 +35,23 @@ struct SvmcPass {
     mcs_philox_keys keys;
     uint32_t sweep_lo, sweep_hi;
     uint32_t replica_offset;
+    int always_refine; // MCS_ALWAYS_REFINE=1: evaluate the refinement call for every thread (timing / test hook)
 };
 
-// Rotor attempt (svmc.pyx:92-115) given the z-field of the site; (u0, u1) are its two 32-bit uniforms.
-__device__ __forceinline__ void svmc_decide(const SvmcPass &a, float zfield, float &th, float &cz, uint32_t u0,
-                                            uint32_t u1)
+// Rotor attempt (svmc.pyx:92-115) given the z-field of the site, from ONE 32-bit Philox word x:
+//   * proposal: the high 20 bits, theta' = pi (x >> 12) 2^-20 (or the TF displacement);
+//   * acceptance: exp(-dE/T) > u (svmc.pyx:112-115) with u = (v + r) / 4096, v = the low 12 bits of x and
+//     r in [0, 1) 32 more bits of a SECOND Philox call that is evaluated only when it matters (lazily refined
+//     uniform, as in the Ising kernels): with t = 4096 exp(-dE/T) the move is certainly accepted if v + 1 <= t,
+//     certainly rejected if v >= t, and only for floor(t) == v (probability 2^-12 per attempt) is r needed.
+//     dE <= 0 is accepted outright (t >= 4096 > v anyway, except 0 * inf at T = 0); NaN (inf - inf) is rejected.
+// Returns true if the attempt is undecided; th / cz are updated for decided accepts, (thp, cp, t - v) are kept
+// for the refinement.
+__device__ __forceinline__ bool svmc_decide(const SvmcPass &a, float zfield, float &th, float &cz, uint32_t x,
+                                            float &thp_out, float &cp_out, float &gap)
 {
     const float kPi = 3.14159265358979323846f;
-    const float f0 = (float)(u0 >> 8) * (1.0f / 16777216.0f); // [0, 1)
+    const float f0 = (float)(x >> 12) * (1.0f / 1048576.0f); // [0, 1)
     float thp;
     if (!a.tf) {
         thp = kPi * f0; // svmc.pyx:95
@@ -54,12 +63,17 @@ __device__ __forceinline__ void svmc_decide(const SvmcPass &a, float zfield, flo
     __sincosf(thp, &sp, &cp);
     const float si = __sinf(th);
     const float dE = a.b_coef * (cp - cz) * zfield + a.a_coef * (si - sp); // svmc.pyx:96-110
-    // Metropolis (svmc.pyx:112-115): dE <= 0 or exp(-dE/T) > u  <=>  dE * (-log2 e / T) > log2 u
-    const float lu = __log2f((float)u1 + 1.0f) - 32.0f;
-    if (dE <= 0.0f || dE * a.nl2e_over_t >= lu) {
+    const float t = exp2f(fmaf(dE, a.nl2e_over_t, 12.0f));                 // 4096 exp(-dE/T)
+    const float v = (float)(x & 0xFFFu);
+    const bool yes = (dE <= 0.0f) | (v + 1.0f <= t), no = !yes & (v >= t); // dE <= 0 explicit: T = 0 gives 0 * inf
+    if (yes) {
         th = thp;
         cz = cp;
     }
+    thp_out = thp;
+    cp_out = cp;
+    gap = t - v; // undecided: accept iff r < gap
+    return !(yes | no);
 }
 
 // A lane owns FOUR consecutive replicas of one site (128-bit loads of theta, cos theta and of every
@@ -94,16 +108,26 @@ __global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_con
         z.z = fmaf(jv, c.z, z.z);
         z.w = fmaf(jv, c.w, z.w);
     }
-    uint32_t ra[4], rb[4];
-    // one Philox call per pair of replicas; the counter is the GLOBAL pair index, so a shard starting at an
-    // even replica_offset reproduces the un-sharded run
-    const uint32_t c0 = (a.replica_offset >> 1) + (uint32_t)(r >> 1);
-    mcs_philox4x32_10_rk(c0, (uint32_t)site, a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_SVMC, a.keys, ra);
-    mcs_philox4x32_10_rk(c0 + 1u, (uint32_t)site, a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_SVMC, a.keys, rb);
-    svmc_decide(a, z.x, th.x, cz.x, ra[0], ra[1]);
-    svmc_decide(a, z.y, th.y, cz.y, ra[2], ra[3]);
-    svmc_decide(a, z.z, th.z, cz.z, rb[0], rb[1]);
-    svmc_decide(a, z.w, th.w, cz.w, rb[2], rb[3]);
+    // one Philox call per four replicas; the counter is the GLOBAL quad index, so a shard starting at a multiple
+    // of four reproduces the un-sharded run
+    uint32_t x[4];
+    const uint32_t c0 = (a.replica_offset >> 2) + (uint32_t)(r >> 2);
+    const uint32_t c3 = (a.sweep_hi << 8) | MCS_TAG_SVMC;
+    mcs_philox4x32_10_rk(c0, (uint32_t)site, a.sweep_lo, c3, a.keys, x);
+    float tp[4], cp[4], gap[4];
+    const bool u0 = svmc_decide(a, z.x, th.x, cz.x, x[0], tp[0], cp[0], gap[0]);
+    const bool u1 = svmc_decide(a, z.y, th.y, cz.y, x[1], tp[1], cp[1], gap[1]);
+    const bool u2 = svmc_decide(a, z.z, th.z, cz.z, x[2], tp[2], cp[2], gap[2]);
+    const bool u3 = svmc_decide(a, z.w, th.w, cz.w, x[3], tp[3], cp[3], gap[3]);
+    if ((u0 | u1 | u2 | u3) || a.always_refine) { // rare (2^-10 per thread): the low half of the uniforms
+        uint32_t f[4];
+        mcs_philox4x32_10_rk(c0, (uint32_t)site, a.sweep_lo, c3 | MCS_TAG_REFINE, a.keys, f);
+        const float k32 = 1.0f / 4294967296.0f;
+        if (u0 && (float)f[0] * k32 < gap[0]) { th.x = tp[0]; cz.x = cp[0]; }
+        if (u1 && (float)f[1] * k32 < gap[1]) { th.y = tp[1]; cz.y = cp[1]; }
+        if (u2 && (float)f[2] * k32 < gap[2]) { th.z = tp[2]; cz.z = cp[2]; }
+        if (u3 && (float)f[3] * k32 < gap[3]) { th.w = tp[3]; cz.w = cp[3]; }
+    }
     *th_ptr = th;
     *cz_ptr = cz;
 }
@@ -168,7 +192,7 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
                            int tf, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
 {
     mcs_instance *inst = st->inst;
-    MCS_REQUIRE((replica_offset & 1) == 0, MCS_EINVAL, "mcs_svmc_sweeps: replica_offset must be even");
+    MCS_REQUIRE((replica_offset & 3) == 0, MCS_EINVAL, "mcs_svmc_sweeps: replica_offset must be a multiple of 4");
     MCS_CUDA(cudaSetDevice(inst->device));
     SvmcPass a;
     a.theta = st->d_theta;
@@ -183,6 +207,7 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
     a.tf = tf ? 1 : 0;
     a.keys = mcs_philox_expand(seed);
     a.replica_offset = (uint32_t)replica_offset;
+    a.always_refine = mcs_tie_threshold() == 0xFFFFFFFFu ? 1 : 0;
     a.nl2e_over_t = (float)(-1.4426950408889634 / (double)temp); // temp is a C float (svmc.pyx:24)
     uint64_t sweep = sweep_offset;
     MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
