@@ -88,19 +88,20 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sa_lut_pass_kernel(const __grid
         for (int j = 0; j < NPL; ++j) dE += ((e >> j) & 1) ? -c[j] : c[j];
         s_lut[e] = ~mcs_accept_threshold(dE, a.nl2e_over_t);
     }
-    if (WARPS == 1)
-        __syncwarp();
-    else
-        __syncthreads();
-    if (g >= a.G) return;
-
+    // the state loads are issued BEFORE the barrier that publishes the table: their latency hides behind it
     const uint32_t G32 = (uint32_t)a.G;
-    uint32_t *Vg = a.V + g;
+    const bool live = g < G32;
+    uint32_t *Vg = a.V + (live ? g : 0u);
     mcs_pdl_wait(); // everything above depends on the instance and the schedule only
     const uint32_t v = Vg[(uint64_t)(uint32_t)site * G32];
     uint32_t pl[NPL];
 #pragma unroll
     for (int j = 0; j < NPL; ++j) pl[j] = j < NQ ? v ^ Vg[(uint64_t)(uint32_t)nb[j] * G32] : v;
+    if (WARPS == 1)
+        __syncwarp();
+    else
+        __syncthreads();
+    if (!live) return;
     const uint32_t c0 = a.word_offset + g, c1 = (uint32_t)site, c2 = a.sweep_lo, c3hi = a.sweep_hi << 8;
     uint2 *bounce = s_bounce + threadIdx.x;
     uint32_t rej = 0, flags = 0;
