@@ -17,7 +17,8 @@ def shard(R, rank, world):
 
 
 def shard_aligned(R, rank, world, align=32):
-    """As shard() but every boundary is a multiple of `align` (SA packs 32 restarts per word)."""
+    """As shard() but every boundary is a multiple of `align` (SA packs 32 restarts per word, SVMC draws one
+    Philox call per four reads: their replica_offset must be a multiple of 32 / 4)."""
     blocks = (int(R) + align - 1) // align
     lo, hi = shard(blocks, rank, world)
     return min(lo * align, R), min(hi * align, R)

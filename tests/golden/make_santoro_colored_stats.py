@@ -25,7 +25,7 @@ from oracle import oracle as orc  # noqa: E402
 from tests import instances as inst  # noqa: E402
 
 N, P = 6400, 20
-TAUS = (60, 146, 354)
+TAUS = (60, 146, 354, 857)
 COLORS = ((np.arange(N) // 80 + np.arange(N) % 80) & 1).astype(np.int32)  # checkerboard (row + col) & 1
 
 

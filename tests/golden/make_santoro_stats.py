@@ -35,7 +35,7 @@ from tests import instances as inst  # noqa: E402
 
 N = 6400
 P = 20
-TAUS = (60, 146, 354)
+TAUS = (60, 146, 354, 857)
 
 
 def _init():
