@@ -457,7 +457,7 @@ def _tier_c(name, got, ref_cell):
     assert 0.6 <= got.std(ddof=1) / ref.std(ddof=1) <= 1.6, msg
 
 
-@pytest.mark.parametrize("tau", [60, 146, 354])
+@pytest.mark.parametrize("tau", [60, 146, 354, 857])
 def test_santoro_sa_residual_energy_matches_reference(mcs, tau):
     """Tier (c), CA protocol of santoro80.py:258-262: 256 anneals from the same initial states as the
     reference run; acceptance = _tier_c."""
@@ -473,7 +473,7 @@ def test_santoro_sa_residual_energy_matches_reference(mcs, tau):
 
 
 @pytest.mark.parametrize("glob", [1, 0])
-@pytest.mark.parametrize("tau", [60, 146, 354])
+@pytest.mark.parametrize("tau", [60, 146, 354, 857])
 def test_santoro_piqmc_residual_energy_matches_reference(mcs, tau, glob):
     """Tier (c), PIQMC protocol of santoro80.py:279-298 (P = 20, PT = 1, Gamma 3 -> 1e-8 in tau steps, one
     sweep each, best slice), started from the SAME 256 pre-annealed states as the reference run."""
