@@ -203,7 +203,7 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
     constexpr int kMaxWin = 16;
     long long win[kMaxWin];
     int nwin = 0;
-    const bool windows = R >= 1024 && !mcs_dense_supported(inst, (int)P);
+    const bool windows = st->Rpad >= 384 && !mcs_dense_supported(inst, (int)P);
     if (windows && !inst->s_in) {
         MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_in, cudaStreamNonBlocking));
         MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_out, cudaStreamNonBlocking));
@@ -256,7 +256,14 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
                 q = *end == ',' ? end + 1 : end;
             }
             win[nwin++] = left;
-        } else if (gbs >= 16.0 || left < 12 * e) { // fast link: [e, big, 2e]
+        } else if (left < 12 * e) { // small batch: one more window, or [rest - e, e] behind a slow link
+            if (gbs < 16.0 && left >= 3 * e) {
+                win[nwin++] = left - e;
+                win[nwin++] = e;
+            } else {
+                win[nwin++] = left;
+            }
+        } else if (gbs >= 16.0) { // fast link: [e, big, 2e]
             win[nwin++] = left - 2 * e;
             win[nwin++] = 2 * e;
         } else { // slow link: e, 2e, 4e, 4e, ..., 2e, e
