@@ -98,6 +98,8 @@ struct mcs_state {
     size_t stage_bytes = 0;
     void *d_S16 = nullptr;    // dense sweeps: spins as bf16 +-1, [Cpad][Npad], column = (replica, slice)
     long long S16_cols = 0;
+    double *d_eout = nullptr;    // per-replica energies of mcs_state_energies (kept: no cudaMalloc per call)
+    size_t eout_bytes = 0;
     int32_t *d_labels = nullptr; // cluster moves: union-find parents [(N P + 1)][replicas]
     size_t labels_bytes = 0;
     // active replica window [v0, v0 + vR) of a PIQMC batch (vR < 0: everything).  Replicas are independent, so

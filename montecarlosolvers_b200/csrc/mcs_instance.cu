@@ -307,6 +307,7 @@ static void state_release_device(mcs_state *st)
     cudaFree(st->d_cosz);
     cudaFree(st->d_stage);
     cudaFree(st->d_S16);
+    cudaFree(st->d_eout);
     st->d_S16 = nullptr;
     st->S16_cols = 0;
     cudaFree(st->d_labels);
