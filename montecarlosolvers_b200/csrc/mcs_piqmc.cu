@@ -53,6 +53,7 @@ struct PiqmcPass {
     uint32_t replica_offset;
     int global_moves;
     uint32_t tie_thr; // 0x20000; 0xffffffff evaluates the refinement call for every attempt (test hook)
+    long long half;   // fused mode (P <= 32, two replicas per thread): replica r is paired with r + half
 };
 
 __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
@@ -62,6 +63,21 @@ __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
 __device__ __forceinline__ uint64_t rotr_ring(uint64_t w, int P, uint64_t mask)
 {
     return ((w >> 1) | (w << (P - 1))) & mask; // bit k <- bit k+1
+}
+
+__device__ __forceinline__ uint64_t b0_shift(int P) { return 0x0000000100000001ull << (P - 1); }
+
+// Fused mode: two world lines of P <= 32 slices in one 64-bit word (replica A in the low, replica B in the high
+// half); the Trotter ring closes inside each half.
+__device__ __forceinline__ uint64_t rotl_ring2(uint64_t w, int P, uint64_t pm2)
+{
+    const uint64_t b0 = 0x0000000100000001ull;
+    return ((w << 1) & pm2 & ~b0) | ((w >> (P - 1)) & b0);
+}
+__device__ __forceinline__ uint64_t rotr_ring2(uint64_t w, int P, uint64_t pm2)
+{
+    const uint64_t bp = b0_shift(P);
+    return ((w >> 1) & pm2 & ~bp) | ((w << (P - 1)) & bp);
 }
 
 // Pattern-index bits live at bit positions SH .. SH+NPL+1 of a field of an index word: one BYTE per slice up to
@@ -183,30 +199,33 @@ __device__ __forceinline__ void refine_pair(uint32_t &rej, const uint32_t (&m)[L
 }
 
 // groups GA and GB (same half, same parity) share one Philox call; rej accumulates REJECT bits
-template <int NPL, int GA, int GB, int HALF>
+template <int NPL, int GA, int GB>
 __device__ __forceinline__ void decide_pair(uint32_t &rej, uint32_t &flags, uint32_t accA, uint32_t accB,
                                             const uint32_t *lut, uint32_t c0, uint32_t c1, uint32_t c2,
-                                            uint32_t c3hi, const mcs_philox_keys &keys, const mcs_pow2_table &pow2,
+                                            uint32_t c3, const mcs_philox_keys &keys, const mcs_pow2_table &pow2,
                                             uint32_t tie_thr, uint2 *slot)
 {
     uint32_t chA, chB;
-    mcs_decide_call<LutGeom<NPL>::SH>(chA, chB, flags, accA, accB, lut, c0, c1, c2,
-                                      c3hi | (uint32_t)(HALF * 8 + GA), keys, pow2, tie_thr, slot);
+    mcs_decide_call<LutGeom<NPL>::SH>(chA, chB, flags, accA, accB, lut, c0, c1, c2, c3, keys, pow2, tie_thr, slot);
     rej = chA * pow2.up[7 - GA] + rej;
     rej = chB * pow2.up[7 - GB] + rej;
 }
 
 // One Trotter-parity phase of a word: attempts every slice k with k % 2 == PARITY that is in `allowed`,
 // against the (complemented) thresholds in lut[].  Returns the flip mask.
-template <int NPL, int PARITY, bool FULL>
+// FUSE: the two 32-bit halves are two replicas (counters c0h[0], c0h[1]) of P <= 32 slices each; every half then
+// uses the tags and the skip rule of half 0, so a replica gets exactly the decisions it would get alone.
+template <int NPL, int PARITY, bool FULL, bool FUSE>
 __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w, int P, uint64_t pmask,
-                                          uint64_t allowed, const uint32_t *lut, uint32_t c0, uint32_t c1,
+                                          uint64_t allowed, const uint32_t *lut, const uint32_t (&c0h)[2], uint32_t c1,
                                           uint32_t c2, uint32_t c3hi, const mcs_philox_keys &keys,
                                           const mcs_pow2_table &pow2, uint32_t tie_thr, uint2 *bounce, int nthreads)
 {
     constexpr int NPP = LutGeom<NPL>::NPP, NPAIR = LutGeom<NPL>::NPAIR;
-    const uint64_t tl = w ^ rotl_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k-1
-    const uint64_t tr = w ^ rotr_ring(w, P, pmask); // bit k: slice k anti-aligned with slice k+1
+    // bit k: slice k anti-aligned with slice k-1 / k+1
+    const uint64_t tl = w ^ (FUSE ? rotl_ring2(w, P, pmask) : rotl_ring(w, P, pmask));
+    const uint64_t tr = w ^ (FUSE ? rotr_ring2(w, P, pmask) : rotr_ring(w, P, pmask));
+    const uint32_t c0 = c0h[0];
     uint32_t m[2][NPAIR];
 #pragma unroll
     for (int H = 0; H < 2; ++H)
@@ -249,11 +268,12 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
     // pair q = 2 H + (GA > 3) is flags bit 3 - q after the four Horner steps; a pair entirely beyond the last
     // slice is skipped (warp-uniform branch) but still shifts the flags
 #define MCS_PAIR(H, GA, GB)                                                                                  \
-    if (FULL || 32 * H + 7 - (GB) < P) {                                                                     \
+    if (FULL || (FUSE ? 0 : 32 * H) + 7 - (GB) < P) {                                                        \
         const uint32_t accA = gather_index<NPP, (GA), PARITY>(m[H], pow2);                                   \
         const uint32_t accB = gather_index<NPP, (GB), PARITY>(m[H], pow2);                                   \
-        decide_pair<NPL, (GA), (GB), H>(rej[H], flags, accA, accB, lut, c0, c1, c2, c3hi, keys, pow2, tie_thr, \
-                                        bounce + (2 * H + (GA) / 4) * nthreads);                                    \
+        decide_pair<NPL, (GA), (GB)>(rej[H], flags, accA, accB, lut, c0h[FUSE ? H : 0], c1, c2,              \
+                                     c3hi | (uint32_t)((FUSE ? 0 : H) * 8 + (GA)), keys, pow2, tie_thr,      \
+                                     bounce + (2 * H + (GA) / 4) * nthreads);                                \
     } else {                                                                                                 \
         flags *= 2u;                                                                                         \
     }
@@ -263,7 +283,8 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
     if (flags) { // rare (about 3 % of the warp-phases): Horner order, pair 0 ended at bit 3 ... pair 3 at bit 0
 #define MCS_REFINE(H, GA, GB, BIT)                                                                           \
     if (flags & (BIT))                                                                                       \
-        refine_pair<NPL, (GA), (GB), PARITY>(rej[H], m[H], lut, c0, c1, c2, c3hi | (uint32_t)(H * 8 + (GA)), keys, pow2);
+        refine_pair<NPL, (GA), (GB), PARITY>(rej[H], m[H], lut, c0h[FUSE ? H : 0], c1, c2,                   \
+                                             c3hi | (uint32_t)((FUSE ? 0 : H) * 8 + (GA)), keys, pow2);
         MCS_REFINE(0, 1 - PARITY, 3 - PARITY, 8u) MCS_REFINE(0, 5 - PARITY, 7 - PARITY, 4u)
         MCS_REFINE(1, 1 - PARITY, 3 - PARITY, 2u) MCS_REFINE(1, 5 - PARITY, 7 - PARITY, 1u)
 #undef MCS_REFINE
@@ -281,9 +302,13 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
 #ifndef MCS_LUT_MINBLOCKS
 #define MCS_LUT_MINBLOCKS(NPL) ((NPL) >= 7 ? 4 : (NPL) >= 5 ? 6 : 8)
 #endif
-template <int NPL, int WARPS, bool FULL, int FLD>
+// FUSE: P <= 32 and the thread owns TWO replicas, r and r + a.half, as the low and the high half of one working
+//       word -- a word's worth of Philox calls, transpositions and decisions then serves 2 P instead of P
+//       attempts (P = 20: 6.5e11 -> 1.0e12 attempts/s).  The decisions of a replica do not depend on the mode.
+template <int NPL, int WARPS, bool FULL, int FLD, bool FUSE>
 __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
+    static_assert(!(FULL && FUSE), "fused mode is for P <= 32");
     constexpr int ENT = LutGeom<NPL>::ENT, NQ = NPL - FLD;
     __shared__ uint32_t s_lut[ENT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -315,64 +340,87 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
         s_lut[e] = ~mcs_accept_threshold(dE, a.nl2e_over_t);
     }
 
-    // ---- this lane's world line and its in-plane anti-alignment planes ------------------------
+    // ---- this lane's world line(s) and the in-plane anti-alignment planes ----------------------
     const int P = FULL ? 64 : a.P;
-    const uint64_t pmask = (FULL || P == 64) ? ~0ull : ((1ull << P) - 1ull);
+    const uint64_t pm1 = (FULL || P == 64) ? ~0ull : ((1ull << P) - 1ull); // one world line
+    const uint64_t pmask = FUSE ? (pm1 | (pm1 << 32)) : pm1;                 // the working word
     // row offsets as one IMAD.WIDE.U32 each (site indices and Rpad are below 2^32)
     const uint32_t rpad = (uint32_t)a.Rpad;
-    const uint64_t *Wr = a.W + r;
+    const uint64_t *Wr = a.W + r, *Wr2 = Wr + (FUSE ? a.half : 0);
     mcs_pdl_wait(); // everything above depends on the instance and the schedule only
-    uint64_t w = Wr[(uint64_t)(uint32_t)site * rpad];
+    auto load = [&](int row) -> uint64_t {
+        const uint64_t lo = Wr[(uint64_t)(uint32_t)row * rpad];
+        return FUSE ? (lo | (Wr2[(uint64_t)(uint32_t)row * rpad] << 32)) : lo;
+    };
+    uint64_t w = load(site);
     uint64_t pl[NPL];
 #pragma unroll
-    for (int j = 0; j < NPL; ++j)
-        pl[j] = j < NQ ? (w ^ Wr[(uint64_t)(uint32_t)nb[j] * rpad]) & pmask : w; // field plane: bit set <=> s = -1
+    for (int j = 0; j < NPL; ++j) pl[j] = j < NQ ? (w ^ load(nb[j])) & pmask : w; // field plane: bit set <=> s = -1
     if (WARPS == 1)
         __syncwarp();
     else
         __syncthreads();
     const uint32_t *lut = s_lut;
-    const uint32_t c0 = a.replica_offset + (uint32_t)r, c1 = (uint32_t)site, c2 = a.sweep_lo;
+    const uint32_t c0h[2] = {a.replica_offset + (uint32_t)r, a.replica_offset + (uint32_t)(r + a.half)};
+    const uint32_t c1 = (uint32_t)site, c2 = a.sweep_lo;
     const uint32_t c3hi = a.sweep_hi << 8;
     const bool oddP = !FULL && (P & 1) != 0;
+    const uint64_t last = FUSE ? b0_shift(P) : (1ull << (P - 1)); // slice P-1 of every world line in the word
     uint64_t even_allowed = 0x5555555555555555ull & pmask;
-    if (oddP) even_allowed &= ~(1ull << (P - 1)); // slice P-1 neighbours slice 0: handled alone below
+    if (oddP) even_allowed &= ~last; // slice P-1 neighbours slice 0: handled alone below
     const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
 
     // [phase][call][thread]: private slots for the index fields (8 bytes per call, 16 with half-word fields)
     __shared__ __align__(16) uint2 s_bounce[(LutGeom<NPL>::FW == 16 ? 16 : 8) * WARPS * 32];
     constexpr int kSlot = LutGeom<NPL>::FW == 16 ? 2 : 1; // uint2 per thread and call
     uint2 *bounce = s_bounce + kSlot * threadIdx.x;
-    w ^= phase<NPL, 0, FULL>(pl, w, P, pmask, even_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr, bounce,
-                             WARPS * 32);
-    w ^= phase<NPL, 1, FULL>(pl, w, P, pmask, odd_allowed, lut, c0, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
-                             bounce + 4 * kSlot * WARPS * 32, WARPS * 32);
+    w ^= phase<NPL, 0, FULL, FUSE>(pl, w, P, pmask, even_allowed, lut, c0h, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
+                                   bounce, WARPS * 32);
+    w ^= phase<NPL, 1, FULL, FUSE>(pl, w, P, pmask, odd_allowed, lut, c0h, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
+                                   bounce + 4 * kSlot * WARPS * 32, WARPS * 32);
     if (oddP) {
-        const int k = P - 1;
-        const uint64_t tl = w ^ rotl_ring(w, P, pmask), tr = w ^ rotr_ring(w, P, pmask);
-        uint32_t idx = 0;
+        const uint64_t tl = w ^ (FUSE ? rotl_ring2(w, P, pmask) : rotl_ring(w, P, pmask));
+        const uint64_t tr = w ^ (FUSE ? rotr_ring2(w, P, pmask) : rotr_ring(w, P, pmask));
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) idx |= (uint32_t)((pl[j] >> k) & 1ull) << j;
-        idx |= (uint32_t)((tl >> k) & 1ull) << NPL;
-        idx |= (uint32_t)((tr >> k) & 1ull) << (NPL + 1);
-        uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
-        if (rnd[0] <= ~lut[idx]) w ^= 1ull << k;
+        for (int hh = 0; hh < (FUSE ? 2 : 1); ++hh) {
+            const int k = P - 1 + 32 * hh;
+            uint32_t idx = 0;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) idx |= (uint32_t)((pl[j] >> k) & 1ull) << j;
+            idx |= (uint32_t)((tl >> k) & 1ull) << NPL;
+            idx |= (uint32_t)((tr >> k) & 1ull) << (NPL + 1);
+            uint32_t rnd[4];
+            mcs_philox4x32_10_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
+            if (rnd[0] <= ~lut[idx]) w ^= 1ull << k;
+        }
     }
 
     // ---- world-line move: flip all P slices of this site (qmc.pyx:405-438) ---------------------
     if (a.global_moves) {
-        float dE = 0.0f;
+        float dE[2] = {0.0f, 0.0f};
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-            const uint64_t x = j < NQ ? (w ^ Wr[(uint64_t)(uint32_t)nb[j] * rpad]) & pmask : w & pmask;
-            dE += c[j] * (float)(P - 2 * __popcll(x));
+            const uint64_t x = j < NQ ? (w ^ load(nb[j])) & pmask : w & pmask;
+            if (FUSE) {
+                dE[0] += c[j] * (float)(P - 2 * __popc((uint32_t)x));
+                dE[1] += c[j] * (float)(P - 2 * __popc((uint32_t)(x >> 32)));
+            } else {
+                dE[0] += c[j] * (float)(P - 2 * __popcll(x));
+            }
         }
-        uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
-        if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
+#pragma unroll
+        for (int hh = 0; hh < (FUSE ? 2 : 1); ++hh) {
+            uint32_t rnd[4];
+            mcs_philox4x32_10_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
+            if (rnd[0] <= mcs_accept_threshold(dE[hh], a.nl2e_over_t)) w ^= FUSE ? (pm1 << (32 * hh)) : pm1;
+        }
     }
-    a.W[(uint64_t)(uint32_t)site * rpad + r] = w;
+    if (FUSE) {
+        a.W[(uint64_t)(uint32_t)site * rpad + r] = w & 0xFFFFFFFFull;
+        a.W[(uint64_t)(uint32_t)site * rpad + r + a.half] = w >> 32;
+    } else {
+        a.W[(uint64_t)(uint32_t)site * rpad + r] = w;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -709,19 +757,35 @@ __global__ void piqmc_energy_kernel(const uint64_t *__restrict__ W, const int32_
 // launchers
 // ------------------------------------------------------------------------------------------
 template <int NPL, int FLD>
-static void launch_lut_wf(int warps, const PiqmcPass &a, cudaStream_t s)
+static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
 {
     // a.G = warps of work per site; `warps` divides it, so a CTA never straddles two sites
+    PiqmcPass a = a0;
     const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
+    static const bool no_fuse = getenv("MCS_NO_FUSE") != nullptr; // tests: one replica per thread for every P
+    if (LutGeom<NPL>::FW == 8 && a.P <= 32 && a.G % 2 == 0 && !no_fuse) {
+        // two replicas per thread: r and r + half, half = the window's replicas / 2
+        const int gf = a.G / 2, wf = (gf % 4 == 0) ? 4 : (gf % 2 == 0) ? 2 : 1;
+        a.half = (long long)gf * 32;
+        const dim3 grid((unsigned)(gf / wf), ny, nz);
+        if (wf == 4)
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, LutGeom<NPL>::FW == 8>, grid, dim3(128), s, a);
+        else if (wf == 2)
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, LutGeom<NPL>::FW == 8>, grid, dim3(64), s, a);
+        else
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, LutGeom<NPL>::FW == 8>, grid, dim3(32), s, a);
+        return;
+    }
+    a.half = 0;
     const dim3 grid((unsigned)(a.G / warps), ny, nz);
     if (a.P == 64 && warps == 4)
-        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD>, grid, dim3(128), s, a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD, false>, grid, dim3(128), s, a);
     else if (warps == 4)
-        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD>, grid, dim3(128), s, a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, false>, grid, dim3(128), s, a);
     else if (warps == 2)
-        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD>, grid, dim3(64), s, a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, false>, grid, dim3(64), s, a);
     else
-        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD>, grid, dim3(32), s, a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, false>, grid, dim3(32), s, a);
 }
 
 template <int NPL>
