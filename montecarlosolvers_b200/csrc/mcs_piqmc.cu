@@ -762,7 +762,7 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
     // a.G = warps of work per site; `warps` divides it, so a CTA never straddles two sites
     PiqmcPass a = a0;
     const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
-    static const bool no_fuse = getenv("MCS_NO_FUSE") != nullptr; // tests: one replica per thread for every P
+    const bool no_fuse = getenv("MCS_NO_FUSE") != nullptr; // tests: one replica per thread for every P
     if (LutGeom<NPL>::FW == 8 && a.P <= 32 && a.G % 2 == 0 && !no_fuse) {
         // two replicas per thread: r and r + half, half = the window's replicas / 2
         const int gf = a.G / 2, wf = (gf % 4 == 0) ? 4 : (gf % 2 == 0) ? 2 : 1;

@@ -375,6 +375,34 @@ def test_sa_lazily_refined_uniforms_equal_always_refined(mcs, case):
     assert R * S * n / 2.0 ** 15 > 50
 
 
+@pytest.mark.parametrize("P", [2, 7, 20, 31, 32])
+def test_two_replicas_per_thread_do_not_change_any_decision(mcs, P):
+    """For P <= 32 the PIQMC pass handles replicas r and r + R/2 in the two halves of one working word
+    (mcs_piqmc.cu, FUSE).  Every replica keeps its own Philox counter and the tags of half 0, so the trajectories
+    must equal those of the one-replica-per-thread kernel (MCS_NO_FUSE=1) bit for bit -- odd and even P, fields,
+    world-line moves, a batch that is (192) and one that is not (96: falls back by itself) a multiple of 64."""
+    _, nbs = inst.torus(6, seed=31, fields=True)
+    n, S = 36, 25
+    A, B = np.linspace(2.5, 0.05, S), np.ones(S)
+    I = mcs.Instance(nbs)
+    for R in (192, 96):
+        c0 = (2 * np.random.RandomState(P).randint(2, size=(R, n, P)) - 1).astype(np.int8)
+        out = []
+        for no_fuse in (False, True):
+            if no_fuse:
+                os.environ["MCS_NO_FUSE"] = "1"
+            try:
+                st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+                st.upload_spins(c0)
+                st.piqmc_sweeps(A, B, 2, 1.0 / P, global_moves=True, seed=17)
+                out.append(st.download_spins())
+                st.close()
+            finally:
+                os.environ.pop("MCS_NO_FUSE", None)
+        assert not np.array_equal(out[0], c0)
+        assert np.array_equal(out[0], out[1]), (P, R)
+
+
 def test_time_dependent_tables_production(mcs):
     """Noisy* production path: constant tables == the static instance bit for bit (same Philox stream);
     a table that switches the couplings on over time is honoured step by step."""
