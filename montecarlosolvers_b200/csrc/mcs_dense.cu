@@ -780,13 +780,15 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
         st->S16_cols = Cpad;
     }
     __nv_bfloat16 *S16 = (__nv_bfloat16 *)st->d_S16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // opt-in shared-memory sizes are a per-device property of the function: set them once per device
+    static bool attr_set[64] = {};
+    const int dev = inst->device;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         MCS_CUDA(cudaFuncSetAttribute(dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemBytes));
         MCS_CUDA(cudaFuncSetAttribute(dense_block_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemBytesTc));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     // MCS_DENSE_IMPL=wmma selects the legacy-tensor-path variant (cross-check); default: tcgen05 + TMA
     const char *impl = getenv("MCS_DENSE_IMPL");
