@@ -82,6 +82,18 @@ int mcs_instance_colors(const mcs_instance *inst, int32_t *color /* [nspins] */)
 /* dense instances only: enable = 0 routes sweeps through the general coloured kernels instead of the
  * blocked tensor-core path (used to cross-check the two)                                      */
 int mcs_instance_set_dense(mcs_instance *inst, int enable);
+/* Which dynamics mcs_piqmc_sweeps / mcs_sa_sweeps and the one-shot *_anneal calls run on this instance:
+ *   MCS_DYN_COLORED   (default) colour class by colour class, Trotter parity by parity -- the fastest order;
+ *                     same Boltzmann distribution, but an anneal relaxes slightly faster per sweep than the
+ *                     reference's (residual energies 6-9 % lower on santoro_80x80);
+ *   MCS_DYN_REFERENCE the reference's own order in distribution: per (replica, sweep, slice) a fresh uniformly
+ *                     random visiting permutation, strictly sequential visits, slices in order (qmc.pyx:99-143,
+ *                     sa.pyx:73-99), then the world-line moves in one more permutation (qmc.pyx:405-438).  Executed
+ *                     as dependency waves of the orientation the permutation induces on the interaction graph, one
+ *                     CTA per replica with the world lines in shared memory (needs N (P > 32 ? 15 : 11) bytes
+ *                     <= 227 KB).  Not available for dense instances and the Ohmic-bath sweeps.               */
+enum { MCS_DYN_COLORED = 0, MCS_DYN_REFERENCE = 1 };
+int mcs_instance_set_dynamics(mcs_instance *inst, int dynamics);
 /* CUDA-event stopwatch on the instance's stream: start ... stop returns milliseconds.      */
 int mcs_timer_start(mcs_instance *inst);
 int mcs_timer_stop(mcs_instance *inst, double *ms);

@@ -4,6 +4,7 @@ There is no CPU fallback: if the shared library is missing (and cannot be built 
 import of any compute entry point raises, and every compute call fails with MCS_ENODEVICE when no
 CUDA device is visible.
 """
+import contextlib
 import ctypes
 import hashlib
 import os
@@ -17,6 +18,7 @@ SO_PATH = os.environ.get("MCS_B200_LIB") or os.path.join(_HERE, "libmcs_b200.so"
 
 MCS_OK, MCS_EINVAL, MCS_ENODEVICE, MCS_EZERODIV, MCS_EUNSUPPORTED, MCS_ENOMEM = 0, -1, -2, -3, -4, -5
 KIND_PIQMC, KIND_SA, KIND_SVMC = 1, 2, 3
+DYNAMICS = {"colored": 0, "coloured": 0, "checkerboard": 0, 0: 0, None: 0, "reference": 1, 1: 1}
 
 c_i64 = ctypes.c_int64
 c_u64 = ctypes.c_uint64
@@ -40,6 +42,7 @@ SIGNATURES = {
     "mcs_instance_info": (ctypes.c_int, [c_vp, c_i64p]),
     "mcs_instance_colors": (ctypes.c_int, [c_vp, c_i32p]),
     "mcs_instance_set_dense": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "mcs_instance_set_dynamics": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "mcs_timer_start": (ctypes.c_int, [c_vp]),
     "mcs_timer_stop": (ctypes.c_int, [c_vp, c_dp]),
     "mcs_synchronize": (ctypes.c_int, [c_vp]),
@@ -204,6 +207,29 @@ class Instance(object):
         self.ncolors, self.maxdeg = int(info[2]), int(info[3])
         self.has_field, self.lut_kernels = bool(info[4]), bool(info[6])
         self.dense = bool(int(info[7]) >> 32)
+        self.dynamics = "colored"
+        # One-shot calls share this instance's scratch batch, staging buffer and stream, and ctypes releases the
+        # GIL during the C call: concurrent Python threads annealing the same problem serialise on this lock.
+        self.lock = threading.RLock()
+
+    def set_dynamics(self, dynamics):
+        """"colored" (default, fastest) or "reference" (the reference's random-permutation sequential order in
+        distribution, include/mcs_b200.h: mcs_instance_set_dynamics)."""
+        mode = DYNAMICS.get(dynamics)
+        if mode is None:
+            raise ValueError("dynamics must be 'colored' or 'reference', got %r" % (dynamics,))
+        check(load().mcs_instance_set_dynamics(self._h, mode))
+        self.dynamics = "reference" if mode else "colored"
+
+    @contextlib.contextmanager
+    def using(self, dynamics=None):
+        """Serialise the one-shot calls on this instance and run them with the given dynamics."""
+        with self.lock:
+            self.set_dynamics(dynamics)
+            try:
+                yield self
+            finally:
+                self.set_dynamics(None)
 
     def colors(self):
         out = np.empty(self.nspins, dtype=np.int32)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmcs_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["mcs_instance.cu", "mcs_piqmc.cu", "mcs_sa.cu", "mcs_svmc.cu", "mcs_dense.cu", "mcs_cluster.cu", "mcs_exact.cu", "mcs_api.cu"]
+SOURCES = ["mcs_instance.cu", "mcs_piqmc.cu", "mcs_sa.cu", "mcs_svmc.cu", "mcs_refdyn.cu", "mcs_dense.cu", "mcs_cluster.cu", "mcs_exact.cu", "mcs_api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr"]

@@ -206,7 +206,8 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
     constexpr int kMaxWin = 16;
     long long win[kMaxWin];
     int nwin = 0;
-    const bool windows = st->Rpad >= 384 && !mcs_dense_supported(inst, (int)P);
+    // (reference dynamics: one CTA per replica for the whole schedule -- windows would only underfill the GPU)
+    const bool windows = st->Rpad >= 384 && !mcs_dense_supported(inst, (int)P) && inst->dynamics == MCS_DYN_COLORED;
     if (windows && !inst->s_in) {
         MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_in, cudaStreamNonBlocking));
         MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_out, cudaStreamNonBlocking));

@@ -56,6 +56,7 @@ struct mcs_instance {
     bool dense = false;  // near-complete graph: blocked tensor-core sweeps (mcs_dense.cu)
     int64_t Npad = 0;    // N rounded up to the dense block size (128)
     int64_t launches = 0;
+    int dynamics = 0;    // MCS_DYN_COLORED / MCS_DYN_REFERENCE: what *_sweeps and the one-shot calls run
     std::vector<struct mcs_state *> states; // live replica batches (orphaned if the instance dies first)
     struct mcs_state *scratch[4] = {nullptr, nullptr, nullptr, nullptr}; // per-kind batch reused by the
                                                                          // one-shot host-buffer calls
@@ -437,6 +438,10 @@ __device__ __forceinline__ uint32_t mcs_accept_threshold(float dE, float nl2e_ov
 int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,
                             int global_moves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset,
                             const double *lookuptable /* nullptr: no Ohmic bath */);
+// reference dynamics (mcs_refdyn.cu): random-permutation sequential sweeps executed as dependency waves
+int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const double *B, int64_t S, int mcsteps,
+                             float temp, int global_moves, uint64_t seed, uint64_t replica_offset,
+                             uint64_t sweep_offset);
 int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double temp, int nmoves, uint64_t seed,
                              uint64_t replica_offset, uint64_t sweep_offset);
 bool mcs_dense_supported(const mcs_instance *inst, int P);

@@ -378,6 +378,15 @@ extern "C" int mcs_instance_set_dense(mcs_instance *inst, int enable)
     return MCS_OK;
 }
 
+extern "C" int mcs_instance_set_dynamics(mcs_instance *inst, int dynamics)
+{
+    MCS_REQUIRE(inst, MCS_EINVAL, "mcs_instance_set_dynamics: NULL instance");
+    MCS_REQUIRE(dynamics == MCS_DYN_COLORED || dynamics == MCS_DYN_REFERENCE, MCS_EINVAL,
+                "mcs_instance_set_dynamics: unknown mode %d", dynamics);
+    inst->dynamics = dynamics;
+    return MCS_OK;
+}
+
 extern "C" int mcs_instance_colors(const mcs_instance *inst, int32_t *color)
 {
     MCS_REQUIRE(inst && color, MCS_EINVAL, "mcs_instance_colors: NULL argument");

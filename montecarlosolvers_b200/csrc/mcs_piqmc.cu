@@ -832,6 +832,12 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     const double teff = (double)temp * (double)P; // qmc.pyx:85: temp is a C float
     MCS_REQUIRE(teff != 0.0 || S == 0, MCS_EZERODIV, "float division");
     MCS_CUDA(cudaSetDevice(inst->device));
+    if (inst->dynamics == MCS_DYN_REFERENCE) {
+        MCS_REQUIRE(!lookuptable, MCS_EUNSUPPORTED,
+                    "reference dynamics: the Ohmic-bath sweeps are served by the coloured kernel or the exact replay");
+        return mcs_launch_refdyn_sweeps(st, MCS_KIND_PIQMC, A, B, S, mcsteps, temp, global_moves, seed, replica_offset,
+                                        sweep_offset);
+    }
     if (!lookuptable && mcs_dense_supported(inst, P))
         return mcs_launch_dense_sweeps(st, MCS_KIND_PIQMC, A, B, S, mcsteps, temp, global_moves, seed, replica_offset,
                                        sweep_offset);

@@ -1,0 +1,386 @@
+// mcs_refdyn.cu -- "reference dynamics" production sweeps (sm_100a).
+//
+// The reference visits the sites of a slice strictly one after another in a fresh random permutation
+// (Fisher-Yates, qmc.pyx:102-108; sa.pyx:73-79), slice after slice (qmc.pyx:99), then (QuantumAnnealGlobal)
+// the world lines in one more permutation (qmc.pyx:405-438).  The coloured kernels of mcs_piqmc.cu / mcs_sa.cu
+// sample the same Boltzmann distribution but in checkerboard order, and an anneal is a non-equilibrium
+// process: their residual energies come out 6-9 % lower than the reference's.
+//
+// This file reproduces the reference's dynamics IN DISTRIBUTION at production speed.  The outcome of a
+// sequential sweep in visiting order pi depends on pi only through the orientation it induces on the edges of
+// the interaction graph ("which endpoint is visited first"): any execution that respects that acyclic
+// orientation produces the identical state.  So, per (replica, sweep, slice):
+//   1. every site draws a random 16-bit priority from Philox (ties broken by the site index: the induced
+//      orientation is that of a uniformly random permutation up to 2^-16 ties per edge);
+//   2. a site is visited as soon as all its neighbours with a smaller priority have been visited -- the sites
+//      whose predecessor count is zero form the ready queue of the current round, finishing a site decrements
+//      the counters of its later neighbours and pushes those that reach zero into the next round's queue.
+//      A slice takes about 15 rounds on the 80x80 lattice instead of 6400 sequential visits;
+//   3. slices are processed in order, so slice k sees slice k-1 already updated and slice k+1 stale
+//      (qmc.pyx:127-138), exactly like the reference.
+// One CTA owns one replica for the WHOLE schedule: its world lines live bit-packed in shared memory (51 KB at
+// N = 6400, P = 64), the schedule loop runs inside the kernel (one launch per call), and the only global traffic
+// is the coupling table (L2-resident, shared by all CTAs).
+//
+// The acceptance arithmetic is the production one: fp32 dE in ELL order, threshold T = ceil(exp(-dE/teff) 2^32) - 1,
+// accept iff a 32-bit uniform u <= T (qmc.pyx:140-143); u = (v << 16) | r with r drawn lazily only when v alone
+// does not decide.  `sequential = 1` (test hook) lets thread 0 walk the sites in increasing (priority, index)
+// order instead: the two executions must agree bit for bit (tests/test_gpu_refdyn.py).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <type_traits>
+#include <vector>
+
+#include "mcs_common.cuh"
+
+namespace {
+
+constexpr uint32_t kTagPrio = 0x20u;   // c3 low byte: priorities + upper half of the acceptance uniforms
+constexpr uint32_t kTagRefine = 0x21u; // lower half of the acceptance uniforms (lazy)
+constexpr uint32_t kTagProp = 0x22u;   // SVMC proposals
+
+struct RefdynArgs {
+    uint64_t *W;  // PIQMC [N][Rpad] (window base), bit k = slice k
+    uint32_t *V;  // SA    [N][G], bit b of word g = replica 32 g + b
+    const int32_t *ell_idx; // [N][dpad]
+    const float *ell_J;     // [nsteps][N][dpad]
+    const float *h;         // [nsteps][N]
+    long long ellJ_stride, h_stride; // elements between the tables of consecutive schedule steps (0: static)
+    const float *bcoef;  // [S]  -2 B          (qmc.pyx:96; SA: -2)
+    const float *jperp2; // [S]  2 J_perp      (qmc.pyx:95)
+    const float *nl2e;   // [S]  -log2(e)/teff (SA: -log2(e)/sched[t])
+    long long Rpad, G;
+    int N, Npad, dpad, field, P, S, mcsteps, global_moves, sequential;
+    uint32_t replica_offset;
+    uint64_t sweep_offset;
+    mcs_philox_keys keys;
+    int *err; // device flag: set when a pass could not make progress (cannot happen for an acyclic orientation)
+};
+
+__device__ __forceinline__ int rd_popc(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int rd_popc(uint64_t x) { return __popcll(x); }
+
+// Warp-aggregated append: every lane of a converged warp calls this; lanes with cond push `site`.
+__device__ __forceinline__ void rd_push(bool cond, uint32_t site, uint16_t *queue, int *counter, int base, int lane)
+{
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, cond);
+    if (mask == 0u) return;
+    const int leader = __ffs(mask) - 1;
+    int pos = 0;
+    if (lane == leader) pos = atomicAdd(counter, __popc(mask));
+    pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
+    if (cond) queue[base + pos + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)site;
+}
+
+// Metropolis rule of qmc.pyx:140-143 / sa.pyx:96-99 on a lazily refined 32-bit uniform.  Strict "never" when
+// exp(-dE/teff) underflows to 0 or dE is NaN (the reference compares 0 > rand()/RAND_MAX: false).
+template <typename Refine>
+__device__ __forceinline__ bool rd_accept(float dE, float nl2e, uint32_t v16, Refine refine)
+{
+    if (dE <= 0.0f) return true;
+    const float t = ceilf(exp2f(dE * nl2e) * 4294967296.0f);
+    if (!(t >= 1.0f)) return false;
+    if (t >= 4294967296.0f) return true;
+    const uint32_t T = (uint32_t)t - 1u, Thi = T >> 16;
+    if (v16 < Thi) return true;
+    if (v16 > Thi) return false;
+    return ((v16 << 16) | refine()) <= T;
+}
+
+enum { RD_LOCAL = 0, RD_GLOBAL = 1, RD_SA = 2 };
+
+template <typename WT, int MODE>
+__device__ __forceinline__ void rd_attempt(const RefdynArgs &a, WT *w, const uint32_t *pu, int i, int k, int P,
+                                           WT pmask, const float *ellJ, const float *hrow, float bcoef,
+                                           float jperp2, float nl2e, uint32_t c0, uint32_t c2, uint32_t c3base)
+{
+    const WT wi = w[i];
+    const int32_t *idx = a.ell_idx + (size_t)i * a.dpad;
+    const float *Jr = ellJ + (size_t)i * a.dpad;
+    float dE = 0.0f;
+    for (int j = 0; j < a.dpad; ++j) {
+        const int nb = __ldg(idx + j);
+        const float cj = bcoef * __ldg(Jr + j); // padding: nb == i, J = 0
+        const WT x = wi ^ w[nb];
+        if (MODE == RD_GLOBAL)
+            dE += cj * (float)(P - 2 * rd_popc((WT)(x & pmask)));
+        else
+            dE += ((x >> k) & (WT)1) ? -cj : cj;
+    }
+    if (a.field) {
+        const float hc = bcoef * __ldg(hrow + i);
+        if (MODE == RD_GLOBAL)
+            dE += hc * (float)(P - 2 * rd_popc((WT)(wi & pmask)));
+        else
+            dE += ((wi >> k) & (WT)1) ? -hc : hc;
+    }
+    if (MODE == RD_LOCAL) { // qmc.pyx:127-138 (for P == 2 both neighbours are the same slice, both counted)
+        const int kl = k == 0 ? P - 1 : k - 1, kr = k == P - 1 ? 0 : k + 1;
+        const int anti = (int)(((wi >> kl) ^ (wi >> k)) & (WT)1) + (int)(((wi >> kr) ^ (wi >> k)) & (WT)1);
+        dE += jperp2 * (float)(2 - 2 * anti);
+    }
+    const bool acc = rd_accept(dE, nl2e, pu[i] >> 16, [&]() -> uint32_t {
+        uint32_t x[4];
+        mcs_philox4x32_10_rk(c0, (uint32_t)i >> 2, c2, c3base | kTagRefine, a.keys, x);
+        const int q = i & 3;
+        return (q == 0 ? x[0] : q == 1 ? x[1] : q == 2 ? x[2] : x[3]) >> 16;
+    });
+    if (acc) w[i] = wi ^ (MODE == RD_GLOBAL ? pmask : (WT)((WT)1 << k));
+}
+
+// Shared memory: w[Npad] | pu[Npad] (v:16 | priority:16) | cnt[Npad] bytes (open predecessors) | queue[Npad] u16
+template <typename WT, bool SA>
+__global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant__ RefdynArgs a)
+{
+    extern __shared__ __align__(16) unsigned char rd_smem[];
+    __shared__ int s_cntr[3];
+    const int N = a.N, Npad = a.Npad, T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
+    WT *w = reinterpret_cast<WT *>(rd_smem);
+    uint32_t *pu = reinterpret_cast<uint32_t *>(w + Npad);
+    uint32_t *cnt32 = pu + Npad;
+    uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt32);
+    uint16_t *queue = reinterpret_cast<uint16_t *>(cnt32 + Npad / 4);
+    const long long r = blockIdx.x;
+    const int P = SA ? 1 : a.P;
+    const WT pmask = (P == (int)(8 * sizeof(WT))) ? (WT)~(WT)0 : (WT)(((WT)1 << P) - (WT)1);
+    const uint32_t c0 = a.replica_offset + (uint32_t)r;
+
+    for (int i = tid; i < Npad; i += T) {
+        WT v = 0;
+        if (i < N) v = SA ? (WT)((a.V[(size_t)i * a.G + (r >> 5)] >> (r & 31)) & 1u) : (WT)a.W[(size_t)i * a.Rpad + r];
+        w[i] = v;
+    }
+    if (tid < 3) s_cntr[tid] = 0;
+    __syncthreads();
+
+    int rnd = 0; // running round number (uniform): round q counts its pushes in s_cntr[q % 3]
+    // one pass = every site visited once, in the order of this pass's priorities
+    auto pass = [&](auto mode_tag, int k, uint32_t c2, uint32_t c3base, const float *ellJ, const float *hrow,
+                    float bcoef, float jperp2, float nl2e) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        for (int q = tid; q < Npad / 4; q += T) { // priorities and the upper halves of the uniforms
+            uint32_t x[4];
+            mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
+            reinterpret_cast<uint4 *>(pu)[q] = make_uint4(x[0], x[1], x[2], x[3]);
+        }
+        __syncthreads();
+        auto key = [&](int s) -> uint32_t { return (pu[s] << 16) | (uint32_t)s; };
+        if (a.sequential) { // test hook: thread 0 walks the sites in increasing (priority, index) order
+            if (tid == 0) {
+                for (int i = 0; i < N; ++i) cnt8[i] = 0;
+                for (int n = 0; n < N; ++n) {
+                    int best = -1;
+                    uint32_t bk = 0xFFFFFFFFu;
+                    for (int i = 0; i < N; ++i)
+                        if (!cnt8[i] && key(i) <= bk) {
+                            bk = key(i);
+                            best = i;
+                        }
+                    rd_attempt<WT, MODE>(a, w, pu, best, k, P, pmask, ellJ, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
+                    cnt8[best] = 1;
+                }
+            }
+            __syncthreads();
+            return;
+        }
+        // round 0: open-predecessor counts; sites without predecessors start the queue
+        int *cn = &s_cntr[rnd % 3];
+        for (int i0 = wbase; i0 < N; i0 += T) {
+            const int i = i0 + lane;
+            const bool active = i < N;
+            int c = 0;
+            if (active) {
+                const uint32_t ki = key(i);
+                const int32_t *idx = a.ell_idx + (size_t)i * a.dpad;
+                for (int j = 0; j < a.dpad; ++j) {
+                    const int nb = __ldg(idx + j);
+                    c += (nb != i && key(nb) < ki) ? 1 : 0;
+                }
+                cnt8[i] = (uint8_t)c;
+            }
+            rd_push(active && c == 0, (uint32_t)i, queue, cn, 0, lane);
+        }
+        __syncthreads();
+        int head = 0, tail = *(volatile int *)cn;
+        if (tid == 0) s_cntr[(rnd + 2) % 3] = 0; // last read before the barrier above; next used in round rnd + 2
+        ++rnd;
+        while (head < N) {
+            if (tail == head) { // no progress: impossible for an acyclic orientation
+                if (tid == 0 && a.err) atomicExch(a.err, 1);
+                break;
+            }
+            cn = &s_cntr[rnd % 3];
+            for (int e0 = head + wbase; e0 < tail; e0 += T) {
+                const int e = e0 + lane;
+                const bool active = e < tail;
+                const int i = active ? (int)queue[e] : 0;
+                if (active)
+                    rd_attempt<WT, MODE>(a, w, pu, i, k, P, pmask, ellJ, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
+                const uint32_t ki = key(i);
+                const int32_t *idx = a.ell_idx + (size_t)i * a.dpad;
+                for (int j = 0; j < a.dpad; ++j) { // tell the later neighbours
+                    const int nb = active ? __ldg(idx + j) : i;
+                    bool ready = false;
+                    if (nb != i && key(nb) > ki) {
+                        const int sh = 8 * (nb & 3);
+                        const uint32_t old = atomicSub(&cnt32[nb >> 2], 1u << sh);
+                        ready = ((old >> sh) & 0xFFu) == 1u;
+                    }
+                    rd_push(ready, (uint32_t)nb, queue, cn, tail, lane);
+                }
+            }
+            __syncthreads();
+            head = tail;
+            tail += *(volatile int *)cn;
+            if (tid == 0) s_cntr[(rnd + 2) % 3] = 0;
+            ++rnd;
+        }
+    };
+
+    for (int f = 0; f < a.S; ++f) {
+        const float *ellJ = a.ell_J + (size_t)f * a.ellJ_stride;
+        const float *hrow = a.h + (size_t)f * a.h_stride;
+        const float bcoef = __ldg(&a.bcoef[f]), jperp2 = __ldg(&a.jperp2[f]), nl2e = __ldg(&a.nl2e[f]);
+        for (int step = 0; step < a.mcsteps; ++step) {
+            const uint64_t sweep = a.sweep_offset + (uint64_t)f * (uint64_t)a.mcsteps + (uint64_t)step;
+            const uint32_t c2 = (uint32_t)sweep, c3hi = (uint32_t)(sweep >> 32) << 16;
+            if (SA) {
+                pass(std::integral_constant<int, RD_SA>(), 0, c2, c3hi, ellJ, hrow, bcoef, jperp2, nl2e);
+            } else {
+                for (int k = 0; k < P; ++k)
+                    pass(std::integral_constant<int, RD_LOCAL>(), k, c2, c3hi | ((uint32_t)k << 8), ellJ, hrow, bcoef,
+                         jperp2, nl2e);
+                if (a.global_moves)
+                    pass(std::integral_constant<int, RD_GLOBAL>(), 0, c2, c3hi | (64u << 8), ellJ, hrow, bcoef, jperp2,
+                         nl2e);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += T) {
+        if (SA) {
+            const uint32_t bit = 1u << (r & 31);
+            uint32_t *p = &a.V[(size_t)i * a.G + (r >> 5)];
+            if (w[i] & (WT)1)
+                atomicOr(p, bit);
+            else
+                atomicAnd(p, ~bit);
+        } else {
+            a.W[(size_t)i * a.Rpad + r] = (uint64_t)w[i];
+        }
+    }
+}
+
+template <typename WT, bool SA>
+int launch_ising(const RefdynArgs &a, long long replicas, int threads, size_t smem, cudaStream_t s)
+{
+    static size_t configured[64] = {}; // opt-in dynamic shared memory granted so far, per device
+    int dev = 0;
+    MCS_CUDA(cudaGetDevice(&dev));
+    if (smem > 48 * 1024 && configured[dev & 63] < smem) {
+        MCS_CUDA(cudaFuncSetAttribute(refdyn_ising_kernel<WT, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        configured[dev & 63] = smem;
+    }
+    refdyn_ising_kernel<WT, SA><<<(unsigned)replicas, threads, smem, s>>>(a);
+    return MCS_OK;
+}
+
+} // namespace
+
+// kind = MCS_KIND_PIQMC: (A, B, temp) as mcs_piqmc_sweeps; MCS_KIND_SA: A = the temperature schedule, B = nullptr
+int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const double *B, int64_t S, int mcsteps,
+                             float temp, int global_moves, uint64_t seed, uint64_t replica_offset,
+                             uint64_t sweep_offset)
+{
+    mcs_instance *inst = st->inst;
+    MCS_REQUIRE(!inst->dense, MCS_EUNSUPPORTED,
+                "reference dynamics: dense instances have a total visiting order (no site parallelism); use the "
+                "blocked tensor-core sweeps or the exact kernel");
+    MCS_REQUIRE(inst->N <= 65536, MCS_EUNSUPPORTED, "reference dynamics: at most 65536 sites");
+    MCS_REQUIRE(inst->maxdeg <= 255, MCS_EUNSUPPORTED, "reference dynamics: degree <= 255");
+    MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
+                "time-dependent instance has %lld tables but the schedule has %lld steps", (long long)inst->nsteps,
+                (long long)S);
+    if (S == 0 || mcsteps == 0) return MCS_OK;
+    MCS_CUDA(cudaSetDevice(inst->device));
+    const int P = kind == MCS_KIND_PIQMC ? (int)st->P : 1;
+    const bool wide = P > 32;
+    const int N = (int)inst->N, Npad = (N + 3) & ~3;
+    const size_t smem = (size_t)Npad * ((wide ? 8 : 4) + 4 + 1 + 2);
+    MCS_REQUIRE(smem <= 227 * 1024 - 64, MCS_EUNSUPPORTED,
+                "reference dynamics: a replica's world lines (%zu bytes) do not fit one SM's shared memory", smem);
+    std::vector<float> sched((size_t)3 * S);
+    float *bc = sched.data(), *jp = bc + S, *nl = jp + S;
+    if (kind == MCS_KIND_PIQMC) {
+        const double teff = (double)temp * (double)P; // qmc.pyx:85
+        MCS_REQUIRE(teff != 0.0, MCS_EZERODIV, "float division");
+        for (int64_t f = 0; f < S; ++f) {
+            bc[f] = (float)(-2.0 * B[f]);                                    // qmc.pyx:96
+            jp[f] = (float)(2.0 * (-0.5 * teff * log(tanh(A[f] / teff))));   // qmc.pyx:95
+            nl[f] = (float)(-1.4426950408889634 / teff);
+        }
+    } else {
+        for (int64_t t = 0; t < S; ++t) {
+            bc[t] = -2.0f; // sa.pyx:84-94
+            jp[t] = 0.0f;
+            nl[t] = (float)(-1.4426950408889634 / A[t]); // exp(-ediff/temp), sa.pyx:98
+        }
+    }
+    float *d_sched = nullptr;
+    int *d_err = nullptr;
+    MCS_CUDA(cudaMallocAsync((void **)&d_sched, sched.size() * sizeof(float) + sizeof(int), inst->stream));
+    d_err = reinterpret_cast<int *>(d_sched + sched.size());
+    MCS_CUDA(cudaMemcpyAsync(d_sched, sched.data(), sched.size() * sizeof(float), cudaMemcpyHostToDevice, inst->stream));
+    MCS_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), inst->stream));
+    RefdynArgs a;
+    a.W = kind == MCS_KIND_PIQMC ? st->d_W + st->win_lo() : nullptr;
+    a.V = kind == MCS_KIND_SA ? st->d_V : nullptr;
+    a.ell_idx = inst->d_ell_idx;
+    a.ell_J = inst->d_ell_J;
+    a.h = inst->d_h;
+    a.ellJ_stride = inst->nsteps > 1 ? (long long)inst->N * inst->dpad : 0;
+    a.h_stride = inst->nsteps > 1 ? (long long)inst->N : 0;
+    a.bcoef = d_sched;
+    a.jperp2 = d_sched + S;
+    a.nl2e = d_sched + 2 * S;
+    a.Rpad = st->Rpad;
+    a.G = st->G;
+    a.N = N;
+    a.Npad = Npad;
+    a.dpad = inst->dpad;
+    a.field = inst->has_field ? 1 : 0;
+    a.P = P;
+    a.S = (int)S;
+    a.mcsteps = mcsteps;
+    a.global_moves = global_moves ? 1 : 0;
+    a.sequential = getenv("MCS_REFDYN_SEQUENTIAL") != nullptr ? 1 : 0;
+    a.replica_offset = (uint32_t)(replica_offset + (kind == MCS_KIND_PIQMC ? (uint64_t)st->win_lo() : 0ull));
+    a.sweep_offset = sweep_offset;
+    a.keys = mcs_philox_expand(seed);
+    a.err = d_err;
+    const long long replicas = kind == MCS_KIND_PIQMC ? st->win_valid() : st->R;
+    int threads = std::min(512, std::max(32, ((N / 6 + 31) / 32) * 32));
+    if (const char *e = getenv("MCS_REFDYN_THREADS")) threads = std::max(32, std::min(512, atoi(e) / 32 * 32));
+    int rc;
+    if (kind == MCS_KIND_SA)
+        rc = launch_ising<uint32_t, true>(a, replicas, threads, smem, inst->stream);
+    else if (wide)
+        rc = launch_ising<uint64_t, false>(a, replicas, threads, smem, inst->stream);
+    else
+        rc = launch_ising<uint32_t, false>(a, replicas, threads, smem, inst->stream);
+    MCS_TRY(rc);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    if (getenv("MCS_REFDYN_CHECK")) { // tests: surface the (impossible) stalled-pass flag
+        int h_err = 0;
+        MCS_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, inst->stream));
+        MCS_CUDA(cudaStreamSynchronize(inst->stream));
+        MCS_CUDA(cudaFreeAsync(d_sched, inst->stream));
+        MCS_REQUIRE(h_err == 0, MCS_EINVAL, "reference dynamics: a pass stalled (cyclic orientation?)");
+        return MCS_OK;
+    }
+    MCS_CUDA(cudaFreeAsync(d_sched, inst->stream));
+    return MCS_OK;
+}

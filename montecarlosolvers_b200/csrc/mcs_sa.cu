@@ -287,6 +287,9 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
     MCS_REQUIRE((replica_offset & 31) == 0, MCS_EINVAL,
                 "mcs_sa_sweeps: replica_offset must be a multiple of 32 (restarts are packed 32 per word)");
     MCS_CUDA(cudaSetDevice(inst->device));
+    if (inst->dynamics == MCS_DYN_REFERENCE)
+        return mcs_launch_refdyn_sweeps(st, MCS_KIND_SA, sched, nullptr, S, mcsteps, 0.0f, 0, seed, replica_offset,
+                                        sweep_offset);
     if (mcs_dense_supported(inst, 1))
         return mcs_launch_dense_sweeps(st, MCS_KIND_SA, sched, nullptr, S, mcsteps, 0.0f, 0, seed, replica_offset,
                                        sweep_offset);

@@ -4,7 +4,9 @@ Same names and positional arguments as /root/reference/solvers/qmc.pyx; `confs` 
 and the functions return None.  Extensions (keyword only): a leading replica axis on `confs`
 ([R, N, P]: R independent anneals in one call), `seed=` for the counter-based RNG, `exact=True` +
 `libc_seed=` for the bit-exact sequential replay of the reference, `energies=True` to get the
-final per-slice classical energies back.
+final per-slice classical energies back, `dynamics="reference"` for production sweeps that follow the
+reference's visiting order in distribution (a fresh random permutation per slice, sequential visits, slices in
+order -- qmc.pyx:99-143) instead of the faster checkerboard order.
 """
 import numpy as np
 
@@ -16,7 +18,7 @@ __all__ = ["QuantumAnneal", "QuantumAnnealGlobal", "DissipativeQuantumAnneal", "
 
 
 def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable, seed, exact, libc_seed, device,
-         energies, replica_offset, rand_stream=None):
+         energies, replica_offset, rand_stream=None, dynamics=None):
     _run.last_consumed = None
     A = _lib.f64(A_sched)
     B = _lib.f64(B_sched)
@@ -27,9 +29,22 @@ def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable,
     nbs = C.check_nbs(nbs)
     a8, batched, need_copy = C.spins_in(confs, 2, "confs")
     R, N, P = a8.shape
+    if _lib.DYNAMICS.get(dynamics) is None:
+        raise ValueError("dynamics must be 'colored' or 'reference', got %r" % (dynamics,))
     inst = _lib.instance_for(nbs, device)
     if inst.nspins != N:
         raise ValueError("confs has %d spins but nbs describes %d" % (N, inst.nspins))
+    with inst.using(dynamics):  # one call at a time per instance (shared scratch batch and stream)
+        e_out = _execute(inst, A, B, mcsteps, temp, a8, R, N, P, global_moves, lookuptable, seed, exact, libc_seed,
+                         energies, replica_offset, rand_stream)
+    C.spins_out(confs, a8, batched, need_copy)
+    if energies:
+        return e_out if batched else e_out[0]
+    return None
+
+
+def _execute(inst, A, B, mcsteps, temp, a8, R, N, P, global_moves, lookuptable, seed, exact, libc_seed, energies,
+             replica_offset, rand_stream):
     L = _lib.load()
     temp = float(np.float32(temp))  # C float in the reference signature (qmc.pyx:28)
     e_out = np.empty((R, P), dtype=np.float64) if energies else None
@@ -81,13 +96,10 @@ def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable,
         _lib.check(L.mcs_piqmc_anneal(inst._h, _lib.dptr(A), _lib.dptr(B), A.size, int(mcsteps), temp,
                                       a8.ctypes.data, R, P, int(bool(global_moves)), _lib.next_seed(seed),
                                       int(replica_offset), _lib.dptr(e_out) if energies else None))
-    C.spins_out(confs, a8, batched, need_copy)
-    if energies:
-        return e_out if batched else e_out[0]
-    return None
+    return e_out
 
 
-def QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, seed=None, exact=False,
+def QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, seed=None, exact=False, dynamics=None,
                   libc_seed=None, device=None, energies=False, replica_offset=0, rand_stream=None):
     """QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads)
 
@@ -97,17 +109,17 @@ def QuantumAnneal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, se
     inert in the reference too: OpenMP is disabled in its setup.py:10-11).
     Returns None; spins are flipped in place within `confs` ([N, P] or [R, N, P])."""
     return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, False, None, seed, exact or rand_stream is not None,
-                libc_seed, device, energies, replica_offset, rand_stream=rand_stream)
+                libc_seed, device, energies, replica_offset, rand_stream=rand_stream, dynamics=dynamics)
 
 
-def QuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, seed=None, exact=False,
+def QuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, seed=None, exact=False, dynamics=None,
                         libc_seed=None, device=None, energies=False, replica_offset=0, rand_stream=None):
     """QuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads)
 
     As QuantumAnneal plus one world-line move per spin per sweep (all P slices of a spin flipped
     together, reference qmc.pyx:284-438)."""
     return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, None, seed, exact or rand_stream is not None,
-                libc_seed, device, energies, replica_offset, rand_stream=rand_stream)
+                libc_seed, device, energies, replica_offset, rand_stream=rand_stream, dynamics=dynamics)
 
 
 def DissipativeQuantumAnneal(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *, seed=None,

@@ -13,7 +13,7 @@ __all__ = ["Anneal", "AnnealMA", "Anneal_parallel", "NoisyAnneal"]
 
 
 def _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset, randuni=None,
-         nbs_ndim=3):
+         nbs_ndim=3, dynamics=None):
     sched = np.asarray(sched)
     if sched.dtype != np.float64:
         raise ValueError("Buffer dtype mismatch, expected 'float64_t' but got '%s'" % sched.dtype)
@@ -25,9 +25,20 @@ def _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, re
         raise ValueError("nbs needs one table per schedule step")
     a8, batched, need_copy = C.spins_in(svec, 1, "svec")
     R, N = a8.shape
+    if _lib.DYNAMICS.get(dynamics) is None:
+        raise ValueError("dynamics must be 'colored' or 'reference', got %r" % (dynamics,))
     inst = _lib.instance_for(nbs, device)
     if inst.nspins != N:
         raise ValueError("svec has %d spins but nbs describes %d" % (N, inst.nspins))
+    with inst.using(dynamics):  # one call at a time per instance (shared scratch batch and stream)
+        e_out = _execute(inst, sched, mcsteps, a8, R, seed, exact, libc_seed, energies, replica_offset, randuni)
+    C.spins_out(svec, a8, batched, need_copy)
+    if energies:
+        return e_out if batched else e_out[0]
+    return None
+
+
+def _execute(inst, sched, mcsteps, a8, R, seed, exact, libc_seed, energies, replica_offset, randuni):
     L = _lib.load()
     e_out = np.empty(R, dtype=np.float64) if energies else None
     if exact:
@@ -46,24 +57,22 @@ def _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, re
         _lib.check(L.mcs_sa_anneal(inst._h, _lib.dptr(sched), sched.size, int(mcsteps), a8.ctypes.data, R,
                                    _lib.next_seed(seed), int(replica_offset),
                                    _lib.dptr(e_out) if energies else None))
-    C.spins_out(svec, a8, batched, need_copy)
-    if energies:
-        return e_out if batched else e_out[0]
-    return None
+    return e_out
 
 
 def Anneal(sched, mcsteps, svec, nbs, *, seed=None, exact=False, libc_seed=None, device=None, energies=False,
-           replica_offset=0):
+           dynamics=None, replica_offset=0):
     """Anneal(sched, mcsteps, svec, nbs)
 
     Thermal annealing: for every temperature in `sched`, `mcsteps` Metropolis sweeps over all spins
     (reference sa.pyx:19-101).  A schedule may end at T = 0 (only downhill moves are then accepted).
     Returns None; spins are flipped in place within `svec` ([N] or [R, N])."""
-    return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset)
+    return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset,
+                dynamics=dynamics)
 
 
 def AnnealMA(sched, mcsteps, svec, nbs, *, seed=None, exact=False, libc_seed=None, device=None, energies=False,
-             replica_offset=0):
+             dynamics=None, replica_offset=0):
     """AnnealMA(sched, mcsteps, svec, nbs)
 
     Reference sa.pyx:108-193: same sweeps as Anneal with the acceptance uniforms pre-drawn from
@@ -73,19 +82,21 @@ def AnnealMA(sched, mcsteps, svec, nbs, *, seed=None, exact=False, libc_seed=Non
     if exact:
         n = svec.shape[-1]
         ru = np.random.uniform(size=(np.asarray(sched).size, int(mcsteps), n, 1))
-    return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset, randuni=ru)
+    return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset, randuni=ru,
+                dynamics=dynamics)
 
 
 def Anneal_parallel(sched, mcsteps, svec, nbs, nthreads=1, *, seed=None, exact=False, libc_seed=None, device=None,
-                    energies=False, replica_offset=0):
+                    dynamics=None, energies=False, replica_offset=0):
     """Anneal_parallel(sched, mcsteps, svec, nbs, nthreads)
 
     Reference sa.pyx:201-284; identical to Anneal (its OpenMP pragmas are dead at build)."""
-    return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset)
+    return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset,
+                dynamics=dynamics)
 
 
 def NoisyAnneal(sched, mcsteps, svec, nbs, *, seed=None, exact=False, libc_seed=None, device=None, energies=False,
-                replica_offset=0):
+                dynamics=None, replica_offset=0):
     """NoisyAnneal(sched, mcsteps, svec, nbs)
 
     Annealing with time-dependent couplings, `nbs` is [len(sched), nspins, maxnb, 2] and temperature step
@@ -97,7 +108,7 @@ def NoisyAnneal(sched, mcsteps, svec, nbs, *, seed=None, exact=False, libc_seed=
     if exact:
         ru = np.random.uniform(size=(np.asarray(sched).size, int(mcsteps), svec.shape[-1], 1))
     return _run(sched, mcsteps, svec, nbs, seed, exact, libc_seed, device, energies, replica_offset, randuni=ru,
-                nbs_ndim=4)
+                nbs_ndim=4, dynamics=dynamics)
 
 
 def delta_e(svec, nbs, device=None):
