@@ -120,6 +120,13 @@ int mcs_state_init_random(mcs_state *st, uint64_t seed, uint64_t replica_offset)
 /* fixed-order fp64 classical energies, bit-identical to the oracle's definition of
  * tools.ClassicalIsingEnergy (tools.pyx:99-118): out is [R][P] (PIQMC) or [R] (SA).        */
 int mcs_state_energies(mcs_state *st, double *host_out);
+/* Best Trotter slice of every anneal, evaluated on the device: per-slice energies as above -> arg-min over the
+ * slices (first minimum) -> that slice's spins.  This is the post-processing of the reference's example
+ * (santoro80.py:290-296: E = min over slices of ClassicalIsingEnergy(confs[:, k])) without moving the world lines:
+ * best_energy float64 [R], best_slice int32 [R], best_conf int8 [R][N]; any of them may be NULL.
+ * on_device != 0: the pointers are DEVICE pointers on the instance's GPU (optional tensor handoff: e.g.
+ * torch.Tensor.data_ptr()); the work is queued on the instance's stream, mcs_synchronize() waits for it.        */
+int mcs_state_best(mcs_state *st, double *best_energy, int32_t *best_slice, int8_t *best_conf, int on_device);
 /* SVMC energy B*(sum J cos cos + sum h cos) - A*sum sin per replica, out [R]               */
 int mcs_state_svmc_energies(mcs_state *st, double a, double b, double *host_out);
 
@@ -168,6 +175,15 @@ int mcs_piqmc_anneal(mcs_instance *inst, const double *A_sched, const double *B_
                      int64_t schedsize, int mcsteps, float temp, int8_t *confs /* [R][N][P] */,
                      int64_t R, int64_t P, int global_moves, uint64_t seed, uint64_t replica_offset,
                      double *energies_out /* [R][P] */);
+/* The example's per-anneal protocol in one call (santoro80.py:286-296): confs = tile(state, P) -> QuantumAnneal
+ * [Global] -> best slice.  spins_in is int8 [R][N] when input_tiled != 0 (one start configuration per anneal, copied
+ * to all P slices on the device) or the full [R][N][P] otherwise; outputs as mcs_state_best plus the per-slice
+ * energies [R][P]; any output may be NULL.  Host traffic R N bytes in and R (N + 8 P + 12) out, not 2 R N P.      */
+int mcs_piqmc_anneal_best(mcs_instance *inst, const double *A_sched, const double *B_sched, int64_t schedsize,
+                          int mcsteps, float temp, const int8_t *spins_in, int input_tiled, int64_t R, int64_t P,
+                          int global_moves, uint64_t seed, uint64_t replica_offset,
+                          double *energies_out /* [R][P] */, double *best_energy /* [R] */,
+                          int32_t *best_slice /* [R] */, int8_t *best_conf /* [R][N] */);
 int mcs_sa_anneal(mcs_instance *inst, const double *sched, int64_t schedsize, int mcsteps,
                   int8_t *svec /* [R][N] */, int64_t R, uint64_t seed, uint64_t replica_offset,
                   double *energies_out /* [R] */);

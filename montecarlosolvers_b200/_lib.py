@@ -56,6 +56,7 @@ SIGNATURES = {
     "mcs_state_download_angles": (ctypes.c_int, [c_vp, c_vp]),
     "mcs_state_init_random": (ctypes.c_int, [c_vp, c_u64, c_u64]),
     "mcs_state_energies": (ctypes.c_int, [c_vp, c_dp]),
+    "mcs_state_best": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int]),
     "mcs_state_svmc_energies": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, c_dp]),
     "mcs_piqmc_sweeps": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                         c_u64, c_u64, c_u64]),
@@ -68,6 +69,8 @@ SIGNATURES = {
                                          c_u64, c_u64]),
     "mcs_piqmc_anneal": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_vp, c_i64, c_i64,
                                         ctypes.c_int, c_u64, c_u64, c_dp]),
+    "mcs_piqmc_anneal_best": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_vp, ctypes.c_int,
+                                             c_i64, c_i64, ctypes.c_int, c_u64, c_u64, c_dp, c_dp, c_i32p, c_vp]),
     "mcs_sa_anneal": (ctypes.c_int, [c_vp, c_dp, c_i64, ctypes.c_int, c_vp, c_i64, c_u64, c_u64, c_dp]),
     "mcs_svmc_anneal": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_vp, c_i64,
                                        ctypes.c_int, c_u64, c_u64]),
@@ -317,6 +320,20 @@ class State(object):
         out = np.empty((self.R, self.P) if self.kind == KIND_PIQMC else (self.R,), dtype=np.float64)
         check(load().mcs_state_energies(self._h, dptr(out)))
         return out
+
+    def best(self, conf=True):
+        """(best-slice energy float64 [R], best slice int32 [R], that slice's spins int8 [R, N] or None), evaluated
+        on the device (santoro80.py:290-296 without downloading the world lines)."""
+        e = np.empty(self.R, dtype=np.float64)
+        k = np.empty(self.R, dtype=np.int32)
+        c = np.empty((self.R, self.inst.nspins), dtype=np.int8) if conf else None
+        check(load().mcs_state_best(self._h, e.ctypes.data, k.ctypes.data, c.ctypes.data if conf else None, 0))
+        return e, k, c
+
+    def best_into(self, energy_ptr, slice_ptr, conf_ptr):
+        """As best(), into DEVICE buffers given by address (e.g. torch.Tensor.data_ptr()); asynchronous on the
+        instance's stream -- call inst.synchronize() before another stream reads them."""
+        check(load().mcs_state_best(self._h, energy_ptr or None, slice_ptr or None, conf_ptr or None, 1))
 
     def svmc_energies(self, a, b):
         out = np.empty(self.R, dtype=np.float64)

@@ -12,6 +12,8 @@ int mcs_piqmc_pack(mcs_state *st, const int8_t *d_in);
 int mcs_piqmc_unpack(mcs_state *st, int8_t *d_out);
 int mcs_piqmc_init(mcs_state *st, uint64_t seed, uint64_t replica_offset);
 int mcs_piqmc_energy(mcs_state *st, double *d_out);
+int mcs_piqmc_tile(mcs_state *st, const int8_t *d_in);
+int mcs_piqmc_best(mcs_state *st, const double *d_E, double *d_ebest, int32_t *d_kbest, int8_t *d_conf);
 int mcs_sa_pack(mcs_state *st, const int8_t *d_in);
 int mcs_sa_unpack(mcs_state *st, int8_t *d_out);
 int mcs_sa_init(mcs_state *st, uint64_t seed, uint64_t replica_offset);
@@ -111,6 +113,45 @@ extern "C" int mcs_state_energies(mcs_state *st, double *host_out)
     MCS_TRY(st->kind == MCS_KIND_PIQMC ? mcs_piqmc_energy(st, d_out) : mcs_sa_energy(st, d_out));
     MCS_CUDA(cudaMemcpyAsync(host_out, d_out, bytes, cudaMemcpyDeviceToHost, st->inst->stream));
     MCS_CUDA(cudaStreamSynchronize(st->inst->stream));
+    return MCS_OK;
+}
+
+// Best slice per anneal, computed on the device (fixed-order fp64 energies -> arg-min -> that slice's spins).
+// on_device != 0: the three output pointers are DEVICE pointers on this instance's GPU (tensor handoff); the work is
+// queued on the instance's stream and the caller synchronises (mcs_synchronize).  Otherwise host pointers, synchronous.
+extern "C" int mcs_state_best(mcs_state *st, double *best_energy, int32_t *best_slice, int8_t *best_conf, int on_device)
+{
+    MCS_REQUIRE(st && st->inst && st->kind == MCS_KIND_PIQMC, MCS_EINVAL, "mcs_state_best: needs a PIQMC state");
+    MCS_CUDA(cudaSetDevice(st->inst->device));
+    const size_t R = (size_t)st->R, N = (size_t)st->inst->N;
+    double *d_E = nullptr;
+    MCS_TRY(state_energy_buffer(st, R * st->P * sizeof(double), &d_E));
+    MCS_TRY(mcs_piqmc_energy(st, d_E));
+    const size_t need = R * (sizeof(double) + sizeof(int32_t)) + R * N;
+    if (st->best_bytes < need) {
+        MCS_CUDA(cudaStreamSynchronize(st->inst->stream));
+        if (st->d_best) MCS_CUDA(cudaFree(st->d_best));
+        st->d_best = nullptr;
+        st->best_bytes = 0;
+        MCS_CUDA(cudaMalloc(&st->d_best, need));
+        st->best_bytes = need;
+    }
+    double *d_eb = (double *)st->d_best;
+    int32_t *d_kb = (int32_t *)(d_eb + R);
+    int8_t *d_cf = (int8_t *)(d_kb + R);
+    cudaStream_t s = st->inst->stream;
+    if (on_device) {
+        // arg-min always lands in the batch's own buffer (the extraction needs it); copies are device-to-device
+        MCS_TRY(mcs_piqmc_best(st, d_E, d_eb, d_kb, best_conf ? best_conf : nullptr));
+        if (best_energy) MCS_CUDA(cudaMemcpyAsync(best_energy, d_eb, R * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        if (best_slice) MCS_CUDA(cudaMemcpyAsync(best_slice, d_kb, R * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        return MCS_OK;
+    }
+    MCS_TRY(mcs_piqmc_best(st, d_E, d_eb, d_kb, best_conf ? d_cf : nullptr));
+    if (best_energy) MCS_CUDA(cudaMemcpyAsync(best_energy, d_eb, R * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (best_slice) MCS_CUDA(cudaMemcpyAsync(best_slice, d_kb, R * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (best_conf) MCS_CUDA(cudaMemcpyAsync(best_conf, d_cf, R * N, cudaMemcpyDeviceToHost, s));
+    MCS_CUDA(cudaStreamSynchronize(s));
     return MCS_OK;
 }
 
@@ -343,6 +384,38 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
             cudaEventDestroy(tr_c1[q]);
             cudaEventDestroy(tr_dn[q]);
         }
+    }
+    return MCS_OK;
+}
+
+// The example's protocol fused into one call (santoro80.py:286-296): tile the start configuration over the slices,
+// anneal, evaluate every slice, return the best one.  Host traffic: R N bytes in, R (N + 8 P + 12) bytes out
+// instead of 2 R N P.
+extern "C" int mcs_piqmc_anneal_best(mcs_instance *inst, const double *A, const double *B, int64_t S, int mcsteps,
+                                     float temp, const int8_t *spins_in, int input_tiled, int64_t R, int64_t P,
+                                     int global_moves, uint64_t seed, uint64_t replica_offset, double *energies_out,
+                                     double *best_energy, int32_t *best_slice, int8_t *best_conf)
+{
+    MCS_REQUIRE(inst && spins_in, MCS_EINVAL, "mcs_piqmc_anneal_best: NULL argument");
+    MCS_REQUIRE((double)temp * (double)P != 0.0 || S == 0, MCS_EZERODIV, "float division");
+    MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_piqmc_anneal_best: bad schedule");
+    mcs_state *st = nullptr;
+    MCS_TRY(mcs_instance_scratch_state(inst, MCS_KIND_PIQMC, R, P, &st));
+    MCS_CUDA(cudaSetDevice(inst->device));
+    if (input_tiled) {
+        const size_t bytes = (size_t)R * inst->N;
+        MCS_TRY(mcs_state_reserve_stage(st, bytes));
+        MCS_CUDA(cudaMemcpyAsync(st->d_stage, spins_in, bytes, cudaMemcpyHostToDevice, inst->stream));
+        MCS_TRY(mcs_piqmc_tile(st, (const int8_t *)st->d_stage));
+    } else {
+        MCS_TRY(mcs_state_upload_spins(st, spins_in));
+    }
+    MCS_TRY(mcs_launch_piqmc_sweeps(st, A, B, S, mcsteps, temp, global_moves, seed, replica_offset, 0, nullptr));
+    MCS_TRY(mcs_state_best(st, best_energy, best_slice, best_conf, 0));
+    if (energies_out) { // mcs_state_best left the per-slice energies in the batch's buffer
+        MCS_CUDA(cudaMemcpyAsync(energies_out, st->d_eout, (size_t)R * P * sizeof(double), cudaMemcpyDeviceToHost,
+                                 inst->stream));
+        MCS_CUDA(cudaStreamSynchronize(inst->stream));
     }
     return MCS_OK;
 }

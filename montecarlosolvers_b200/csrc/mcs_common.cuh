@@ -101,6 +101,8 @@ struct mcs_state {
     long long S16_cols = 0;
     double *d_eout = nullptr;    // per-replica energies of mcs_state_energies (kept: no cudaMalloc per call)
     size_t eout_bytes = 0;
+    void *d_best = nullptr;      // best-slice results: ebest f64[R] | kbest i32[R] | conf i8[R][N]
+    size_t best_bytes = 0;
     int32_t *d_labels = nullptr; // cluster moves: union-find parents [(N P + 1)][replicas]
     size_t labels_bytes = 0;
     // active replica window [v0, v0 + vR) of a PIQMC batch (vR < 0: everything).  Replicas are independent, so

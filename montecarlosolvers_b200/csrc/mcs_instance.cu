@@ -308,6 +308,11 @@ static void state_release_device(mcs_state *st)
     cudaFree(st->d_stage);
     cudaFree(st->d_S16);
     cudaFree(st->d_eout);
+    st->d_eout = nullptr;
+    st->eout_bytes = 0;
+    cudaFree(st->d_best);
+    st->d_best = nullptr;
+    st->best_bytes = 0;
     st->d_S16 = nullptr;
     st->S16_cols = 0;
     cudaFree(st->d_labels);

@@ -696,6 +696,63 @@ __global__ void __launch_bounds__(1024) piqmc_unpack_kernel(const uint64_t *__re
     }
 }
 
+// int8 [R][N] -> W: every slice of a world line starts from that spin, i.e. confs = np.tile(state, (P, 1)).T of
+// the example (santoro80.py:286) done on the device: 1/P of the host traffic of the full [R][N][P] upload.
+__global__ void __launch_bounds__(1024) piqmc_tile_kernel(const int8_t *__restrict__ in, uint64_t *__restrict__ W,
+                                                          long long N, long long R, long long Rpad, int P)
+{
+    __shared__ int8_t tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long i0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+    {
+        const long long r = r0 + ty, i = i0 + tx;
+        tile[ty][tx] = (r < R && i < N) ? in[r * N + i] : (int8_t)1;
+    }
+    __syncthreads();
+    const long long i = i0 + ty, r = r0 + tx;
+    const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
+    if (i < N) W[i * Rpad + r] = tile[tx][ty] < 0 ? pmask : 0ull;
+}
+
+// Best slice of every anneal (santoro80.py:290-296 only ever uses the min-over-slices energy): arg-min over the
+// fixed-order fp64 energies [R][P] (first minimum, like np.argmin) ...
+__global__ void piqmc_argmin_kernel(const double *__restrict__ E, double *__restrict__ ebest, int32_t *__restrict__ kbest,
+                                    long long R, int P)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double best = E[r * P];
+    int kb = 0;
+    for (int k = 1; k < P; ++k) {
+        const double e = E[r * P + k];
+        if (e < best) {
+            best = e;
+            kb = k;
+        }
+    }
+    ebest[r] = best;
+    kbest[r] = kb;
+}
+
+// ... and that slice's spins as int8 [R][N] (N bytes per anneal instead of N P)
+__global__ void __launch_bounds__(1024) piqmc_extract_kernel(const uint64_t *__restrict__ W,
+                                                             const int32_t *__restrict__ kbest, int8_t *__restrict__ out,
+                                                             long long N, long long R, long long Rpad)
+{
+    __shared__ int8_t tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long i0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+    {
+        const long long i = i0 + ty, r = r0 + tx;
+        int8_t v = 1;
+        if (i < N && r < R) v = ((W[i * Rpad + r] >> kbest[r]) & 1ull) ? -1 : 1;
+        tile[ty][tx] = v;
+    }
+    __syncthreads();
+    const long long r = r0 + ty, i = i0 + tx;
+    if (r < R && i < N) out[r * N + i] = tile[tx][ty];
+}
+
 __global__ void piqmc_init_kernel(uint64_t *W, long long N, long long R, long long Rpad, int P, uint32_t key0,
                                   uint32_t key1, uint32_t replica_offset)
 {
@@ -936,6 +993,33 @@ int mcs_piqmc_unpack(mcs_state *st, int8_t *d_out)
                                                                  d_out + st->win_lo() * inst->N * st->P, inst->N,
                                                                  st->win_valid(), st->Rpad, (int)st->P);
     inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+int mcs_piqmc_tile(mcs_state *st, const int8_t *d_in)
+{
+    mcs_instance *inst = st->inst;
+    dim3 grid((unsigned)((inst->N + 31) / 32), (unsigned)(st->Rpad / 32));
+    piqmc_tile_kernel<<<grid, dim3(32, 32), 0, inst->stream>>>(d_in, st->d_W, inst->N, st->R, st->Rpad, (int)st->P);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    return MCS_OK;
+}
+
+// d_E: energies [R][P] (mcs_piqmc_energy); outputs on the device
+int mcs_piqmc_best(mcs_state *st, const double *d_E, double *d_ebest, int32_t *d_kbest, int8_t *d_conf)
+{
+    mcs_instance *inst = st->inst;
+    piqmc_argmin_kernel<<<(unsigned)((st->R + 127) / 128), 128, 0, inst->stream>>>(d_E, d_ebest, d_kbest, st->R,
+                                                                                  (int)st->P);
+    inst->launches++;
+    if (d_conf) {
+        dim3 grid((unsigned)((inst->N + 31) / 32), (unsigned)(st->Rpad / 32));
+        piqmc_extract_kernel<<<grid, dim3(32, 32), 0, inst->stream>>>(st->d_W, d_kbest, d_conf, inst->N, st->R,
+                                                                      st->Rpad);
+        inst->launches++;
+    }
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
 }

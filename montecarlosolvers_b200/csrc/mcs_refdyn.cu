@@ -55,13 +55,35 @@ struct RefdynArgs {
     uint32_t replica_offset;
     uint64_t sweep_offset;
     mcs_philox_keys keys;
+    long long *prof; // MCS_REFDYN_PROF=1: per-CTA cycle counters {priorities, counts, rounds, #rounds, #passes}
     int *err; // device flag: set when a pass could not make progress (cannot happen for an acyclic orientation)
 };
 
 __device__ __forceinline__ int rd_popc(uint32_t x) { return __popc(x); }
 __device__ __forceinline__ int rd_popc(uint64_t x) { return __popcll(x); }
 
-// Warp-aggregated append: every lane of a converged warp calls this; lanes with cond push `site`.
+// Warp-aggregated append of up to DP sites per lane: every lane of a converged warp calls this with the bit mask
+// of its ready neighbours (bit j <-> nb[j]).  One shared-memory atomic per warp.
+template <int DP>
+__device__ __forceinline__ void rd_push_many(uint32_t rmask, const int (&nb)[DP], uint16_t *queue, int *counter,
+                                             int base, int lane)
+{
+    if (__ballot_sync(0xFFFFFFFFu, rmask != 0u) == 0u) return;
+    const int n = __popc(rmask);
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    int pos = 0;
+    if (lane == 31) pos = atomicAdd(counter, incl);
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 31) + base + incl - n;
+#pragma unroll
+    for (int j = 0; j < DP; ++j)
+        if ((rmask >> j) & 1u) queue[pos++] = (uint16_t)nb[j];
+}
+
 __device__ __forceinline__ void rd_push(bool cond, uint32_t site, uint16_t *queue, int *counter, int base, int lane)
 {
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, cond);
@@ -90,24 +112,65 @@ __device__ __forceinline__ bool rd_accept(float dE, float nl2e, uint32_t v16, Re
 
 enum { RD_LOCAL = 0, RD_GLOBAL = 1, RD_SA = 2 };
 
-template <typename WT, int MODE>
-__device__ __forceinline__ void rd_attempt(const RefdynArgs &a, WT *w, const uint32_t *pu, int i, int k, int P,
-                                           WT pmask, const float *ellJ, const float *hrow, float bcoef,
-                                           float jperp2, float nl2e, uint32_t c0, uint32_t c2, uint32_t c3base)
+// Lower 16 bits of site i's acceptance uniform.  Needed once in 2^16 attempts: out of line, so that ptxas cannot
+// if-convert the Philox call into the hot path (it did: 15 % of the executed instructions, ncu r2_refdyn_v2).
+static __device__ __noinline__ uint32_t rd_refine_draw(uint32_t c0, uint32_t i, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1)
 {
-    const WT wi = w[i];
-    const int32_t *idx = a.ell_idx + (size_t)i * a.dpad;
-    const float *Jr = ellJ + (size_t)i * a.dpad;
+    uint32_t x[4];
+    mcs_philox4x32_10(c0, i >> 2, c2, c3, k0, k1, x);
+    return x[i & 3u] >> 16;
+}
+
+// Entries [j0, j0 + DP) of site i's ELL row, all loads issued together (the table is L2-resident: one round trip
+// per chunk instead of one per entry).  Entries beyond the row read as (i, 0): the padding convention of the table.
+template <int DP, bool WITH_J>
+__device__ __forceinline__ void rd_load_row(const RefdynArgs &a, const float *ellJ, int i, int j0, int (&nb)[DP],
+                                            float (&J)[DP])
+{
+    const int32_t *idx = a.ell_idx + (size_t)i * a.dpad + j0;
+    const float *Jr = ellJ + (size_t)i * a.dpad + j0;
+    if (DP == 4 && a.dpad == 4) { // 16-byte rows (the 2-D lattices)
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(idx));
+        nb[0] = v.x, nb[1] = v.y, nb[2] = v.z, nb[3 % DP] = v.w;
+        if (WITH_J) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(Jr));
+            J[0] = f.x, J[1] = f.y, J[2] = f.z, J[3 % DP] = f.w;
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < DP; ++j) {
+        const bool in = j0 + j < a.dpad;
+        nb[j] = in ? __ldg(idx + j) : i;
+        if (WITH_J) J[j] = in ? __ldg(Jr + j) : 0.0f;
+    }
+}
+
+// In-plane part of the energy difference over one chunk of the row (fp32, ELL order)
+template <typename WT, int MODE, int DP>
+__device__ __forceinline__ float rd_row_dE(const WT *w, WT wi, const int (&nb)[DP], const float (&J)[DP], float bcoef,
+                                           int k, int P, WT pmask)
+{
     float dE = 0.0f;
-    for (int j = 0; j < a.dpad; ++j) {
-        const int nb = __ldg(idx + j);
-        const float cj = bcoef * __ldg(Jr + j); // padding: nb == i, J = 0
-        const WT x = wi ^ w[nb];
+#pragma unroll
+    for (int j = 0; j < DP; ++j) {
+        const float cj = bcoef * J[j]; // padding: nb == i, J = 0
+        const WT x = wi ^ w[nb[j]];
         if (MODE == RD_GLOBAL)
             dE += cj * (float)(P - 2 * rd_popc((WT)(x & pmask)));
         else
             dE += ((x >> k) & (WT)1) ? -cj : cj;
     }
+    return dE;
+}
+
+// Field and Trotter terms, acceptance, flip
+template <typename WT, int MODE>
+__device__ __forceinline__ void rd_finish(const RefdynArgs &a, WT *w, const uint32_t *pu, int i, WT wi, float dE, int k,
+                                          int P, WT pmask, const float *hrow, float bcoef, float jperp2, float nl2e,
+                                          uint32_t c0, uint32_t c2, uint32_t c3base)
+{
     if (a.field) {
         const float hc = bcoef * __ldg(hrow + i);
         if (MODE == RD_GLOBAL)
@@ -121,16 +184,30 @@ __device__ __forceinline__ void rd_attempt(const RefdynArgs &a, WT *w, const uin
         dE += jperp2 * (float)(2 - 2 * anti);
     }
     const bool acc = rd_accept(dE, nl2e, pu[i] >> 16, [&]() -> uint32_t {
-        uint32_t x[4];
-        mcs_philox4x32_10_rk(c0, (uint32_t)i >> 2, c2, c3base | kTagRefine, a.keys, x);
-        const int q = i & 3;
-        return (q == 0 ? x[0] : q == 1 ? x[1] : q == 2 ? x[2] : x[3]) >> 16;
+        return rd_refine_draw(c0, (uint32_t)i, c2, c3base | kTagRefine, a.keys.rk[0], a.keys.rk[1]);
     });
     if (acc) w[i] = wi ^ (MODE == RD_GLOBAL ? pmask : (WT)((WT)1 << k));
 }
 
+template <typename WT, int MODE, int DP>
+__device__ __forceinline__ void rd_attempt(const RefdynArgs &a, WT *w, const uint32_t *pu, int i, int k, int P,
+                                           WT pmask, const float *ellJ, const float *hrow, float bcoef,
+                                           float jperp2, float nl2e, uint32_t c0, uint32_t c2, uint32_t c3base)
+{
+    const WT wi = w[i];
+    float dE = 0.0f;
+    for (int j0 = 0; j0 < a.dpad; j0 += DP) {
+        int nb[DP];
+        float J[DP];
+        rd_load_row<DP, true>(a, ellJ, i, j0, nb, J);
+        dE += rd_row_dE<WT, MODE, DP>(w, wi, nb, J, bcoef, k, P, pmask);
+    }
+    rd_finish<WT, MODE>(a, w, pu, i, wi, dE, k, P, pmask, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
+}
+
 // Shared memory: w[Npad] | pu[Npad] (v:16 | priority:16) | cnt[Npad] bytes (open predecessors) | queue[Npad] u16
-template <typename WT, bool SA>
+// DP: chunk of the ELL row held in registers (4: rows of at most 4 entries are one chunk; 8 otherwise)
+template <typename WT, bool SA, int DP>
 __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant__ RefdynArgs a)
 {
     extern __shared__ __align__(16) unsigned char rd_smem[];
@@ -145,6 +222,7 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
     const int P = SA ? 1 : a.P;
     const WT pmask = (P == (int)(8 * sizeof(WT))) ? (WT)~(WT)0 : (WT)(((WT)1 << P) - (WT)1);
     const uint32_t c0 = a.replica_offset + (uint32_t)r;
+    const bool one_chunk = a.dpad <= DP;
 
     for (int i = tid; i < Npad; i += T) {
         WT v = 0;
@@ -154,11 +232,14 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
     if (tid < 3) s_cntr[tid] = 0;
     __syncthreads();
 
+    long long pf0 = 0, pf1 = 0, pf2 = 0;
+    int pf_rounds = 0, pf_passes = 0;
     int rnd = 0; // running round number (uniform): round q counts its pushes in s_cntr[q % 3]
     // one pass = every site visited once, in the order of this pass's priorities
     auto pass = [&](auto mode_tag, int k, uint32_t c2, uint32_t c3base, const float *ellJ, const float *hrow,
                     float bcoef, float jperp2, float nl2e) {
         constexpr int MODE = decltype(mode_tag)::value;
+        long long t0 = a.prof ? clock64() : 0;
         for (int q = tid; q < Npad / 4; q += T) { // priorities and the upper halves of the uniforms
             uint32_t x[4];
             mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
@@ -177,35 +258,51 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
                             bk = key(i);
                             best = i;
                         }
-                    rd_attempt<WT, MODE>(a, w, pu, best, k, P, pmask, ellJ, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
+                    rd_attempt<WT, MODE, DP>(a, w, pu, best, k, P, pmask, ellJ, hrow, bcoef, jperp2, nl2e, c0, c2,
+                                             c3base);
                     cnt8[best] = 1;
                 }
             }
             __syncthreads();
             return;
         }
-        // round 0: open-predecessor counts; sites without predecessors start the queue
+        if (a.prof) {
+            const long long t1 = clock64();
+            pf0 += t1 - t0;
+            t0 = t1;
+        }
+        // round 0: open-predecessor counts (independent iterations: the loads of several sites overlap) ...
+#pragma unroll 2
+        for (int i = tid; i < N; i += T) {
+            const uint32_t ki = key(i);
+            int c = 0;
+            for (int j0 = 0; j0 < a.dpad; j0 += DP) {
+                int nb[DP];
+                float J[DP];
+                rd_load_row<DP, false>(a, ellJ, i, j0, nb, J);
+#pragma unroll
+                for (int j = 0; j < DP; ++j) c += (nb[j] != i && key(nb[j]) < ki) ? 1 : 0;
+            }
+            cnt8[i] = (uint8_t)c;
+        }
+        // ... then the sites without predecessors start the queue (each thread re-reads its own bytes)
         int *cn = &s_cntr[rnd % 3];
         for (int i0 = wbase; i0 < N; i0 += T) {
             const int i = i0 + lane;
-            const bool active = i < N;
-            int c = 0;
-            if (active) {
-                const uint32_t ki = key(i);
-                const int32_t *idx = a.ell_idx + (size_t)i * a.dpad;
-                for (int j = 0; j < a.dpad; ++j) {
-                    const int nb = __ldg(idx + j);
-                    c += (nb != i && key(nb) < ki) ? 1 : 0;
-                }
-                cnt8[i] = (uint8_t)c;
-            }
-            rd_push(active && c == 0, (uint32_t)i, queue, cn, 0, lane);
+            rd_push(i < N && cnt8[i] == 0, (uint32_t)i, queue, cn, 0, lane);
         }
         __syncthreads();
         int head = 0, tail = *(volatile int *)cn;
         if (tid == 0) s_cntr[(rnd + 2) % 3] = 0; // last read before the barrier above; next used in round rnd + 2
         ++rnd;
+        if (a.prof) {
+            const long long t1 = clock64();
+            pf1 += t1 - t0;
+            t0 = t1;
+            pf_passes += 1;
+        }
         while (head < N) {
+            pf_rounds += 1;
             if (tail == head) { // no progress: impossible for an acyclic orientation
                 if (tid == 0 && a.err) atomicExch(a.err, 1);
                 break;
@@ -215,19 +312,48 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
                 const int e = e0 + lane;
                 const bool active = e < tail;
                 const int i = active ? (int)queue[e] : 0;
-                if (active)
-                    rd_attempt<WT, MODE>(a, w, pu, i, k, P, pmask, ellJ, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
                 const uint32_t ki = key(i);
-                const int32_t *idx = a.ell_idx + (size_t)i * a.dpad;
-                for (int j = 0; j < a.dpad; ++j) { // tell the later neighbours
-                    const int nb = active ? __ldg(idx + j) : i;
-                    bool ready = false;
-                    if (nb != i && key(nb) > ki) {
-                        const int sh = 8 * (nb & 3);
-                        const uint32_t old = atomicSub(&cnt32[nb >> 2], 1u << sh);
-                        ready = ((old >> sh) & 0xFFu) == 1u;
+                const WT wi = w[i];
+                float dE = 0.0f;
+                for (int j0 = 0; j0 < a.dpad; j0 += DP) {
+                    int nb[DP];
+                    float J[DP];
+                    rd_load_row<DP, true>(a, ellJ, i, j0, nb, J);
+                    if (active) dE += rd_row_dE<WT, MODE, DP>(w, wi, nb, J, bcoef, k, P, pmask);
+                    if (!one_chunk) continue;
+                    // rows of one chunk: attempt, then tell the later neighbours, from the same registers
+                    if (active)
+                        rd_finish<WT, MODE>(a, w, pu, i, wi, dE, k, P, pmask, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
+                    uint32_t rmask = 0u;
+#pragma unroll
+                    for (int j = 0; j < DP; ++j) {
+                        const int nbj = nb[j];
+                        if (active && nbj != i && key(nbj) > ki) {
+                            const int sh = 8 * (nbj & 3);
+                            const uint32_t old = atomicSub(&cnt32[nbj >> 2], 1u << sh);
+                            if (((old >> sh) & 0xFFu) == 1u) rmask |= 1u << j;
+                        }
                     }
-                    rd_push(ready, (uint32_t)nb, queue, cn, tail, lane);
+                    rd_push_many<DP>(rmask, nb, queue, cn, tail, lane);
+                }
+                if (one_chunk) continue;
+                if (active)
+                    rd_finish<WT, MODE>(a, w, pu, i, wi, dE, k, P, pmask, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
+                for (int j0 = 0; j0 < a.dpad; j0 += DP) { // long rows: second walk for the notifications
+                    int nb[DP];
+                    float J[DP];
+                    rd_load_row<DP, false>(a, ellJ, i, j0, nb, J);
+                    uint32_t rmask = 0u;
+#pragma unroll
+                    for (int j = 0; j < DP; ++j) {
+                        const int nbj = nb[j];
+                        if (active && nbj != i && key(nbj) > ki) {
+                            const int sh = 8 * (nbj & 3);
+                            const uint32_t old = atomicSub(&cnt32[nbj >> 2], 1u << sh);
+                            if (((old >> sh) & 0xFFu) == 1u) rmask |= 1u << j;
+                        }
+                    }
+                    rd_push_many<DP>(rmask, nb, queue, cn, tail, lane);
                 }
             }
             __syncthreads();
@@ -236,6 +362,7 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
             if (tid == 0) s_cntr[(rnd + 2) % 3] = 0;
             ++rnd;
         }
+        if (a.prof) pf2 += clock64() - t0;
     };
 
     for (int f = 0; f < a.S; ++f) {
@@ -258,6 +385,10 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
         }
     }
     __syncthreads();
+    if (a.prof && tid == 0) {
+        long long *o = a.prof + (size_t)blockIdx.x * 5;
+        o[0] = pf0, o[1] = pf1, o[2] = pf2, o[3] = pf_rounds, o[4] = pf_passes;
+    }
     for (int i = tid; i < N; i += T) {
         if (SA) {
             const uint32_t bit = 1u << (r & 31);
@@ -272,19 +403,26 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
     }
 }
 
-template <typename WT, bool SA>
-int launch_ising(const RefdynArgs &a, long long replicas, int threads, size_t smem, cudaStream_t s)
+template <typename WT, bool SA, int DP>
+int launch_ising_dp(const RefdynArgs &a, long long replicas, int threads, size_t smem, cudaStream_t s)
 {
     static size_t configured[64] = {}; // opt-in dynamic shared memory granted so far, per device
     int dev = 0;
     MCS_CUDA(cudaGetDevice(&dev));
     if (smem > 48 * 1024 && configured[dev & 63] < smem) {
-        MCS_CUDA(cudaFuncSetAttribute(refdyn_ising_kernel<WT, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MCS_CUDA(cudaFuncSetAttribute(refdyn_ising_kernel<WT, SA, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         configured[dev & 63] = smem;
     }
-    refdyn_ising_kernel<WT, SA><<<(unsigned)replicas, threads, smem, s>>>(a);
+    refdyn_ising_kernel<WT, SA, DP><<<(unsigned)replicas, threads, smem, s>>>(a);
     return MCS_OK;
+}
+
+template <typename WT, bool SA>
+int launch_ising(const RefdynArgs &a, long long replicas, int threads, size_t smem, cudaStream_t s)
+{
+    return a.dpad <= 4 ? launch_ising_dp<WT, SA, 4>(a, replicas, threads, smem, s)
+                       : launch_ising_dp<WT, SA, 8>(a, replicas, threads, smem, s);
 }
 
 } // namespace
@@ -360,9 +498,15 @@ int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const dou
     a.sweep_offset = sweep_offset;
     a.keys = mcs_philox_expand(seed);
     a.err = d_err;
+    a.prof = nullptr;
     const long long replicas = kind == MCS_KIND_PIQMC ? st->win_valid() : st->R;
     int threads = std::min(512, std::max(32, ((N / 6 + 31) / 32) * 32));
     if (const char *e = getenv("MCS_REFDYN_THREADS")) threads = std::max(32, std::min(512, atoi(e) / 32 * 32));
+    long long *d_prof = nullptr;
+    if (getenv("MCS_REFDYN_PROF")) {
+        MCS_CUDA(cudaMalloc((void **)&d_prof, (size_t)replicas * 5 * sizeof(long long)));
+        a.prof = d_prof;
+    }
     int rc;
     if (kind == MCS_KIND_SA)
         rc = launch_ising<uint32_t, true>(a, replicas, threads, smem, inst->stream);
@@ -373,6 +517,18 @@ int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const dou
     MCS_TRY(rc);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
+    if (d_prof) {
+        std::vector<long long> hp((size_t)replicas * 5);
+        MCS_CUDA(cudaMemcpyAsync(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost, inst->stream));
+        MCS_CUDA(cudaStreamSynchronize(inst->stream));
+        cudaFree(d_prof);
+        double s[5] = {0, 0, 0, 0, 0};
+        for (long long r = 0; r < replicas; ++r)
+            for (int q = 0; q < 5; ++q) s[q] += (double)hp[(size_t)r * 5 + q] / (double)replicas;
+        fprintf(stderr, "[mcs refdyn] %lld CTAs x %d threads, smem %zu: per pass %.0f cycles priorities, %.0f counts, "
+                        "%.0f rounds (%.1f rounds, %.0f cycles each); %.0f passes\n",
+                replicas, threads, smem, s[0] / s[4], s[1] / s[4], s[2] / s[4], s[3] / s[4], s[2] / s[3], s[4]);
+    }
     if (getenv("MCS_REFDYN_CHECK")) { // tests: surface the (impossible) stalled-pass flag
         int h_err = 0;
         MCS_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, inst->stream));

@@ -13,7 +13,7 @@ import numpy as np
 from . import _common as C
 from . import _lib
 
-__all__ = ["QuantumAnneal", "QuantumAnnealGlobal", "DissipativeQuantumAnneal", "DissipativeQuantumAnnealGlobal",
+__all__ = ["QuantumAnneal", "QuantumAnnealGlobal", "anneal_best_slice", "DissipativeQuantumAnneal", "DissipativeQuantumAnnealGlobal",
            "QuantumAnnealSW", "QuantumAnnealWCL", "QuantumAnnealWC"]
 
 
@@ -141,6 +141,44 @@ def DissipativeQuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, lookuptable,
     Reference qmc.pyx:444-609: bath term + one world-line move per spin per sweep."""
     return _run(A_sched, B_sched, mcsteps, temp, confs, nbs, True, lookuptable, seed, exact, libc_seed, device,
                 energies, replica_offset)
+
+
+def anneal_best_slice(A_sched, B_sched, mcsteps, temp, states, nbs, slices, *, global_moves=True, seed=None,
+                      dynamics=None, device=None, replica_offset=0, per_slice_energies=False):
+    """The per-anneal protocol of the reference's example (santoro80.py:286-296) in one device round trip:
+    confs = tile(state, slices) -> QuantumAnneal[Global] -> E_k = ClassicalIsingEnergy(confs[:, k]) -> best slice.
+
+    `states` is int8/int [R, N] (or [N]): one start configuration per anneal.  Returns (best_energy float64 [R],
+    best_slice int32 [R], best_conf int8 [R, N]) and, with per_slice_energies=True, the energies [R, slices] as a
+    fourth item.  Host traffic is R N bytes each way instead of the R N P of the drop-in call."""
+    A, B = _lib.f64(A_sched), _lib.f64(B_sched)
+    if A.ndim != 1 or B.ndim != 1:
+        raise ValueError("Buffer has wrong number of dimensions (expected 1)")
+    if B.size < A.size:
+        raise ValueError("B_sched is shorter than A_sched (undefined behaviour in the reference)")
+    nbs = C.check_nbs(nbs)
+    a8, batched, _ = C.spins_in(states, 1, "states")
+    R, N = a8.shape
+    P = int(slices)
+    if _lib.DYNAMICS.get(dynamics) is None:
+        raise ValueError("dynamics must be 'colored' or 'reference', got %r" % (dynamics,))
+    inst = _lib.instance_for(nbs, device)
+    if inst.nspins != N:
+        raise ValueError("states has %d spins but nbs describes %d" % (N, inst.nspins))
+    e_best = np.empty(R, dtype=np.float64)
+    k_best = np.empty(R, dtype=np.int32)
+    conf = np.empty((R, N), dtype=np.int8)
+    e_all = np.empty((R, P), dtype=np.float64) if per_slice_energies else None
+    with inst.using(dynamics):
+        _lib.check(_lib.load().mcs_piqmc_anneal_best(
+            inst._h, _lib.dptr(A), _lib.dptr(B), A.size, int(mcsteps), float(np.float32(temp)), a8.ctypes.data, 1, R, P,
+            int(bool(global_moves)), _lib.next_seed(seed), int(replica_offset),
+            _lib.dptr(e_all) if per_slice_energies else None, _lib.dptr(e_best),
+            k_best.ctypes.data_as(_lib.c_i32p), conf.ctypes.data))
+    out = (e_best, k_best, conf) if batched else (e_best[0], k_best[0], conf[0])
+    if per_slice_energies:
+        out = out + ((e_all if batched else e_all[0]),)
+    return out
 
 
 def last_rand_consumed():

@@ -23,6 +23,11 @@ def _worker(rank, world, port, R, q):
     all_c = (2 * rng.randint(2, size=(R, 11)) - 1).astype(np.int8)
     e, best, conf = parallel.gather_best(all_e[lo:hi], all_c[lo:hi], lo, R)
     ok = np.array_equal(e, all_e) and best == int(np.argmin(all_e)) and np.array_equal(conf, all_c[best])
+    # device-resident form (torch tensors; CPU tensors under gloo, CUDA tensors under NCCL on the GPU box)
+    import torch
+    e2, best2, conf2 = parallel.gather_best_device(torch.from_numpy(all_e[lo:hi].copy()),
+                                                   torch.from_numpy(all_c[lo:hi].copy()), lo, R)
+    ok = ok and np.array_equal(e2.numpy(), all_e) and best2 == best and np.array_equal(conf2.numpy(), all_c[best])
     q.put((rank, bool(ok), lo, hi))
     dist.barrier()
     dist.destroy_process_group()
@@ -53,3 +58,6 @@ def test_single_process_gather_is_identity():
     c = np.arange(6, dtype=np.int8).reshape(3, 2)
     ee, b, cc = parallel.gather_best(e, c, 0, 3)
     assert b == 1 and np.array_equal(cc, c[1]) and np.array_equal(ee, e)
+    import torch
+    e2, b2, c2 = parallel.gather_best_device(torch.from_numpy(e), torch.from_numpy(c), 0, 3)
+    assert b2 == 1 and np.array_equal(c2.numpy(), c[1]) and np.array_equal(e2.numpy(), e)
