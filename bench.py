@@ -14,6 +14,16 @@ the rank's shard = 1000 sweeps = 2000 kernel launches (one per checkerboard colo
 Timing: W warm-up steps, then K steps bracketed by barrier + device sync, CUDA events recorded on the
 stream the kernels are launched on (mcs_timer_start/stop), max over ranks.  L2 is flushed between timed
 steps (256 MiB memset) -- and at N = 1 the 210 MB state is larger than L2 anyway.
+
+`e2e` = the same anneal through the one-shot C-ABI call mcs_piqmc_anneal_best with HOST buffers: the example's
+per-anneal protocol (santoro80.py:286-296: tile the start state over the slices, anneal, evaluate every slice, keep
+the best) -- start states int8 [R, N] in, per-slice energies + best energy / slice / configuration out; at N > 1 the
+path's only collective (gather the per-anneal best energies, broadcast the winner) runs inside the timed region.
+`e2e_full_confs` is the drop-in shaped call (mcs_piqmc_anneal: int8 [R, N, P] world lines both ways).
+
+`configs` (rank 0, N = 1): the other BASELINE configs and the two reference-order modes, each with its own value,
+dominant kernel, roofline object and -- from the reference arm run as a subprocess -- the matching reference
+function timed on the host cores (bounded samples).
 """
 import argparse
 import json
@@ -31,6 +41,11 @@ sys.path.insert(0, ROOT)
 N_SIDE, NSPINS, P_SLICES, SCHED = 80, 6400, 64, 1000
 METRIC = "spin-flip attempts/s, PIQMC 80x80 P=64"
 UNIT = "attempts/s"
+
+
+def workload_name(R_total, world, S):
+    return ("80x80 PIQMC P=64, %d anneals total (%d per GPU), A=linspace(3,1e-8,%d), B=1, mcsteps=1, T=1/64 "
+            "(BASELINE configs[2])" % (R_total, R_total // max(world, 1), S))
 
 
 def load_instance():
@@ -56,15 +71,76 @@ def load_instance():
     return tools.GenerateNeighbors(NSPINS, J, 4), name
 
 
+def chimera_instance(m=16, seed=0):
+    """cfg4: Chimera C_m, m x m cells of K_{4,4}, J = +-1 from default_rng(seed), no fields."""
+    from montecarlosolvers_b200 import tools
+    import scipy.sparse as sps
+    rng = np.random.default_rng(seed)
+    n = 8 * m * m
+    J = sps.dok_matrix((n, n))
+
+    def q(r, c, side, k):
+        return ((r * m + c) * 2 + side) * 4 + k
+
+    for r in range(m):
+        for c in range(m):
+            for a in range(4):
+                for b in range(4):
+                    J[q(r, c, 0, a), q(r, c, 1, b)] = float(rng.choice([-1.0, 1.0]))
+                if r + 1 < m:
+                    J[q(r, c, 0, a), q(r + 1, c, 0, a)] = float(rng.choice([-1.0, 1.0]))
+                if c + 1 < m:
+                    J[q(r, c, 1, a), q(r, c + 1, 1, a)] = float(rng.choice([-1.0, 1.0]))
+    return tools.GenerateNeighbors(n, J, 6)
+
+
+def sk_instance(n=2048, seed=0):
+    """cfg5: dense SK couplings J_ij ~ N(0, 1)/sqrt(n), reference table float64 [n, n-1, 2]."""
+    rng = np.random.default_rng(seed)
+    Jm = np.triu(rng.normal(size=(n, n)) / np.sqrt(n), 1)
+    full = Jm + Jm.T
+    nb = np.zeros((n, n - 1, 2))
+    ar = np.arange(n)
+    for i in range(n):
+        idx = np.delete(ar, i)
+        nb[i, :, 0] = idx
+        nb[i, :, 1] = full[i, idx]
+    return nb
+
+
+def load_peaks():
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(ppath):
+        with open(ppath) as f:
+            return json.load(f)
+    return {}
+
+
+def hbm_roofline(attempts_per_s, bytes_per_attempt, peaks, kernel, ms_per_launch=None, note=None):
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = attempts_per_s * bytes_per_attempt / 1e9
+    out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+           "kernel": kernel, "algorithmic_bytes_per_attempt": bytes_per_attempt,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+    if ms_per_launch is not None:
+        out["ms_per_launch"] = ms_per_launch
+    if note:
+        out["note"] = note
+    return out
+
+
 def roofline(achieved, peak, have_peaks, R, ms_per_launch, bytes_per_launch, n_pass, args):
-    """The base contract's HBM roofline of the pass kernel, plus what ncu says actually binds it.  The ncu
-    numbers come from the committed capture profiles/r01_piqmc_lut_pass_ncu.json (profiles/capture.sh +
+    """The base contract's HBM roofline of the pass kernel, plus what ncu says actually binds it.  The ncu numbers
+    come from the newest committed capture profiles/r0*_piqmc_lut_pass_ncu.json (profiles/capture.sh +
     profiles/summarize_ncu.py), taken at 4096 replicas per GPU; traffic scales linearly with the replicas."""
-    prof, src = None, os.path.join("profiles", "r01_piqmc_lut_pass_ncu.json")
-    try:
-        prof = json.load(open(os.path.join(ROOT, src)))
-    except (OSError, ValueError):
-        pass
+    prof, src = None, None
+    for rnd in ("r02", "r01"):
+        cand = os.path.join("profiles", "%s_piqmc_lut_pass_ncu.json" % rnd)
+        try:
+            prof, src = json.load(open(os.path.join(ROOT, cand))), cand
+            break
+        except (OSError, ValueError):
+            continue
     attempts_per_launch = bytes_per_launch / 0.25
     out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
            "traffic": args.traffic, "kernel": "piqmc_lut_pass_kernel<4,4,true,0,false>", "ms_per_launch": ms_per_launch,
@@ -135,32 +211,66 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle/_ref compiled reference if it travelled here, else the C port)
 # ------------------------------------------------------------------------------------------------
+_CPU = {}  # tables inherited by the forked workers
+
+
+def _strided(n_total, n):
+    """n schedule steps spread evenly over a schedule of n_total steps (hot AND cold end)."""
+    n = max(1, min(n, n_total))
+    return np.unique(np.linspace(0, n_total - 1, n).round().astype(int))
+
+
+def _cpu_call(kind, what, seed):
+    """One reference call on this core; returns (attempts, callable)."""
+    tab = _CPU[what["table"]]
+    if kind == "reference":
+        import importlib
+        qmc, sa, svmc = (importlib.import_module("solvers." + m) for m in ("qmc", "sa", "svmc"))
+    else:
+        from oracle import oracle as orc
+        qmc = sa = svmc = orc
+    rs = np.random.RandomState(seed)
+    solver, n = what["solver"], tab.shape[0]
+    kw = {} if kind == "reference" else {"rng": 1000 + seed}
+    if solver in ("QuantumAnneal", "QuantumAnnealGlobal"):
+        P, idx = what["P"], _strided(what["sched"], what["sweeps"])
+        A = np.linspace(3.0, 1e-8, what["sched"])[idx].copy()
+        B = np.ones(A.size)
+        s0 = (2 * rs.randint(2, size=n) - 1).astype(np.int64)
+        confs = np.tile(s0, (P, 1)).T.copy(order="F")  # as the example passes it (santoro80.py:286)
+        fn = getattr(qmc, solver)
+        return A.size * P * n, lambda: fn(A, B, 1, 1.0 / P, confs, tab, 1, **kw)
+    if solver == "Anneal":
+        sched = np.linspace(3.0, 0.0, what["sched"])[_strided(what["sched"], what["sweeps"])].copy()
+        s0 = (2 * rs.randint(2, size=n) - 1).astype(np.int64)
+        return sched.size * n, lambda: sa.Anneal(sched, 1, s0, tab, **kw)
+    if solver == "SpinVectorMonteCarloCompact":
+        idx = _strided(what["sched"], what["sweeps"])
+        s = np.linspace(1e-3, 1.0, what["sched"])[idx]
+        A, B = (3.0 * (1 - s)).copy(), s.copy()
+        v = np.full((what["reads"], n), np.pi / 2)
+        np.random.seed(seed)
+        return A.size * what["reads"] * n, lambda: svmc.SpinVectorMonteCarloCompact(A, B, 1, 0.1, v, tab, **kw)
+    raise ValueError(solver)
+
+
 def _cpu_worker(args):
-    kind, nbs, sweeps, seed = args
-    A = np.linspace(3.0, 1e-8, SCHED)[:sweeps].copy()
-    B = np.ones(sweeps)
-    s0 = (2 * np.random.RandomState(seed).randint(2, size=NSPINS) - 1).astype(np.int64)
-    confs = np.tile(s0, (P_SLICES, 1)).T.copy(order="F")  # as the example passes it (santoro80.py:286)
+    kind, what, seed, barrier = args
     if kind == "reference":
         import ctypes
-        import importlib
-        from oracle import build_ref
-        build_ref.import_ref()
-        fn = importlib.import_module("solvers.qmc").QuantumAnneal
         ctypes.CDLL(None).srand(1000 + seed)
-        t0 = time.perf_counter()
-        fn(A, B, 1, 1.0 / P_SLICES, confs, nbs, 1)
-        return time.perf_counter() - t0
-    from oracle import oracle as orc
-    rng = orc.LibcRand(1000 + seed)
-    t0 = time.perf_counter()
-    orc.QuantumAnneal(A, B, 1, 1.0 / P_SLICES, confs, nbs, 1, rng=rng)
-    return time.perf_counter() - t0
+    attempts, call = _cpu_call(kind, what, seed)
+    barrier.wait()  # every worker is forked, imported and has its inputs: only the reference call is timed
+    t0 = time.time()
+    call()
+    t1 = time.time()
+    return attempts, t0, t1
 
 
-def cpu_arm(nbs, sweeps, cores=None, want="auto"):
-    """Aggregate attempts/s of `cores` independent single-threaded reference anneals (the reference is
-    single-threaded: its OpenMP flags are commented out, setup.py:10-11), `sweeps` sweeps each."""
+def cpu_arm(what, cores=None, want="auto"):
+    """Aggregate attempts/s of `cores` independent single-threaded reference calls (the reference is
+    single-threaded: its OpenMP flags are commented out, setup.py:10-11).  Timed from the first worker's start to
+    the last worker's end of the reference call itself (pool start-up, imports and input preparation excluded)."""
     import multiprocessing as mp
     from oracle import build_ref
     from oracle import oracle as orc
@@ -169,59 +279,249 @@ def cpu_arm(nbs, sweeps, cores=None, want="auto"):
         build_ref.build(verbose=False)
         if build_ref.import_ref() is not None:
             kind = "reference"
+            import importlib
+            for m in ("qmc", "sa", "svmc"):  # mapped in the PARENT too: visible to a dlopen audit of this process
+                importlib.import_module("solvers." + m)
     if kind == "port":
         orc.build()
+        orc.lib()
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("fork")
+    barrier = ctx.Manager().Barrier(cores)
     with ctx.Pool(cores) as pool:
-        t0 = time.perf_counter()
-        times = pool.map(_cpu_worker, [(kind, nbs, sweeps, s) for s in range(cores)])
-        wall = time.perf_counter() - t0
-    attempts = cores * sweeps * P_SLICES * NSPINS
-    one = sweeps * P_SLICES * NSPINS / float(np.median(times))
-    return {"value": attempts / wall, "unit": UNIT, "cores": cores, "kind": kind,
-            "value_1core": one,
-            "sample": "%d independent anneals (one per core), %d sweeps of the 80x80 P=64 schedule each, "
-                      "qmc.QuantumAnneal" % (cores, sweeps)}
+        res = pool.map(_cpu_worker, [(kind, what, s, barrier) for s in range(cores)], chunksize=1)
+    attempts = sum(r[0] for r in res)
+    wall = max(r[2] for r in res) - min(r[1] for r in res)
+    one = float(np.median([r[0] / (r[2] - r[1]) for r in res]))
+    return {"value": attempts / wall, "unit": UNIT, "cores": cores, "kind": kind, "value_1core": one,
+            "cpu_model": _cpu_model(),
+            "sample": "%d independent %s calls (one per core), %s" % (cores, what["solver"], what["desc"])}
 
 
-def cpu_baseline_subprocess(sweeps):
-    """The reference arm of this file in its own process (one bounded step); returns its cpu_baseline object."""
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_workloads(cpu_sweeps):
+    """The reference function matching every bench entry, as bounded samples of the same workloads."""
+    return {
+        "cfg3": {"table": "santoro", "solver": "QuantumAnneal", "P": 64, "sched": SCHED, "sweeps": cpu_sweeps,
+                 "desc": "80x80 P=64, %d sweeps spread evenly over the 1000-step schedule" % cpu_sweeps},
+        "cfg1": {"table": "santoro", "solver": "QuantumAnnealGlobal", "P": 20, "sched": 354, "sweeps": 2 * cpu_sweeps,
+                 "desc": "80x80 P=20 (examples/santoro80.py), %d sweeps spread over the 354-step schedule" % (
+                     2 * cpu_sweeps)},
+        "cfg2": {"table": "santoro", "solver": "Anneal", "sched": 1000, "sweeps": 1000,
+                 "desc": "80x80, the full 1000-temperature schedule, one restart per core"},
+        "cfg4": {"table": "chimera", "solver": "SpinVectorMonteCarloCompact", "sched": 1000, "sweeps": 400, "reads": 1,
+                 "desc": "Chimera C16 (2048 rotors), 1 read, 400 sweeps spread over the 1000-step schedule"},
+        "cfg5": {"table": "sk", "solver": "QuantumAnneal", "P": 32, "sched": 200, "sweeps": 2,
+                 "desc": "dense SK N=2048 P=32 on the reference's [2048, 2047, 2] table, 2 sweeps"},
+    }
+
+
+def cpu_tables(names):
+    for n in names:
+        if n in _CPU:
+            continue
+        if n == "santoro":
+            _CPU[n] = load_instance()[0]
+        elif n == "chimera":
+            _CPU[n] = chimera_instance(16)
+        elif n == "sk":
+            _CPU[n] = sk_instance(2048)
+
+
+def cpu_baseline_subprocess(sweeps, configs):
+    """The reference arm of this file in its own process; returns {"cfg3": cpu_baseline, "cfg1": ..., ...}."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
-           "--cpu-sweeps", str(sweeps)]
+           "--cpu-sweeps", str(sweeps), "--cpu-configs", ",".join(configs)]
     try:
         p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
-        return json.loads(p.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        line = json.loads(p.stdout.strip().splitlines()[-1])
+        out = dict(line.get("cpu_configs") or {})
+        out["cfg3"] = line["cpu_baseline"]
+        return out
     except Exception as e:  # noqa: BLE001 -- the GPU line must still be printed
-        return {"error": "cpu baseline failed: %r" % (e,)}
+        return {"cfg3": {"error": "cpu baseline failed: %r" % (e,)}}
 
 
 def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    nbs, name = load_instance()
-    sweeps = args.cpu_sweeps
+    wl = cpu_workloads(args.cpu_sweeps)
+    cpu_tables(["santoro"])
+    name = load_instance()[1]
     vals = []
     for _ in range(args.warmup):
-        cpu_arm(nbs, max(1, sweeps // 8))
+        cpu_arm(dict(wl["cfg3"], sweeps=max(1, args.cpu_sweeps // 8)))
     t0 = time.perf_counter()
     last = None
     for _ in range(args.steps):
-        last = cpu_arm(nbs, sweeps)
+        last = cpu_arm(wl["cfg3"])
         vals.append(last["value"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
+    extra = {}
+    for c in [c for c in (args.cpu_configs or "").split(",") if c and c != "cfg3"]:
+        try:
+            cpu_tables([wl[c]["table"]])
+            extra[c] = cpu_arm(wl[c])
+        except Exception as e:  # noqa: BLE001
+            extra[c] = {"error": repr(e)}
+    world = max(1, args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": name,
-            "config": {"workload": "80x80 PIQMC P=64, reference CPU path on the host cores; each step = a bounded "
-                                   "sample: one anneal per core, %d sweeps each" % sweeps},
+            "config": {"workload": workload_name(args.anneals, world, args.sched)},
+            "sampling": "reference CPU path on the host cores; each step = a bounded sample of that workload: one "
+                        "qmc.QuantumAnneal call per core, %d sweeps spread evenly over the schedule" % args.cpu_sweeps,
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if extra:
+        line["cpu_configs"] = extra
     out["line"] = line
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configs + the reference-order modes (rank 0, one GPU)
+# ------------------------------------------------------------------------------------------------
+def timed(inst, fn, reps=3):
+    fn()
+    inst.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        inst.timer_start()
+        fn()
+        best = min(best, inst.timer_stop())
+    return best
+
+
+def run_configs(mcs, inst, peaks, which):
+    out = {}
+    K = mcs._lib
+    if "cfg1" in which:  # examples/santoro80.py: P = 20, world-line moves, tau = 354
+        P, tau, R = 20, 354, 4096
+        A, B = np.linspace(3.0, 1e-8, tau), np.ones(tau)
+        st = mcs.State(inst, K.KIND_PIQMC, R, P)
+        st.init_random(1)
+        l0 = inst.launches
+        ms = timed(inst, lambda: st.piqmc_sweeps(A, B, 1, 1.0 / P, global_moves=True, seed=2), reps=2)
+        v = R * tau * P * NSPINS / (ms * 1e-3)
+        out["cfg1"] = {"workload": "examples/santoro80.py protocol: 80x80 PIQMC P=20 with world-line moves "
+                                   "(QuantumAnnealGlobal), tau=354, %d anneals" % R, "value": v, "unit": UNIT,
+                       "ms": ms, "gpu_launches": (inst.launches - l0) // 3,
+                       "roofline": hbm_roofline(v, 0.25, peaks, "piqmc_lut_pass_kernel<4,4,false,0,true> (two replicas "
+                                                "per thread)", ms / (2 * tau))}
+        st.close()
+    if "cfg2" in which:  # sa.Anneal, 1024 restarts
+        tau, R = 1000, 1024
+        sched = np.linspace(3.0, 0.0, tau)
+        st = mcs.State(inst, K.KIND_SA, R, 1)
+        st.init_random(1)
+        ms = timed(inst, lambda: st.sa_sweeps(sched, 1, seed=2), reps=3)
+        v = R * tau * NSPINS / (ms * 1e-3)
+        out["cfg2"] = {"workload": "sa.Anneal on 80x80 Santoro, %d restarts, linspace(3,0,1000), 1 sweep each" % R,
+                       "value": v, "unit": UNIT, "ms": ms,
+                       "roofline": hbm_roofline(v, 0.25, peaks, "sa_lut_pass_kernel<4,*,0>", ms / (2 * tau),
+                                                "latency bound at this batch size: one colour pass of 1024 restarts "
+                                                "is a single wave of 100 warps")}
+        st.close()
+    if "refdyn" in which:  # cfg3 shape, the reference's own visiting order in distribution
+        P, R, S = 64, 4096, 4
+        inst.set_dynamics("reference")
+        try:
+            A, B = np.linspace(3.0, 1e-8, SCHED)[_strided(SCHED, S)].copy(), np.ones(S)
+            st = mcs.State(inst, K.KIND_PIQMC, R, P)
+            st.init_random(1)
+            ms = timed(inst, lambda: st.piqmc_sweeps(A, B, 1, 1.0 / P, seed=2), reps=2)
+            v = R * S * P * NSPINS / (ms * 1e-3)
+            out["cfg3_reference_dynamics"] = {
+                "workload": "80x80 PIQMC P=64, %d anneals, %d sweeps spread over the schedule, dynamics=reference "
+                            "(fresh random permutation per slice, sequential visits, slices in order; parity tier c "
+                            "two-sided vs the reference: tests/test_gpu_refdyn.py)" % (R, S),
+                "value": v, "unit": UNIT, "ms": ms,
+                "roofline": hbm_roofline(v, 0.25, peaks, "refdyn_ising_kernel<u64,false,4>", ms,
+                                         "latency / barrier bound: dependency waves of ~550 sites, one CTA per anneal")}
+            st.close()
+        finally:
+            inst.set_dynamics("colored")
+    if "exact" in which:  # bit-exact sequential replay of the reference (glibc rand stream, fp64)
+        P, R, S = 64, 4096, 2
+        confs = np.repeat((2 * np.random.RandomState(0).randint(2, size=(R, NSPINS, 1)) - 1).astype(np.int8), P, axis=2)
+        A, B = np.linspace(3.0, 1e-8, SCHED)[_strided(SCHED, S)].copy(), np.ones(S)
+        t0 = time.perf_counter()
+        mcs.qmc.QuantumAnneal(A, B, 1, 1.0 / P, confs, inst, 1, exact=True, libc_seed=1000)
+        dt = time.perf_counter() - t0
+        out["cfg3_exact_replay"] = {
+            "workload": "80x80 PIQMC P=64, %d anneals, %d sweeps, exact=True: bit-exact replay of the reference's "
+                        "trajectories (Fisher-Yates from glibc rand(), sequential fp64 visits); wall clock of the "
+                        "C-ABI call incl. host copies" % (R, S),
+            "value": R * S * P * NSPINS / dt, "unit": UNIT, "ms": dt * 1e3,
+            "roofline": {"bound": "latency", "note": "one sequential chain per anneal by construction (the rand() "
+                                                     "stream and the visiting order are serial): parity tier (b), "
+                                                     "not a throughput path"}}
+        del confs
+    if "cfg4" in which:  # SVMC on Chimera C16, 2048 reads
+        cn = chimera_instance(16)
+        ci = mcs.Instance(cn, device=inst.device)
+        s = np.linspace(1e-3, 1.0, 1000)
+        A4, B4 = 3.0 * (1 - s), s
+        st = mcs.State(ci, K.KIND_SVMC, 2048, 1)
+        st.init_random(0)
+        ms = timed(ci, lambda: st.svmc_sweeps(A4, B4, 1, 0.1, tf=False, seed=5), reps=3)
+        v = 2048 * 1000 * 2048 / (ms * 1e-3)
+        out["cfg4"] = {"workload": "svmc.SpinVectorMonteCarloCompact on Chimera C16 (2048 rotors, %d colours), 2048 "
+                                   "reads, A=3(1-s), B=s, s=linspace(1e-3,1,1000), T=0.1" % ci.ncolors,
+                       "value": v, "unit": UNIT, "ms": ms,
+                       "roofline": hbm_roofline(v, 8.0, peaks, "svmc_pass_kernel", ms / (1000 * ci.ncolors),
+                                                "SURVEY 8d: 8 B per attempt (theta and cos theta, fp32, read + write); "
+                                                "the 33.5 MB state is L2 resident, the kernel is bound by the latency "
+                                                "of the dependent neighbour loads, not by HBM")}
+        st.close()
+        ci.close()
+    if "cfg5" in which:  # dense SK, tensor-core local fields + sequential decisions; Swendsen-Wang on the same state
+        n, P5, R5, S5 = 2048, 32, 128, 20
+        di = mcs.Instance(sk_instance(n), device=inst.device)
+        A5, B5 = np.linspace(3.0, 1e-8, 200)[_strided(200, S5)].copy(), np.ones(S5)
+        st = mcs.State(di, K.KIND_PIQMC, R5, P5)
+        st.init_random(1)
+        ms = timed(di, lambda: st.piqmc_sweeps(A5, B5, 1, 1.0 / P5, global_moves=True, seed=2), reps=2)
+        cols = R5 * P5
+        flops = S5 * 2.0 * n * n * cols  # SURVEY 8d: 2 N^2 flop per replica-slice column and sweep
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = flops / (ms * 1e-3) / 1e12
+        o = {"workload": "dense SK N=2048 PIQMC P=32 with world-line moves, %d replicas (%d columns), %d sweeps: "
+                         "local fields by tcgen05 GEMM, sequential in-block decisions" % (R5, cols, S5),
+             "value": S5 * n * cols / (ms * 1e-3), "unit": UNIT, "ms": ms, "ms_per_sweep": ms / S5,
+             "roofline": {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                          "traffic": None, "kernel": "dense_block_kernel_tc",
+                          "algorithmic_flops_per_sweep": 2.0 * n * n * cols,
+                          "executed_bf16_tflops": 2 * ach,
+                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                          "note": "J is split hi + lo into two bf16 operands (16 mantissa bits): the tensor pipe "
+                                  "executes twice the algorithmic flops; the sweep is bound by the 2048 sequential "
+                                  "site decisions, not by the GEMM"}}
+        try:
+            st.cluster_moves(1.0, 1.0, 1.0 / P5, nmoves=1, seed=3)
+            ms_sw = timed(di, lambda: st.cluster_moves(1.0, 1.0, 1.0 / P5, nmoves=2, seed=3, sweep_offset=1), reps=1) / 2
+            o["swendsen_wang"] = {"ms_per_move": ms_sw, "cluster_sites_per_s": n * cols / (ms_sw * 1e-3),
+                                  "kernel": "cluster_{init,union,flip}_kernel (GPU union-find)"}
+        except Exception as e:  # noqa: BLE001
+            o["swendsen_wang"] = {"error": repr(e)}
+        out["cfg5"] = o
+        st.close()
+        di.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -292,71 +592,80 @@ def run_ours(args, out):
     attempts_step_all = float(R_total) * S * P_SLICES * NSPINS
     value = attempts_step_all * args.steps / (ms_total * 1e-3)
 
-    def post():
-        # final energies + the collective the path has: gather per-anneal best-slice energies, broadcast the best
-        e = st.energies()
-        best_local = e.min(axis=1)
-        conf = st.download_spins()
-        kbest = e.argmin(axis=1)
-        best_conf = np.ascontiguousarray(conf[np.arange(R), :, kbest])
-        del conf
-        return parallel.gather_best(best_local, best_conf, lo, R_total, device=dev)
+    # final result of the resident batch: best slice per anneal on the device (fixed-order fp64 energies -> arg-min
+    # -> that slice's spins), then the collective the path has -- all device buffers, no world-line download
+    e_dev = torch.empty(R, dtype=torch.float64, device=dev)
+    k_dev = torch.empty(R, dtype=torch.int32, device=dev)
+    c_dev = torch.empty((R, NSPINS), dtype=torch.int8, device=dev)
+    st.best_into(e_dev.data_ptr(), k_dev.data_ptr(), c_dev.data_ptr())
+    inst.synchronize()
+    e_all, best, best_conf = parallel.gather_best_device(e_dev, c_dev, lo, R_total)
+    energies = e_all.cpu().numpy()
 
-    if not os.environ.get("BENCH_POST_LAST"):
-        energies, best, _ = post()
-
-    # ---- e2e: host buffers through the one-shot C-ABI call (H2D + pack + sweeps + unpack + D2H + energies)
-    e2e = None
+    # ---- e2e: host buffers through the one-shot C-ABI call (H2D + tile + sweeps + best slice + D2H) + the gather
+    e2e, e2e_full = None, None
+    L = mcs._lib.load()
     if args.e2e_steps > 0:
-        host = mcs.empty_pinned((R, NSPINS, P_SLICES), np.int8)
-        e_host = mcs.empty_pinned((R, P_SLICES), np.float64)
         rs = np.random.RandomState(rank)
-        s0 = (2 * rs.randint(2, size=(R, NSPINS, 1)) - 1).astype(np.int8)
-        L = mcs._lib.load()
+        h_in = mcs.empty_pinned((R, NSPINS), np.int8)
+        h_in[...] = (2 * rs.randint(2, size=(R, NSPINS)) - 1).astype(np.int8)
+        h_e = mcs.empty_pinned((R, P_SLICES), np.float64)
+        h_eb = mcs.empty_pinned((R,), np.float64)
+        h_kb = mcs.empty_pinned((R,), np.int32)
+        h_cf = mcs.empty_pinned((R, NSPINS), np.int8)
         times = []
         for it in range(args.e2e_steps + 1):  # first one is warm-up
-            host[...] = s0  # fresh anneal: broadcast over slices (not timed: input preparation)
             barrier()
             t0 = time.perf_counter()
-            mcs._lib.check(L.mcs_piqmc_anneal(inst._h, mcs._lib.dptr(A), mcs._lib.dptr(B), S, 1, temp,
-                                              host.ctypes.data, R, P_SLICES, 0, seed + it, lo,
-                                              mcs._lib.dptr(e_host)))
+            mcs._lib.check(L.mcs_piqmc_anneal_best(
+                inst._h, mcs._lib.dptr(A), mcs._lib.dptr(B), S, 1, temp, h_in.ctypes.data, 1, R, P_SLICES, 0,
+                seed + it, lo, mcs._lib.dptr(h_e), mcs._lib.dptr(h_eb), h_kb.ctypes.data_as(mcs._lib.c_i32p),
+                h_cf.ctypes.data))
+            if dist is not None:  # the path's one exchange step, inside the timed region
+                parallel.gather_best(h_eb, h_cf, lo, R_total, device=dev)
             barrier()
             times.append(time.perf_counter() - t0)
-        # median of the timed calls: the host link of these boxes is occasionally slow for a whole call (every call is
-        # listed in ms_each_rank0); host_link_gbs gives the pinned-copy rate seen right after, for context
         tt = torch.tensor([float(np.median(times[1:]))], dtype=torch.float64, device=dev)
-        link = {}
-        try:
-            hp = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
-            dp = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-            for key, dst, src in (("h2d", dp, hp), ("d2h", hp, dp)):
-                dst.copy_(src, non_blocking=True)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                dst.copy_(src, non_blocking=True)
-                torch.cuda.synchronize()
-                link[key] = round((256 << 20) / (time.perf_counter() - t0) / 1e9, 1)
-            del hp, dp
-        except Exception:  # noqa: BLE001
-            pass
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": attempts_step_all / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(R) * NSPINS * P_SLICES,
-               "d2h_bytes_per_step": int(R) * NSPINS * P_SLICES + int(R) * P_SLICES * 8,
+               "h2d_bytes_per_step": int(R) * NSPINS,
+               "d2h_bytes_per_step": int(R) * (NSPINS + P_SLICES * 8 + 12),
                "ms_per_step": 1e3 * float(tt.item()), "ms_each_rank0": [round(1e3 * x, 1) for x in times[1:]],
-               "host_link_gbs": link,
-               "api": "mcs_piqmc_anneal (C ABI one-shot: pinned int8 [R,N,P] in/out + float64 energies out)"}
+               "api": "mcs_piqmc_anneal_best (C ABI one-shot, the example's protocol santoro80.py:286-296: pinned int8 "
+                      "[R,N] start states in -> tiled over the slices on the device -> anneal -> float64 energies "
+                      "[R,P], best energy / slice [R] and best configuration int8 [R,N] out)"
+                      + ("; + parallel.gather_best (NCCL all_gather of the best energies, broadcast of the winner)"
+                         if dist is not None else "")}
+        del h_in, h_e, h_eb, h_kb, h_cf
+        # the drop-in shaped call: full world lines both ways
+        if args.e2e_full_steps > 0:
+            host = mcs.empty_pinned((R, NSPINS, P_SLICES), np.int8)
+            e_host = mcs.empty_pinned((R, P_SLICES), np.float64)
+            s0 = (2 * rs.randint(2, size=(R, NSPINS, 1)) - 1).astype(np.int8)
+            times = []
+            for it in range(args.e2e_full_steps + 1):
+                host[...] = s0  # fresh anneal: broadcast over slices (not timed: input preparation)
+                barrier()
+                t0 = time.perf_counter()
+                mcs._lib.check(L.mcs_piqmc_anneal(inst._h, mcs._lib.dptr(A), mcs._lib.dptr(B), S, 1, temp,
+                                                  host.ctypes.data, R, P_SLICES, 0, seed + it, lo,
+                                                  mcs._lib.dptr(e_host)))
+                barrier()
+                times.append(time.perf_counter() - t0)
+            tt = torch.tensor([float(np.median(times[1:]))], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_full = {"value": attempts_step_all / float(tt.item()), "unit": UNIT,
+                        "h2d_bytes_per_step": int(R) * NSPINS * P_SLICES,
+                        "d2h_bytes_per_step": int(R) * NSPINS * P_SLICES + int(R) * P_SLICES * 8,
+                        "ms_per_step": 1e3 * float(tt.item()),
+                        "api": "mcs_piqmc_anneal (drop-in shaped: pinned int8 [R,N,P] world lines in/out + energies)"}
+            del host, e_host
+        inst.trim()
 
-    if os.environ.get("BENCH_POST_LAST"):
-        energies, best, _ = post()
     if rank == 0:
-        peaks = {}
-        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.isfile(ppath):
-            with open(ppath) as f:
-                peaks = json.load(f)
+        peaks = load_peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # dominant kernel: piqmc_lut_pass_kernel, one launch per colour class per sweep.
         # algorithmic bytes: 0.25 B per attempt (read + write of one bit-packed spin), DESIGN.md section 4
@@ -370,9 +679,8 @@ def run_ours(args, out):
             "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "dtype_detail": "bit-packed spins in u64 words (bit k = Trotter slice k); u32 acceptance thresholds from f32 energies; u32 Philox",
             "data": name + ", Philox-initialised spins",
-            "config": {"workload": "80x80 PIQMC P=64, %d anneals total (%d per GPU), A=linspace(3,1e-8,%d), B=1, "
-                                   "mcsteps=1, T=1/64 (BASELINE configs[2])" % (R_total, R, S),
-                       "l2": "flushed between timed steps (256 MiB memset); state %.0f MB per GPU" % (
+            "config": {"workload": workload_name(R_total, world, S)},
+            "timing": {"l2": "flushed between timed steps (256 MiB memset); state %.0f MB per GPU" % (
                            R * NSPINS * 8 / 1e6),
                        "timer": "CUDA events on the launch stream (mcs_timer_*), max over ranks",
                        "wall_s_timed_region": wall},
@@ -380,17 +688,43 @@ def run_ours(args, out):
             "clocks": clocks,
             "roofline": roofline(achieved, peak, bool(peaks), R, ms_per_launch, bytes_per_launch, n_pass, args),
             "e2e": e2e,
+            "e2e_full_confs": e2e_full,
             "result": {"best_residual_energy_per_spin": None, "mean_best_slice_energy": float(np.mean(energies)),
-                       "best_anneal": int(best)},
+                       "best_anneal": int(best),
+                       "best_conf_energy_check": None},
         }
         gs = os.path.join(ROOT, "tests", "golden", "santoro80.npz")
         if os.path.isfile(gs):
             egs = float(np.load(gs)["e_gs_per_spin"])
             line["result"]["best_residual_energy_per_spin"] = float(np.min(energies)) / NSPINS - egs
             line["result"]["mean_residual_energy_per_spin"] = float(np.mean(energies)) / NSPINS - egs
-        # CPU baseline (rank 0, N = 1 only), AFTER every GPU measurement and in a separate interpreter: loading all
+        # the broadcast configuration really has the winning energy (host recomputation, sparse)
+        try:
+            sc = best_conf.cpu().numpy().astype(np.float64)
+            idx, Jc = nbs[:, :, 0].astype(int), nbs[:, :, 1]
+            line["result"]["best_conf_energy_check"] = float(0.5 * np.sum(Jc * sc[:, None] * sc[idx])) - float(
+                np.min(energies))
+        except Exception:  # noqa: BLE001
+            pass
+        which = [c for c in (args.configs or "").split(",") if c] if world == 1 else []
+        if which:
+            try:
+                line["configs"] = run_configs(mcs, inst, peaks, which)
+            except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
+                line["configs"] = {"error": repr(e)}
+        # CPU baselines (rank 0, N = 1 only), AFTER every GPU measurement and in a separate interpreter: loading all
         # host cores first left the pinned buffers of the e2e leg on slower pages (e2e +15 % when it ran first)
-        line["cpu_baseline"] = cpu_baseline_subprocess(args.cpu_sweeps) if (world == 1 and args.cpu_sweeps > 0) else None
+        line["cpu_baseline"] = None
+        if world == 1 and args.cpu_sweeps > 0:
+            cpu = cpu_baseline_subprocess(args.cpu_sweeps, [c for c in which if c.startswith("cfg") and "_" not in c])
+            line["cpu_baseline"] = cpu.get("cfg3")
+            for c, v in cpu.items():
+                if c != "cfg3" and isinstance(line.get("configs"), dict) and c in line["configs"]:
+                    line["configs"][c]["cpu_baseline"] = v
+            if isinstance(line.get("configs"), dict):
+                for c in ("cfg3_reference_dynamics", "cfg3_exact_replay"):
+                    if c in line["configs"]:
+                        line["configs"][c]["cpu_baseline"] = cpu.get("cfg3")
         out["line"] = line
     if dist is not None:
         dist.barrier()
@@ -424,10 +758,14 @@ def main():
     ap.add_argument("--anneals", type=int, default=4096, help="total anneals over all ranks")
     ap.add_argument("--sched", type=int, default=SCHED, help="schedule length (sweeps per step)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-full-steps", type=int, default=2, help="timed calls of the drop-in shaped e2e variant")
     ap.add_argument("--cpu-sweeps", type=int, default=40, help="sweeps per core for the CPU baseline sample")
+    ap.add_argument("--configs", default="cfg1,cfg2,refdyn,exact,cfg4,cfg5",
+                    help="extra entries measured on rank 0 at N = 1 (empty: none)")
+    ap.add_argument("--cpu-configs", default="", help="(reference arm) also time these configs' reference functions")
     ap.add_argument("--traffic", type=float, default=None,
                     help="ncu dram__bytes_read+write per launch of the dominant kernel; default: the committed "
-                         "capture profiles/r01_piqmc_lut_pass_ncu_full.txt scaled to this run's replicas")
+                         "capture profiles/r0*_piqmc_lut_pass_ncu.json scaled to this run's replicas")
     args = ap.parse_args()
     out = {}
     with _StdoutToStderr():

@@ -590,3 +590,38 @@ def test_edge_cases_empty_schedule_single_replica_and_extreme_slices(mcs):
     b32 = b8.astype(np.int32)
     mcs.qmc.QuantumAnneal(np.linspace(2, 0.1, 5), np.ones(5), 1, 0.25, b32, nbs, 1, seed=3)
     assert b32.dtype == np.int32 and set(np.unique(b32)) <= {-1, 1}
+
+
+def test_anneal_best_slice_equals_the_separate_calls(mcs):
+    """mcs_piqmc_anneal_best / mcs_state_best (the example's tile -> anneal -> best-slice protocol,
+    santoro80.py:286-296, fused on the device) against the drop-in call followed by host post-processing:
+    same seed -> same world lines -> identical per-slice energies, arg-min slice and configuration."""
+    import torch
+    _, nbs = inst.torus(10, seed=4, fields=True)
+    n, P, R = 100, 12, 70
+    s0 = (2 * np.random.RandomState(5).randint(2, size=(R, n)) - 1).astype(np.int8)
+    A, B = np.linspace(2.5, 0.05, 25), np.ones(25)
+    confs = np.ascontiguousarray(np.repeat(s0[:, :, None], P, axis=2))
+    e_ref = mcs.qmc.QuantumAnnealGlobal(A, B, 1, 1.0 / P, confs, nbs, 1, seed=31, energies=True)
+    eb, kb, cb, e_all = mcs.qmc.anneal_best_slice(A, B, 1, 1.0 / P, s0, nbs, P, global_moves=True, seed=31,
+                                                  per_slice_energies=True)
+    assert np.array_equal(e_all, e_ref)
+    assert np.array_equal(kb, e_ref.argmin(axis=1)) and np.array_equal(eb, e_ref.min(axis=1))
+    assert np.array_equal(cb, confs[np.arange(R), :, kb])
+    for r in (0, 33, 69):
+        assert abs(eb[r] - orc.ising_energy(cb[r].astype(np.int64), nbs)) < 1e-9
+    # single anneal form and the device-pointer handoff (torch tensors) agree with the host form
+    e1, k1, c1 = mcs.qmc.anneal_best_slice(A, B, 1, 1.0 / P, s0[7].astype(np.int64), nbs, P, seed=31, replica_offset=7)
+    assert e1 == eb[7] and k1 == kb[7] and np.array_equal(c1, cb[7])
+    I = mcs.Instance(nbs)
+    st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+    st.upload_spins(confs)
+    e_h, k_h, c_h = st.best()
+    dev = torch.device("cuda", 0)
+    e_d = torch.empty(R, dtype=torch.float64, device=dev)
+    k_d = torch.empty(R, dtype=torch.int32, device=dev)
+    c_d = torch.empty((R, n), dtype=torch.int8, device=dev)
+    st.best_into(e_d.data_ptr(), k_d.data_ptr(), c_d.data_ptr())
+    I.synchronize()
+    assert np.array_equal(e_d.cpu().numpy(), e_h) and np.array_equal(k_d.cpu().numpy(), k_h)
+    assert np.array_equal(c_d.cpu().numpy(), c_h) and np.array_equal(e_h, eb)
