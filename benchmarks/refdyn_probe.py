@@ -45,6 +45,24 @@ def main():
     ms = inst.timer_stop()
     print(json.dumps({"mode": "reference dynamics", "solver": "SA", "R": R, "sweeps": 8 * S, "ms": ms,
                       "attempts_per_s": R * 8 * S * N / (ms * 1e-3)}), flush=True)
+    st.close()
+    # cfg4 shape: rotors on Chimera C16
+    from bench import chimera_instance
+    ci = mcs.Instance(chimera_instance(16))
+    ci.set_dynamics("reference")
+    Rv = min(R, 2048)
+    sv = mcs.State(ci, mcs._lib.KIND_SVMC, Rv, 1)
+    s = np.linspace(1e-3, 1.0, 1000)[400:400 + 8 * S]
+    A, B = (3.0 * (1 - s)).copy(), s.copy()
+    for tf in (0, 1):
+        sv.init_random(1)
+        sv.svmc_sweeps(A[:1], B[:1], 1, 0.1, tf=tf, seed=2)
+        ci.synchronize()
+        ci.timer_start()
+        sv.svmc_sweeps(A, B, 1, 0.1, tf=tf, seed=2)
+        ms = ci.timer_stop()
+        print(json.dumps({"mode": "reference dynamics", "solver": "SVMC%s" % ("-TF" if tf else ""), "R": Rv,
+                          "sweeps": 8 * S, "ms": ms, "attempts_per_s": Rv * 8 * S * 2048 / (ms * 1e-3)}), flush=True)
 
 
 if __name__ == "__main__":

@@ -22,6 +22,9 @@
 // N = 6400, P = 64), the schedule loop runs inside the kernel (one launch per call), and the only global traffic
 // is the coupling table (L2-resident, shared by all CTAs).
 //
+// The spin-vector solvers (svmc.pyx:78-117, 181-229) shuffle and visit the same way (svmc.pyx:83-91): refdyn_svmc_kernel
+// runs the rotor attempt on the same wave machinery (theta and cos theta of one read in shared memory).
+//
 // The acceptance arithmetic is the production one: fp32 dE in ELL order, threshold T = ceil(exp(-dE/teff) 2^32) - 1,
 // accept iff a 32-bit uniform u <= T (qmc.pyx:140-143); u = (v << 16) | r with r drawn lazily only when v alone
 // does not decide.  `sequential = 1` (test hook) lets thread 0 walk the sites in increasing (priority, index)
@@ -43,6 +46,7 @@ constexpr uint32_t kTagProp = 0x22u;   // SVMC proposals
 struct RefdynArgs {
     uint64_t *W;  // PIQMC [N][Rpad] (window base), bit k = slice k
     uint32_t *V;  // SA    [N][G], bit b of word g = replica 32 g + b
+    float *theta, *cosz; // SVMC [N][Rpad]
     const int32_t *ell_idx; // [N][dpad]
     const float *ell_J;     // [nsteps][N][dpad]
     const float *h;         // [nsteps][N]
@@ -50,8 +54,9 @@ struct RefdynArgs {
     const float *bcoef;  // [S]  -2 B          (qmc.pyx:96; SA: -2)
     const float *jperp2; // [S]  2 J_perp      (qmc.pyx:95)
     const float *nl2e;   // [S]  -log2(e)/teff (SA: -log2(e)/sched[t])
+    const float *acoef;  // [S]  SVMC only: A; there bcoef = B and jperp2 = min(1, A/B) (svmc.pyx:198-202)
     long long Rpad, G;
-    int N, Npad, dpad, field, P, S, mcsteps, global_moves, sequential;
+    int N, Npad, dpad, field, P, S, mcsteps, global_moves, tf, sequential;
     uint32_t replica_offset;
     uint64_t sweep_offset;
     mcs_philox_keys keys;
@@ -189,40 +194,220 @@ __device__ __forceinline__ void rd_finish(const RefdynArgs &a, WT *w, const uint
     if (acc) w[i] = wi ^ (MODE == RD_GLOBAL ? pmask : (WT)((WT)1 << k));
 }
 
-template <typename WT, int MODE, int DP>
-__device__ __forceinline__ void rd_attempt(const RefdynArgs &a, WT *w, const uint32_t *pu, int i, int k, int P,
-                                           WT pmask, const float *ellJ, const float *hrow, float bcoef,
-                                           float jperp2, float nl2e, uint32_t c0, uint32_t c2, uint32_t c3base)
+// ---- the wave machinery, shared by the Ising and the rotor kernels ---------------------------------------------
+// Per-CTA bookkeeping of the dependency waves.  Shared memory: pu[Npad] (upper half of the acceptance uniform : 16 |
+// priority : 16), cnt[Npad] bytes (open predecessors, packed four to a word), queue[Npad] u16, cntr[3].
+struct RdWaves {
+    uint32_t *pu;
+    uint32_t *cnt32;
+    uint16_t *queue;
+    int *cntr;   // round q counts its pushes in cntr[q % 3]
+    int rnd = 0; // running round number (uniform over the CTA)
+    long long pf0 = 0, pf1 = 0, pf2 = 0;
+    int pf_rounds = 0, pf_passes = 0;
+};
+
+// A `Site` policy supplies the solver-specific part of a visit:
+//   draw(q)              priorities + uniforms of sites 4q .. 4q+3 for this pass (into wv.pu and its own arrays)
+//   Acc begin(i)         start of a visit (reads the site's own state)
+//   row(acc, nb, J)      one chunk of the coupling row (reads the neighbours' state)
+//   finish(i, acc)       remaining terms, acceptance, write-back
+template <int DP, typename Site>
+__device__ __forceinline__ void rd_visit(const RefdynArgs &a, const float *ellJ, Site &site, int i)
 {
-    const WT wi = w[i];
-    float dE = 0.0f;
+    typename Site::Acc acc = site.begin(i);
     for (int j0 = 0; j0 < a.dpad; j0 += DP) {
         int nb[DP];
         float J[DP];
         rd_load_row<DP, true>(a, ellJ, i, j0, nb, J);
-        dE += rd_row_dE<WT, MODE, DP>(w, wi, nb, J, bcoef, k, P, pmask);
+        site.row(acc, nb, J);
     }
-    rd_finish<WT, MODE>(a, w, pu, i, wi, dE, k, P, pmask, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
+    site.finish(i, acc);
 }
 
-// Shared memory: w[Npad] | pu[Npad] (v:16 | priority:16) | cnt[Npad] bytes (open predecessors) | queue[Npad] u16
+// one pass = every site visited once, in the order of this pass's priorities
+template <int DP, typename Site>
+__device__ __forceinline__ void rd_pass(const RefdynArgs &a, RdWaves &wv, const float *ellJ, Site &site)
+{
+    const int N = a.N, Npad = a.Npad, T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
+    const bool one_chunk = a.dpad <= DP;
+    const uint32_t *pu = wv.pu;
+    uint32_t *cnt32 = wv.cnt32;
+    uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt32);
+    uint16_t *queue = wv.queue;
+    long long t0 = a.prof ? clock64() : 0;
+    for (int q = tid; q < Npad / 4; q += T) site.draw(q);
+    __syncthreads();
+    auto key = [&](int s) -> uint32_t { return (pu[s] << 16) | (uint32_t)s; };
+    if (a.sequential) { // test hook: thread 0 walks the sites in increasing (priority, index) order
+        if (tid == 0) {
+            for (int i = 0; i < N; ++i) cnt8[i] = 0;
+            for (int n = 0; n < N; ++n) {
+                int best = -1;
+                uint32_t bk = 0xFFFFFFFFu;
+                for (int i = 0; i < N; ++i)
+                    if (!cnt8[i] && key(i) <= bk) {
+                        bk = key(i);
+                        best = i;
+                    }
+                rd_visit<DP>(a, ellJ, site, best);
+                cnt8[best] = 1;
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    if (a.prof) {
+        const long long t1 = clock64();
+        wv.pf0 += t1 - t0;
+        t0 = t1;
+    }
+    // round 0: open-predecessor counts (independent iterations: the loads of several sites overlap) ...
+#pragma unroll 2
+    for (int i = tid; i < N; i += T) {
+        const uint32_t ki = key(i);
+        int c = 0;
+        for (int j0 = 0; j0 < a.dpad; j0 += DP) {
+            int nb[DP];
+            float J[DP];
+            rd_load_row<DP, false>(a, ellJ, i, j0, nb, J);
+#pragma unroll
+            for (int j = 0; j < DP; ++j) c += (nb[j] != i && key(nb[j]) < ki) ? 1 : 0;
+        }
+        cnt8[i] = (uint8_t)c;
+    }
+    // ... then the sites without predecessors start the queue (each thread re-reads its own bytes)
+    int *cn = &wv.cntr[wv.rnd % 3];
+    for (int i0 = wbase; i0 < N; i0 += T) {
+        const int i = i0 + lane;
+        rd_push(i < N && cnt8[i] == 0, (uint32_t)i, queue, cn, 0, lane);
+    }
+    __syncthreads();
+    int head = 0, tail = *(volatile int *)cn;
+    if (tid == 0) wv.cntr[(wv.rnd + 2) % 3] = 0; // last read before the barrier above; next used in round rnd + 2
+    ++wv.rnd;
+    if (a.prof) {
+        const long long t1 = clock64();
+        wv.pf1 += t1 - t0;
+        t0 = t1;
+        wv.pf_passes += 1;
+    }
+    // notifications of a finished site: decrement the open-predecessor count of its later neighbours and queue
+    // those that reach zero
+    auto notify = [&](bool active, int i, uint32_t ki, const int (&nb)[DP]) {
+        uint32_t rmask = 0u;
+#pragma unroll
+        for (int j = 0; j < DP; ++j) {
+            const int nbj = nb[j];
+            if (active && nbj != i && key(nbj) > ki) {
+                const int sh = 8 * (nbj & 3);
+                const uint32_t old = atomicSub(&cnt32[nbj >> 2], 1u << sh);
+                if (((old >> sh) & 0xFFu) == 1u) rmask |= 1u << j;
+            }
+        }
+        rd_push_many<DP>(rmask, nb, queue, cn, tail, lane);
+    };
+    while (head < N) {
+        wv.pf_rounds += 1;
+        if (tail == head) { // no progress: impossible for an acyclic orientation
+            if (tid == 0 && a.err) atomicExch(a.err, 1);
+            break;
+        }
+        cn = &wv.cntr[wv.rnd % 3];
+        for (int e0 = head + wbase; e0 < tail; e0 += T) {
+            const int e = e0 + lane;
+            const bool active = e < tail;
+            const int i = active ? (int)queue[e] : 0;
+            const uint32_t ki = key(i);
+            typename Site::Acc acc = site.begin(i);
+            for (int j0 = 0; j0 < a.dpad; j0 += DP) {
+                int nb[DP];
+                float J[DP];
+                rd_load_row<DP, true>(a, ellJ, i, j0, nb, J);
+                if (active) site.row(acc, nb, J);
+                if (!one_chunk) continue;
+                // rows of one chunk: attempt, then tell the later neighbours, from the same registers
+                if (active) site.finish(i, acc);
+                notify(active, i, ki, nb);
+            }
+            if (one_chunk) continue;
+            if (active) site.finish(i, acc);
+            for (int j0 = 0; j0 < a.dpad; j0 += DP) { // long rows: second walk for the notifications
+                int nb[DP];
+                float J[DP];
+                rd_load_row<DP, false>(a, ellJ, i, j0, nb, J);
+                notify(active, i, ki, nb);
+            }
+        }
+        __syncthreads();
+        head = tail;
+        tail += *(volatile int *)cn;
+        if (tid == 0) wv.cntr[(wv.rnd + 2) % 3] = 0;
+        ++wv.rnd;
+    }
+    if (a.prof) wv.pf2 += clock64() - t0;
+}
+
+__device__ __forceinline__ void rd_store_prof(const RefdynArgs &a, const RdWaves &wv)
+{
+    if (a.prof && threadIdx.x == 0) {
+        long long *o = a.prof + (size_t)blockIdx.x * 5;
+        o[0] = wv.pf0, o[1] = wv.pf1, o[2] = wv.pf2, o[3] = wv.pf_rounds, o[4] = wv.pf_passes;
+    }
+}
+
+// ---- Ising sites (PIQMC slices, world lines, SA) ----------------------------------------------------------------
+template <typename WT, int MODE>
+struct IsingSite {
+    struct Acc {
+        WT wi;
+        float dE;
+    };
+    const RefdynArgs &a;
+    WT *w;
+    uint32_t *pu;
+    int k, P;
+    WT pmask;
+    const float *hrow;
+    float bcoef, jperp2, nl2e;
+    uint32_t c0, c2, c3base;
+
+    __device__ __forceinline__ void draw(int q) const
+    { // priorities and the upper halves of the uniforms
+        uint32_t x[4];
+        mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
+        reinterpret_cast<uint4 *>(pu)[q] = make_uint4(x[0], x[1], x[2], x[3]);
+    }
+    __device__ __forceinline__ Acc begin(int i) const { return Acc{w[i], 0.0f}; }
+    template <int DP>
+    __device__ __forceinline__ void row(Acc &acc, const int (&nb)[DP], const float (&J)[DP]) const
+    {
+        acc.dE += rd_row_dE<WT, MODE, DP>(w, acc.wi, nb, J, bcoef, k, P, pmask);
+    }
+    __device__ __forceinline__ void finish(int i, const Acc &acc) const
+    {
+        rd_finish<WT, MODE>(a, w, pu, i, acc.wi, acc.dE, k, P, pmask, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
+    }
+};
+
+// Shared memory: w[Npad] | pu[Npad] | cnt[Npad] bytes | queue[Npad] u16
 // DP: chunk of the ELL row held in registers (4: rows of at most 4 entries are one chunk; 8 otherwise)
 template <typename WT, bool SA, int DP>
 __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant__ RefdynArgs a)
 {
     extern __shared__ __align__(16) unsigned char rd_smem[];
     __shared__ int s_cntr[3];
-    const int N = a.N, Npad = a.Npad, T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
+    const int N = a.N, Npad = a.Npad, T = blockDim.x, tid = threadIdx.x;
     WT *w = reinterpret_cast<WT *>(rd_smem);
-    uint32_t *pu = reinterpret_cast<uint32_t *>(w + Npad);
-    uint32_t *cnt32 = pu + Npad;
-    uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt32);
-    uint16_t *queue = reinterpret_cast<uint16_t *>(cnt32 + Npad / 4);
+    RdWaves wv;
+    wv.pu = reinterpret_cast<uint32_t *>(w + Npad);
+    wv.cnt32 = wv.pu + Npad;
+    wv.queue = reinterpret_cast<uint16_t *>(wv.cnt32 + Npad / 4);
+    wv.cntr = s_cntr;
     const long long r = blockIdx.x;
     const int P = SA ? 1 : a.P;
     const WT pmask = (P == (int)(8 * sizeof(WT))) ? (WT)~(WT)0 : (WT)(((WT)1 << P) - (WT)1);
     const uint32_t c0 = a.replica_offset + (uint32_t)r;
-    const bool one_chunk = a.dpad <= DP;
 
     for (int i = tid; i < Npad; i += T) {
         WT v = 0;
@@ -232,139 +417,6 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
     if (tid < 3) s_cntr[tid] = 0;
     __syncthreads();
 
-    long long pf0 = 0, pf1 = 0, pf2 = 0;
-    int pf_rounds = 0, pf_passes = 0;
-    int rnd = 0; // running round number (uniform): round q counts its pushes in s_cntr[q % 3]
-    // one pass = every site visited once, in the order of this pass's priorities
-    auto pass = [&](auto mode_tag, int k, uint32_t c2, uint32_t c3base, const float *ellJ, const float *hrow,
-                    float bcoef, float jperp2, float nl2e) {
-        constexpr int MODE = decltype(mode_tag)::value;
-        long long t0 = a.prof ? clock64() : 0;
-        for (int q = tid; q < Npad / 4; q += T) { // priorities and the upper halves of the uniforms
-            uint32_t x[4];
-            mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
-            reinterpret_cast<uint4 *>(pu)[q] = make_uint4(x[0], x[1], x[2], x[3]);
-        }
-        __syncthreads();
-        auto key = [&](int s) -> uint32_t { return (pu[s] << 16) | (uint32_t)s; };
-        if (a.sequential) { // test hook: thread 0 walks the sites in increasing (priority, index) order
-            if (tid == 0) {
-                for (int i = 0; i < N; ++i) cnt8[i] = 0;
-                for (int n = 0; n < N; ++n) {
-                    int best = -1;
-                    uint32_t bk = 0xFFFFFFFFu;
-                    for (int i = 0; i < N; ++i)
-                        if (!cnt8[i] && key(i) <= bk) {
-                            bk = key(i);
-                            best = i;
-                        }
-                    rd_attempt<WT, MODE, DP>(a, w, pu, best, k, P, pmask, ellJ, hrow, bcoef, jperp2, nl2e, c0, c2,
-                                             c3base);
-                    cnt8[best] = 1;
-                }
-            }
-            __syncthreads();
-            return;
-        }
-        if (a.prof) {
-            const long long t1 = clock64();
-            pf0 += t1 - t0;
-            t0 = t1;
-        }
-        // round 0: open-predecessor counts (independent iterations: the loads of several sites overlap) ...
-#pragma unroll 2
-        for (int i = tid; i < N; i += T) {
-            const uint32_t ki = key(i);
-            int c = 0;
-            for (int j0 = 0; j0 < a.dpad; j0 += DP) {
-                int nb[DP];
-                float J[DP];
-                rd_load_row<DP, false>(a, ellJ, i, j0, nb, J);
-#pragma unroll
-                for (int j = 0; j < DP; ++j) c += (nb[j] != i && key(nb[j]) < ki) ? 1 : 0;
-            }
-            cnt8[i] = (uint8_t)c;
-        }
-        // ... then the sites without predecessors start the queue (each thread re-reads its own bytes)
-        int *cn = &s_cntr[rnd % 3];
-        for (int i0 = wbase; i0 < N; i0 += T) {
-            const int i = i0 + lane;
-            rd_push(i < N && cnt8[i] == 0, (uint32_t)i, queue, cn, 0, lane);
-        }
-        __syncthreads();
-        int head = 0, tail = *(volatile int *)cn;
-        if (tid == 0) s_cntr[(rnd + 2) % 3] = 0; // last read before the barrier above; next used in round rnd + 2
-        ++rnd;
-        if (a.prof) {
-            const long long t1 = clock64();
-            pf1 += t1 - t0;
-            t0 = t1;
-            pf_passes += 1;
-        }
-        while (head < N) {
-            pf_rounds += 1;
-            if (tail == head) { // no progress: impossible for an acyclic orientation
-                if (tid == 0 && a.err) atomicExch(a.err, 1);
-                break;
-            }
-            cn = &s_cntr[rnd % 3];
-            for (int e0 = head + wbase; e0 < tail; e0 += T) {
-                const int e = e0 + lane;
-                const bool active = e < tail;
-                const int i = active ? (int)queue[e] : 0;
-                const uint32_t ki = key(i);
-                const WT wi = w[i];
-                float dE = 0.0f;
-                for (int j0 = 0; j0 < a.dpad; j0 += DP) {
-                    int nb[DP];
-                    float J[DP];
-                    rd_load_row<DP, true>(a, ellJ, i, j0, nb, J);
-                    if (active) dE += rd_row_dE<WT, MODE, DP>(w, wi, nb, J, bcoef, k, P, pmask);
-                    if (!one_chunk) continue;
-                    // rows of one chunk: attempt, then tell the later neighbours, from the same registers
-                    if (active)
-                        rd_finish<WT, MODE>(a, w, pu, i, wi, dE, k, P, pmask, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
-                    uint32_t rmask = 0u;
-#pragma unroll
-                    for (int j = 0; j < DP; ++j) {
-                        const int nbj = nb[j];
-                        if (active && nbj != i && key(nbj) > ki) {
-                            const int sh = 8 * (nbj & 3);
-                            const uint32_t old = atomicSub(&cnt32[nbj >> 2], 1u << sh);
-                            if (((old >> sh) & 0xFFu) == 1u) rmask |= 1u << j;
-                        }
-                    }
-                    rd_push_many<DP>(rmask, nb, queue, cn, tail, lane);
-                }
-                if (one_chunk) continue;
-                if (active)
-                    rd_finish<WT, MODE>(a, w, pu, i, wi, dE, k, P, pmask, hrow, bcoef, jperp2, nl2e, c0, c2, c3base);
-                for (int j0 = 0; j0 < a.dpad; j0 += DP) { // long rows: second walk for the notifications
-                    int nb[DP];
-                    float J[DP];
-                    rd_load_row<DP, false>(a, ellJ, i, j0, nb, J);
-                    uint32_t rmask = 0u;
-#pragma unroll
-                    for (int j = 0; j < DP; ++j) {
-                        const int nbj = nb[j];
-                        if (active && nbj != i && key(nbj) > ki) {
-                            const int sh = 8 * (nbj & 3);
-                            const uint32_t old = atomicSub(&cnt32[nbj >> 2], 1u << sh);
-                            if (((old >> sh) & 0xFFu) == 1u) rmask |= 1u << j;
-                        }
-                    }
-                    rd_push_many<DP>(rmask, nb, queue, cn, tail, lane);
-                }
-            }
-            __syncthreads();
-            head = tail;
-            tail += *(volatile int *)cn;
-            if (tid == 0) s_cntr[(rnd + 2) % 3] = 0;
-            ++rnd;
-        }
-        if (a.prof) pf2 += clock64() - t0;
-    };
-
     for (int f = 0; f < a.S; ++f) {
         const float *ellJ = a.ell_J + (size_t)f * a.ellJ_stride;
         const float *hrow = a.h + (size_t)f * a.h_stride;
@@ -373,22 +425,24 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
             const uint64_t sweep = a.sweep_offset + (uint64_t)f * (uint64_t)a.mcsteps + (uint64_t)step;
             const uint32_t c2 = (uint32_t)sweep, c3hi = (uint32_t)(sweep >> 32) << 16;
             if (SA) {
-                pass(std::integral_constant<int, RD_SA>(), 0, c2, c3hi, ellJ, hrow, bcoef, jperp2, nl2e);
+                IsingSite<WT, RD_SA> site{a, w, wv.pu, 0, P, pmask, hrow, bcoef, jperp2, nl2e, c0, c2, c3hi};
+                rd_pass<DP>(a, wv, ellJ, site);
             } else {
-                for (int k = 0; k < P; ++k)
-                    pass(std::integral_constant<int, RD_LOCAL>(), k, c2, c3hi | ((uint32_t)k << 8), ellJ, hrow, bcoef,
-                         jperp2, nl2e);
-                if (a.global_moves)
-                    pass(std::integral_constant<int, RD_GLOBAL>(), 0, c2, c3hi | (64u << 8), ellJ, hrow, bcoef, jperp2,
-                         nl2e);
+                for (int k = 0; k < P; ++k) {
+                    IsingSite<WT, RD_LOCAL> site{a,     w,      wv.pu, k,  P,  pmask,
+                                                 hrow,  bcoef,  jperp2, nl2e, c0, c2, c3hi | ((uint32_t)k << 8)};
+                    rd_pass<DP>(a, wv, ellJ, site);
+                }
+                if (a.global_moves) {
+                    IsingSite<WT, RD_GLOBAL> site{a,     w,      wv.pu, 0,  P,  pmask,
+                                                  hrow,  bcoef,  jperp2, nl2e, c0, c2, c3hi | (64u << 8)};
+                    rd_pass<DP>(a, wv, ellJ, site);
+                }
             }
         }
     }
     __syncthreads();
-    if (a.prof && tid == 0) {
-        long long *o = a.prof + (size_t)blockIdx.x * 5;
-        o[0] = pf0, o[1] = pf1, o[2] = pf2, o[3] = pf_rounds, o[4] = pf_passes;
-    }
+    rd_store_prof(a, wv);
     for (int i = tid; i < N; i += T) {
         if (SA) {
             const uint32_t bit = 1u << (r & 31);
@@ -403,34 +457,129 @@ __global__ void __launch_bounds__(512) refdyn_ising_kernel(const __grid_constant
     }
 }
 
-template <typename WT, bool SA, int DP>
-int launch_ising_dp(const RefdynArgs &a, long long replicas, int threads, size_t smem, cudaStream_t s)
-{
-    static size_t configured[64] = {}; // opt-in dynamic shared memory granted so far, per device
-    int dev = 0;
-    MCS_CUDA(cudaGetDevice(&dev));
-    if (smem > 48 * 1024 && configured[dev & 63] < smem) {
-        MCS_CUDA(cudaFuncSetAttribute(refdyn_ising_kernel<WT, SA, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        configured[dev & 63] = smem;
+// ---- rotor sites (svmc.pyx:78-117, TF: 181-229) ----------------------------------------------------------------
+// Visit of svmc.pyx:92-115 in fp32: z = sum_j J_ij cos(theta_j) + h_i over the ELL row, proposal from a 24-bit
+// uniform (theta' = pi u, or the TF displacement clamped to [0, pi]), dE = B (cos theta' - cos theta_i) z +
+// A (sin theta_i - sin theta'), Metropolis rule as above.
+struct RotorSite {
+    using Acc = float;
+    const RefdynArgs &a;
+    float *th, *cz;  // shared memory: theta and its cosine
+    uint32_t *pu;    // as above
+    uint32_t *prop;  // 32-bit proposal uniform per site
+    const float *hrow;
+    float acoef, bcoef, tfscale, nl2e;
+    uint32_t c0, c2, c3base;
+
+    __device__ __forceinline__ void draw(int q) const
+    {
+        uint32_t x[4];
+        mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
+        reinterpret_cast<uint4 *>(pu)[q] = make_uint4(x[0], x[1], x[2], x[3]);
+        mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagProp, a.keys, x);
+        reinterpret_cast<uint4 *>(prop)[q] = make_uint4(x[0], x[1], x[2], x[3]);
     }
-    refdyn_ising_kernel<WT, SA, DP><<<(unsigned)replicas, threads, smem, s>>>(a);
+    __device__ __forceinline__ Acc begin(int i) const { return a.field ? __ldg(hrow + i) : 0.0f; }
+    template <int DP>
+    __device__ __forceinline__ void row(Acc &z, const int (&nb)[DP], const float (&J)[DP]) const
+    {
+#pragma unroll
+        for (int j = 0; j < DP; ++j) z = fmaf(J[j], cz[nb[j]], z); // padding: J = 0
+    }
+    __device__ __forceinline__ void finish(int i, Acc z) const
+    {
+        const float kPi = 3.14159265358979323846f;
+        const float thi = th[i], ci = cz[i];
+        const float f0 = (float)(prop[i] >> 8) * (1.0f / 16777216.0f); // [0, 1)
+        float thp;
+        if (!a.tf) {
+            thp = kPi * f0; // svmc.pyx:95
+        } else {            // svmc.pyx:198-207
+            thp = thi + tfscale * (2.0f * kPi * f0 - kPi);
+            thp = fminf(fmaxf(thp, 0.0f), kPi);
+        }
+        float sp, cp;
+        __sincosf(thp, &sp, &cp);
+        const float dE = bcoef * (cp - ci) * z + acoef * (__sinf(thi) - sp); // svmc.pyx:96-110
+        const bool acc = rd_accept(dE, nl2e, pu[i] >> 16, [&]() -> uint32_t {
+            return rd_refine_draw(c0, (uint32_t)i, c2, c3base | kTagRefine, a.keys.rk[0], a.keys.rk[1]);
+        });
+        if (acc) {
+            th[i] = thp;
+            cz[i] = cp;
+        }
+    }
+};
+
+// Shared memory: theta[Npad] | cos[Npad] | pu[Npad] | prop[Npad] | cnt[Npad] bytes | queue[Npad] u16
+template <int DP>
+__global__ void __launch_bounds__(512) refdyn_svmc_kernel(const __grid_constant__ RefdynArgs a)
+{
+    extern __shared__ __align__(16) unsigned char rd_smem[];
+    __shared__ int s_cntr[3];
+    const int N = a.N, Npad = a.Npad, T = blockDim.x, tid = threadIdx.x;
+    float *th = reinterpret_cast<float *>(rd_smem), *cz = th + Npad;
+    RdWaves wv;
+    wv.pu = reinterpret_cast<uint32_t *>(cz + Npad);
+    uint32_t *prop = wv.pu + Npad;
+    wv.cnt32 = prop + Npad;
+    wv.queue = reinterpret_cast<uint16_t *>(wv.cnt32 + Npad / 4);
+    wv.cntr = s_cntr;
+    const long long r = blockIdx.x;
+    const uint32_t c0 = a.replica_offset + (uint32_t)r;
+
+    for (int i = tid; i < Npad; i += T) {
+        const float t = i < N ? a.theta[(size_t)i * a.Rpad + r] : 0.0f;
+        th[i] = t;
+        cz[i] = __cosf(t);
+    }
+    if (tid < 3) s_cntr[tid] = 0;
+    __syncthreads();
+
+    for (int f = 0; f < a.S; ++f) {
+        const float *ellJ = a.ell_J + (size_t)f * a.ellJ_stride;
+        const float *hrow = a.h + (size_t)f * a.h_stride;
+        // schedule arrays: bcoef = B, jperp2 = min(1, A / B) (TF scale), acoef = A
+        const float bcoef = __ldg(&a.bcoef[f]), tfscale = __ldg(&a.jperp2[f]), nl2e = __ldg(&a.nl2e[f]);
+        const float acoef = __ldg(&a.acoef[f]);
+        for (int step = 0; step < a.mcsteps; ++step) {
+            const uint64_t sweep = a.sweep_offset + (uint64_t)f * (uint64_t)a.mcsteps + (uint64_t)step;
+            const uint32_t c2 = (uint32_t)sweep, c3hi = (uint32_t)(sweep >> 32) << 16;
+            RotorSite site{a, th, cz, wv.pu, prop, hrow, acoef, bcoef, tfscale, nl2e, c0, c2, c3hi};
+            rd_pass<DP>(a, wv, ellJ, site);
+        }
+    }
+    __syncthreads();
+    rd_store_prof(a, wv);
+    for (int i = tid; i < N; i += T) {
+        a.theta[(size_t)i * a.Rpad + r] = th[i];
+        a.cosz[(size_t)i * a.Rpad + r] = cz[i];
+    }
+}
+
+template <typename K>
+int rd_launch(K kernel, const RefdynArgs &a, long long replicas, int threads, size_t smem, cudaStream_t s)
+{
+    // opt-in dynamic shared memory: the attribute is per (kernel, device) and cheap to set, so set it whenever needed
+    if (smem > 48 * 1024)
+        MCS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)replicas, threads, smem, s>>>(a);
     return MCS_OK;
 }
 
 template <typename WT, bool SA>
 int launch_ising(const RefdynArgs &a, long long replicas, int threads, size_t smem, cudaStream_t s)
 {
-    return a.dpad <= 4 ? launch_ising_dp<WT, SA, 4>(a, replicas, threads, smem, s)
-                       : launch_ising_dp<WT, SA, 8>(a, replicas, threads, smem, s);
+    return a.dpad <= 4 ? rd_launch(refdyn_ising_kernel<WT, SA, 4>, a, replicas, threads, smem, s)
+                       : rd_launch(refdyn_ising_kernel<WT, SA, 8>, a, replicas, threads, smem, s);
 }
 
 } // namespace
 
-// kind = MCS_KIND_PIQMC: (A, B, temp) as mcs_piqmc_sweeps; MCS_KIND_SA: A = the temperature schedule, B = nullptr
+// kind = MCS_KIND_PIQMC: (A, B, temp) as mcs_piqmc_sweeps; MCS_KIND_SA: A = the temperature schedule, B = nullptr;
+// MCS_KIND_SVMC: (A, B, temp) as mcs_svmc_sweeps, `variant` = tf; otherwise `variant` = global_moves
 int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const double *B, int64_t S, int mcsteps,
-                             float temp, int global_moves, uint64_t seed, uint64_t replica_offset,
-                             uint64_t sweep_offset)
+                             float temp, int variant, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
 {
     mcs_instance *inst = st->inst;
     MCS_REQUIRE(!inst->dense, MCS_EUNSUPPORTED,
@@ -446,11 +595,12 @@ int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const dou
     const int P = kind == MCS_KIND_PIQMC ? (int)st->P : 1;
     const bool wide = P > 32;
     const int N = (int)inst->N, Npad = (N + 3) & ~3;
-    const size_t smem = (size_t)Npad * ((wide ? 8 : 4) + 4 + 1 + 2);
+    // per site: state | pu | open-predecessor byte | queue entry (rotors: theta, cos, pu, proposal uniform)
+    const size_t smem = (size_t)Npad * (kind == MCS_KIND_SVMC ? 16 + 1 + 2 : (wide ? 8 : 4) + 4 + 1 + 2);
     MCS_REQUIRE(smem <= 227 * 1024 - 64, MCS_EUNSUPPORTED,
-                "reference dynamics: a replica's world lines (%zu bytes) do not fit one SM's shared memory", smem);
-    std::vector<float> sched((size_t)3 * S);
-    float *bc = sched.data(), *jp = bc + S, *nl = jp + S;
+                "reference dynamics: a replica's state (%zu bytes) does not fit one SM's shared memory", smem);
+    std::vector<float> sched((size_t)4 * S);
+    float *bc = sched.data(), *jp = bc + S, *nl = jp + S, *ac = nl + S;
     if (kind == MCS_KIND_PIQMC) {
         const double teff = (double)temp * (double)P; // qmc.pyx:85
         MCS_REQUIRE(teff != 0.0, MCS_EZERODIV, "float division");
@@ -458,12 +608,22 @@ int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const dou
             bc[f] = (float)(-2.0 * B[f]);                                    // qmc.pyx:96
             jp[f] = (float)(2.0 * (-0.5 * teff * log(tanh(A[f] / teff))));   // qmc.pyx:95
             nl[f] = (float)(-1.4426950408889634 / teff);
+            ac[f] = 0.0f;
         }
-    } else {
+    } else if (kind == MCS_KIND_SA) {
         for (int64_t t = 0; t < S; ++t) {
             bc[t] = -2.0f; // sa.pyx:84-94
             jp[t] = 0.0f;
             nl[t] = (float)(-1.4426950408889634 / A[t]); // exp(-ediff/temp), sa.pyx:98
+            ac[t] = 0.0f;
+        }
+    } else {
+        for (int64_t f = 0; f < S; ++f) {
+            const double ab = A[f] / B[f]; // cdivision: inf / nan allowed (svmc.pyx:198)
+            bc[f] = (float)B[f];
+            jp[f] = (float)((ab > 1) ? 1.0 : ab);
+            nl[f] = (float)(-1.4426950408889634 / (double)temp); // temp is a C float (svmc.pyx:24)
+            ac[f] = (float)A[f];
         }
     }
     float *d_sched = nullptr;
@@ -475,6 +635,8 @@ int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const dou
     RefdynArgs a;
     a.W = kind == MCS_KIND_PIQMC ? st->d_W + st->win_lo() : nullptr;
     a.V = kind == MCS_KIND_SA ? st->d_V : nullptr;
+    a.theta = kind == MCS_KIND_SVMC ? st->d_theta : nullptr;
+    a.cosz = kind == MCS_KIND_SVMC ? st->d_cosz : nullptr;
     a.ell_idx = inst->d_ell_idx;
     a.ell_J = inst->d_ell_J;
     a.h = inst->d_h;
@@ -483,6 +645,7 @@ int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const dou
     a.bcoef = d_sched;
     a.jperp2 = d_sched + S;
     a.nl2e = d_sched + 2 * S;
+    a.acoef = d_sched + 3 * S;
     a.Rpad = st->Rpad;
     a.G = st->G;
     a.N = N;
@@ -492,7 +655,8 @@ int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const dou
     a.P = P;
     a.S = (int)S;
     a.mcsteps = mcsteps;
-    a.global_moves = global_moves ? 1 : 0;
+    a.global_moves = kind == MCS_KIND_PIQMC && variant ? 1 : 0;
+    a.tf = kind == MCS_KIND_SVMC && variant ? 1 : 0;
     a.sequential = getenv("MCS_REFDYN_SEQUENTIAL") != nullptr ? 1 : 0;
     a.replica_offset = (uint32_t)(replica_offset + (kind == MCS_KIND_PIQMC ? (uint64_t)st->win_lo() : 0ull));
     a.sweep_offset = sweep_offset;
@@ -508,7 +672,10 @@ int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const dou
         a.prof = d_prof;
     }
     int rc;
-    if (kind == MCS_KIND_SA)
+    if (kind == MCS_KIND_SVMC)
+        rc = a.dpad <= 4 ? rd_launch(refdyn_svmc_kernel<4>, a, replicas, threads, smem, inst->stream)
+                         : rd_launch(refdyn_svmc_kernel<8>, a, replicas, threads, smem, inst->stream);
+    else if (kind == MCS_KIND_SA)
         rc = launch_ising<uint32_t, true>(a, replicas, threads, smem, inst->stream);
     else if (wide)
         rc = launch_ising<uint64_t, false>(a, replicas, threads, smem, inst->stream);

@@ -201,6 +201,9 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
                            int tf, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
 {
     mcs_instance *inst = st->inst;
+    if (inst->dynamics == MCS_DYN_REFERENCE) // random-permutation sequential sweeps (svmc.pyx:83-115 in distribution)
+        return mcs_launch_refdyn_sweeps(st, MCS_KIND_SVMC, A, B, S, mcsteps, temp, tf, seed, replica_offset,
+                                        sweep_offset);
     MCS_REQUIRE((replica_offset & 3) == 0, MCS_EINVAL, "mcs_svmc_sweeps: replica_offset must be a multiple of 4");
     MCS_CUDA(cudaSetDevice(inst->device));
     SvmcPass a;

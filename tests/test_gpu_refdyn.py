@@ -91,6 +91,35 @@ def test_sa_dependency_waves_equal_a_sequential_sweep_in_priority_order(mcs):
         assert not np.array_equal(waves, s0)
 
 
+@pytest.mark.parametrize("tf", [0, 1])
+def test_svmc_dependency_waves_equal_a_sequential_sweep_in_priority_order(mcs, tf):
+    """Rotor sweeps (svmc.pyx:83-115) on the same wave machinery: bit-identical to one thread walking the sites in
+    priority order; chunked rows (degree > 4), fields, time-dependent tables."""
+    for nbs in (inst.torus(9, seed=3, fields=True)[1], inst.random_graph(60, 170, seed=4, fields=True)[1],
+                np.repeat(inst.torus(6, seed=5, fields=True)[1][None], 7, axis=0) * np.linspace(0.5, 1.5, 7).reshape(
+                    7, 1, 1, 1) ** np.array([0.0, 1.0])):
+        noisy = nbs.ndim == 4
+        n = nbs.shape[-3]
+        R = 1 if noisy else 9
+        v0 = np.random.RandomState(2).uniform(0, np.pi, size=(R, n))
+        A, B = np.linspace(2.0, 0.2, 7), np.linspace(0.3, 1.0, 7)
+
+        def run(seed=31):
+            v = v0.copy()
+            if noisy:
+                (mcs.svmc.NoisySVMCTF if tf else mcs.svmc.NoisySVMC)(A, B, 2, 0.3, v[0], nbs, seed=seed,
+                                                                       dynamics="reference")
+            else:
+                (mcs.svmc.SpinVectorMonteCarloTFCompact if tf else mcs.svmc.SpinVectorMonteCarloCompact)(
+                    A, B, 2, 0.3, v, nbs, seed=seed, dynamics="reference")
+            return v
+
+        waves = run()
+        assert np.array_equal(waves, _with_sequential(run))
+        assert not np.array_equal(waves, v0) and not np.array_equal(waves, run(32))
+        assert waves.min() >= 0.0 and waves.max() <= np.pi + 1e-6
+
+
 def test_results_do_not_depend_on_sharding_or_call_splitting(mcs):
     """Philox counters carry the global replica and sweep numbers: a shard of the batch and a schedule split over
     two calls reproduce the one-call, one-batch result bit for bit."""
