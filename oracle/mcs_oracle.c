@@ -628,3 +628,8 @@ void mcs_oracle_sa_anneal_colored(const double *sched, int schedsize, int mcstep
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Wolff-cluster experiments of the reference (qmc.pyx:612-1621): mcs_oracle_qmc_wolff
+ * -------------------------------------------------------------------------------------- */
+#include "mcs_oracle_wolff.c"

@@ -31,9 +31,9 @@ c_ip = ctypes.POINTER(ctypes.c_int32)
 
 def build(force=False):
     """Compile mcs_oracle.c with gcc (oracle/Makefile)."""
-    src = os.path.join(_HERE, "mcs_oracle.c")
-    if force or not os.path.isfile(_SO) or (
-            os.path.isfile(src) and os.path.getmtime(src) > os.path.getmtime(_SO)):
+    srcs = [os.path.join(_HERE, f) for f in ("mcs_oracle.c", "mcs_oracle_wolff.c")]
+    if force or not os.path.isfile(_SO) or any(
+            os.path.isfile(src) and os.path.getmtime(src) > os.path.getmtime(_SO) for src in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libmcs_oracle.so"])
     return _SO
 
@@ -50,6 +50,7 @@ def lib():
         L.mcs_oracle_svmc_energy.restype = ctypes.c_double
         L.mcs_oracle_qmc_anneal.restype = ctypes.c_int
         L.mcs_oracle_qmc_dissipative.restype = ctypes.c_int
+        L.mcs_oracle_qmc_wolff.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -163,6 +164,59 @@ def DissipativeQuantumAnnealGlobal(A_sched, B_sched, mcsteps, temp, lookuptable,
                                    rng=None):
     """qmc.pyx:444-609."""
     _qmc_diss(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, 1, rng)
+
+
+WOLFF_VARIANTS = {"QuantumAnnealWCL": 0, "DissaptiveQuantumAnnealWCL": 1, "QuantumAnnealWC": 2,
+                  "DissipativeQuantumAnnealWC2": 3, "DissipativeQuantumAnnealWC3": 4}
+
+
+def _qmc_wolff(variant, A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, rng):
+    A = _f64(A_sched)
+    B = _f64(B_sched)
+    lut = _f64(lookuptable) if lookuptable is not None else None
+    _check_spins(confs, 2)
+    nbs = _nbs(nbs)
+    if lut is not None and lut.size < confs.shape[1] - 1:
+        raise ValueError("lookuptable needs slices - 1 entries")
+    rc = lib().mcs_oracle_qmc_wolff(
+        ctypes.c_int(variant), A.ctypes.data_as(c_dp), B.ctypes.data_as(c_dp), ctypes.c_int(A.size),
+        ctypes.c_int(int(mcsteps)), ctypes.c_float(temp), lut.ctypes.data_as(c_dp) if lut is not None else None,
+        confs.ctypes.data_as(c_lp), _estr(confs, 0), _estr(confs, 1), ctypes.c_int(confs.shape[0]),
+        ctypes.c_int(confs.shape[1]), nbs.ctypes.data_as(c_dp), ctypes.c_int(nbs.shape[1]), _rng(rng).ptr)
+    if rc == -1:
+        raise ZeroDivisionError("float division")
+    if rc == -2:
+        raise ValueError("the Wolff experiments need at least two Trotter slices")
+    global last_wolff_overrun
+    last_wolff_overrun = rc == 1
+
+
+last_wolff_overrun = False  # the last call wrote past the reference's `cluster` buffer (undefined behaviour there)
+
+
+def QuantumAnnealWCL(A_sched, B_sched, mcsteps, temp, confs, nbs, rng=None):
+    """qmc.pyx:620-786."""
+    _qmc_wolff(0, A_sched, B_sched, mcsteps, temp, None, confs, nbs, rng)
+
+
+def DissaptiveQuantumAnnealWCL(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, rng=None):
+    """qmc.pyx:792-1000."""
+    _qmc_wolff(1, A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, rng)
+
+
+def QuantumAnnealWC(A_sched, B_sched, mcsteps, temp, confs, nbs, rng=None):
+    """qmc.pyx:1006-1225."""
+    _qmc_wolff(2, A_sched, B_sched, mcsteps, temp, None, confs, nbs, rng)
+
+
+def DissipativeQuantumAnnealWC2(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, rng=None):
+    """qmc.pyx:1231-1446."""
+    _qmc_wolff(3, A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, rng)
+
+
+def DissipativeQuantumAnnealWC3(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, rng=None):
+    """qmc.pyx:1452-1621."""
+    _qmc_wolff(4, A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, rng)
 
 
 def qmc_delta_e(a, b, temp, confs, nbs):

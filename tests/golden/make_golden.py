@@ -139,6 +139,67 @@ def trajectories():
     print("trajectory fixtures written")
 
 
+WOLFF = ("QuantumAnnealWCL", "DissaptiveQuantumAnnealWCL", "QuantumAnnealWC", "DissipativeQuantumAnnealWC2",
+         "DissipativeQuantumAnnealWC3")
+
+
+def wolff_cases():
+    """(key, nbs, P, temp, bath strength, seed, mcsteps) of the Wolff-experiment fixtures"""
+    _, t6 = inst.torus(6, seed=1, fields=True)
+    _, g30 = inst.random_graph(30, 70, seed=3, fields=True)
+    _, t5 = inst.torus(5, seed=2)
+    return [("torus6f_P8", t6, 8, 0.5 / 8, 0.1, 5, 7), ("graph30f_P2", g30, 2, 0.1 / 2, 0.02, 7, 7),
+            ("torus5_P5", t5, 5, 2.0 / 5, 0.5, 6, 7), ("graph30f_P16", g30, 16, 1.0 / 16, 0.05, 9, 4)]
+
+
+def wolff():
+    """Wolff-cluster experiments (qmc.pyx:612-1621) through the compiled reference (oracle/build_ref.py's dtype patch
+    makes them runnable).  A case is kept only if the oracle's replay says the reference stayed inside its
+    `cluster` buffer (it does not check; see oracle/mcs_oracle_wolff.c)."""
+    ok = build_ref.build(verbose=False)
+    ref = build_ref.import_ref()
+    assert ok and ref is not None, "compiled reference unavailable"
+    import importlib
+    from oracle import oracle as orc
+    qmc = importlib.import_module("solvers.qmc")
+    out = {"A": np.linspace(2.0, 0.1, 6), "B": np.linspace(0.4, 1.0, 6)}
+    kept = []
+    for key, nbs, P, temp, alpha, seed, mcsteps in wolff_cases():
+        n = nbs.shape[0]
+        out[key + "_nbs"] = nbs
+        lut = alpha * (np.pi / (P * np.sin(np.pi * np.arange(1, P) / P))) ** 2
+        c0 = (2 * np.random.RandomState(seed).randint(2, size=(n, P)) - 1).astype(np.int64)
+        if seed == 6:
+            c0 = np.tile(inst.random_spins(n, 3), (P, 1)).T.copy().astype(np.int64)
+        out[key + "_in"] = c0.astype(np.int8)
+        out[key + "_par"] = np.array([P, temp, alpha, seed, mcsteps], dtype=np.float64)
+        for name in WOLFF:
+            diss = "iss" in name
+            d = c0.copy()
+            getattr(orc, name)(*((out["A"], out["B"], mcsteps, temp) + ((lut,) if diss else ()) + (d, nbs)), rng=seed)
+            if orc.last_wolff_overrun:
+                print("skipped (reference overruns its buffer):", key, name)
+                continue
+            c = c0.copy()
+            libc.srand(seed)
+            args = (out["A"], out["B"], mcsteps, temp) + ((lut,) if diss else ()) + (c, nbs)
+            if name.endswith(("WC2", "WC3")):
+                args += (1,)
+            getattr(qmc, name)(*args)
+            out["%s_%s_next_rand" % (key, name)] = np.int64(libc.rand())
+            out["%s_%s_out" % (key, name)] = c.astype(np.int8)
+            assert np.array_equal(c, d), (key, name)
+            kept.append("%s_%s" % (key, name))
+    out["cases"] = np.array(kept)
+    np.savez_compressed(os.path.join(HERE, "traj_qmc_wolff.npz"), **out)
+    print("wolff fixtures written:", len(kept), "cases")
+
+
 if __name__ == "__main__":
-    santoro()
-    trajectories()
+    import sys
+    if "wolff" in sys.argv[1:]:
+        wolff()
+    else:
+        santoro()
+        trajectories()
+        wolff()

@@ -76,6 +76,33 @@ def test_svmc_golden():
     assert np.array_equal(v, d["SpinVectorMonteCarloTFCompact"])
 
 
+def wolff_golden_cases():
+    """(case key, function name, call arguments without confs/nbs, input, expected output, next rand())"""
+    d = np.load(os.path.join(G, "traj_qmc_wolff.npz"))
+    for case in d["cases"]:
+        key, name = str(case).rsplit("_", 1)
+        P, temp, alpha, seed, mcsteps = d[key + "_par"]
+        P, seed, mcsteps = int(P), int(seed), int(mcsteps)
+        lut = alpha * (np.pi / (P * np.sin(np.pi * np.arange(1, P) / P))) ** 2
+        yield (key, name, d["A"], d["B"], mcsteps, float(temp), lut if "iss" in name else None, d[key + "_nbs"], seed,
+               d[key + "_in"], d["%s_%s_out" % (key, name)], int(d["%s_%s_next_rand" % (key, name)]))
+
+
+def test_wolff_experiments_golden():
+    """qmc.pyx:612-1621: the five Wolff-cluster functions, fixtures made from the compiled reference."""
+    n = 0
+    for key, name, A, B, mcsteps, temp, lut, nbs, seed, cin, cout, nxt in wolff_golden_cases():
+        c = cin.astype(np.int64)
+        rng = orc.LibcRand(seed)
+        args = (A, B, mcsteps, temp) + ((lut,) if lut is not None else ()) + (c, nbs)
+        getattr(orc, name)(*args, rng=rng)
+        assert np.array_equal(c, cout.astype(np.int64)), (key, name)
+        assert int(rng.draw(1)[0]) == nxt, (key, name)
+        assert not orc.last_wolff_overrun
+        n += 1
+    assert n >= 15
+
+
 def test_delta_e_matches_flip_energy_change():
     """The visit's ediff (qmc.pyx:112-138) equals E(after flip) - E(before) of the PIQMC action."""
     _, nbs = inst.random_graph(20, 40, seed=4)

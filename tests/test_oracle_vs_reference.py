@@ -67,6 +67,41 @@ def test_qmc_irregular_graph_c_order():
     assert np.array_equal(c_ref, c_orc)
 
 
+@pytest.mark.parametrize("name", ["QuantumAnnealWCL", "DissaptiveQuantumAnnealWCL", "QuantumAnnealWC",
+                                  "DissipativeQuantumAnnealWC2", "DissipativeQuantumAnnealWC3"])
+def test_wolff_experiments_bit_exact(name):
+    """qmc.pyx:612-1621 (runnable through build_ref.py's dtype patch): configurations and the number of rand() draws.
+    The oracle runs first: a case in which the reference would write past its unchecked `cluster` buffer is
+    undefined behaviour there and is not compared."""
+    fn_ref, fn_orc = getattr(_ref("qmc"), name), getattr(orc, name)
+    diss, compared = "iss" in name, 0
+    for case, (nbs, P) in enumerate([(inst.torus(6, seed=1, fields=True)[1], 8), (inst.torus(5, seed=2)[1], 5),
+                                     (inst.random_graph(30, 70, seed=3, fields=True)[1], 2),
+                                     (inst.random_graph(20, 40, seed=4, fields=True)[1], 16)]):
+        n = nbs.shape[0]
+        for q, seed in enumerate((5, 6, 7)):
+            c0 = (2 * np.random.RandomState(seed).randint(2, size=(n, P)) - 1).astype(np.int64)
+            if seed == 6:  # all slices equal, Fortran order: what the example passes (santoro80.py:286)
+                c0 = np.tile(inst.random_spins(n, 3), (P, 1)).T.copy(order="F")
+            A, B = np.linspace(2, 0.1, 6), np.linspace(0.4, 1.0, 6)
+            temp = [0.5, 2.0, 0.1][q] / P
+            lut = (np.pi / (P * np.sin(np.pi * np.arange(1, P) / P))) ** 2 * [0.1, 0.5, 0.02][q]
+            c_orc = c0.copy(order="K")
+            rng = orc.LibcRand(seed)
+            fn_orc(*((A, B, 7, temp) + ((lut,) if diss else ()) + (c_orc, nbs)), rng=rng)
+            if orc.last_wolff_overrun:
+                continue
+            c_ref = c0.copy(order="K")
+            libc.srand(seed)
+            args = (A, B, 7, temp) + ((lut,) if diss else ()) + (c_ref, nbs)
+            fn_ref(*(args + ((1,) if name.endswith(("WC2", "WC3")) else ())))
+            assert np.array_equal(c_ref, c_orc), (case, seed)
+            assert int(rng.draw(1)[0]) == libc.rand(), (case, seed)
+            assert not np.array_equal(c_ref, c0)
+            compared += 1
+    assert compared >= 8
+
+
 @pytest.mark.parametrize("glob", [0, 1])
 def test_qmc_dissipative_bit_exact(glob):
     _, nbs = inst.torus(5, seed=9, fields=True)
