@@ -166,6 +166,13 @@ int mcs_svmc_sweeps(mcs_state *st, const double *A_sched, const double *B_sched,
  * SA state: a, b ignored, couplings -J/temp.  Needs a symmetric static table.                     */
 int mcs_cluster_moves(mcs_state *st, double a, double b, float temp, int nmoves, uint64_t seed,
                       uint64_t replica_offset, uint64_t sweep_offset);
+/* The same move for the Ohmic-bath action of the Dissipative solvers (qmc.pyx:268-273): every pair of slices of a
+ * world line at ring distance d carries the additional bond K_d = lookuptable[d-1] (in units of teff).  The bond
+ * graph the reference's DissaptiveQuantumAnnealWCL / WC2 / WC3 grow their clusters on (qmc.pyx:906-925, 1400-1437,
+ * 1598-1610), sampled correctly.  lookuptable float64 [P-1] must be symmetric (table[d-1] == table[P-d-1], as the
+ * documented kernel (pi / (P sin(pi d / P)))^2 is): otherwise it does not define an energy -> MCS_EUNSUPPORTED.  */
+int mcs_cluster_moves_dissipative(mcs_state *st, double a, double b, float temp, const double *lookuptable,
+                                  int nmoves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset);
 
 /* one-shot host-buffer forms (upload, sweep, download [, energies]) -- what the Python
  * drop-ins call.  energies_out may be NULL.  mcs_piqmc_anneal with R >= 1024 cuts the batch
@@ -202,6 +209,22 @@ int mcs_exact_qmc(mcs_instance *inst, const double *A_sched, const double *B_sch
                   int mcsteps, float temp, const double *lookuptable, int8_t *confs /* [R][N][P] */,
                   int64_t R, int64_t P, int global_moves, const uint32_t *libc_seeds /* [R] */,
                   const int32_t *rand_stream, int64_t stream_len, int64_t *consumed /* [R] or NULL */);
+/* The reference's Wolff-cluster experiments (qmc.pyx:612-1621, "Function under test"), replayed as written:
+ *   MCS_WOLFF_WCL       qmc.QuantumAnnealWCL             (qmc.pyx:620-786)    one single-cluster move per step,
+ *   MCS_WOLFF_DISS_WCL  qmc.DissaptiveQuantumAnnealWCL   (qmc.pyx:792-1000)   same with Ohmic-bath bonds,
+ *   MCS_WOLFF_WC        qmc.QuantumAnnealWC              (qmc.pyx:1006-1225)  bond test on the full energy change,
+ *   MCS_WOLFF_DISS_WC2  qmc.DissipativeQuantumAnnealWC2  (qmc.pyx:1231-1446)  local sweep + N bath clusters per step,
+ *   MCS_WOLFF_DISS_WC3  qmc.DissipativeQuantumAnnealWC3  (qmc.pyx:1452-1621)  N P bath clusters per step.
+ * Single-cluster growth from an explicit stack is sequential, so these exist only as replay: one thread per
+ * replica, glibc rand() stream of libc_seeds[r].  As shipped the reference functions raise on Linux (np.intc
+ * scratch typed np.int_t); with that dtype corrected they run, and this call reproduces them bit for bit.
+ * lookuptable float64 [P-1] for the DISS variants (else NULL).  overrun[r] (may be NULL) is set when replica r made
+ * the reference write past its unchecked `cluster` buffer -- undefined behaviour there, well defined here.       */
+enum { MCS_WOLFF_WCL = 0, MCS_WOLFF_DISS_WCL = 1, MCS_WOLFF_WC = 2, MCS_WOLFF_DISS_WC2 = 3, MCS_WOLFF_DISS_WC3 = 4 };
+int mcs_exact_qmc_wolff(mcs_instance *inst, int variant, const double *A_sched, const double *B_sched,
+                        int64_t schedsize, int mcsteps, float temp, const double *lookuptable,
+                        int8_t *confs /* [R][N][P] */, int64_t R, int64_t P, const uint32_t *libc_seeds /* [R] */,
+                        int64_t *consumed /* [R] or NULL */, int32_t *overrun /* [R] or NULL */);
 /* sa.Anneal / Anneal_parallel (sa.pyx:19-101, 201-284); randuni != NULL: sa.AnnealMA
  * (sa.pyx:108-193), float64 [schedsize][mcsteps][N] shared by all replicas                  */
 int mcs_exact_sa(mcs_instance *inst, const double *sched, int64_t schedsize, int mcsteps,

@@ -67,6 +67,8 @@ SIGNATURES = {
                                        c_u64, c_u64, c_u64]),
     "mcs_cluster_moves": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_int, c_u64,
                                          c_u64, c_u64]),
+    "mcs_cluster_moves_dissipative": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_float, c_dp,
+                                                     ctypes.c_int, c_u64, c_u64, c_u64]),
     "mcs_piqmc_anneal": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_vp, c_i64, c_i64,
                                         ctypes.c_int, c_u64, c_u64, c_dp]),
     "mcs_piqmc_anneal_best": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_vp, ctypes.c_int,
@@ -76,6 +78,8 @@ SIGNATURES = {
                                        ctypes.c_int, c_u64, c_u64]),
     "mcs_exact_qmc": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_dp, c_vp, c_i64, c_i64,
                                      ctypes.c_int, c_u32p, c_i32p, c_i64, c_i64p]),
+    "mcs_exact_qmc_wolff": (ctypes.c_int, [c_vp, ctypes.c_int, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_dp,
+                                           c_vp, c_i64, c_i64, c_u32p, c_i64p, c_i32p]),
     "mcs_exact_sa": (ctypes.c_int, [c_vp, c_dp, c_i64, ctypes.c_int, c_vp, c_i64, c_u32p, c_dp, c_i64p]),
     "mcs_exact_svmc": (ctypes.c_int, [c_vp, c_dp, c_dp, c_i64, ctypes.c_int, ctypes.c_float, c_vp, c_i64,
                                       ctypes.c_int, c_u32p, c_dp, ctypes.c_int]),
@@ -99,9 +103,15 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
+        from . import build as _build
         if not os.path.isfile(SO_PATH):
-            from . import build as _build
             _build.build()  # raises when nvcc is absent: no CPU fallback
+        elif not _build.up_to_date() and os.path.isdir(_build.CSRC):
+            try:  # a source is newer than the binary: rebuild where nvcc exists, else say so and load what is there
+                _build.build()
+            except RuntimeError:
+                import warnings
+                warnings.warn("libmcs_b200.so is older than its sources and nvcc is not available to rebuild it")
         L = ctypes.CDLL(SO_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
@@ -359,10 +369,19 @@ class State(object):
                                                   dptr(lut), int(bool(global_moves)), int(seed) & (2 ** 64 - 1),
                                                   int(replica_offset), int(sweep_offset)))
 
-    def cluster_moves(self, a, b, temp, nmoves=1, seed=0, replica_offset=0, sweep_offset=0):
-        """Swendsen-Wang moves at transverse field a, longitudinal coefficient b, temperature temp (SA: a, b unused)."""
-        check(load().mcs_cluster_moves(self._h, float(a), float(b), float(temp), int(nmoves),
-                                       int(seed) & (2 ** 64 - 1), int(replica_offset), int(sweep_offset)))
+    def cluster_moves(self, a, b, temp, nmoves=1, seed=0, replica_offset=0, sweep_offset=0, lookuptable=None):
+        """Swendsen-Wang moves at transverse field a, longitudinal coefficient b, temperature temp (SA: a, b unused);
+        lookuptable [P-1]: with the Ohmic-bath bonds of the Dissipative solvers (qmc.pyx:268-273)."""
+        if lookuptable is None:
+            check(load().mcs_cluster_moves(self._h, float(a), float(b), float(temp), int(nmoves),
+                                           int(seed) & (2 ** 64 - 1), int(replica_offset), int(sweep_offset)))
+            return
+        lut = f64(lookuptable)
+        if lut.size < self.P - 1:
+            raise ValueError("lookuptable needs P-1 entries")
+        check(load().mcs_cluster_moves_dissipative(self._h, float(a), float(b), float(temp), dptr(lut), int(nmoves),
+                                                   int(seed) & (2 ** 64 - 1), int(replica_offset),
+                                                   int(sweep_offset)))
 
     def sa_sweeps(self, sched, mcsteps, seed=0, replica_offset=0, sweep_offset=0):
         sched = f64(sched)

@@ -29,23 +29,54 @@ def _nvcc():
     raise RuntimeError("nvcc not found; libmcs_b200.so cannot be built (there is no CPU fallback)")
 
 
-def _deps():
-    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    d.append(os.path.join(os.path.dirname(HERE), "include", "mcs_b200.h"))
-    d.append(os.path.abspath(__file__))
-    return d
+def _sha(paths, extra=""):
+    import hashlib
+    h = hashlib.sha256(extra.encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(p.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
+def _headers():
+    hs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    return hs + [os.path.join(os.path.dirname(HERE), "include", "mcs_b200.h")]
+
+
+def _flags(src):
+    return ARCH + COMMON + EXTRA.get(src, [])
+
+
+def _src_hash(src):
+    """Content hash of everything one object file depends on (its source, every header, the flags)."""
+    return _sha([os.path.join(CSRC, src)] + _headers(), " ".join(_flags(src)))
+
+
+def _lib_hash():
+    return _sha([], " ".join(_src_hash(s) for s in SOURCES))
+
+
+def _read(path):
+    try:
+        with open(path) as f:
+            return f.read().strip()
+    except OSError:
+        return None
+
+
+STAMP = OUT + ".srchash"
 
 
 def up_to_date():
-    if not os.path.isfile(OUT):
-        return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(p) <= t for p in _deps() if os.path.isfile(p))
+    """True when the shared object was built from exactly the sources on disk (content hash, not mtimes: the
+    snapshot that carries the tree to the GPU box does not keep them)."""
+    return os.path.isfile(OUT) and os.path.isdir(CSRC) and _read(STAMP) == _lib_hash()
 
 
 def build(force=False, verbose=False, ptxas_info=False):
-    """Build the shared library if any source is newer; returns its path."""
-    if not force and up_to_date():
+    """Build the shared library if any source changed (per-object: only what changed is recompiled); returns its
+    path."""
+    if not force and not ptxas_info and up_to_date():
         return OUT
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
@@ -53,24 +84,35 @@ def build(force=False, verbose=False, ptxas_info=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc] + ARCH + COMMON + EXTRA.get(src, []) + (["-Xptxas", "-v"] if ptxas_info else []) + \
+        objs.append(obj)
+        want = _src_hash(src)
+        if not force and not ptxas_info and os.path.isfile(obj) and _read(obj + ".srchash") == want:
+            continue
+        cmd = [nvcc] + _flags(src) + (["-Xptxas", "-v"] if ptxas_info else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
+        procs.append((src, obj, want,
+                      subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
-    for src, p in procs:
+    for src, obj, want, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0 or verbose or ptxas_info:
             sys.stdout.write(out)
+        if p.returncode == 0:
+            with open(obj + ".srchash", "w") as f:
+                f.write(want)
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libmcs_b200.so")
-    cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs
+    tmp = OUT + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    os.replace(tmp, OUT)  # atomic: a concurrent loader never sees a half-written library
+    with open(STAMP, "w") as f:
+        f.write(_lib_hash())
     return OUT
 
 

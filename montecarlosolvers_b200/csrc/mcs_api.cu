@@ -212,7 +212,16 @@ extern "C" int mcs_cluster_moves(mcs_state *st, double a, double b, float temp, 
     MCS_REQUIRE(st && st->inst && (st->kind == MCS_KIND_PIQMC || st->kind == MCS_KIND_SA), MCS_EINVAL,
                 "mcs_cluster_moves: needs a PIQMC or SA state");
     MCS_REQUIRE(nmoves >= 0, MCS_EINVAL, "mcs_cluster_moves: nmoves < 0");
-    return mcs_launch_cluster_moves(st, a, b, (double)temp, nmoves, seed, replica_offset, sweep_offset);
+    return mcs_launch_cluster_moves(st, a, b, (double)temp, nullptr, nmoves, seed, replica_offset, sweep_offset);
+}
+
+extern "C" int mcs_cluster_moves_dissipative(mcs_state *st, double a, double b, float temp, const double *lookuptable,
+                                             int nmoves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
+{
+    MCS_REQUIRE(st && st->kind == MCS_KIND_PIQMC, MCS_EINVAL, "mcs_cluster_moves_dissipative: needs a PIQMC state");
+    MCS_REQUIRE(lookuptable, MCS_EINVAL, "mcs_cluster_moves_dissipative: lookuptable is NULL");
+    MCS_REQUIRE(nmoves >= 0, MCS_EINVAL, "mcs_cluster_moves_dissipative: nmoves < 0");
+    return mcs_launch_cluster_moves(st, a, b, (double)temp, lookuptable, nmoves, seed, replica_offset, sweep_offset);
 }
 
 // ---- one-shot host-buffer forms ----------------------------------------------------------------

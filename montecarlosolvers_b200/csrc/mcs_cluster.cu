@@ -33,11 +33,13 @@ struct ClusterArgs {
     int P, dpad;
     float kin;   // in-plane factor:  K_ij = kin * J_ij   (= -B/teff, or -1/T for SA)
     float kperp; // Trotter coupling  J_perp / teff
+    int nbath;       // Ohmic bath: number of distances d = 1 .. nbath (= P / 2) that carry a bond, 0 = no bath
+    float kbath[32]; // K_d = lookuptable[d-1] (qmc.pyx:268-273 in units of teff; symmetric: table[d-1] == table[P-d-1])
     mcs_philox_keys keys;
     uint32_t sweep_lo, sweep_hi, replica_offset;
 };
 
-enum { TAG_CL_BOND = 64, TAG_CL_TROTTER = 64 + 16, TAG_CL_GHOST = 64 + 32, TAG_CL_FLIP = 64 + 48 };
+enum { TAG_CL_BOND = 64, TAG_CL_TROTTER = 64 + 16, TAG_CL_GHOST = 64 + 32, TAG_CL_FLIP = 64 + 48, TAG_CL_BATH = 128 };
 
 __device__ __forceinline__ int32_t uf_find(int32_t *L, long long stride, long long r, int32_t v)
 {
@@ -145,6 +147,21 @@ __global__ void cluster_union_kernel(const __grid_constant__ ClusterArgs a)
             uf_union(a.L, a.Rl, r, (int32_t)(i * P + k), (int32_t)(i * P + (k + 1 == P ? 0 : k + 1)));
         }
     }
+    // Ohmic bath (qmc.pyx:268-273): dE = sum_d 2 teff s_k s_{k+d} table[d-1], i.e. every pair of slices of a world
+    // line at ring distance d carries the bond K_d = table[d-1] in units of teff (ferromagnetic for table > 0);
+    // pairs (k, k+d), each once: all k for d < P/2, k < P/2 for d = P/2
+    for (int d = 1; d <= a.nbath; ++d) {
+        const float K = a.kbath[d - 1];
+        if (K == 0.0f) continue;
+        const uint64_t far = ((w >> d) | (w << (P - d))) & pmask; // bit k = slice (k + d) mod P
+        uint64_t sat = (K > 0.0f ? ~(w ^ far) : (w ^ far)) & pmask;
+        if (2 * d == P) sat &= (1ull << d) - 1ull;
+        const uint64_t act = bernoulli_mask(a, c0, (uint32_t)(i * 32 + (d - 1)), TAG_CL_BATH, prob_threshold(2.0f * fabsf(K)), sat);
+        for (uint64_t m = act; m; m &= m - 1) {
+            const int k = __ffsll((long long)m) - 1;
+            uf_union(a.L, a.Rl, r, (int32_t)(i * P + k), (int32_t)(i * P + (k + d >= P ? k + d - P : k + d)));
+        }
+    }
     // field: bond to the ghost spin (+1)
     const float hv = __ldg(&a.h[i]);
     if (hv != 0.0f) {
@@ -185,9 +202,10 @@ __global__ void cluster_flip_kernel(const __grid_constant__ ClusterArgs a)
 
 } // namespace
 
-// kind: MCS_KIND_PIQMC (coef_a = Gamma, coef_b = B, temp = T) or MCS_KIND_SA (temp = T)
-int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double temp, int nmoves, uint64_t seed,
-                             uint64_t replica_offset, uint64_t sweep_offset)
+// kind: MCS_KIND_PIQMC (coef_a = Gamma, coef_b = B, temp = T) or MCS_KIND_SA (temp = T);
+// lookuptable != nullptr (PIQMC only): Ohmic-bath bonds of the Dissipative solvers, float64 [P-1]
+int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double temp, const double *lookuptable,
+                             int nmoves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset)
 {
     mcs_instance *inst = st->inst;
     MCS_REQUIRE(inst->nsteps == 1, MCS_EUNSUPPORTED, "cluster moves need a static coupling table");
@@ -227,6 +245,22 @@ int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double
         MCS_REQUIRE(temp > 0.0, MCS_EINVAL, "cluster moves need T > 0");
         a.kin = (float)(-1.0 / temp);
         a.kperp = 0.0f;
+    }
+    a.nbath = 0;
+    for (float &kb : a.kbath) kb = 0.0f;
+    if (lookuptable) {
+        MCS_REQUIRE(st->kind == MCS_KIND_PIQMC, MCS_EINVAL, "cluster moves: the bath couples Trotter slices (PIQMC only)");
+        // a pair of slices at ring distance d is reached as d from one end and as P - d from the other
+        // (qmc.pyx:268-273): the table defines an energy only if it is symmetric, like the documented kernel
+        // (pi / (P sin(pi d / P)))^2 (qmc.pyx:162-163)
+        for (int d = 1; d < P; ++d) {
+            const double x = lookuptable[d - 1], y = lookuptable[P - d - 1];
+            MCS_REQUIRE(fabs(x - y) <= 1e-9 * std::max(1.0, std::max(fabs(x), fabs(y))), MCS_EUNSUPPORTED,
+                        "cluster moves: lookuptable[%d] != lookuptable[%d]: an asymmetric bath table is not an energy "
+                        "function, no cluster move can sample it", d - 1, P - d - 1);
+        }
+        a.nbath = P / 2;
+        for (int d = 1; d <= a.nbath; ++d) a.kbath[d - 1] = (float)lookuptable[d - 1];
     }
     a.keys = mcs_philox_expand(seed);
     a.replica_offset = (uint32_t)replica_offset;

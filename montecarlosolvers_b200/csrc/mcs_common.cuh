@@ -444,8 +444,8 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
 int mcs_launch_refdyn_sweeps(mcs_state *st, int kind, const double *A, const double *B, int64_t S, int mcsteps,
                              float temp, int variant /* PIQMC: global_moves; SVMC: tf */, uint64_t seed,
                              uint64_t replica_offset, uint64_t sweep_offset);
-int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double temp, int nmoves, uint64_t seed,
-                             uint64_t replica_offset, uint64_t sweep_offset);
+int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double temp, const double *lookuptable,
+                             int nmoves, uint64_t seed, uint64_t replica_offset, uint64_t sweep_offset);
 bool mcs_dense_supported(const mcs_instance *inst, int P);
 int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const double *B, int64_t S, int mcsteps,
                             float temp, int global_moves, uint64_t seed, uint64_t replica_offset,

@@ -385,6 +385,327 @@ __global__ void probe_sa_delta_e_kernel(const int8_t *svec, const int32_t *tab_i
 }
 
 // RAII device buffer for the one-shot exact / probe calls
+// ------------------------------------------------------------------------------------------------------------
+// Wolff-cluster experiments of the reference, qmc.pyx:612-1621 ("Function under test"): QuantumAnnealWCL (:620-786),
+// DissaptiveQuantumAnnealWCL (:792-1000), QuantumAnnealWC (:1006-1225), DissipativeQuantumAnnealWC2 (:1231-1446),
+// DissipativeQuantumAnnealWC3 (:1452-1621).  Single-cluster growth with an explicit stack is sequential by
+// construction, so these are served by the replay path only: one thread per replica, the reference's rand() stream,
+// fp64 in the reference's association order.  They are replayed AS WRITTEN (seed spin not flipped in WCL / WC / WC2,
+// padded table rows walked in full, `spinidx` / `bslice` / `jval` carried over between loops where the reference
+// does so, WC2 / WC3's inverted final tests): the bar is identical results, not a better algorithm -- the working
+// cluster move of this library is Swendsen-Wang (mcs_cluster.cu).
+// ------------------------------------------------------------------------------------------------------------
+struct ExactWolffArgs {
+    int8_t *confs;       // [R][N][P]
+    int32_t *perm;       // [R][N]        (WC2, WC3)
+    int32_t *cl;         // [R][N P + 2]  explicit stack, node = spin * P + slice
+    const LibcState *st; // [R]
+    long long *consumed; // [R]
+    int *overrun;        // [R] 1: the reference would have written past its `cluster` buffer (it does not check)
+    const double *jperp; // [S]
+    const double *bcoef; // [S]  +B (qmc.pyx:696)
+    const double *lut;   // [P-1] or nullptr
+    const int32_t *tab_idx;
+    const double *tab_J;
+    long long R;
+    int N, P, maxnb, S, mcsteps, variant;
+    double teff;
+};
+
+struct WolffCtx {
+    const ExactWolffArgs &a;
+    int8_t *conf;
+    int32_t *cl;
+    Rng &rng;
+    int stack, stackidx, cluster_count, max_rows;
+    double r;
+
+    __device__ __forceinline__ int8_t &cf(int spin, int slice) { return conf[(long long)spin * a.P + slice]; }
+    __device__ __forceinline__ int idx(int s, int si) const { return a.tab_idx[(long long)s * a.maxnb + si]; }
+    __device__ __forceinline__ double J(int s, int si) const { return a.tab_J[(long long)s * a.maxnb + si]; }
+    __device__ __forceinline__ void start(int spin, int slice)
+    {
+        cl[0] = spin * a.P + slice;
+        stack = 1, stackidx = 1, cluster_count = 0, r = 1.0;
+    }
+    __device__ __forceinline__ void push(int spin, int slice) // qmc.pyx:731-736
+    {
+        cl[stackidx] = spin * a.P + slice;
+        if (stackidx > max_rows) max_rows = stackidx;
+        cf(spin, slice) = -cf(spin, slice);
+        stack += 1;
+        stackidx += 1;
+    }
+    // growth attempt, qmc.pyx:726-736
+    __device__ __forceinline__ void attempt(int spin, int slice, double ediff, bool update_r)
+    {
+        if (ediff < 0) {
+            const double p = __dadd_rn(1.0, -exp(__ddiv_rn(ediff, a.teff)));
+            if (__dmul_rn(r, p) > rng.uniform()) {
+                if (update_r) r = __dmul_rn(r, p);
+                push(spin, slice);
+            }
+        }
+    }
+    // "add bias energy", qmc.pyx:722-725
+    __device__ __forceinline__ double bias(int s, double b_coeff, int k, double ediff) const
+    {
+        for (int si2 = 0; si2 < a.maxnb; ++si2)
+            if (idx(s, si2) == s)
+                ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(__dmul_rn(-2.0, b_coeff), J(s, si2)), (double)k));
+        return ediff;
+    }
+};
+
+__device__ __forceinline__ void trotter_nb(int islice, int P, int &tl, int &tr)
+{
+    if (islice == 0) {
+        tl = P - 1;
+        tr = 1;
+    } else if (islice == P - 1) {
+        tl = P - 2;
+        tr = 0;
+    } else {
+        tl = islice - 1;
+        tr = islice + 1;
+    }
+}
+
+__global__ void exact_wolff_kernel(const ExactWolffArgs a)
+{
+    const long long rep = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep >= a.R) return;
+    const int N = a.N, P = a.P, maxnb = a.maxnb, variant = a.variant;
+    const double teff = a.teff;
+    int32_t *perm = a.perm + rep * (long long)N;
+    Rng rng;
+    rng.s = a.st[rep];
+    rng.stream = nullptr;
+    rng.pos = 0;
+    rng.len = 0;
+    WolffCtx w{a, a.confs + rep * (long long)N * P, a.cl + rep * ((long long)N * P + 2), rng, 0, 0, 0, 0, 1.0};
+    // function-scope variables of the reference (qmc.pyx:1054-1070, 1284-1318, 1506-1540)
+    int ispin = 0, islice = 0, spinidx = 0, tleft = 0, tright = 0, tleft2 = 0, tright2 = 0, bslice = 0, k = 0;
+    double jval = 0.0, ediff = 0.0, e_total = 0.0;
+    for (int f = 0; f < a.S; ++f) {
+        const double jperp = a.jperp[f], b_coeff = a.bcoef[f];
+        const double m2b = __dmul_rn(-2.0, b_coeff), p2j = __dmul_rn(2.0, jperp), p2t = __dmul_rn(2.0, teff);
+        for (int step = 0; step < a.mcsteps; ++step) {
+            if (variant <= 2) { // one single-cluster move per step
+                ispin = rng.next() % N;
+                islice = rng.next() % P;
+                if (variant == 1) { // walk to a start point that aligns with the local field, qmc.pyx:879-893
+                    const int j = islice * N + ispin;
+                    for (int i = 1; i < N * P; ++i) {
+                        ediff = 0.0;
+                        for (int si = 0; si < maxnb; ++si) {
+                            spinidx = w.idx(ispin, si);
+                            jval = w.J(ispin, si);
+                            if (spinidx == ispin)
+                                ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(__dmul_rn(-2.0, jval), b_coeff),
+                                                                   (double)w.cf(ispin, islice)));
+                        }
+                        if (ediff <= 0) break;
+                        if (exp(__ddiv_rn(__dmul_rn(-1.0, ediff), teff)) > rng.uniform()) break;
+                        ispin = (j + i) % N;
+                        islice = ((j + i) / N) % P;
+                    }
+                }
+                w.start(ispin, islice);
+                k = w.cf(ispin, islice);
+                if (variant == 1) w.cf(ispin, islice) = -w.cf(ispin, islice); // qmc.pyx:898 (commented out at :704)
+                for (;;) {
+                    ispin = w.cl[w.cluster_count] / P;
+                    islice = w.cl[w.cluster_count] % P;
+                    if (variant == 1) { // bath neighbours first, qmc.pyx:906-925
+                        for (int b = 1; b < P; ++b) {
+                            bslice = (islice + b) % P;
+                            if (w.cf(ispin, bslice) == k) {
+                                ediff = __dadd_rn(0.0, __dmul_rn(__dmul_rn(-2.0, teff), a.lut[b - 1]));
+                                w.attempt(ispin, bslice, w.bias(ispin, b_coeff, k, ediff), true);
+                            }
+                        }
+                    }
+                    if (variant != 2) { // qmc.pyx:708-781 / 926-995
+                        for (int si = 0; si < maxnb; ++si) {
+                            spinidx = w.idx(ispin, si);
+                            if (w.cf(spinidx, islice) == k) {
+                                ediff = __dadd_rn(0.0, __dmul_rn(__dmul_rn(2.0, b_coeff), w.J(ispin, si)));
+                                w.attempt(spinidx, islice, w.bias(spinidx, b_coeff, k, ediff), true);
+                            }
+                        }
+                        trotter_nb(islice, P, tleft, tright);
+                        if (w.cf(ispin, tleft) == k) {
+                            ediff = __dadd_rn(0.0, __dmul_rn(-2.0, jperp));
+                            w.attempt(ispin, tleft, w.bias(ispin, b_coeff, k, ediff), true);
+                        }
+                        if (w.cf(ispin, tright) == k) {
+                            ediff = __dadd_rn(0.0, __dmul_rn(-2.0, jperp));
+                            w.attempt(ispin, tright, w.bias(ispin, b_coeff, k, ediff), true);
+                        }
+                    } else { // QuantumAnnealWC: energy change of the candidate, qmc.pyx:1112-1220
+                        trotter_nb(islice, P, tleft, tright);
+                        for (int side = 0; side < 2; ++side) {
+                            const int ts = side == 0 ? tleft : tright;
+                            if (w.cf(ispin, ts) == k) {
+                                ediff = 0.0;
+                                for (int si2 = 0; si2 < maxnb; ++si2) {
+                                    const int spinidx2 = w.idx(ispin, si2);
+                                    jval = w.J(spinidx, si2); // `spinidx` is left over from the last spatial loop
+                                    const double t = __dmul_rn(__dmul_rn(m2b, jval), (double)k);
+                                    ediff = __dadd_rn(ediff, spinidx == spinidx2 ? t : __dmul_rn(t, (double)w.cf(spinidx2, ts)));
+                                }
+                                trotter_nb(ts, P, tleft2, tright2);
+                                ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(p2j, (double)k), (double)w.cf(ispin, tleft2)));
+                                ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(p2j, (double)k), (double)w.cf(ispin, tright2)));
+                                w.attempt(ispin, ts, ediff, false);
+                            }
+                        }
+                        for (int si = 0; si < maxnb; ++si) {
+                            spinidx = w.idx(ispin, si);
+                            if (w.cf(spinidx, islice) == k) {
+                                ediff = 0.0;
+                                for (int si2 = 0; si2 < maxnb; ++si2) {
+                                    const int spinidx2 = w.idx(spinidx, si2);
+                                    jval = w.J(spinidx, si2);
+                                    const double t = __dmul_rn(__dmul_rn(m2b, jval), (double)k);
+                                    ediff = __dadd_rn(ediff, spinidx == spinidx2 ? t : __dmul_rn(t, (double)w.cf(spinidx2, islice)));
+                                }
+                                trotter_nb(islice, P, tleft2, tright2);
+                                ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(p2j, (double)k), (double)w.cf(spinidx, tleft2)));
+                                ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(p2j, (double)k), (double)w.cf(spinidx, tright2)));
+                                w.attempt(spinidx, islice, ediff, false);
+                            }
+                        }
+                    }
+                    w.cluster_count += 1;
+                    w.stack -= 1;
+                    if (w.stack == 0) break;
+                }
+            } else if (variant == 3) {
+                // local sweep whose bath term starts from a stale slice (qmc.pyx:1325-1375) ...
+                for (int loop_slice = 0; loop_slice < P; ++loop_slice) {
+                    islice = loop_slice;
+                    shuffle(rng, perm, N);
+                    for (int sidx = 0; sidx < N; ++sidx) {
+                        ispin = perm[sidx];
+                        const double s = (double)w.cf(ispin, islice), m2bs = __dmul_rn(m2b, s);
+                        double e = 0.0;
+                        for (int si = 0; si < maxnb; ++si) {
+                            spinidx = w.idx(ispin, si);
+                            jval = w.J(ispin, si);
+                            if (spinidx == ispin)
+                                e = __dadd_rn(e, __dmul_rn(m2bs, jval));
+                            else
+                                e = __dadd_rn(e, __dmul_rn(m2bs, __dmul_rn(jval, (double)w.cf(spinidx, islice))));
+                        }
+                        trotter_nb(islice, P, tleft, tright);
+                        e = __dadd_rn(e, __dmul_rn(__dmul_rn(2.0, s), __dmul_rn(jperp, (double)w.cf(ispin, tleft))));
+                        e = __dadd_rn(e, __dmul_rn(__dmul_rn(2.0, s), __dmul_rn(jperp, (double)w.cf(ispin, tright))));
+                        for (int b2 = 1; b2 < P; ++b2) {
+                            const int cslice = (bslice + b2) % P; // `bslice`, not islice (qmc.pyx:1364)
+                            const double ss = (double)((int)w.cf(ispin, islice) * (int)w.cf(ispin, cslice));
+                            e = __dadd_rn(e, __dmul_rn(__dmul_rn(p2t, ss), a.lut[b2 - 1]));
+                        }
+                        bool flip = e <= 0.0;
+                        if (!flip) flip = exp(__ddiv_rn(__dmul_rn(-1.0, e), teff)) > rng.uniform();
+                        if (flip) w.cf(ispin, islice) = -w.cf(ispin, islice);
+                    }
+                }
+                // ... then one bath-only cluster per spin, Metropolis on its accumulated energy (qmc.pyx:1376-1446)
+                shuffle(rng, perm, N);
+                for (int sidx2 = 0; sidx2 < N; ++sidx2) {
+                    ispin = perm[sidx2];
+                    islice = rng.next() % P;
+                    w.start(ispin, islice);
+                    k = w.cf(ispin, islice);
+                    e_total = 0.0;
+                    for (;;) {
+                        ispin = w.cl[w.cluster_count] / P;
+                        islice = w.cl[w.cluster_count] % P;
+                        for (int b = 1; b < P; ++b) {
+                            bslice = (islice + b) % P;
+                            if (w.cf(ispin, bslice) != k) continue;
+                            const double p = __dadd_rn(1.0, -exp(__dmul_rn(-2.0, a.lut[b - 1])));
+                            if (!(__dmul_rn(w.r, p) > rng.uniform())) continue;
+                            ediff = 0.0;
+                            for (int si2 = 0; si2 < maxnb; ++si2) {
+                                const int spinidx2 = w.idx(ispin, si2);
+                                if (ispin == spinidx2)
+                                    ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(m2b, w.J(ispin, si2)), (double)k));
+                                else // `jval` is whatever the local sweep left behind (qmc.pyx:1414)
+                                    ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(__dmul_rn(m2b, jval), (double)k),
+                                                                       (double)w.cf(spinidx2, bslice)));
+                            }
+                            trotter_nb(bslice, P, tleft2, tright2);
+                            ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(p2j, (double)k), (double)w.cf(ispin, tleft2)));
+                            ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(p2j, (double)k), (double)w.cf(ispin, tright2)));
+                            for (int b2 = 1; b2 < P; ++b2) {
+                                const int cslice = (bslice + b2) % P;
+                                ediff = __dadd_rn(ediff, __dmul_rn(__dmul_rn(p2t, (double)(k * (int)w.cf(ispin, cslice))),
+                                                                   a.lut[b2 - 1]));
+                            }
+                            w.r = __dmul_rn(w.r, p);
+                            e_total = __dadd_rn(e_total, ediff);
+                            w.push(ispin, bslice);
+                        }
+                        w.cluster_count += 1;
+                        w.stack -= 1;
+                        if (w.stack == 0) break;
+                    }
+                    if (e_total > 0 && exp(__ddiv_rn(__dmul_rn(-1.0, e_total), teff)) > rng.uniform())
+                        for (int i = 1; i < w.cluster_count; ++i) w.conf[w.cl[i]] = -w.conf[w.cl[i]]; // node = flat index
+                }
+            } else { // DissipativeQuantumAnnealWC3: N P bath clusters per step, qmc.pyx:1546-1621
+                shuffle(rng, perm, N);
+                for (int loop_slice = 0; loop_slice < P; ++loop_slice) {
+                    islice = loop_slice; // the body overwrites islice; Cython iterates on a temporary
+                    for (int sidx2 = 0; sidx2 < N; ++sidx2) {
+                        e_total = 0.0;
+                        ispin = perm[sidx2];
+                        w.start(ispin, islice);
+                        k = w.cf(ispin, islice);
+                        w.cf(ispin, islice) = -w.cf(ispin, islice);
+                        const double m2bk = __dmul_rn(m2b, (double)k), p2k = __dmul_rn(2.0, (double)k);
+                        for (;;) {
+                            ispin = w.cl[w.cluster_count] / P;
+                            islice = w.cl[w.cluster_count] % P;
+                            for (int si = 0; si < maxnb; ++si) {
+                                spinidx = w.idx(ispin, si);
+                                jval = w.J(ispin, si);
+                                if (spinidx == ispin)
+                                    e_total = __dadd_rn(e_total, __dmul_rn(m2bk, jval));
+                                else
+                                    e_total = __dadd_rn(e_total, __dmul_rn(m2bk, __dmul_rn(jval, (double)w.cf(spinidx, islice))));
+                            }
+                            trotter_nb(islice, P, tleft, tright);
+                            e_total = __dadd_rn(e_total, __dmul_rn(p2k, __dmul_rn(jperp, (double)w.cf(ispin, tleft))));
+                            e_total = __dadd_rn(e_total, __dmul_rn(p2k, __dmul_rn(jperp, (double)w.cf(ispin, tright))));
+                            for (int b = 1; b < P; ++b) {
+                                bslice = (islice + b) % P;
+                                if (w.cf(ispin, bslice) != k) continue;
+                                const double p = __dadd_rn(1.0, -exp(__dmul_rn(-2.0, a.lut[b - 1])));
+                                if (__dmul_rn(w.r, p) > rng.uniform()) {
+                                    w.r = __dmul_rn(w.r, p);
+                                    w.push(ispin, bslice);
+                                }
+                            }
+                            w.cluster_count += 1;
+                            w.stack -= 1;
+                            if (w.stack == 0) break;
+                        }
+                        if (e_total > 0.0 &&
+                            __dadd_rn(1.0, -exp(__ddiv_rn(__dmul_rn(-1.0, e_total), teff))) > rng.uniform())
+                            for (int i = 0; i < w.cluster_count; ++i) w.conf[w.cl[i]] = -w.conf[w.cl[i]];
+                    }
+                }
+            }
+        }
+    }
+    a.consumed[rep] = rng.pos;
+    a.overrun[rep] = w.max_rows >= ((variant == 3 || variant == 4) ? P : N * P) ? 1 : 0;
+}
+
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf()
@@ -477,6 +798,72 @@ extern "C" int mcs_exact_qmc(mcs_instance *inst, const double *A, const double *
     MCS_CUDA(cudaMemcpyAsync(confs, d_conf.p, cbytes, cudaMemcpyDeviceToHost, s));
     if (consumed)
         MCS_CUDA(cudaMemcpyAsync(consumed, d_cons.p, (size_t)R * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    MCS_CUDA(cudaStreamSynchronize(s));
+    return MCS_OK;
+}
+
+extern "C" int mcs_exact_qmc_wolff(mcs_instance *inst, int variant, const double *A, const double *B, int64_t S,
+                                   int mcsteps, float temp, const double *lookuptable, int8_t *confs, int64_t R,
+                                   int64_t P, const uint32_t *libc_seeds, int64_t *consumed, int32_t *overrun)
+{
+    MCS_REQUIRE(inst && confs && R > 0 && libc_seeds && (S == 0 || (A && B)), MCS_EINVAL,
+                "mcs_exact_qmc_wolff: bad argument");
+    MCS_REQUIRE(variant >= MCS_WOLFF_WCL && variant <= MCS_WOLFF_DISS_WC3, MCS_EINVAL,
+                "mcs_exact_qmc_wolff: unknown variant %d", variant);
+    MCS_REQUIRE(P >= 2, MCS_EINVAL, "mcs_exact_qmc_wolff: P >= 2 required (the reference indexes slice 1)");
+    const bool bath = variant == MCS_WOLFF_DISS_WCL || variant == MCS_WOLFF_DISS_WC2 || variant == MCS_WOLFF_DISS_WC3;
+    MCS_REQUIRE(!bath || lookuptable, MCS_EINVAL, "mcs_exact_qmc_wolff: this variant needs lookuptable[P-1]");
+    MCS_REQUIRE(inst->nsteps == 1, MCS_EUNSUPPORTED, "mcs_exact_qmc_wolff: static tables only");
+    MCS_REQUIRE(inst->N * P < (1ll << 30), MCS_EUNSUPPORTED, "mcs_exact_qmc_wolff: N * P too large");
+    const double teff = (double)temp * (double)P;
+    MCS_REQUIRE(teff != 0.0 || S == 0, MCS_EZERODIV, "float division");
+    MCS_CUDA(cudaSetDevice(inst->device));
+    cudaStream_t s = inst->stream;
+    std::vector<double> jperp((size_t)S), bcoef((size_t)S);
+    for (int64_t f = 0; f < S; ++f) {
+        jperp[f] = -0.5 * teff * log(tanh(A[f] / teff)); // qmc.pyx:695, host libm like the reference
+        bcoef[f] = B[f];                                 // qmc.pyx:696: +B in these functions
+    }
+    std::vector<LibcState> states;
+    make_states(libc_seeds, R, states);
+    DevBuf d_conf, d_perm, d_cl, d_st, d_cons, d_over, d_jp, d_bc, d_lut;
+    const size_t cbytes = (size_t)R * inst->N * P;
+    MCS_TRY(d_conf.put(confs, cbytes, s));
+    MCS_TRY(d_perm.alloc((size_t)R * inst->N * sizeof(int32_t)));
+    MCS_TRY(d_cl.alloc((size_t)R * ((size_t)inst->N * P + 2) * sizeof(int32_t)));
+    MCS_TRY(d_st.put(states.data(), states.size() * sizeof(LibcState), s));
+    MCS_TRY(d_cons.alloc((size_t)R * sizeof(long long)));
+    MCS_TRY(d_over.alloc((size_t)R * sizeof(int)));
+    MCS_TRY(d_jp.put(jperp.data(), jperp.size() * sizeof(double), s));
+    MCS_TRY(d_bc.put(bcoef.data(), bcoef.size() * sizeof(double), s));
+    if (bath) MCS_TRY(d_lut.put(lookuptable, (size_t)(P - 1) * sizeof(double), s));
+    ExactWolffArgs a;
+    a.confs = d_conf.as<int8_t>();
+    a.perm = d_perm.as<int32_t>();
+    a.cl = d_cl.as<int32_t>();
+    a.st = d_st.as<LibcState>();
+    a.consumed = d_cons.as<long long>();
+    a.overrun = d_over.as<int>();
+    a.jperp = d_jp.as<double>();
+    a.bcoef = d_bc.as<double>();
+    a.lut = bath ? d_lut.as<double>() : nullptr;
+    a.tab_idx = inst->d_tab_idx;
+    a.tab_J = inst->d_tab_J;
+    a.R = R;
+    a.N = (int)inst->N;
+    a.P = (int)P;
+    a.maxnb = (int)inst->maxnb;
+    a.S = (int)S;
+    a.mcsteps = mcsteps;
+    a.variant = variant;
+    a.teff = teff;
+    exact_wolff_kernel<<<(unsigned)((R + 31) / 32), 32, 0, s>>>(a);
+    inst->launches++;
+    MCS_CUDA(cudaGetLastError());
+    MCS_CUDA(cudaMemcpyAsync(confs, d_conf.p, cbytes, cudaMemcpyDeviceToHost, s));
+    if (consumed)
+        MCS_CUDA(cudaMemcpyAsync(consumed, d_cons.p, (size_t)R * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    if (overrun) MCS_CUDA(cudaMemcpyAsync(overrun, d_over.p, (size_t)R * sizeof(int), cudaMemcpyDeviceToHost, s));
     MCS_CUDA(cudaStreamSynchronize(s));
     return MCS_OK;
 }

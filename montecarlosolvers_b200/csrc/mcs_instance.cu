@@ -257,8 +257,17 @@ extern "C" int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int6
         (rc = upload(&inst->d_ell_idx, ell_idx)) || (rc = upload(&inst->d_ell_J, ell_J)) ||
         (rc = upload(&inst->d_h, hf)) || (rc = upload(&inst->d_order, inst->order)))
         return fail(rc);
-    // dense instances (SK-like): the coupling matrix itself, fp32 and split into two bf16 halves
-    inst->dense = nsteps == 1 && maxdeg >= 48 && nspins <= 32768;
+    // dense instances (SK-like): the coupling matrix itself, fp32 and split into two bf16 halves.  Decided from the
+    // DENSITY of the graph (at least a quarter of all pairs coupled), not from one hub: a sparse graph with a few
+    // high-degree sites stays with the coloured kernels.  The blocked path needs 8 Npad^2 bytes on the device.
+    int64_t nnz = 0;
+    for (int64_t i = 0; i < nspins; ++i) nnz += (int64_t)quad[0][i].size(); // both orientations of every bond
+    inst->dense = nsteps == 1 && maxdeg >= 48 && nspins <= 32768 && 4 * nnz >= nspins * (nspins - 1);
+    if (inst->dense) {
+        size_t free_b = 0, total_b = 0;
+        const size_t need = (size_t)((nspins + 127) / 128 * 128) * (size_t)((nspins + 127) / 128 * 128) * 8u;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need > free_b / 2) inst->dense = false;
+    }
     if (inst->dense) {
         const int64_t Np = (nspins + 127) / 128 * 128;
         inst->Npad = Np;

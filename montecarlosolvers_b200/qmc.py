@@ -14,7 +14,8 @@ from . import _common as C
 from . import _lib
 
 __all__ = ["QuantumAnneal", "QuantumAnnealGlobal", "anneal_best_slice", "DissipativeQuantumAnneal", "DissipativeQuantumAnnealGlobal",
-           "QuantumAnnealSW", "QuantumAnnealWCL", "QuantumAnnealWC"]
+           "QuantumAnnealSW", "QuantumAnnealWCL", "QuantumAnnealWC", "DissaptiveQuantumAnnealWCL",
+           "DissipativeQuantumAnnealWC2", "DissipativeQuantumAnnealWC3"]
 
 
 def _run(A_sched, B_sched, mcsteps, temp, confs, nbs, global_moves, lookuptable, seed, exact, libc_seed, device,
@@ -214,14 +215,15 @@ def delta_e_global(b, confs, nbs, device=None):
 
 
 def QuantumAnnealSW(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, cluster_every=1, global_moves=False,
-                    seed=None, device=None, energies=False, replica_offset=0):
+                    lookuptable=None, seed=None, device=None, energies=False, replica_offset=0):
     """QuantumAnnealSW(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads)
 
     PIQMC with Swendsen-Wang cluster moves on the (space x Trotter) lattice: for every field value, `mcsteps`
     times { one single-spin sweep; every `cluster_every`-th time one cluster move (GPU union-find) }.
-    The reference advertises cluster updates (README.md:4) but ships only experimental single-cluster
-    Wolff variants (qmc.pyx:620-1621) that raise on Linux; this is the working replacement, validated
-    against exact enumeration (no trajectory parity is possible)."""
+    `lookuptable` [P-1] adds the Ohmic bath of the Dissipative solvers to both (qmc.pyx:268-273).
+    The reference advertises cluster updates (README.md:4) but ships only the experimental single-cluster
+    Wolff variants of qmc.pyx:612-1621 (replayed bit-exactly by QuantumAnnealWCL & co. with exact=True); this is
+    the working cluster move, validated against exact enumeration."""
     A = _lib.f64(A_sched)
     B = _lib.f64(B_sched)
     if B.size < A.size:
@@ -229,6 +231,11 @@ def QuantumAnnealSW(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, 
     nbs = C.check_nbs(nbs)
     a8, batched, need_copy = C.spins_in(confs, 2, "confs")
     R, N, P = a8.shape
+    lut = None
+    if lookuptable is not None:
+        lut = _lib.f64(lookuptable)
+        if lut.ndim != 1 or lut.size < P - 1:
+            raise ValueError("lookuptable needs slices - 1 entries")
     inst = _lib.instance_for(nbs, device)
     if inst.nspins != N:
         raise ValueError("confs has %d spins but nbs describes %d" % (N, inst.nspins))
@@ -241,10 +248,15 @@ def QuantumAnnealSW(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, 
         sweep = 0
         for f in range(A.size):
             for step in range(int(mcsteps)):
-                st.piqmc_sweeps(A[f:f + 1], B[f:f + 1], 1, temp, global_moves=global_moves, seed=sd,
-                                replica_offset=replica_offset, sweep_offset=sweep)
+                if lut is None:
+                    st.piqmc_sweeps(A[f:f + 1], B[f:f + 1], 1, temp, global_moves=global_moves, seed=sd,
+                                    replica_offset=replica_offset, sweep_offset=sweep)
+                else:
+                    st.piqmc_sweeps_dissipative(A[f:f + 1], B[f:f + 1], 1, temp, lut, global_moves=global_moves,
+                                                seed=sd, replica_offset=replica_offset, sweep_offset=sweep)
                 if cluster_every and (sweep + 1) % int(cluster_every) == 0:
-                    st.cluster_moves(A[f], B[f], temp, 1, seed=sd, replica_offset=replica_offset, sweep_offset=sweep)
+                    st.cluster_moves(A[f], B[f], temp, 1, seed=sd, replica_offset=replica_offset, sweep_offset=sweep,
+                                     lookuptable=lut)
                 sweep += 1
         st.download_spins(a8)
         if energies:
@@ -257,13 +269,106 @@ def QuantumAnnealSW(A_sched, B_sched, mcsteps, temp, confs, nbs, nthreads=1, *, 
     return None
 
 
-def QuantumAnnealWCL(A_sched, B_sched, mcsteps, temp, confs, nbs, **kw):
+WOLFF_VARIANTS = {"QuantumAnnealWCL": 0, "DissaptiveQuantumAnnealWCL": 1, "QuantumAnnealWC": 2,
+                  "DissipativeQuantumAnnealWC2": 3, "DissipativeQuantumAnnealWC3": 4}
+
+
+def _wolff(name, A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, exact, libc_seed, kw):
+    """The reference's Wolff-cluster experiments (qmc.pyx:612-1621).  exact=True replays the reference function
+    itself (sequential single-cluster growth, its rand() stream after srand(libc_seed), replica r <-> libc_seed + r)
+    bit for bit.  Otherwise the call runs this library's working cluster dynamics with the same call surface: per
+    step one single-spin sweep plus one Swendsen-Wang move on the same bond graph (QuantumAnnealSW)."""
+    if not exact:
+        if libc_seed is not None:
+            raise ValueError("libc_seed= needs exact=True")
+        return QuantumAnnealSW(A_sched, B_sched, mcsteps, temp, confs, nbs, 1, lookuptable=lookuptable, **kw)
+    if kw.get("energies") or kw.get("cluster_every", 1) != 1 or kw.get("global_moves"):
+        raise ValueError("exact=True replays the reference function as it is: no energies / cluster_every / "
+                         "global_moves")
+    A, B = _lib.f64(A_sched), _lib.f64(B_sched)
+    if A.ndim != 1 or B.ndim != 1:
+        raise ValueError("Buffer has wrong number of dimensions (expected 1)")
+    if B.size < A.size:
+        raise ValueError("B_sched is shorter than A_sched (undefined behaviour in the reference)")
+    nbs = C.check_nbs(nbs)
+    a8, batched, need_copy = C.spins_in(confs, 2, "confs")
+    R, N, P = a8.shape
+    if P < 2:
+        raise ValueError("the Wolff experiments index Trotter slice 1: at least two slices")
+    lut = None
+    if lookuptable is not None:
+        lut = _lib.f64(lookuptable)
+        if lut.ndim != 1 or lut.size < P - 1:
+            raise ValueError("lookuptable needs slices - 1 entries")
+    inst = _lib.instance_for(nbs, kw.get("device"))
+    if inst.nspins != N:
+        raise ValueError("confs has %d spins but nbs describes %d" % (N, inst.nspins))
+    temp = float(np.float32(temp))
+    if temp * P == 0 and A.size:
+        raise ZeroDivisionError("float division")
+    seeds = C.seeds_u32(libc_seed, R)
+    consumed = np.zeros(R, dtype=np.int64)
+    overrun = np.zeros(R, dtype=np.int32)
+    with inst.using(None):
+        _lib.check(_lib.load().mcs_exact_qmc_wolff(
+            inst._h, WOLFF_VARIANTS[name], _lib.dptr(A), _lib.dptr(B), A.size, int(mcsteps), temp,
+            _lib.dptr(lut) if lut is not None else None, a8.ctypes.data, R, P, C.u32p(seeds),
+            consumed.ctypes.data_as(_lib.c_i64p), overrun.ctypes.data_as(_lib.c_i32p)))
+    _run.last_consumed = consumed
+    _wolff.last_overrun = overrun.astype(bool)
+    C.spins_out(confs, a8, batched, need_copy)
+    return None
+
+
+_wolff.last_overrun = None
+
+
+def last_wolff_overrun():
+    """bool [R]: replicas of the last exact Wolff call in which the REFERENCE would have written past its unchecked
+    `cluster` buffer (qmc.pyx:685, 1310: the un-flipped seed re-joined a full cluster) -- undefined behaviour there,
+    well defined here."""
+    return _wolff.last_overrun
+
+
+def QuantumAnnealWCL(A_sched, B_sched, mcsteps, temp, confs, nbs, *, exact=False, libc_seed=None, **kw):
     """QuantumAnnealWCL(A_sched, B_sched, mcsteps, temp, confs, nbs)
 
-    Same call surface as the reference's cluster-move experiment (qmc.pyx:620-786, no `nthreads`).  The
-    reference grows ONE Wolff cluster per step with a non-standard cumulative rule and crashes on Linux;
-    here every step is a single-spin sweep plus a full Swendsen-Wang move (see QuantumAnnealSW)."""
-    return QuantumAnnealSW(A_sched, B_sched, mcsteps, temp, confs, nbs, 1, **kw)
+    Reference qmc.pyx:620-786 (no `nthreads`): one single-cluster Wolff move per step, bond test on the bond
+    energy and the candidate's field.  See _wolff for exact= / the production dynamics."""
+    return _wolff("QuantumAnnealWCL", A_sched, B_sched, mcsteps, temp, None, confs, nbs, exact, libc_seed, kw)
 
 
-QuantumAnnealWC = QuantumAnnealWCL
+def QuantumAnnealWC(A_sched, B_sched, mcsteps, temp, confs, nbs, *, exact=False, libc_seed=None, **kw):
+    """QuantumAnnealWC(A_sched, B_sched, mcsteps, temp, confs, nbs)
+
+    Reference qmc.pyx:1006-1225: as WCL with the bond test on the candidate's full energy change."""
+    return _wolff("QuantumAnnealWC", A_sched, B_sched, mcsteps, temp, None, confs, nbs, exact, libc_seed, kw)
+
+
+def DissaptiveQuantumAnnealWCL(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, *, exact=False,
+                               libc_seed=None, **kw):
+    """DissaptiveQuantumAnnealWCL(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs)
+
+    Reference qmc.pyx:792-1000 (the reference's spelling): WCL with Ohmic-bath bonds between all slices of a world
+    line."""
+    return _wolff("DissaptiveQuantumAnnealWCL", A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, exact,
+                  libc_seed, kw)
+
+
+def DissipativeQuantumAnnealWC2(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *, exact=False,
+                                libc_seed=None, **kw):
+    """DissipativeQuantumAnnealWC2(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads)
+
+    Reference qmc.pyx:1231-1446: per step a local sweep, then one bath-only cluster per spin with a Metropolis
+    test on the cluster's remaining energy change."""
+    return _wolff("DissipativeQuantumAnnealWC2", A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, exact,
+                  libc_seed, kw)
+
+
+def DissipativeQuantumAnnealWC3(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads=1, *, exact=False,
+                                libc_seed=None, **kw):
+    """DissipativeQuantumAnnealWC3(A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, nthreads)
+
+    Reference qmc.pyx:1452-1621: per step one bath-only cluster per (spin, slice)."""
+    return _wolff("DissipativeQuantumAnnealWC3", A_sched, B_sched, mcsteps, temp, lookuptable, confs, nbs, exact,
+                  libc_seed, kw)

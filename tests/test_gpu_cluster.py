@@ -1,6 +1,8 @@
-"""Swendsen-Wang cluster moves (GPU union-find).  The reference has no working cluster code to compare with
-(parity unpinned), so correctness = the moves leave the exact Boltzmann distribution
-invariant AND are ergodic on their own: cluster-only dynamics must reproduce full-enumeration averages."""
+"""Swendsen-Wang cluster moves (GPU union-find).  The reference advertises Swendsen-Wang (README.md:4) but has no
+such code (its experimental single-cluster Wolff functions are replayed bit-exactly, tests/test_gpu_exact.py), so
+correctness of THIS move = it leaves the exact Boltzmann distribution invariant AND is ergodic on its own:
+cluster-only dynamics must reproduce full-enumeration averages -- also with the Ohmic-bath bonds of the Dissipative
+solvers (qmc.pyx:268-273)."""
 import numpy as np
 import pytest
 
@@ -60,6 +62,83 @@ def test_sw_moves_sample_the_exact_distribution(mcs, case, mix):
     es, ls = np.array(es).mean(axis=0), np.array(ls).mean(axis=0)
     assert abs(es.mean() - e_exact) <= 4.5 * es.std(ddof=1) / np.sqrt(R), (es.mean(), e_exact)
     assert abs(ls.mean() - l_exact) <= 4.5 * ls.std(ddof=1) / np.sqrt(R), (ls.mean(), l_exact)
+
+
+@pytest.mark.parametrize("case", ["ring_P4_bath", "glass_fields_P5_bath", "torus_P2_bath", "pair_P6_antibath"])
+@pytest.mark.parametrize("mix", ["cluster_only", "cluster_plus_local"])
+def test_sw_moves_with_bath_bonds_sample_the_exact_distribution(mcs, case, mix):
+    """The action of DissipativeQuantumAnneal / DissaptiveQuantumAnnealWCL / WC2 / WC3 (qmc.pyx:268-273): bonds
+    K_d = lookuptable[d-1] between all pairs of slices of a world line.  4096 replicas, 4.5 standard errors on <E_cl>
+    and the Trotter link correlation against full enumeration (even and odd P, P = 2, a negative table)."""
+    import scipy.sparse as sps
+    b = 0.9
+    if case == "ring_P4_bath":
+        J = sps.dok_matrix((3, 3))
+        for i in range(3):
+            J[i, (i + 1) % 3] = -0.7
+        nbs, P, alpha = orc.GenerateNeighbors(3, J, 2), 4, 0.4
+    elif case == "glass_fields_P5_bath":
+        # (b = 0.3: with the full couplings this 3-spin glass has a metastable state that cluster-only dynamics
+        # leaves once in ~700 moves -- slow mixing, not a wrong distribution)
+        (_, nbs), P, alpha, b = inst.random_graph(3, 3, seed=5, fields=True), 5, 0.6, 0.3
+    elif case == "torus_P2_bath":
+        (_, nbs), P, alpha = inst.torus(2, seed=2, fields=True), 2, 0.3
+    else:
+        J = sps.dok_matrix((2, 2))
+        J[0, 1] = 0.9
+        J[0, 0] = -0.2
+        nbs, P, alpha = orc.GenerateNeighbors(2, J, 2), 6, -0.25
+    lut = alpha * (np.pi / (P * np.sin(np.pi * np.arange(1, P) / P))) ** 2
+    a, temp = 1.0, 1.0 / P
+    e_exact, l_exact = _piqmc_exact(nbs, P, a, b, temp, lut=lut)
+    n = nbs.shape[0]
+    R = 4096
+    I = mcs.Instance(nbs)
+    st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+    st.init_random(3)
+
+    def step(t):
+        if mix == "cluster_plus_local":
+            st.piqmc_sweeps_dissipative(np.array([a]), np.array([b]), 1, temp, lut, seed=5, sweep_offset=t)
+        st.cluster_moves(a, b, temp, 1, seed=5, sweep_offset=t, lookuptable=lut)
+
+    for t in range(200):
+        step(t)
+    es, ls = [], []
+    for t in range(200, 320):
+        step(t)
+        if t % 3 == 0:
+            c = st.download_spins().astype(np.float64)
+            es.append(st.energies().mean(axis=1))
+            ls.append((c * np.roll(c, -1, axis=2)).sum(axis=(1, 2)) / (n * P))
+    es, ls = np.array(es).mean(axis=0), np.array(ls).mean(axis=0)
+    assert abs(es.mean() - e_exact) <= 4.5 * es.std(ddof=1) / np.sqrt(R), (es.mean(), e_exact)
+    assert abs(ls.mean() - l_exact) <= 4.5 * ls.std(ddof=1) / np.sqrt(R), (ls.mean(), l_exact)
+    # the bath must matter in this test: without it the exact averages are different
+    e0, l0 = _piqmc_exact(nbs, P, a, b, temp)
+    assert abs(l0 - l_exact) > 10 * ls.std(ddof=1) / np.sqrt(R)
+
+
+def test_sw_bath_table_must_be_symmetric_and_dissipative_names_run(mcs):
+    _, nbs = inst.torus(4, seed=2, fields=True)
+    P = 6
+    I = mcs.Instance(nbs)
+    st = mcs.State(I, mcs._lib.KIND_PIQMC, 8, P)
+    st.init_random(1)
+    with pytest.raises(NotImplementedError):
+        st.cluster_moves(1.0, 1.0, 1.0 / P, 1, lookuptable=np.linspace(0.1, 0.5, P - 1))
+    lut = 0.2 * (np.pi / (P * np.sin(np.pi * np.arange(1, P) / P))) ** 2
+    A, B = np.linspace(2.0, 0.05, 30), np.ones(30)
+    conf = (2 * np.random.RandomState(0).randint(2, size=(16, 16, P)) - 1).astype(np.int8)
+    c0 = conf.copy()
+    for fn, extra in ((mcs.qmc.DissaptiveQuantumAnnealWCL, ()), (mcs.qmc.DissipativeQuantumAnnealWC2, (1,)),
+                      (mcs.qmc.DissipativeQuantumAnnealWC3, (1,))):
+        c = c0.copy()
+        assert fn(A, B, 1, 0.3 / P, lut, c, nbs, *extra, seed=3) is None
+        assert not np.array_equal(c, c0)
+        e = np.array([[orc.ising_energy(c[r, :, k].astype(np.int64), nbs) for k in range(P)] for r in range(16)])
+        e0 = np.array([[orc.ising_energy(c0[r, :, k].astype(np.int64), nbs) for k in range(P)] for r in range(16)])
+        assert e.min(axis=1).mean() < e0.min(axis=1).mean() - 5.0
 
 
 def test_sw_moves_sa_state_and_critical_ferromagnet(mcs):

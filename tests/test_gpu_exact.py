@@ -203,3 +203,46 @@ def test_exact_replay_fed_the_references_own_random_numbers(mcs):
         assert stream[used] == int(d["P%d_g%d_next_rand" % (P, glob)])
         with pytest.raises(ValueError):
             fn(d["A"], d["B"], int(d["mcsteps"]), 1.0 / P, c.copy(), d["nbs"], 1, rand_stream=stream[:100])
+
+
+def test_exact_wolff_experiments_golden(mcs):
+    """qmc.pyx:612-1621, the reference's five Wolff-cluster functions: the replay kernel against fixtures made from
+    the compiled reference (tests/golden/make_golden.py wolff) -- configurations and rand() draws consumed."""
+    from tests.test_oracle_golden import wolff_golden_cases
+    n = 0
+    for key, name, A, B, mcsteps, temp, lut, nbs, seed, cin, cout, nxt in wolff_golden_cases():
+        c = cin.copy()
+        args = (A, B, mcsteps, temp) + ((lut,) if lut is not None else ()) + (c, nbs)
+        args += (1,) if name.endswith(("WC2", "WC3")) else ()
+        assert getattr(mcs.qmc, name)(*args, exact=True, libc_seed=seed) is None
+        assert np.array_equal(c, cout), (key, name)
+        assert orc.LibcRand(seed).draw(int(mcs.qmc.last_rand_consumed()[0]) + 1)[-1] == nxt, (key, name)
+        assert not mcs.qmc.last_wolff_overrun()[0]
+        n += 1
+    assert n >= 15
+
+
+@pytest.mark.parametrize("name", ["QuantumAnnealWCL", "DissaptiveQuantumAnnealWCL", "QuantumAnnealWC",
+                                  "DissipativeQuantumAnnealWC2", "DissipativeQuantumAnnealWC3"])
+def test_exact_wolff_experiments_batch_vs_oracle(mcs, name):
+    """A batch of replicas (replica r <-> srand(seed + r)) against the oracle, including replicas in which the
+    reference itself would overrun its `cluster` buffer (flag equal to the oracle's)."""
+    _, nbs = inst.random_graph(24, 50, seed=8, fields=True)
+    n, P, R = nbs.shape[0], 4, 24
+    A, B = np.linspace(1.5, 0.2, 5), np.linspace(0.5, 1.0, 5)
+    lut = 0.6 * (np.pi / (P * np.sin(np.pi * np.arange(1, P) / P))) ** 2
+    diss = "iss" in name
+    c0 = (2 * np.random.RandomState(4).randint(2, size=(R, n, P)) - 1).astype(np.int8)
+    c0[::3] = c0[::3, :, :1]  # some replicas with aligned world lines (full bath clusters)
+    c = c0.copy()
+    args = (A, B, 5, 1.2 / P) + ((lut,) if diss else ())
+    getattr(mcs.qmc, name)(*(args + (c, nbs)), exact=True, libc_seed=300)
+    used, over = mcs.qmc.last_rand_consumed(), mcs.qmc.last_wolff_overrun()
+    for r in range(R):
+        d = c0[r].astype(np.int64)
+        rng = orc.LibcRand(300 + r)
+        getattr(orc, name)(*(args + (d, nbs)), rng=rng)
+        assert np.array_equal(c[r], d.astype(np.int8)), r
+        assert bool(over[r]) == bool(orc.last_wolff_overrun), r
+        assert orc.LibcRand(300 + r).draw(int(used[r]) + 1)[-1] == rng.draw(1)[0], r
+    assert not np.array_equal(c, c0)
