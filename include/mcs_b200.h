@@ -144,7 +144,8 @@ int mcs_piqmc_sweeps(mcs_state *st, const double *A_sched, const double *B_sched
 /* qmc.DissipativeQuantumAnneal[Global] (qmc.pyx:223-278, 523-609): as above plus the Ohmic-bath
  * term sum_{d=1}^{P-1} 2 teff s_k s_{k+d} lookuptable[d-1] (qmc.pyx:268-273), lookuptable float64
  * [P-1].  The bath couples all slices of a world line, so slices are visited in order inside a
- * word; colour classes and replicas stay parallel.  Needs degree + field <= 6.               */
+ * word; colour classes and replicas stay parallel (coupling planes in registers up to degree +
+ * field = 8, a row-walking variant beyond).                                                  */
 int mcs_piqmc_sweeps_dissipative(mcs_state *st, const double *A_sched, const double *B_sched,
                                  int64_t schedsize, int mcsteps, float temp, const double *lookuptable,
                                  int global_moves, uint64_t seed, uint64_t replica_offset,
@@ -199,9 +200,14 @@ int mcs_svmc_anneal(mcs_instance *inst, const double *A_sched, const double *B_s
                     uint64_t replica_offset);
 
 /* ---- exact (sequential-order) kernels: bit-exact replay of the reference ---------------
- * One GPU thread per replica runs the reference's own visiting order in fp64: Fisher-Yates
- * shuffle from a glibc rand() stream (qmc.pyx:102-108), sequential Metropolis visits in table
- * order without FMA contraction.  libc_seeds[r] plays the role of srand(seed) before the
+ * Each replica runs the reference's own visiting order in fp64: Fisher-Yates shuffle from a glibc
+ * rand() stream (qmc.pyx:102-108), sequential Metropolis visits in table order without FMA
+ * contraction.  mcs_exact_qmc / mcs_exact_sa give a replica one WARP (state in shared memory): the
+ * rand() stream is produced 31 values per step, and runs of shuffle iterations / visits that cannot
+ * influence one another (no shared position / no two adjacent sites) are executed at once -- the
+ * trajectory is the sequential one bit for bit (7.8e9 attempts/s at 80x80, P = 64, 4096 replicas).
+ * Instances that do not fit (N > 65535, rows longer than 64 entries, P > 64) and the SVMC / Wolff
+ * replays use one thread per replica.  libc_seeds[r] plays the role of srand(seed) before the
  * r-th reference call; if rand_stream != NULL it is used instead (int32 [R][stream_len] of
  * recorded rand() outputs) and consumed[r] returns how many values replica r used.
  * lookuptable != NULL selects the Dissipative variants (qmc.pyx:149-278, 444-609).          */

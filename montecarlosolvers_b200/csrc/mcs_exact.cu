@@ -10,6 +10,7 @@
 //
 // This file is compiled with -fmad=false as well; it is a validation path, not the fast path.
 #include <cmath>
+#include <cstdio>
 #include <vector>
 
 #include "mcs_common.cuh"
@@ -148,6 +149,7 @@ struct ExactQmcArgs {
     long long R;
     int N, P, maxnb, S, mcsteps, global_moves;
     double teff;
+    long long *prof = nullptr; // MCS_EXACT_PROF=1: [R][4] cycle / window counters of the warp kernel
 };
 
 __global__ void exact_qmc_kernel(const ExactQmcArgs a)
@@ -248,6 +250,477 @@ __global__ void exact_sa_kernel(const ExactSaArgs a)
         }
     }
     if (a.consumed) a.consumed[r] = rng.pos;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Warp-per-replica replay (the path mcs_exact_qmc / mcs_exact_sa take whenever a replica fits shared memory).
+//
+// The reference's trajectory is a strictly sequential program, but three parts of it parallelise over the 32
+// lanes of a warp WITHOUT changing a single bit of the result:
+//   1. glibc rand() is the additive generator x_n = x_{n-31} + x_{n-3} (mod 2^32), output x_n >> 1.  With
+//      y_l = x_{n0-31+l} known for a whole block, x_{n0+l} = y_l + x_{n0+l-3}: three interleaved prefix sums,
+//      i.e. 31 outputs per five warp shuffles.
+//   2. The Fisher-Yates loop `for i = N..1: j = rand() % i; swap(p[i-1], p[j])` (qmc.pyx:102-108): consecutive
+//      iterations commute unless they touch the same position.  A window of up to 32 iterations is cut at the
+//      first lane whose {i-1, j} meets an earlier lane's j (match.any + redux.or); the lanes before the cut
+//      swap at once.
+//   3. The visits: a visit reads only its site's table neighbours (and, for PIQMC, other slices of its own
+//      world line, which nobody else touches during that slice's sweep), so a run of consecutive visits without
+//      two adjacent sites gives the same ediffs whether executed in order or at once.  The window is cut at the
+//      first lane with a neighbour visited earlier in the window (byte marks in shared memory).  The uniform of
+//      a visit is only drawn when ediff > 0 (qmc.pyx:140-143): its index in the stream is the window's base plus
+//      the number of earlier lanes that drew one (ballot + popc).
+// One warp owns one replica: spins bit-packed (PIQMC: one word per site, bit k = slice k) or as bytes (SA) in
+// shared memory together with the permutation (u16), the marks and a 256-entry window of the rand() stream.
+// Arithmetic is the thread-per-replica kernels': fp64, table order, __dmul_rn / __dadd_rn.
+// ------------------------------------------------------------------------------------------------------------
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct WarpRng {
+    uint32_t *ring; // shared [256]: raw generator words x_n at index n & 255 (x_{-31..-1} = the seeded state)
+    long long pos;  // values consumed so far
+    long long gen;  // values generated so far (multiple of 31)
+    const int32_t *stream; // recorded rand() outputs instead of a seeded state (or nullptr)
+    long long len;
+
+    __device__ __forceinline__ void init(const LibcState &s, const int32_t *str, long long n, int lane)
+    {
+        pos = gen = 0;
+        stream = str;
+        len = n;
+        if (lane < 31) ring[(lane - 31) & 255] = (uint32_t)s.r[(s.f + lane) % 31]; // oldest first: x_{n-31} sits at r[f]
+        __syncwarp();
+    }
+    // make values pos .. pos + n - 1 available (n <= 64); warp-uniform
+    __device__ __forceinline__ void ensure(int n, int lane)
+    {
+        if (stream) return;
+        while (gen - pos < n) {
+            uint32_t v = ring[(gen - 31 + lane) & 255]; // lane 31 reads x_{gen}: garbage, never stored
+            if (lane < 3) v += ring[(gen - 3 + lane) & 255];
+#pragma unroll
+            for (int d = 3; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, v, d);
+                if (lane >= d) v += t;
+            }
+            if (lane < 31) ring[(gen + lane) & 255] = v;
+            gen += 31;
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ int32_t at(long long idx) const
+    {
+        if (stream) return idx < len ? stream[idx] : 0;
+        return (int32_t)(ring[idx & 255] >> 1);
+    }
+};
+
+struct WarpCtx {
+    WarpRng rng;
+    uint16_t *perm; // shared [N]
+    uint8_t *mark;  // shared [N], 0 outside a window
+    int32_t *ring_idx; // shared [64][8]: table rows of the visits ahead (index column)
+    double *ring_J;    // shared [64][8]: ... coupling column
+    const int32_t *tab_idx;
+    const double *tab_J;
+    int N, maxnb, lane;
+    uint32_t lt; // lanes below this one
+    long long pf[4] = {0, 0, 0, 0}; // MCS_EXACT_PROF: cycles in shuffles, cycles in visits, shuffle windows, visit windows
+    bool prof = false;
+};
+
+// r % i for 0 <= r < 2^31, 1 <= i < 2^16 without the 140-cycle integer division: fp32 quotient estimate (within 5
+// of the true one for i >= 256), exact remainder by correction
+__device__ __forceinline__ int fast_mod(int32_t r, int i)
+{
+    if (i < 256) return r % i;
+    const uint32_t q = __float2uint_rz(__uint2float_rz((uint32_t)r) * __frcp_rn((float)i));
+    int rem = (int)((uint32_t)r - q * (uint32_t)i);
+    while (rem < 0) rem += i;
+    while (rem >= i) rem -= i;
+    return rem;
+}
+
+// qmc.pyx:102-108 / sa.pyx:73-79
+__device__ __forceinline__ void warp_shuffle(WarpCtx &c)
+{
+    const int N = c.N, lane = c.lane;
+    const long long t0 = c.prof ? clock64() : 0;
+    for (int i = lane; i < N; i += 32) c.perm[i] = (uint16_t)i;
+    __syncwarp();
+    int cur = N;
+    while (cur > 0) {
+        c.pf[2] += 1;
+        c.rng.ensure(32, lane);
+        const int i = cur - lane;
+        const bool valid = i >= 1;
+        const int j = valid ? fast_mod(c.rng.at(c.rng.pos + lane), i) : 0;
+        const int A = i - 1;
+        // (a) an earlier lane has the same j.  Cheap test first (the marks are all zero between visits): every
+        // lane writes its number at mark[j]; if every lane reads its own number back no two lanes share a j.
+        // match.any (379 cycles on B200) only runs for windows that do have a duplicate.
+        if (valid) c.mark[j] = (uint8_t)(lane + 1);
+        __syncwarp();
+        const bool lost = valid && c.mark[j] != (uint8_t)(lane + 1);
+        const uint32_t any_lost = __ballot_sync(kFull, lost);
+        if (valid) c.mark[j] = 0;
+        uint32_t same = 0u;
+        if (any_lost) same = __match_any_sync(kFull, valid ? j : 0x10000 + lane) & c.lt;
+        // (b) an earlier lane's j is this lane's own position i - 1
+        const int t = cur - 1 - j; // the lane whose own position is j
+        const uint32_t hit = __reduce_or_sync(kFull, (valid && t > lane && t < 32) ? (1u << t) : 0u);
+        const bool conflict = !valid || same != 0u || ((hit >> lane) & 1u);
+        const uint32_t cb = __ballot_sync(kFull, conflict);
+        const int ncommit = cb ? __ffs(cb) - 1 : 32; // >= 1: lane 0 never conflicts
+        uint16_t pa = 0, pj = 0;
+        if (lane < ncommit) {
+            pa = c.perm[A];
+            pj = c.perm[j];
+        }
+        __syncwarp();
+        if (lane < ncommit) {
+            c.perm[A] = pj;
+            c.perm[j] = pa;
+        }
+        __syncwarp();
+        c.rng.pos += ncommit;
+        cur -= ncommit;
+    }
+    if (c.prof) c.pf[0] += clock64() - t0;
+}
+
+// Table rows of the visits ahead, staged in shared memory by cp.async: slot (position & 63) holds the row of the
+// site visited at that position of the sweep (RW entries of the index and of the coupling column; rows longer than
+// 8 entries are read from the table directly instead, RW = 0).  A window needs positions [cur, cur + 32); the next
+// one starts at most 32 further on, so while a window is being decided the rows up to cur + nrun + 32 are requested
+// and have a whole window's arithmetic to arrive: no table latency on the critical path.
+constexpr int kRowRing = 64;
+
+template <int RW>
+struct RowRing {
+    int32_t *idx; // shared [64][RW]
+    double *J;    // shared [64][RW]
+};
+
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem, int bytes)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem);
+    if (bytes == 16)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem) : "memory");
+    else if (bytes == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem) : "memory");
+}
+
+// request the table row of `site` into slot `pos & 63`
+template <int RW>
+__device__ __forceinline__ void stage_row(const WarpCtx &c, const RowRing<RW> &ring, int pos, int site)
+{
+    const int32_t *ri = c.tab_idx + (long long)site * c.maxnb;
+    const double *rj = c.tab_J + (long long)site * c.maxnb;
+    int32_t *di = ring.idx + (pos & (kRowRing - 1)) * RW;
+    double *dj = ring.J + (pos & (kRowRing - 1)) * RW;
+    if ((c.maxnb & 3) == 0) { // rows are 16-byte multiples (both arrays come from cudaMalloc)
+        for (int si = 0; si < c.maxnb; si += 4) {
+            cp_async(di + si, ri + si, 16);
+            cp_async(dj + si, rj + si, 16);
+            cp_async(dj + si + 2, rj + si + 2, 16);
+        }
+    } else {
+        for (int si = 0; si < c.maxnb; ++si) {
+            cp_async(di + si, ri + si, 4);
+            cp_async(dj + si, rj + si, 8);
+        }
+    }
+}
+
+// One sweep's visits in permutation order.  V: double ediff(site, idx row, J row); void flip(site); `scale` = the
+// Metropolis temperature (teff or sched[t]); ru != nullptr: acceptance uniforms indexed by visit position
+// (sa.pyx:190) instead of rand().
+template <int RW, typename V>
+__device__ __forceinline__ void warp_visits(WarpCtx &c, V &v, double scale, const double *ru)
+{
+    const int N = c.N, lane = c.lane;
+    const long long t0 = c.prof ? clock64() : 0;
+    RowRing<RW> ring{c.ring_idx, c.ring_J};
+    const float inv_scale = 1.0f / (float)scale;
+    int filled = 0; // rows of positions < filled are staged or on their way
+    if (RW > 0) {
+        for (int p = lane; p < min(N, kRowRing); p += 32) stage_row<RW>(c, ring, p, (int)c.perm[p]);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        filled = min(N, kRowRing);
+    }
+    int cur = 0;
+    while (cur < N) {
+        c.pf[3] += 1;
+        if (!ru) c.rng.ensure(32, lane);
+        const int sidx = cur + lane;
+        const bool valid = sidx < N;
+        const int site = valid ? (int)c.perm[sidx] : 0;
+        if (valid) c.mark[site] = (uint8_t)(lane + 1);
+        if (RW > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const int32_t *ri = RW > 0 ? ring.idx + (sidx & (kRowRing - 1)) * RW : c.tab_idx + (long long)site * c.maxnb;
+        const double *rj = RW > 0 ? ring.J + (sidx & (kRowRing - 1)) * RW : c.tab_J + (long long)site * c.maxnb;
+        bool conflict = !valid;
+        if (valid) { // a table neighbour is visited earlier in this window
+            for (int si = 0; si < c.maxnb; ++si) {
+                const int j = ri[si];
+                const int m = c.mark[j];
+                if (j != site && m != 0 && m - 1 < lane) conflict = true;
+            }
+        }
+        const uint32_t cb = __ballot_sync(kFull, conflict);
+        const int nrun = cb ? __ffs(cb) - 1 : 32; // >= 1
+        if (valid) c.mark[site] = 0;
+        if (RW > 0) { // rows the next window can reach: positions < cur + nrun + 32 (at most 32 new ones)
+            const int upto = min(N, cur + nrun + 32), pp = filled + lane;
+            if (pp < upto) stage_row<RW>(c, ring, pp, (int)c.perm[pp]);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            filled = max(filled, upto);
+        }
+        __syncwarp();
+        const bool active = lane < nrun;
+        const double e = active ? v.ediff(site, ri, rj) : 0.0;
+        const bool draws = active && !(e <= 0.0); // the `elif` of qmc.pyx:142 is evaluated (NaN included)
+        const uint32_t db = __ballot_sync(kFull, draws);
+        bool flip = active && e <= 0.0;
+        if (draws) {
+            // exp(-e / scale) > u, decided in fp32 whenever the two sides are further apart than fp32 can blur
+            // (relative error of either side < 4e-5 for |e / scale| < 100, beyond which exp underflows): the
+            // fp64 division, exp and division of the reference expression run only for near ties (and NaN)
+            const int32_t r = ru ? 0 : c.rng.at(c.rng.pos + __popc(db & c.lt));
+            const float uf = ru ? (float)ru[sidx] : (float)r * (1.0f / 2147483647.0f);
+            const float evf = __expf(-(float)e * inv_scale);
+            if (fabsf(evf - uf) > 1e-3f * fmaxf(evf, uf)) {
+                flip = evf > uf;
+            } else {
+                const double u = ru ? ru[sidx] : __ddiv_rn((double)r, 2147483647.0);
+                flip = exp(__ddiv_rn(__dmul_rn(-1.0, e), scale)) > u;
+            }
+        }
+        if (!ru) c.rng.pos += __popc(db);
+        __syncwarp(); // every ediff of the window is computed before any spin of it changes
+        if (flip) v.flip(site);
+        __syncwarp();
+        cur += nrun;
+    }
+    if (RW > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (c.prof) c.pf[1] += clock64() - t0;
+}
+
+template <typename V>
+__device__ __forceinline__ void warp_visits_any(WarpCtx &c, V &v, double scale, const double *ru)
+{
+    if (c.maxnb <= 4)
+        warp_visits<4>(c, v, scale, ru);
+    else if (c.maxnb <= 8)
+        warp_visits<8>(c, v, scale, ru);
+    else
+        warp_visits<0>(c, v, scale, ru);
+}
+
+template <typename WT>
+struct QmcVisit {
+    WT *w; // shared [N]: bit k = slice k, bit set <=> spin -1
+    const int32_t *tab_idx;
+    const double *tab_J;
+    const double *lut;
+    int maxnb, P, k;
+    bool global;
+    double b_coeff, jperp, teff;
+
+    __device__ __forceinline__ double spin(WT word, int k_) const { return ((word >> k_) & (WT)1) ? -1.0 : 1.0; }
+    // qmc.pyx:112-125; (ri, rj) = the site's table row (shared-memory copy or the table itself)
+    __device__ __forceinline__ double inplane(int site, const int32_t *ri, const double *rj, WT wi, int k_,
+                                              double acc) const
+    {
+        const double bs = __dmul_rn(b_coeff, spin(wi, k_));
+        for (int si = 0; si < maxnb; ++si) {
+            const int spinidx = ri[si];
+            const double jval = rj[si];
+            if (spinidx == site)
+                acc = __dadd_rn(acc, __dmul_rn(bs, jval));
+            else
+                acc = __dadd_rn(acc, __dmul_rn(bs, __dmul_rn(jval, spin(w[spinidx], k_))));
+        }
+        return acc;
+    }
+    __device__ __forceinline__ double ediff(int site, const int32_t *ri, const double *rj) const
+    {
+        const WT wi = w[site];
+        if (global) { // qmc.pyx:416-431
+            double e = 0.0;
+            for (int k_ = 0; k_ < P; ++k_) e = inplane(site, ri, rj, wi, k_, e);
+            return e;
+        }
+        double e = inplane(site, ri, rj, wi, k, 0.0);
+        const int tleft = k == 0 ? P - 1 : (k == P - 1 ? P - 2 : k - 1); // qmc.pyx:127-135
+        const int tright = k == 0 ? 1 : (k == P - 1 ? 0 : k + 1);
+        const double s2 = __dmul_rn(2.0, spin(wi, k));
+        e = __dadd_rn(e, __dmul_rn(s2, __dmul_rn(jperp, spin(wi, tleft))));
+        e = __dadd_rn(e, __dmul_rn(s2, __dmul_rn(jperp, spin(wi, tright))));
+        if (lut) { // qmc.pyx:268-273
+            const double t2 = __dmul_rn(2.0, teff);
+            for (int d = 1; d < P; ++d) {
+                const int bslice = (k + d) % P;
+                const double ss = (((wi >> k) ^ (wi >> bslice)) & (WT)1) ? -1.0 : 1.0;
+                e = __dadd_rn(e, __dmul_rn(__dmul_rn(t2, ss), lut[d - 1]));
+            }
+        }
+        return e;
+    }
+    __device__ __forceinline__ void flip(int site) const
+    {
+        const WT pmask = P == (int)(8 * sizeof(WT)) ? (WT)~(WT)0 : (WT)(((WT)1 << P) - (WT)1);
+        w[site] ^= global ? pmask : (WT)((WT)1 << k);
+    }
+};
+
+// shared memory: row ring (J | idx) | w[N] words | perm[N] u16 | rand() window [256] | mark[N] u8
+template <typename WT>
+__global__ void __launch_bounds__(32) exact_qmc_warp_kernel(const ExactQmcArgs a)
+{
+    extern __shared__ __align__(16) unsigned char ex_smem[];
+    const int N = a.N, P = a.P, lane = threadIdx.x;
+    const long long r = blockIdx.x;
+    const int rw = a.maxnb <= 4 ? 4 : (a.maxnb <= 8 ? 8 : 0); // staged row length (0: rows read from the table)
+    WarpCtx c;
+    c.ring_J = reinterpret_cast<double *>(ex_smem);
+    c.ring_idx = reinterpret_cast<int32_t *>(c.ring_J + kRowRing * rw);
+    WT *w = reinterpret_cast<WT *>(c.ring_idx + kRowRing * rw);
+    c.perm = reinterpret_cast<uint16_t *>(w + N);
+    c.rng.ring = reinterpret_cast<uint32_t *>(c.perm + ((N + 1) & ~1));
+    c.mark = reinterpret_cast<uint8_t *>(c.rng.ring + 256);
+    c.tab_idx = a.tab_idx;
+    c.tab_J = a.tab_J;
+    c.N = N;
+    c.maxnb = a.maxnb;
+    c.lane = lane;
+    c.lt = (1u << lane) - 1u;
+    c.prof = a.prof != nullptr;
+    int8_t *conf = a.confs + r * (long long)N * P;
+    for (int i = lane; i < N; i += 32) {
+        WT word = 0;
+        for (int k = 0; k < P; ++k)
+            if (conf[(long long)i * P + k] < 0) word |= (WT)1 << k;
+        w[i] = word;
+        c.mark[i] = 0;
+    }
+    c.rng.init(a.st[r], a.stream ? a.stream + r * a.stream_len : nullptr, a.stream_len, lane);
+    QmcVisit<WT> v;
+    v.w = w;
+    v.tab_idx = a.tab_idx;
+    v.tab_J = a.tab_J;
+    v.lut = a.lut;
+    v.maxnb = a.maxnb;
+    v.P = P;
+    v.teff = a.teff;
+    for (int f = 0; f < a.S; ++f) {
+        v.jperp = a.jperp[f];
+        v.b_coeff = a.bcoef[f];
+        for (int step = 0; step < a.mcsteps; ++step) {
+            v.global = false;
+            for (int islice = 0; islice < P; ++islice) {
+                warp_shuffle(c);
+                v.k = islice;
+                warp_visits_any(c, v, a.teff, nullptr);
+            }
+            if (a.global_moves) { // qmc.pyx:405-438
+                warp_shuffle(c);
+                v.global = true;
+                warp_visits_any(c, v, a.teff, nullptr);
+            }
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) {
+        const WT word = w[i];
+        for (int k = 0; k < P; ++k) conf[(long long)i * P + k] = ((word >> k) & (WT)1) ? -1 : 1;
+    }
+    if (a.consumed && lane == 0) a.consumed[r] = c.rng.pos;
+    if (a.prof && lane == 0)
+        for (int q = 0; q < 4; ++q) a.prof[r * 4 + q] = c.pf[q];
+}
+
+struct SaVisit {
+    int8_t *sv; // shared [N]
+    const int32_t *tab_idx;
+    const double *tab_J;
+    int maxnb;
+    __device__ __forceinline__ double ediff(int site, const int32_t *ri, const double *rj) const
+    { // sa.pyx:84-94
+        const double m2s = __dmul_rn(-2.0, (double)sv[site]);
+        double e = 0.0;
+        for (int si = 0; si < maxnb; ++si) {
+            const int spinidx = ri[si];
+            const double jval = rj[si];
+            if (spinidx == site)
+                e = __dadd_rn(e, __dmul_rn(m2s, jval));
+            else
+                e = __dadd_rn(e, __dmul_rn(m2s, __dmul_rn(jval, (double)sv[spinidx])));
+        }
+        return e;
+    }
+    __device__ __forceinline__ void flip(int site) const { sv[site] = -sv[site]; }
+};
+
+// shared memory: row ring (J | idx) | perm[N] u16 | rand() window [256] | sv[N] i8 | mark[N] u8
+__global__ void __launch_bounds__(32) exact_sa_warp_kernel(const ExactSaArgs a)
+{
+    extern __shared__ __align__(16) unsigned char ex_smem[];
+    const int N = a.N, lane = threadIdx.x;
+    const long long r = blockIdx.x;
+    const int rw = a.maxnb <= 4 ? 4 : (a.maxnb <= 8 ? 8 : 0);
+    WarpCtx c;
+    c.ring_J = reinterpret_cast<double *>(ex_smem);
+    c.ring_idx = reinterpret_cast<int32_t *>(c.ring_J + kRowRing * rw);
+    c.perm = reinterpret_cast<uint16_t *>(c.ring_idx + kRowRing * rw);
+    c.rng.ring = reinterpret_cast<uint32_t *>(c.perm + ((N + 1) & ~1));
+    int8_t *sv = reinterpret_cast<int8_t *>(c.rng.ring + 256);
+    c.mark = reinterpret_cast<uint8_t *>(sv + N);
+    c.N = N;
+    c.maxnb = a.maxnb;
+    c.lane = lane;
+    c.lt = (1u << lane) - 1u;
+    int8_t *gsv = a.svec + r * (long long)N;
+    for (int i = lane; i < N; i += 32) {
+        sv[i] = gsv[i];
+        c.mark[i] = 0;
+    }
+    c.rng.init(a.st[r], nullptr, 0, lane);
+    SaVisit v;
+    v.sv = sv;
+    v.maxnb = a.maxnb;
+    for (int t = 0; t < a.S; ++t) {
+        c.tab_idx = v.tab_idx = a.tab_idx + t * a.tab_stride; // NoisyAnneal: nbs[itemp] (sa.pyx:363-365)
+        c.tab_J = v.tab_J = a.tab_J + t * a.tab_stride;
+        for (int step = 0; step < a.mcsteps; ++step) {
+            warp_shuffle(c);
+            warp_visits_any(c, v, a.sched[t], a.randuni ? a.randuni + ((long long)t * a.mcsteps + step) * N : nullptr);
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) gsv[i] = sv[i];
+    if (a.consumed && lane == 0) a.consumed[r] = c.rng.pos;
+}
+
+// Launch helper: returns false when a replica does not fit (caller falls back to the thread-per-replica kernel)
+template <typename K, typename A>
+int launch_warp_replay(K kernel, const A &a, long long R, size_t smem, cudaStream_t s)
+{
+    if (smem > 48 * 1024)
+        MCS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)R, 32, smem, s>>>(a);
+    return MCS_OK;
+}
+
+bool warp_replay_wanted(const mcs_instance *inst, size_t smem)
+{
+    if (getenv("MCS_EXACT_LEGACY")) return false; // tests: the thread-per-replica kernels
+    // u16 permutation entries; very long rows make every window one visit long (complete graphs): no gain
+    return inst->N <= 65535 && smem <= 227 * 1024 - 1024 && inst->maxnb <= 64;
 }
 
 struct ExactSvmcArgs {
@@ -792,7 +1265,47 @@ extern "C" int mcs_exact_qmc(mcs_instance *inst, const double *A, const double *
     a.mcsteps = mcsteps;
     a.global_moves = global_moves ? 1 : 0;
     a.teff = teff;
-    exact_qmc_kernel<<<(unsigned)((R + 31) / 32), 32, 0, s>>>(a);
+    const bool trace = getenv("MCS_TRACE_EXACT") != nullptr;
+    if (trace) MCS_CUDA(cudaEventRecord(inst->ev0, s));
+    // per replica in shared memory: words | u16 permutation | rand() window | marks
+    const size_t wbytes = P > 32 ? 8 : 4;
+    const size_t rowring = (size_t)64 * 12 * (inst->maxnb <= 4 ? 4 : (inst->maxnb <= 8 ? 8 : 0));
+    const size_t smem =
+        rowring + (size_t)inst->N * wbytes + (((size_t)inst->N + 1) & ~(size_t)1) * 2 + 1024 + (size_t)inst->N;
+    DevBuf d_prof;
+    if (getenv("MCS_EXACT_PROF")) {
+        MCS_TRY(d_prof.alloc((size_t)R * 4 * sizeof(long long)));
+        MCS_CUDA(cudaMemsetAsync(d_prof.p, 0, (size_t)R * 4 * sizeof(long long), s));
+        a.prof = d_prof.as<long long>();
+    }
+    if (P <= 64 && warp_replay_wanted(inst, smem)) {
+        if (P > 32)
+            MCS_TRY(launch_warp_replay(exact_qmc_warp_kernel<uint64_t>, a, R, smem, s));
+        else
+            MCS_TRY(launch_warp_replay(exact_qmc_warp_kernel<uint32_t>, a, R, smem, s));
+    } else {
+        exact_qmc_kernel<<<(unsigned)((R + 31) / 32), 32, 0, s>>>(a);
+    }
+    if (a.prof) {
+        std::vector<long long> hp((size_t)R * 4);
+        MCS_CUDA(cudaMemcpyAsync(hp.data(), d_prof.p, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+        MCS_CUDA(cudaStreamSynchronize(s));
+        double q[4] = {0, 0, 0, 0};
+        for (int64_t r = 0; r < R; ++r)
+            for (int x = 0; x < 4; ++x) q[x] += (double)hp[(size_t)r * 4 + x] / (double)R;
+        fprintf(stderr, "[mcs exact] per replica: shuffles %.0f cycles in %.0f windows (%.0f each), visits %.0f cycles in "
+                        "%.0f windows (%.0f each)\n", q[0], q[2], q[0] / std::max(1.0, q[2]), q[1], q[3],
+                q[1] / std::max(1.0, q[3]));
+    }
+    if (trace) {
+        float ms = 0.0f;
+        MCS_CUDA(cudaEventRecord(inst->ev1, s));
+        MCS_CUDA(cudaEventSynchronize(inst->ev1));
+        MCS_CUDA(cudaEventElapsedTime(&ms, inst->ev0, inst->ev1));
+        fprintf(stderr, "[mcs exact] qmc replay kernel: %.3f ms, %.3e attempts/s (R %lld, N %lld, P %lld, %lld sweeps)\n", ms,
+                (double)R * inst->N * P * S * mcsteps / (ms * 1e-3), (long long)R, (long long)inst->N, (long long)P,
+                (long long)(S * mcsteps));
+    }
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     MCS_CUDA(cudaMemcpyAsync(confs, d_conf.p, cbytes, cudaMemcpyDeviceToHost, s));
@@ -900,7 +1413,12 @@ extern "C" int mcs_exact_sa(mcs_instance *inst, const double *sched, int64_t S, 
     a.maxnb = (int)inst->maxnb;
     a.S = (int)S;
     a.mcsteps = mcsteps;
-    exact_sa_kernel<<<(unsigned)((R + 31) / 32), 32, 0, s>>>(a);
+    const size_t rowring = (size_t)64 * 12 * (inst->maxnb <= 4 ? 4 : (inst->maxnb <= 8 ? 8 : 0));
+    const size_t smem = rowring + (((size_t)inst->N + 1) & ~(size_t)1) * 2 + 1024 + 2 * (size_t)inst->N;
+    if (warp_replay_wanted(inst, smem))
+        MCS_TRY(launch_warp_replay(exact_sa_warp_kernel, a, R, smem, s));
+    else
+        exact_sa_kernel<<<(unsigned)((R + 31) / 32), 32, 0, s>>>(a);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     MCS_CUDA(cudaMemcpyAsync(svec, d_sv.p, bytes, cudaMemcpyDeviceToHost, s));

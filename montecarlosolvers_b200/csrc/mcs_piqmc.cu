@@ -533,6 +533,9 @@ struct BathArgs {
     float c0;          // 2 teff sum_d lookuptable[d-1]
 };
 
+// NPL > 0: the site's coupling planes (degree + field <= NPL) live in registers.  NPL == 0: any degree -- the
+// in-plane term of every slice walks the ELL row and re-reads the neighbours' words (L1 hits: the lines are this
+// warp's own, replicas on lanes).
 template <int NPL>
 __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __grid_constant__ PiqmcPass a,
                                                                       const BathArgs bath)
@@ -552,30 +555,34 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __gr
     if (item >= (long long)a.nsites * a.G) return;
     const int site = a.sites[item / a.G];
     const long long r = (item % a.G) * 32 + lane;
+    constexpr int NREG = NPL > 0 ? NPL : 1;
 
-    float c[NPL];
-    int nb[NPL];
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        if (j < a.nq) {
-            nb[j] = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
-            c[j] = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
-        } else {
-            nb[j] = site;
-            c[j] = (a.field && j == a.nq) ? a.bcoef * __ldg(&a.h[site]) : 0.0f;
-        }
-    }
+    float c[NREG];
+    int nb[NREG];
     const int P = a.P;
     const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
     uint64_t w = a.W[(long long)site * a.Rpad + r];
-    uint64_t pl[NPL];
+    uint64_t pl[NREG];
+    if (NPL > 0) {
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        if (j < a.nq)
-            pl[j] = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
-        else
-            pl[j] = (a.field && j == a.nq) ? w : 0ull;
+        for (int j = 0; j < NREG; ++j) {
+            if (j < a.nq) {
+                nb[j] = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+                c[j] = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+            } else {
+                nb[j] = site;
+                c[j] = (a.field && j == a.nq) ? a.bcoef * __ldg(&a.h[site]) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) {
+            if (j < a.nq)
+                pl[j] = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
+            else
+                pl[j] = (a.field && j == a.nq) ? w : 0ull;
+        }
     }
+    const float hc = a.field ? a.bcoef * __ldg(&a.h[site]) : 0.0f; // NPL == 0 only
     const uint32_t c0 = a.replica_offset + (uint32_t)r, c1 = (uint32_t)site, c2 = a.sweep_lo;
     const uint32_t c3hi = a.sweep_hi << 8;
     const int nbytes = (P + 7) >> 3;
@@ -584,8 +591,18 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __gr
         if ((k & 3) == 0) mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(k >> 2), a.keys, rnd);
         const uint32_t sk = (uint32_t)(w >> k) & 1u;
         float dE = 0.0f;
+        if (NPL > 0) {
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) dE += ((pl[j] >> k) & 1ull) ? -c[j] : c[j];
+            for (int j = 0; j < NREG; ++j) dE += ((pl[j] >> k) & 1ull) ? -c[j] : c[j];
+        } else {
+            dE = sk ? -hc : hc;
+            for (int j = 0; j < a.dpad; ++j) { // padding entries: J = 0, index = the site itself
+                const float cj = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+                const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+                const uint32_t sj = (uint32_t)(a.W[(long long)nbj * a.Rpad + r] >> k) & 1u;
+                dE += (sj ^ sk) ? -cj : cj;
+            }
+        }
         const int kl = k == 0 ? P - 1 : k - 1, kr = k == P - 1 ? 0 : k + 1;
         const int anti = (int)(((uint32_t)(w >> kl) & 1u) ^ sk) + (int)(((uint32_t)(w >> kr) & 1u) ^ sk);
         dE += a.jperp2 * (float)(2 - 2 * anti);
@@ -599,14 +616,24 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __gr
     }
     if (a.global_moves) { // a world-line flip leaves every s_k s_k' invariant: no bath term (qmc.pyx:575-609)
         float dE = 0.0f;
+        if (NPL > 0) {
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            uint64_t x;
-            if (j < a.nq)
-                x = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
-            else
-                x = (a.field && j == a.nq) ? w : 0ull;
-            dE += c[j] * (float)(P - 2 * __popcll(x));
+            for (int j = 0; j < NREG; ++j) {
+                uint64_t x;
+                if (j < a.nq)
+                    x = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
+                else
+                    x = (a.field && j == a.nq) ? w : 0ull;
+                dE += c[j] * (float)(P - 2 * __popcll(x));
+            }
+        } else {
+            dE = hc * (float)(P - 2 * __popcll(w & pmask));
+            for (int j = 0; j < a.dpad; ++j) {
+                const float cj = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
+                const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
+                if (nbj == site) continue; // padding
+                dE += cj * (float)(P - 2 * __popcll((w ^ a.W[(long long)nbj * a.Rpad + r]) & pmask));
+            }
         }
         mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
         if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
@@ -876,7 +903,10 @@ static void launch_bath(int npl, unsigned grid, cudaStream_t s, const PiqmcPass 
     case 3: piqmc_bath_pass_kernel<3><<<grid, kWarps * 32, 0, s>>>(a, b); break;
     case 4: piqmc_bath_pass_kernel<4><<<grid, kWarps * 32, 0, s>>>(a, b); break;
     case 5: piqmc_bath_pass_kernel<5><<<grid, kWarps * 32, 0, s>>>(a, b); break;
-    default: piqmc_bath_pass_kernel<6><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    case 6: piqmc_bath_pass_kernel<6><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    case 7: piqmc_bath_pass_kernel<7><<<grid, kWarps * 32, 0, s>>>(a, b); break; // Chimera with local fields
+    case 8: piqmc_bath_pass_kernel<8><<<grid, kWarps * 32, 0, s>>>(a, b); break;
+    default: piqmc_bath_pass_kernel<0><<<grid, kWarps * 32, 0, s>>>(a, b); break; // any degree: row walk
     }
 }
 
@@ -903,9 +933,6 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     bath.c0 = 0.0f;
     float *d_lut4 = nullptr;
     if (lookuptable) {
-        MCS_REQUIRE(inst->maxdeg + (inst->has_field ? 1 : 0) <= 6, MCS_EUNSUPPORTED,
-                    "dissipative sweeps: the production kernel keeps a site's neighbour planes in registers "
-                    "(degree + field <= 6); use the exact kernel for this instance");
         float h4[64];
         double sum = 0.0;
         for (int d = 0; d < 64; ++d) h4[d] = 0.0f;

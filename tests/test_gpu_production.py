@@ -188,6 +188,35 @@ def test_dissipative_piqmc_samples_the_exact_boltzmann_distribution(mcs, P, glob
     assert not np.array_equal(c, c0)
 
 
+@pytest.mark.parametrize("case", ["k7_fields_7_register_planes", "circulant8_8_register_planes", "k9_fields_row_walk"])
+def test_dissipative_piqmc_high_degree_instances(mcs, case):
+    """The Ohmic-bath kernel beyond degree + field = 6 (Chimera with local fields has 7): 7 and 8
+    coupling planes in registers, and the any-degree variant that walks the row.  P = 2, full enumeration, 4.5
+    standard errors over 4096 replicas."""
+    if case == "k7_fields_7_register_planes":
+        J, nbs = inst.random_graph(7, 21, seed=4, fields=True)
+        want = 7
+    elif case == "circulant8_8_register_planes":
+        J, nbs = inst.circulant(8, offsets=(1, 2, 3, 4), seed=5, fields=True)
+        want = 8
+    else:
+        J, nbs = inst.random_graph(9, 36, seed=6, fields=True)
+        want = 9
+    I = mcs.Instance(nbs)
+    assert I.maxdeg + int(I.has_field) == want, (I.maxdeg, I.has_field)
+    P = 2
+    lut = np.array([0.35])
+    a, b, temp = 0.9, 0.25, 1.1 / P
+    e_exact, l_exact = _piqmc_exact(nbs, P, a, b, temp, lut=lut)
+    e0, l0 = _piqmc_exact(nbs, P, a, b, temp)
+    assert abs(l_exact - l0) > 0.02
+    e, e_sem, l, l_sem, _ = _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, global_moves=True, lut=lut, burn=600)
+    print("%s: E %.4f +- %.4f (exact %.4f), link %.4f +- %.4f (exact %.4f)" % (case, e, e_sem, e_exact, l, l_sem,
+                                                                              l_exact))
+    assert abs(e - e_exact) <= 4.5 * e_sem, (e, e_exact, e_sem)
+    assert abs(l - l_exact) <= 4.5 * l_sem, (l, l_exact, l_sem)
+
+
 @pytest.mark.parametrize("case", ["graph10_lut", "circulant10_7planes", "circulant10_8planes", "k10_direct"])
 def test_sa_samples_the_exact_boltzmann_distribution(mcs, case):
     """Fixed temperature, 4096 restarts; tolerance 4.5 standard errors on <E>."""
