@@ -84,7 +84,7 @@ __device__ __forceinline__ uint64_t bernoulli_mask(const ClusterArgs &a, uint32_
     for (int g = 0; g < (a.P + 3) / 4; ++g) {
         if (((want >> (4 * g)) & 0xFull) == 0) continue; // no candidate bond among these four slices
         uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (tagbase + (uint32_t)g), a.keys, rnd);
+        mcs_philox4x32_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (tagbase + (uint32_t)g), a.keys, rnd);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (rnd[j] < p_thr) m |= 1ull << (4 * g + j);
@@ -189,7 +189,7 @@ __global__ void cluster_flip_kernel(const __grid_constant__ ClusterArgs a)
         const int32_t root = uf_find(a.L, a.Rl, r, (int32_t)(i * P + k));
         if (root == groot) continue; // tied to the field: stays
         uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, (uint32_t)root, a.sweep_lo, (a.sweep_hi << 8) | TAG_CL_FLIP, a.keys, rnd);
+        mcs_philox4x32_rk(c0, (uint32_t)root, a.sweep_lo, (a.sweep_hi << 8) | TAG_CL_FLIP, a.keys, rnd);
         if (rnd[0] & 1u) flip |= 1ull << k;
     }
     if (!flip) return;

@@ -118,20 +118,27 @@ int mcs_state_reserve_stage(mcs_state *st, size_t bytes);
 int mcs_instance_scratch_state(mcs_instance *inst, int kind, int64_t R, int64_t P, mcs_state **out);
 
 // ------------------------------------------------------------------------------------------
-// Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  Key = the user's 64-bit seed
+// Philox4x32 counter-based RNG (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11) with
+// MCS_PHILOX_ROUNDS = 7 rounds: the fewest for which the authors report a clean BigCrush ("Philox4x32-7 is
+// Crush-resistant", their Table 2); ten is their default with a safety margin.  The generator is the binding
+// cost of the sweep kernels (45 % of the PIQMC pass at ten rounds), so the margin is spent here:
+// -DMCS_PHILOX_ROUNDS=10 restores it.  Key = the user's 64-bit seed
 // (uniform over the launch); counter = (replica or word index, site, sweep, call tag), so a
 // replica's stream does not depend on launch geometry or on how replicas are sharded over GPUs.
 // ------------------------------------------------------------------------------------------
+#ifndef MCS_PHILOX_ROUNDS
+#define MCS_PHILOX_ROUNDS 7
+#endif
 #define MCS_PHILOX_M0 0xD2511F53u
 #define MCS_PHILOX_M1 0xCD9E8D57u
 #define MCS_PHILOX_W0 0x9E3779B9u
 #define MCS_PHILOX_W1 0xBB67AE85u
 
-__host__ __device__ __forceinline__ void mcs_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+__host__ __device__ __forceinline__ void mcs_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                            uint32_t k0, uint32_t k1, uint32_t out[4])
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < MCS_PHILOX_ROUNDS; ++r) {
 #ifdef __CUDA_ARCH__
         uint32_t hi0 = __umulhi(MCS_PHILOX_M0, c0), lo0 = MCS_PHILOX_M0 * c0;
         uint32_t hi1 = __umulhi(MCS_PHILOX_M1, c2), lo1 = MCS_PHILOX_M1 * c2;
@@ -155,18 +162,18 @@ __host__ __device__ __forceinline__ void mcs_philox4x32_10(uint32_t c0, uint32_t
     out[3] = c3;
 }
 
-// Same generator with the ten round keys precomputed on the host (rk[2r] = k0 + r W0,
+// Same generator with the round keys precomputed on the host (rk[2r] = k0 + r W0,
 // rk[2r+1] = k1 + r W1).  The keys then sit in the kernel-parameter constant bank and feed the
 // 3-input XOR directly: 4 instructions per round (2 IMAD.WIDE + 2 LOP3) instead of 6.
 struct mcs_philox_keys {
-    uint32_t rk[20];
+    uint32_t rk[2 * MCS_PHILOX_ROUNDS];
 };
 
 inline mcs_philox_keys mcs_philox_expand(uint64_t seed)
 {
     mcs_philox_keys k;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < MCS_PHILOX_ROUNDS; ++r) {
         k.rk[2 * r] = k0;
         k.rk[2 * r + 1] = k1;
         k0 += MCS_PHILOX_W0;
@@ -175,11 +182,11 @@ inline mcs_philox_keys mcs_philox_expand(uint64_t seed)
     return k;
 }
 
-__device__ __forceinline__ void mcs_philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+__device__ __forceinline__ void mcs_philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                      const mcs_philox_keys &k, uint32_t out[4])
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < MCS_PHILOX_ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(MCS_PHILOX_M0, c0), lo0 = MCS_PHILOX_M0 * c0;
         const uint32_t hi1 = __umulhi(MCS_PHILOX_M1, c2), lo1 = MCS_PHILOX_M1 * c2;
         const uint32_t n0 = hi1 ^ c1 ^ k.rk[2 * r];
@@ -325,7 +332,7 @@ __device__ __forceinline__ void mcs_decide_call(uint32_t &chA, uint32_t &chB, ui
                                                 const mcs_pow2_table &pow2, uint32_t tie_thr, uint2 *slot)
 {
     uint32_t x[4];
-    mcs_philox4x32_10_rk(c0, c1, c2, c3, keys, x);
+    mcs_philox4x32_rk(c0, c1, c2, c3, keys, x);
     chA = 0;
     chB = 0;
     uint32_t smin = 0xFFFFFFFFu;
@@ -349,8 +356,8 @@ __device__ __noinline__ uint2 mcs_refine_call(uint32_t accA, uint32_t accB, cons
                                               uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
     uint32_t x[4], f[4];
-    mcs_philox4x32_10(c0, c1, c2, c3, k0, k1, x);
-    mcs_philox4x32_10(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
+    mcs_philox4x32(c0, c1, c2, c3, k0, k1, x);
+    mcs_philox4x32(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
     uint32_t chA = 0, chB = 0; // reject bit of byte i at bit 8 i
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -375,7 +382,7 @@ __device__ __forceinline__ void mcs_decide_call16(uint32_t (&ch)[4], uint32_t &f
                                                   const mcs_pow2_table &pow2, uint32_t tie_thr, uint4 *slot)
 {
     uint32_t x[4];
-    mcs_philox4x32_10_rk(c0, c1, c2, c3, keys, x);
+    mcs_philox4x32_rk(c0, c1, c2, c3, keys, x);
     uint32_t smin = 0xFFFFFFFFu;
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(slot);
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(acc[0]), "r"(acc[1]), "r"(acc[2]),
@@ -400,8 +407,8 @@ static __device__ __noinline__ uint4 mcs_refine_call16(uint32_t a0, uint32_t a1,
                                                 uint32_t k1)
 {
     uint32_t x[4], f[4];
-    mcs_philox4x32_10(c0, c1, c2, c3, k0, k1, x);
-    mcs_philox4x32_10(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
+    mcs_philox4x32(c0, c1, c2, c3, k0, k1, x);
+    mcs_philox4x32(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
     const uint32_t acc[4] = {a0, a1, a2, a3};
     uint32_t ch[4] = {0u, 0u, 0u, 0u}; // reject bit of field i at bit 16 i
 #pragma unroll

@@ -135,14 +135,14 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
         const uint32_t rep = a.replica_offset + (uint32_t)(col / P);
         if ((k & 3) == 0) {
             uint32_t rnd[4];
-            mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(k >> 2), a.keys, rnd);
+            mcs_philox4x32_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(k >> 2), a.keys, rnd);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (k + j < P) uloc[m * kTC + c + j] = __log2f((float)rnd[j] + 1.0f) - 32.0f;
         }
         if (a.global_moves && k == 0) {
             uint32_t rnd[4];
-            mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
+            mcs_philox4x32_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
             uglob[m * (kTC / 2) + c / P] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
         }
     }
@@ -287,7 +287,7 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
         const int m = e / (NREP * G4), rr = (e / G4) % NREP, g = e % G4;
         const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * P) / P);
         uint32_t rnd[4];
-        mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)g, a.keys, rnd);
+        mcs_philox4x32_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)g, a.keys, rnd);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (4 * g + j < P) uloc[m * kTC + rr * P + 4 * g + j] = __log2f((float)rnd[j] + 1.0f) - 32.0f;
@@ -297,7 +297,7 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
             const int m = e / NREP, rr = e % NREP;
             const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * P) / P);
             uint32_t rnd[4];
-            mcs_philox4x32_10_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
+            mcs_philox4x32_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
             uglob[m * (kTC / 2) + rr] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
         }
     }

@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
             idx |= (uint32_t)((tl >> k) & 1ull) << NPL;
             idx |= (uint32_t)((tr >> k) & 1ull) << (NPL + 1);
             uint32_t rnd[4];
-            mcs_philox4x32_10_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
+            mcs_philox4x32_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
             if (rnd[0] <= ~lut[idx]) w ^= 1ull << k;
         }
     }
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
 #pragma unroll
         for (int hh = 0; hh < (FUSE ? 2 : 1); ++hh) {
             uint32_t rnd[4];
-            mcs_philox4x32_10_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
+            mcs_philox4x32_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
             if (rnd[0] <= mcs_accept_threshold(dE[hh], a.nl2e_over_t)) w ^= FUSE ? (pm1 << (32 * hh)) : pm1;
         }
     }
@@ -460,7 +460,7 @@ __device__ __forceinline__ uint64_t phase_direct(const PiqmcPass &a, int site, l
     for (int q4 = 0; q4 < 8; ++q4) {
         if (8 * q4 + PARITY >= P) continue;
         uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(PARITY * 8 + q4), a.keys, rnd);
+        mcs_philox4x32_rk(c0, c1, c2, c3hi | (uint32_t)(PARITY * 8 + q4), a.keys, rnd);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int q = 4 * q4 + i;
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_direct_pass_kernel(const __
             dE += ((x >> k) & 1ull) ? -cj : cj;
         }
         uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
+        mcs_philox4x32_rk(c0, c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
         if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= 1ull << k;
     }
     if (a.global_moves) {
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_direct_pass_kernel(const __
             dE += cj * (float)(P - 2 * __popcll(x));
         }
         uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
+        mcs_philox4x32_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
         if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
     }
     a.W[(long long)site * a.Rpad + r] = w;
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __gr
     const int nbytes = (P + 7) >> 3;
     uint32_t rnd[4];
     for (int k = 0; k < P; ++k) {
-        if ((k & 3) == 0) mcs_philox4x32_10_rk(c0, c1, c2, c3hi | (uint32_t)(k >> 2), a.keys, rnd);
+        if ((k & 3) == 0) mcs_philox4x32_rk(c0, c1, c2, c3hi | (uint32_t)(k >> 2), a.keys, rnd);
         const uint32_t sk = (uint32_t)(w >> k) & 1u;
         float dE = 0.0f;
         if (NPL > 0) {
@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __gr
                 dE += cj * (float)(P - 2 * __popcll((w ^ a.W[(long long)nbj * a.Rpad + r]) & pmask));
             }
         }
-        mcs_philox4x32_10_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
+        mcs_philox4x32_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
         if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
     }
     a.W[(long long)site * a.Rpad + r] = w;
@@ -787,7 +787,7 @@ __global__ void piqmc_init_kernel(uint64_t *W, long long N, long long R, long lo
     if (t >= N * Rpad) return;
     const long long i = t / Rpad, r = t % Rpad;
     uint32_t rnd[4];
-    mcs_philox4x32_10(replica_offset + (uint32_t)r, (uint32_t)i, 0u, MCS_TAG_INIT, key0, key1, rnd);
+    mcs_philox4x32(replica_offset + (uint32_t)r, (uint32_t)i, 0u, MCS_TAG_INIT, key0, key1, rnd);
     const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
     W[i * Rpad + r] = (r < R && (rnd[0] & 1u)) ? pmask : 0ull;
 }

@@ -123,7 +123,7 @@ static __device__ __noinline__ uint32_t rd_refine_draw(uint32_t c0, uint32_t i, 
                                                        uint32_t k1)
 {
     uint32_t x[4];
-    mcs_philox4x32_10(c0, i >> 2, c2, c3, k0, k1, x);
+    mcs_philox4x32(c0, i >> 2, c2, c3, k0, k1, x);
     return x[i & 3u] >> 16;
 }
 
@@ -375,7 +375,7 @@ struct IsingSite {
     __device__ __forceinline__ void draw(int q) const
     { // priorities and the upper halves of the uniforms
         uint32_t x[4];
-        mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
+        mcs_philox4x32_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
         reinterpret_cast<uint4 *>(pu)[q] = make_uint4(x[0], x[1], x[2], x[3]);
     }
     __device__ __forceinline__ Acc begin(int i) const { return Acc{w[i], 0.0f}; }
@@ -474,9 +474,9 @@ struct RotorSite {
     __device__ __forceinline__ void draw(int q) const
     {
         uint32_t x[4];
-        mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
+        mcs_philox4x32_rk(c0, (uint32_t)q, c2, c3base | kTagPrio, a.keys, x);
         reinterpret_cast<uint4 *>(pu)[q] = make_uint4(x[0], x[1], x[2], x[3]);
-        mcs_philox4x32_10_rk(c0, (uint32_t)q, c2, c3base | kTagProp, a.keys, x);
+        mcs_philox4x32_rk(c0, (uint32_t)q, c2, c3base | kTagProp, a.keys, x);
         reinterpret_cast<uint4 *>(prop)[q] = make_uint4(x[0], x[1], x[2], x[3]);
     }
     __device__ __forceinline__ Acc begin(int i) const { return a.field ? __ldg(hrow + i) : 0.0f; }

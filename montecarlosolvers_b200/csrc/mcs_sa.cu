@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kWarps * 32) sa_direct_pass_kernel(const __gri
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         uint32_t rnd[4];
-        mcs_philox4x32_10_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)q, a.keys, rnd);
+        mcs_philox4x32_rk(c0, c1, a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)q, a.keys, rnd);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int b = 8 * i + 7 - q;
@@ -207,7 +207,7 @@ __global__ void sa_init_kernel(uint32_t *V, long long N, long long R, long long 
         if (r >= R) break;
         uint32_t rnd[4];
         // same draw as piqmc_init_kernel: replica r starts from the same spins in both solvers
-        mcs_philox4x32_10(replica_offset + (uint32_t)r, (uint32_t)i, 0u, MCS_TAG_INIT, key0, key1, rnd);
+        mcs_philox4x32(replica_offset + (uint32_t)r, (uint32_t)i, 0u, MCS_TAG_INIT, key0, key1, rnd);
         v |= (rnd[0] & 1u) << b;
     }
     V[i * G + g] = v;

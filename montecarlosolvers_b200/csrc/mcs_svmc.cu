@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_con
     uint32_t x[4];
     const uint32_t c0 = (a.replica_offset >> 2) + (uint32_t)(r >> 2);
     const uint32_t c3 = (a.sweep_hi << 8) | MCS_TAG_SVMC;
-    mcs_philox4x32_10_rk(c0, (uint32_t)site, a.sweep_lo, c3, a.keys, x);
+    mcs_philox4x32_rk(c0, (uint32_t)site, a.sweep_lo, c3, a.keys, x);
     float tp[4], cp[4], gap[4];
     const bool u0 = svmc_decide(a, z.x, th.x, cz.x, x[0], tp[0], cp[0], gap[0]);
     const bool u1 = svmc_decide(a, z.y, th.y, cz.y, x[1], tp[1], cp[1], gap[1]);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kWarps * 32) svmc_pass_kernel(const __grid_con
     const bool u3 = svmc_decide(a, z.w, th.w, cz.w, x[3], tp[3], cp[3], gap[3]);
     if ((u0 | u1 | u2 | u3) || a.always_refine) { // rare (2^-10 per thread): the low half of the uniforms
         uint32_t f[4];
-        mcs_philox4x32_10_rk(c0, (uint32_t)site, a.sweep_lo, c3 | MCS_TAG_REFINE, a.keys, f);
+        mcs_philox4x32_rk(c0, (uint32_t)site, a.sweep_lo, c3 | MCS_TAG_REFINE, a.keys, f);
         const float k32 = 1.0f / 4294967296.0f;
         if (u0 && (float)f[0] * k32 < gap[0]) { th.x = tp[0]; cz.x = cp[0]; }
         if (u1 && (float)f[1] * k32 < gap[1]) { th.y = tp[1]; cz.y = cp[1]; }
