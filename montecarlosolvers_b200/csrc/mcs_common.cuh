@@ -227,6 +227,7 @@ enum {
     MCS_TAG_LAST_SLICE = 16, // PIQMC odd-P closing slice
     MCS_TAG_GLOBAL = 17,     // PIQMC world-line move
     MCS_TAG_SVMC = 18,       // SVMC proposal + acceptance
+    MCS_TAG_GLOBAL2 = 19,    // PIQMC world-line move, members 4.. of a packed group
     MCS_TAG_REFINE = 0x80,   // OR-ed into a group tag: second half of the lazily refined uniforms
     MCS_TAG_INIT = 0x40000000u
 };

@@ -54,6 +54,14 @@ struct PiqmcPass {
     int global_moves;
     uint32_t tie_thr; // 0x20000; 0xffffffff evaluates the refinement call for every attempt (test hook)
     long long half;   // fused mode (P <= 32, two replicas per thread): replica r is paired with r + half
+    // packed mode (even P <= 20): a thread owns `pk` replicas as consecutive P-bit segments of its working word
+    // (pk P <= 64 bits: P = 20 fills 60 of them).  Replicas are grouped on their GLOBAL index: block b = 32 pk
+    // consecutive replicas, lane l of the block's warp owns members b 32 pk + 32 m + l, m = 0 .. pk - 1 (every
+    // member load of a warp is one coalesced 256-byte line)
+    int pk;                // 0: off
+    long long group0;      // global index of the block warp 0 owns
+    long long nvalid;      // replicas of this window that exist (members outside [0, nvalid) are skipped)
+    uint64_t seg_lsb;      // bit 0 of every segment
 };
 
 __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
@@ -79,6 +87,21 @@ __device__ __forceinline__ uint64_t rotr_ring2(uint64_t w, int P, uint64_t pm2)
     const uint64_t bp = b0_shift(P);
     return ((w >> 1) & pm2 & ~bp) | ((w << (P - 1)) & bp);
 }
+
+// Packed mode: pk world lines of P slices each at bit offsets 0, P, 2 P, ...; the ring closes inside each segment
+// (lsb = bit 0 of every segment, msb = lsb << (P - 1)).
+__device__ __forceinline__ uint64_t rotl_seg(uint64_t w, int P, uint64_t lsb)
+{
+    return ((w << 1) & ~lsb) | ((w >> (P - 1)) & lsb);
+}
+__device__ __forceinline__ uint64_t rotr_seg(uint64_t w, int P, uint64_t lsb)
+{
+    const uint64_t msb = lsb << (P - 1);
+    return ((w >> 1) & ~msb) | ((w << (P - 1)) & msb);
+}
+
+// how the working word of a thread is made up
+enum { MODE_PLAIN = 0, MODE_FUSE = 1, MODE_PACK = 2 };
 
 // Pattern-index bits live at bit positions SH .. SH+NPL+1 of a field of an index word: one BYTE per slice up to
 // 8 planes, one HALF WORD per slice for 9 and 10 planes (FW = field width).  Where it fits (up to 6 planes, and
@@ -215,16 +238,23 @@ __device__ __forceinline__ void decide_pair(uint32_t &rej, uint32_t &flags, uint
 // against the (complemented) thresholds in lut[].  Returns the flip mask.
 // FUSE: the two 32-bit halves are two replicas (counters c0h[0], c0h[1]) of P <= 32 slices each; every half then
 // uses the tags and the skip rule of half 0, so a replica gets exactly the decisions it would get alone.
-template <int NPL, int PARITY, bool FULL, bool FUSE>
+// PACK: pk replicas of one group in consecutive P-bit segments, ONE counter (the global group index): the word is
+// treated like a single world line of pk P slices (tags and skip rule of the plain mode with P -> `bits`), only
+// the Trotter ring closes per segment.
+template <int NPL, int PARITY, bool FULL, int MODE>
 __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w, int P, uint64_t pmask,
                                           uint64_t allowed, const uint32_t *lut, const uint32_t (&c0h)[2], uint32_t c1,
                                           uint32_t c2, uint32_t c3hi, const mcs_philox_keys &keys,
-                                          const mcs_pow2_table &pow2, uint32_t tie_thr, uint2 *bounce, int nthreads)
+                                          const mcs_pow2_table &pow2, uint32_t tie_thr, uint2 *bounce, int nthreads,
+                                          uint64_t seg_lsb, int bits)
 {
     constexpr int NPP = LutGeom<NPL>::NPP, NPAIR = LutGeom<NPL>::NPAIR;
+    constexpr bool FUSE = MODE == MODE_FUSE;
     // bit k: slice k anti-aligned with slice k-1 / k+1
-    const uint64_t tl = w ^ (FUSE ? rotl_ring2(w, P, pmask) : rotl_ring(w, P, pmask));
-    const uint64_t tr = w ^ (FUSE ? rotr_ring2(w, P, pmask) : rotr_ring(w, P, pmask));
+    const uint64_t tl = w ^ (MODE == MODE_PACK ? rotl_seg(w, P, seg_lsb)
+                                               : (FUSE ? rotl_ring2(w, P, pmask) : rotl_ring(w, P, pmask)));
+    const uint64_t tr = w ^ (MODE == MODE_PACK ? rotr_seg(w, P, seg_lsb)
+                                               : (FUSE ? rotr_ring2(w, P, pmask) : rotr_ring(w, P, pmask)));
     const uint32_t c0 = c0h[0];
     uint32_t m[2][NPAIR];
 #pragma unroll
@@ -243,7 +273,7 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
         // S0 = 14 + PARITY (q = 0) or 6 + PARITY (q = 1); tag = 8 H + 4 PARITY + q
         uint4 *slot16 = reinterpret_cast<uint4 *>(bounce);
 #define MCS_CALL16(H, Q, S0)                                                                                 \
-    if (FULL || 32 * H + (S0) - 6 < P) {                                                                     \
+    if (FULL || 32 * H + (S0) - 6 < bits) {                                                                  \
         decide_call16<NPL, (S0), PARITY>(rej[H], flags, m[H], lut, c0, c1, c2,                               \
                                          c3hi | (uint32_t)(8 * H + 4 * PARITY + (Q)), keys, pow2, tie_thr,   \
                                          slot16 + (2 * H + (Q)) * nthreads);                                 \
@@ -268,7 +298,7 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
     // pair q = 2 H + (GA > 3) is flags bit 3 - q after the four Horner steps; a pair entirely beyond the last
     // slice is skipped (warp-uniform branch) but still shifts the flags
 #define MCS_PAIR(H, GA, GB)                                                                                  \
-    if (FULL || (FUSE ? 0 : 32 * H) + 7 - (GB) < P) {                                                        \
+    if (FULL || (FUSE ? 0 : 32 * H) + 7 - (GB) < bits) {                                                     \
         const uint32_t accA = gather_index<NPP, (GA), PARITY>(m[H], pow2);                                   \
         const uint32_t accB = gather_index<NPP, (GB), PARITY>(m[H], pow2);                                   \
         decide_pair<NPL, (GA), (GB)>(rej[H], flags, accA, accB, lut, c0h[FUSE ? H : 0], c1, c2,              \
@@ -302,13 +332,19 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
 #ifndef MCS_LUT_MINBLOCKS
 #define MCS_LUT_MINBLOCKS(NPL) ((NPL) >= 7 ? 4 : (NPL) >= 5 ? 6 : 8)
 #endif
-// FUSE: P <= 32 and the thread owns TWO replicas, r and r + a.half, as the low and the high half of one working
+// MODE_FUSE: P <= 32 and the thread owns TWO replicas, r and r + a.half, as the low and the high half of one working
 //       word -- a word's worth of Philox calls, transpositions and decisions then serves 2 P instead of P
 //       attempts (P = 20: 6.5e11 -> 1.0e12 attempts/s).  The decisions of a replica do not depend on the mode.
-template <int NPL, int WARPS, bool FULL, int FLD, bool FUSE>
+// MODE_PACK: even P <= 20 and the thread owns a.pk = min(floor(64 / P), 6) replicas as consecutive P-bit segments:
+//       P = 20 uses 60 of the 64 attempt slots of a word instead of 40.  Groups are defined on GLOBAL replica
+//       indices (see PiqmcPass::pk) and the Philox counter is the group's index, so results do not depend on how
+//       replicas are sharded over GPUs, windows or calls; members that lie outside this window are neither read
+//       nor written.
+template <int NPL, int WARPS, bool FULL, int FLD, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
-    static_assert(!(FULL && FUSE), "fused mode is for P <= 32");
+    static_assert(!(FULL && MODE != MODE_PLAIN), "fused / packed modes are for P <= 32");
+    constexpr bool FUSE = MODE == MODE_FUSE, PACK = MODE == MODE_PACK;
     constexpr int ENT = LutGeom<NPL>::ENT, NQ = NPL - FLD;
     __shared__ uint32_t s_lut[ENT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -316,7 +352,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     const unsigned si = blockIdx.y + 65535u * blockIdx.z;
     if (si >= (unsigned)a.nsites) return; // only when the colour class has more than 65535 sites (CTA-uniform)
     const int site = __ldg(&a.sites[si]);
-    const long long r = ((long long)blockIdx.x * WARPS + warp) * 32 + lane;
+    const long long r = ((long long)blockIdx.x * WARPS + warp) * 32 + lane; // replica (PACK: group) of this thread
 
     // ---- per-site coefficients (CTA-uniform) and the acceptance-threshold table ---------------
     float c[NPL];
@@ -342,17 +378,33 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
 
     // ---- this lane's world line(s) and the in-plane anti-alignment planes ----------------------
     const int P = FULL ? 64 : a.P;
+    const int pk = PACK ? a.pk : 1, bits = PACK ? pk * P : P;
     const uint64_t pm1 = (FULL || P == 64) ? ~0ull : ((1ull << P) - 1ull); // one world line
-    const uint64_t pmask = FUSE ? (pm1 | (pm1 << 32)) : pm1;                 // the working word
+    const uint64_t pmask = FUSE ? (pm1 | (pm1 << 32)) : (PACK ? (bits == 64 ? ~0ull : ((1ull << bits) - 1ull)) : pm1);
     // row offsets as one IMAD.WIDE.U32 each (site indices and Rpad are below 2^32)
     const uint32_t rpad = (uint32_t)a.Rpad;
-    const uint64_t *Wr = a.W + r, *Wr2 = Wr + (FUSE ? a.half : 0);
+    // PACK: member m of this thread is local replica first + 32 m (global index (group0 + warp) 32 pk + 32 m + lane)
+    const long long gwarp = (long long)blockIdx.x * WARPS + warp;
+    const long long first = PACK ? (a.group0 + gwarp) * 32 * pk + lane - (long long)a.replica_offset : r;
+    const uint64_t *Wr = a.W + first, *Wr2 = Wr + (FUSE ? a.half : 0);
+    uint32_t present = 0; // PACK: members that exist in this window
+    if (PACK)
+        for (int m = 0; m < pk; ++m)
+            if (first + 32 * m >= 0 && first + 32 * m < a.nvalid) present |= 1u << m;
     mcs_pdl_wait(); // everything above depends on the instance and the schedule only
     auto load = [&](int row) -> uint64_t {
+        if (PACK) {
+            uint64_t v = 0;
+#pragma unroll
+            for (int m = 0; m < 6; ++m)
+                if ((present >> m) & 1u) v |= Wr[(uint64_t)(uint32_t)row * rpad + 32 * m] << (m * P);
+            return v;
+        }
         const uint64_t lo = Wr[(uint64_t)(uint32_t)row * rpad];
         return FUSE ? (lo | (Wr2[(uint64_t)(uint32_t)row * rpad] << 32)) : lo;
     };
     uint64_t w = load(site);
+    const uint64_t w0 = w;
     uint64_t pl[NPL];
 #pragma unroll
     for (int j = 0; j < NPL; ++j) pl[j] = j < NQ ? (w ^ load(nb[j])) & pmask : w; // field plane: bit set <=> s = -1
@@ -361,10 +413,11 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     else
         __syncthreads();
     const uint32_t *lut = s_lut;
-    const uint32_t c0h[2] = {a.replica_offset + (uint32_t)r, a.replica_offset + (uint32_t)(r + a.half)};
+    const uint32_t c0h[2] = {PACK ? (uint32_t)((a.group0 + gwarp) * 32 + lane) : a.replica_offset + (uint32_t)r,
+                             a.replica_offset + (uint32_t)(r + a.half)};
     const uint32_t c1 = (uint32_t)site, c2 = a.sweep_lo;
     const uint32_t c3hi = a.sweep_hi << 8;
-    const bool oddP = !FULL && (P & 1) != 0;
+    const bool oddP = !FULL && !PACK && (P & 1) != 0;
     const uint64_t last = FUSE ? b0_shift(P) : (1ull << (P - 1)); // slice P-1 of every world line in the word
     uint64_t even_allowed = 0x5555555555555555ull & pmask;
     if (oddP) even_allowed &= ~last; // slice P-1 neighbours slice 0: handled alone below
@@ -374,10 +427,10 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     __shared__ __align__(16) uint2 s_bounce[(LutGeom<NPL>::FW == 16 ? 16 : 8) * WARPS * 32];
     constexpr int kSlot = LutGeom<NPL>::FW == 16 ? 2 : 1; // uint2 per thread and call
     uint2 *bounce = s_bounce + kSlot * threadIdx.x;
-    w ^= phase<NPL, 0, FULL, FUSE>(pl, w, P, pmask, even_allowed, lut, c0h, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
-                                   bounce, WARPS * 32);
-    w ^= phase<NPL, 1, FULL, FUSE>(pl, w, P, pmask, odd_allowed, lut, c0h, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
-                                   bounce + 4 * kSlot * WARPS * 32, WARPS * 32);
+    w ^= phase<NPL, 0, FULL, MODE>(pl, w, P, pmask, even_allowed, lut, c0h, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
+                                   bounce, WARPS * 32, a.seg_lsb, bits);
+    w ^= phase<NPL, 1, FULL, MODE>(pl, w, P, pmask, odd_allowed, lut, c0h, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
+                                   bounce + 4 * kSlot * WARPS * 32, WARPS * 32, a.seg_lsb, bits);
     if (oddP) {
         const uint64_t tl = w ^ (FUSE ? rotl_ring2(w, P, pmask) : rotl_ring(w, P, pmask));
         const uint64_t tr = w ^ (FUSE ? rotr_ring2(w, P, pmask) : rotr_ring(w, P, pmask));
@@ -396,26 +449,48 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     }
 
     // ---- world-line move: flip all P slices of this site (qmc.pyx:405-438) ---------------------
+    // The neighbours belong to other colour classes and have not moved during this launch: their anti-alignment
+    // with the UPDATED word is the old plane XOR this pass's flips (no second read of the neighbour words).
     if (a.global_moves) {
-        float dE[2] = {0.0f, 0.0f};
+        const uint64_t flips = w ^ w0;
+        if (PACK) { // one decision per member; one Philox call serves four members
+            uint32_t rnd[4];
+            for (int m = 0; m < pk; ++m) {
+                if ((m & 3) == 0)
+                    mcs_philox4x32_rk(c0h[0], c1, c2, c3hi | (m == 0 ? MCS_TAG_GLOBAL : MCS_TAG_GLOBAL2), a.keys, rnd);
+                const uint64_t seg = pm1 << (m * P);
+                float dE = 0.0f;
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            const uint64_t x = j < NQ ? (w ^ load(nb[j])) & pmask : w & pmask;
-            if (FUSE) {
-                dE[0] += c[j] * (float)(P - 2 * __popc((uint32_t)x));
-                dE[1] += c[j] * (float)(P - 2 * __popc((uint32_t)(x >> 32)));
-            } else {
-                dE[0] += c[j] * (float)(P - 2 * __popcll(x));
+                for (int j = 0; j < NPL; ++j)
+                    dE += c[j] * (float)(P - 2 * __popcll((j < NQ ? pl[j] ^ flips : w) & seg));
+                const uint32_t u = (m & 3) == 0 ? rnd[0] : (m & 3) == 1 ? rnd[1] : (m & 3) == 2 ? rnd[2] : rnd[3];
+                if (u <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= seg;
+            }
+        } else {
+            float dE[2] = {0.0f, 0.0f};
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                const uint64_t x = (j < NQ ? pl[j] ^ flips : w) & pmask;
+                if (FUSE) {
+                    dE[0] += c[j] * (float)(P - 2 * __popc((uint32_t)x));
+                    dE[1] += c[j] * (float)(P - 2 * __popc((uint32_t)(x >> 32)));
+                } else {
+                    dE[0] += c[j] * (float)(P - 2 * __popcll(x));
+                }
+            }
+#pragma unroll
+            for (int hh = 0; hh < (FUSE ? 2 : 1); ++hh) {
+                uint32_t rnd[4];
+                mcs_philox4x32_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
+                if (rnd[0] <= mcs_accept_threshold(dE[hh], a.nl2e_over_t)) w ^= FUSE ? (pm1 << (32 * hh)) : pm1;
             }
         }
-#pragma unroll
-        for (int hh = 0; hh < (FUSE ? 2 : 1); ++hh) {
-            uint32_t rnd[4];
-            mcs_philox4x32_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
-            if (rnd[0] <= mcs_accept_threshold(dE[hh], a.nl2e_over_t)) w ^= FUSE ? (pm1 << (32 * hh)) : pm1;
-        }
     }
-    if (FUSE) {
+    if (PACK) {
+#pragma unroll
+        for (int m = 0; m < 6; ++m)
+            if ((present >> m) & 1u) a.W[(uint64_t)(uint32_t)site * rpad + first + 32 * m] = (w >> (m * P)) & pm1;
+    } else if (FUSE) {
         a.W[(uint64_t)(uint32_t)site * rpad + r] = w & 0xFFFFFFFFull;
         a.W[(uint64_t)(uint32_t)site * rpad + r + a.half] = w >> 32;
     } else {
@@ -847,29 +922,50 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
     PiqmcPass a = a0;
     const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
     const bool no_fuse = getenv("MCS_NO_FUSE") != nullptr; // tests: one replica per thread for every P
+    const bool no_pack = getenv("MCS_NO_PACK") != nullptr; // tests: at most two replicas per thread
+    if (LutGeom<NPL>::FW == 8 && a.P <= 20 && (a.P & 1) == 0 && !no_fuse && !no_pack) { // pk >= 3
+        // pk = floor(64 / P) replicas per thread (at most 6: loads per thread), blocks of 32 pk GLOBAL replicas per warp
+        a.pk = std::min(64 / a.P, 6);
+        const long long blk = 32ll * a.pk; // replicas per warp
+        a.group0 = (long long)a.replica_offset / blk;
+        const long long gw = ((long long)a.replica_offset + a.nvalid - 1) / blk - a.group0 + 1; // warps
+        const int wf = gw >= 4 ? 4 : (gw >= 2 ? 2 : 1);
+        a.seg_lsb = 0;
+        for (int m = 0; m < a.pk; ++m) a.seg_lsb |= 1ull << (m * a.P);
+        a.half = 0;
+        const dim3 grid((unsigned)((gw + wf - 1) / wf), ny, nz);
+        if (wf == 4)
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN>, grid, dim3(128), s, a);
+        else if (wf == 2)
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN>, grid, dim3(64), s, a);
+        else
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN>, grid, dim3(32), s, a);
+        return;
+    }
+    a.pk = 0;
     if (LutGeom<NPL>::FW == 8 && a.P <= 32 && a.G % 2 == 0 && !no_fuse) {
         // two replicas per thread: r and r + half, half = the window's replicas / 2
         const int gf = a.G / 2, wf = (gf % 4 == 0) ? 4 : (gf % 2 == 0) ? 2 : 1;
         a.half = (long long)gf * 32;
         const dim3 grid((unsigned)(gf / wf), ny, nz);
         if (wf == 4)
-            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, LutGeom<NPL>::FW == 8>, grid, dim3(128), s, a);
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_FUSE : MODE_PLAIN>, grid, dim3(128), s, a);
         else if (wf == 2)
-            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, LutGeom<NPL>::FW == 8>, grid, dim3(64), s, a);
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_FUSE : MODE_PLAIN>, grid, dim3(64), s, a);
         else
-            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, LutGeom<NPL>::FW == 8>, grid, dim3(32), s, a);
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_FUSE : MODE_PLAIN>, grid, dim3(32), s, a);
         return;
     }
     a.half = 0;
     const dim3 grid((unsigned)(a.G / warps), ny, nz);
     if (a.P == 64 && warps == 4)
-        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD, false>, grid, dim3(128), s, a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD, MODE_PLAIN>, grid, dim3(128), s, a);
     else if (warps == 4)
-        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, false>, grid, dim3(128), s, a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, MODE_PLAIN>, grid, dim3(128), s, a);
     else if (warps == 2)
-        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, false>, grid, dim3(64), s, a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, MODE_PLAIN>, grid, dim3(64), s, a);
     else
-        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, false>, grid, dim3(32), s, a);
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, MODE_PLAIN>, grid, dim3(32), s, a);
 }
 
 template <int NPL>
@@ -962,6 +1058,11 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     a.replica_offset = (uint32_t)(replica_offset + (uint64_t)st->win_lo());
     a.global_moves = global_moves ? 1 : 0;
     a.tie_thr = mcs_tie_threshold();
+    a.half = 0;
+    a.pk = 0;
+    a.group0 = 0;
+    a.nvalid = st->win_valid();
+    a.seg_lsb = 0;
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;

@@ -409,27 +409,68 @@ def test_two_replicas_per_thread_do_not_change_any_decision(mcs, P):
     """For P <= 32 the PIQMC pass handles replicas r and r + R/2 in the two halves of one working word
     (mcs_piqmc.cu, FUSE).  Every replica keeps its own Philox counter and the tags of half 0, so the trajectories
     must equal those of the one-replica-per-thread kernel (MCS_NO_FUSE=1) bit for bit -- odd and even P, fields,
-    world-line moves, a batch that is (192) and one that is not (96: falls back by itself) a multiple of 64."""
+    world-line moves, a batch that is (192) and one that is not (96: falls back by itself) a multiple of 64.
+    (MCS_NO_PACK=1: even P <= 20 would otherwise take the packed mode, which has its own random stream.)"""
     _, nbs = inst.torus(6, seed=31, fields=True)
     n, S = 36, 25
     A, B = np.linspace(2.5, 0.05, S), np.ones(S)
     I = mcs.Instance(nbs)
-    for R in (192, 96):
-        c0 = (2 * np.random.RandomState(P).randint(2, size=(R, n, P)) - 1).astype(np.int8)
-        out = []
-        for no_fuse in (False, True):
-            if no_fuse:
-                os.environ["MCS_NO_FUSE"] = "1"
-            try:
-                st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
-                st.upload_spins(c0)
-                st.piqmc_sweeps(A, B, 2, 1.0 / P, global_moves=True, seed=17)
-                out.append(st.download_spins())
-                st.close()
-            finally:
-                os.environ.pop("MCS_NO_FUSE", None)
-        assert not np.array_equal(out[0], c0)
-        assert np.array_equal(out[0], out[1]), (P, R)
+    os.environ["MCS_NO_PACK"] = "1"
+    try:
+        for R in (192, 96):
+            c0 = (2 * np.random.RandomState(P).randint(2, size=(R, n, P)) - 1).astype(np.int8)
+            out = []
+            for no_fuse in (False, True):
+                if no_fuse:
+                    os.environ["MCS_NO_FUSE"] = "1"
+                try:
+                    st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+                    st.upload_spins(c0)
+                    st.piqmc_sweeps(A, B, 2, 1.0 / P, global_moves=True, seed=17)
+                    out.append(st.download_spins())
+                    st.close()
+                finally:
+                    os.environ.pop("MCS_NO_FUSE", None)
+            assert not np.array_equal(out[0], c0)
+            assert np.array_equal(out[0], out[1]), (P, R)
+    finally:
+        os.environ.pop("MCS_NO_PACK", None)
+
+
+@pytest.mark.parametrize("P", [2, 6, 10, 20])
+def test_packed_groups_are_defined_on_global_replica_indices(mcs, P):
+    """Even P <= 20: a thread owns floor(64 / P) (at most 6) replicas as consecutive P-bit segments of its working
+    word (mcs_piqmc.cu, MODE_PACK); groups and Philox counters are functions of the GLOBAL replica index, so a shard
+    that starts in the middle of a group, has a ragged end, or continues a schedule in a second call reproduces the
+    one-batch, one-call result bit for bit; and the mode is really on (differs from the two-per-thread stream)."""
+    _, nbs = inst.torus(6, seed=32, fields=True)
+    n, S, R = 36, 14, 157
+    A, B = np.linspace(2.5, 0.05, S), np.ones(S)
+    I = mcs.Instance(nbs)
+    c0 = (2 * np.random.RandomState(P).randint(2, size=(R, n, P)) - 1).astype(np.int8)
+
+    def run(lo, hi, splits=((0, S),), env=None):
+        if env:
+            os.environ[env] = "1"
+        try:
+            st = mcs.State(I, mcs._lib.KIND_PIQMC, hi - lo, P)
+            st.upload_spins(np.ascontiguousarray(c0[lo:hi]))
+            for a, b in splits:
+                st.piqmc_sweeps(A[a:b], B[a:b], 2, 1.0 / P, global_moves=True, seed=23, replica_offset=lo,
+                                sweep_offset=2 * a)
+            out = st.download_spins()
+            st.close()
+            return out
+        finally:
+            if env:
+                os.environ.pop(env, None)
+
+    full = run(0, R)
+    assert not np.array_equal(full, c0)
+    for lo, hi in ((0, 64), (7, 100), (65, R), (32, 33)):
+        assert np.array_equal(run(lo, hi), full[lo:hi]), (P, lo, hi)
+    assert np.array_equal(run(7, 100, splits=((0, 5), (5, S))), full[7:100])
+    assert not np.array_equal(run(0, R, env="MCS_NO_PACK"), full)
 
 
 def test_time_dependent_tables_production(mcs):
