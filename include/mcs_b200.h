@@ -22,6 +22,11 @@
  *     field (tools.pyx:28-96; consumed at qmc.pyx:114-125, sa.pyx:84-94, svmc.pyx:98-108).
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
  *     MCS_ENODEVICE.
+ *   - threads: the one-shot host-buffer calls (mcs_*_anneal*, mcs_exact_*) may be issued from several threads
+ *     (the reference released the GIL in its loops, qmc.pyx:92, sa.pyx:65); calls on the SAME instance are
+ *     serialised by a lock inside the instance (they share its scratch batches, staging buffer and stream),
+ *     calls on different instances run concurrently.  Calls on an mcs_state are the caller's to order: one
+ *     thread at a time per state and per instance.
  */
 #ifndef MCS_B200_H
 #define MCS_B200_H

@@ -235,6 +235,7 @@ extern "C" int mcs_piqmc_anneal(mcs_instance *inst, const double *A, const doubl
                                 uint64_t replica_offset, double *energies_out)
 {
     MCS_REQUIRE(inst && confs, MCS_EINVAL, "mcs_piqmc_anneal: NULL argument");
+    std::lock_guard<std::recursive_mutex> one_call_at_a_time(inst->call_mutex);
     const auto host_t0 = std::chrono::steady_clock::now();
     auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     MCS_REQUIRE((double)temp * (double)P != 0.0 || S == 0, MCS_EZERODIV, "float division");
@@ -406,6 +407,7 @@ extern "C" int mcs_piqmc_anneal_best(mcs_instance *inst, const double *A, const 
                                      double *best_energy, int32_t *best_slice, int8_t *best_conf)
 {
     MCS_REQUIRE(inst && spins_in, MCS_EINVAL, "mcs_piqmc_anneal_best: NULL argument");
+    std::lock_guard<std::recursive_mutex> one_call_at_a_time(inst->call_mutex);
     MCS_REQUIRE((double)temp * (double)P != 0.0 || S == 0, MCS_EZERODIV, "float division");
     MCS_REQUIRE(S >= 0 && mcsteps >= 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_piqmc_anneal_best: bad schedule");
     mcs_state *st = nullptr;
@@ -433,6 +435,7 @@ extern "C" int mcs_sa_anneal(mcs_instance *inst, const double *sched, int64_t S,
                              uint64_t seed, uint64_t replica_offset, double *energies_out)
 {
     MCS_REQUIRE(inst && svec, MCS_EINVAL, "mcs_sa_anneal: NULL argument");
+    std::lock_guard<std::recursive_mutex> one_call_at_a_time(inst->call_mutex);
     mcs_state *st = nullptr;
     MCS_TRY(mcs_instance_scratch_state(inst, MCS_KIND_SA, R, 1, &st));
     MCS_TRY(mcs_state_upload_spins(st, svec));
@@ -446,6 +449,7 @@ extern "C" int mcs_svmc_anneal(mcs_instance *inst, const double *A, const double
                                float temp, double *svec, int64_t R, int tf, uint64_t seed, uint64_t replica_offset)
 {
     MCS_REQUIRE(inst && svec, MCS_EINVAL, "mcs_svmc_anneal: NULL argument");
+    std::lock_guard<std::recursive_mutex> one_call_at_a_time(inst->call_mutex);
     mcs_state *st = nullptr;
     MCS_TRY(mcs_instance_scratch_state(inst, MCS_KIND_SVMC, R, 1, &st));
     MCS_TRY(mcs_state_upload_angles(st, svec));

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,11 @@ struct mcs_instance {
     int64_t Npad = 0;    // N rounded up to the dense block size (128)
     int64_t launches = 0;
     int dynamics = 0;    // MCS_DYN_COLORED / MCS_DYN_REFERENCE: what *_sweeps and the one-shot calls run
+    // The one-shot host-buffer calls (mcs_*_anneal*, mcs_exact_*) share this instance's scratch batches, staging
+    // buffer, window fields and stream: they hold this lock for their whole duration, so concurrent callers (the
+    // reference released the GIL in its loops, qmc.pyx:92) are serialised per instance instead of corrupting each
+    // other.  Calls on resident mcs_state batches are the caller's to order.
+    std::recursive_mutex call_mutex;
     std::vector<struct mcs_state *> states; // live replica batches (orphaned if the instance dies first)
     struct mcs_state *scratch[4] = {nullptr, nullptr, nullptr, nullptr}; // per-kind batch reused by the
                                                                          // one-shot host-buffer calls
@@ -241,6 +247,21 @@ enum {
 __device__ __forceinline__ void mcs_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void mcs_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// First launch error since the last mcs_take_launch_error() on this thread: the pass launchers sit in loops of
+// thousands of launches; they record a failure here and the sweep function reports it when the loop ends.
+extern thread_local cudaError_t mcs_launch_error;
+inline cudaError_t mcs_note_launch(cudaError_t e)
+{
+    if (e != cudaSuccess && mcs_launch_error == cudaSuccess) mcs_launch_error = e;
+    return e;
+}
+inline cudaError_t mcs_take_launch_error()
+{
+    const cudaError_t e = mcs_launch_error;
+    mcs_launch_error = cudaSuccess;
+    return e;
+}
+
 template <typename Kernel, typename Args>
 inline cudaError_t mcs_launch_pdl(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, const Args &args)
 {
@@ -254,7 +275,7 @@ inline cudaError_t mcs_launch_pdl(Kernel kernel, dim3 grid, dim3 block, cudaStre
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, args);
+    return mcs_note_launch(cudaLaunchKernelEx(&cfg, kernel, args));
 }
 
 // ---- building blocks shared by the bit-packed sweep kernels (mcs_piqmc.cu, mcs_sa.cu) ---------------

@@ -753,7 +753,7 @@ static void launch_dense_tc(unsigned grid, cudaStream_t stream, const DensePass 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, dense_block_kernel_tc, a, maps);
+    mcs_note_launch(cudaLaunchKernelEx(&cfg, dense_block_kernel_tc, a, maps));
 }
 
 bool mcs_dense_supported(const mcs_instance *inst, int P)
@@ -865,6 +865,7 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
                                                                                        st->R, st->G);
     }
     inst->launches++;
+    MCS_CUDA(mcs_take_launch_error());
     MCS_CUDA(cudaGetLastError());
     if (a.trace) { // timestamps of the last block launch: start, GEMM done, prologue done, first strip decided,
                    // first strip applied, all strips done, spins written back

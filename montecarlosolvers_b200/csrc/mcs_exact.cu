@@ -1218,6 +1218,7 @@ extern "C" int mcs_exact_qmc(mcs_instance *inst, const double *A, const double *
                              int64_t *consumed)
 {
     MCS_REQUIRE(inst && confs && R > 0 && (S == 0 || (A && B)), MCS_EINVAL, "mcs_exact_qmc: bad argument");
+    std::lock_guard<std::recursive_mutex> one_call_at_a_time(inst->call_mutex);
     MCS_REQUIRE(P >= 2, MCS_EINVAL, "mcs_exact_qmc: P >= 2 required (P=1 reads out of bounds in the reference)");
     MCS_REQUIRE(libc_seeds || rand_stream, MCS_EINVAL, "mcs_exact_qmc: need libc_seeds or rand_stream");
     MCS_REQUIRE(inst->nsteps == 1, MCS_EUNSUPPORTED, "mcs_exact_qmc: time-dependent tables are an SA / SVMC feature");
@@ -1321,6 +1322,7 @@ extern "C" int mcs_exact_qmc_wolff(mcs_instance *inst, int variant, const double
 {
     MCS_REQUIRE(inst && confs && R > 0 && libc_seeds && (S == 0 || (A && B)), MCS_EINVAL,
                 "mcs_exact_qmc_wolff: bad argument");
+    std::lock_guard<std::recursive_mutex> one_call_at_a_time(inst->call_mutex);
     MCS_REQUIRE(variant >= MCS_WOLFF_WCL && variant <= MCS_WOLFF_DISS_WC3, MCS_EINVAL,
                 "mcs_exact_qmc_wolff: unknown variant %d", variant);
     MCS_REQUIRE(P >= 2, MCS_EINVAL, "mcs_exact_qmc_wolff: P >= 2 required (the reference indexes slice 1)");
@@ -1385,6 +1387,7 @@ extern "C" int mcs_exact_sa(mcs_instance *inst, const double *sched, int64_t S, 
                             const uint32_t *libc_seeds, const double *randuni, int64_t *consumed)
 {
     MCS_REQUIRE(inst && svec && R > 0 && libc_seeds && (S == 0 || sched), MCS_EINVAL, "mcs_exact_sa: bad argument");
+    std::lock_guard<std::recursive_mutex> one_call_at_a_time(inst->call_mutex);
     MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL, "mcs_exact_sa: schedule longer than the tables");
     MCS_CUDA(cudaSetDevice(inst->device));
     cudaStream_t s = inst->stream;
@@ -1434,6 +1437,7 @@ extern "C" int mcs_exact_svmc(mcs_instance *inst, const double *A, const double 
 {
     MCS_REQUIRE(inst && svec && R > 0 && libc_seeds && (S == 0 || (A && B)), MCS_EINVAL,
                 "mcs_exact_svmc: bad argument");
+    std::lock_guard<std::recursive_mutex> one_call_at_a_time(inst->call_mutex);
     MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
                 "mcs_exact_svmc: schedule longer than the tables");
     MCS_REQUIRE(randuni || tf, MCS_EINVAL,

@@ -20,6 +20,7 @@
 // errors
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
+thread_local cudaError_t mcs_launch_error = cudaSuccess;
 
 void mcs_set_error(const char *fmt, ...)
 {

@@ -1097,6 +1097,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
         }
     }
     if (d_lut4) MCS_CUDA(cudaFreeAsync(d_lut4, inst->stream));
+    MCS_CUDA(mcs_take_launch_error());
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
 }

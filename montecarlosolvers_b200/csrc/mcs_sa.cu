@@ -336,6 +336,7 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
             }
         }
     }
+    MCS_CUDA(mcs_take_launch_error());
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
 }

@@ -250,6 +250,7 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
             }
         }
     }
+    MCS_CUDA(mcs_take_launch_error());
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
 }

@@ -695,3 +695,33 @@ def test_anneal_best_slice_equals_the_separate_calls(mcs):
     I.synchronize()
     assert np.array_equal(e_d.cpu().numpy(), e_h) and np.array_equal(k_d.cpu().numpy(), k_h)
     assert np.array_equal(c_d.cpu().numpy(), c_h) and np.array_equal(e_h, eb)
+
+
+def test_one_shot_calls_from_several_threads_on_one_instance(mcs):
+    """The reference released the GIL in its loops (sa.pyx:65), so threaded callers are legitimate.  The C-ABI
+    one-shot calls of ONE instance share its scratch batch, staging buffer and stream: the lock inside the instance
+    must serialise them -- four threads calling mcs_sa_anneal directly (no Python-side lock) get exactly the
+    results of the same calls made one after another."""
+    import threading
+    _, nbs = inst.torus(12, seed=5, fields=True)
+    I = mcs.Instance(nbs)
+    L = mcs._lib.load()
+    sched = np.linspace(3.0, 0.05, 200)
+    n, R = nbs.shape[0], 96
+    starts = [(2 * np.random.RandomState(10 + t).randint(2, size=(R, n)) - 1).astype(np.int8) for t in range(4)]
+
+    def call(buf, seed):
+        mcs._lib.check(L.mcs_sa_anneal(I._h, mcs._lib.dptr(sched), sched.size, 1, buf.ctypes.data, R, seed, 0, None))
+
+    serial = [s.copy() for s in starts]
+    for t in range(4):
+        call(serial[t], 100 + t)
+    for rep in range(3):
+        threaded = [s.copy() for s in starts]
+        th = [threading.Thread(target=call, args=(threaded[t], 100 + t)) for t in range(4)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        for t in range(4):
+            assert np.array_equal(threaded[t], serial[t]), (rep, t)
