@@ -41,6 +41,8 @@ struct DensePass {
     const float *h;                 // [Npad]
     __nv_bfloat16 *S;               // [Cpad][Npad]
     int Npad, N, C, P, i0;
+    int PS;           // columns per replica: P rounded up to a power of two (<= 32) or 64; columns k >= P of a replica
+                      // are dead (spin +1, never attempted, no part in the ring or the world-line sum)
     int trotter;      // 1: PIQMC (columns of a replica form a ring of P slices), 0: SA
     float bcoef;      // -2 B (PIQMC, qmc.pyx:96) or -2 (SA, sa.pyx:91-94)
     float jperp2;     // 2 J_perp
@@ -109,6 +111,7 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
     const int i0 = a.i0;
     const long long ld = a.Npad;
     const int P = INWARP ? PT : a.P;
+    const int PS = INWARP ? PT : a.PS; // columns per replica (>= P)
     const int mend = min(kBS, a.N - i0);
 
     // field strip of this thread -> registers; the tile's shared memory then holds the world-line uniforms
@@ -131,8 +134,8 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
 #pragma unroll 1
     for (int e = tid; e < kBS * kTC; e += kThreads) { // all uniforms of the block
         const int m = e / kTC, c = e % kTC;
-        const int col = col0 + c, k = col % P;
-        const uint32_t rep = a.replica_offset + (uint32_t)(col / P);
+        const int col = col0 + c, k = col % PS;
+        const uint32_t rep = a.replica_offset + (uint32_t)(col / PS);
         if ((k & 3) == 0) {
             uint32_t rnd[4];
             mcs_philox4x32_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)(k >> 2), a.keys, rnd);
@@ -143,7 +146,7 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
         if (a.global_moves && k == 0) {
             uint32_t rnd[4];
             mcs_philox4x32_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
-            uglob[m * (kTC / 2) + c / P] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
+            uglob[m * (kTC / 2) + c / PS] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
         }
     }
     if (row == 0) {
@@ -154,11 +157,12 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
 
     const int c = tid; // decision threads: tid < kTC
     const int col = col0 + c;
-    const int k = col % P; // slice
-    const int cl = c - k + (k == 0 ? P - 1 : k - 1), cr = c - k + (k == P - 1 ? 0 : k + 1);
-    const int crep = c / P;
-    const bool valid = col < a.C;
+    const int k = col % PS; // slice (dead column if k >= P)
+    const int cl = c - k + (k == 0 ? P - 1 : k - 1), cr = k < P ? c - k + (k == P - 1 ? 0 : k + 1) : c;
+    const int crep = c / PS;
+    const bool valid = col < a.C && k < P;
     const bool odd = (k & 1) != 0;
+    const bool lastodd = (P & 1) != 0 && P > 1 && k == P - 1; // odd ring: slice P-1 neighbours slice 0, visited alone
     const float sc = a.nl2e_over_t, bco = a.bcoef, jp2 = a.jperp2;
     const bool trotter = a.trotter != 0, glob = a.global_moves != 0;
 #define MCS_ACCEPT(dE, lg) (valid && ((dE) <= 0.0f || (dE) * sc >= (lg)))
@@ -188,8 +192,8 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
                 }
             } else { // P == 64: the replica spans both decision warps -> shared memory + a 64-thread barrier
 #pragma unroll 1
-                for (int parity = 0; parity < 2; ++parity) {
-                    if ((k & 1) == parity) {
+                for (int parity = 0; parity < ((P & 1) && P > 1 ? 3 : 2); ++parity) {
+                    if (parity == 2 ? lastodd : ((k & 1) == parity && !lastodd)) {
                         const float dE = s * fmaf(jp2, (float)(sb[m * kTC + cl] + sb[m * kTC + cr]), bf);
                         if (MCS_ACCEPT(dE, lu)) {
                             s = -s;
@@ -199,7 +203,7 @@ __device__ __forceinline__ void dense_phase_b_rows(const DensePass &a, float *Hb
                     bar_decide();
                 }
                 if (glob) {
-                    gterm[c] = s * bf;
+                    gterm[c] = valid ? s * bf : 0.0f;
                     bar_decide();
                     float dE = 0.0f;
                     for (int q = 0; q < P; ++q) dE += gterm[c - k + q];
@@ -250,7 +254,7 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
     const int tid = threadIdx.x;
     const int i0 = a.i0;
     const long long ld = a.Npad;
-    constexpr int P = PT;
+    const int P = a.P; // slices that exist; PT = columns per replica (a power of two >= P)
 
     // Prologue: everything phase B needs besides the fields, fetched with as many requests in flight as possible
     // (it is pure latency: 64 KB of J, 16 KB of spins, 2304 Philox calls per CTA).
@@ -280,22 +284,22 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
         }
     }
     // uniforms: one Philox call = four consecutive slices of one (row, replica); calls spread evenly over the threads
-    constexpr int G4 = (P + 3) / 4;               // calls per (row, replica)
-    constexpr int NREP = kTC / P;                 // replicas of this CTA
+    constexpr int G4 = (PT + 3) / 4;              // calls per (row, replica)
+    constexpr int NREP = kTC / PT;                // replicas of this CTA
 #pragma unroll 2
     for (int e = tid; e < kBS * NREP * G4; e += kThreads) {
         const int m = e / (NREP * G4), rr = (e / G4) % NREP, g = e % G4;
-        const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * P) / P);
+        const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * PT) / PT);
         uint32_t rnd[4];
         mcs_philox4x32_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)g, a.keys, rnd);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (4 * g + j < P) uloc[m * kTC + rr * P + 4 * g + j] = __log2f((float)rnd[j] + 1.0f) - 32.0f;
+            if (4 * g + j < PT) uloc[m * kTC + rr * PT + 4 * g + j] = __log2f((float)rnd[j] + 1.0f) - 32.0f;
     }
     if (a.global_moves) {
         for (int e = tid; e < kBS * NREP; e += kThreads) {
             const int m = e / NREP, rr = e % NREP;
-            const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * P) / P);
+            const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * PT) / PT);
             uint32_t rnd[4];
             mcs_philox4x32_rk(rep, (uint32_t)(i0 + m), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
             uglob[m * (kTC / 2) + rr] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
@@ -307,11 +311,13 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
 
     const int c = tid & (kTC - 1); // column of a decision thread (tid < kTC)
     const int col = col0 + c;
-    const int k = col % P; // slice
-    const int cl = c - k + (k == 0 ? P - 1 : k - 1), cr = c - k + (k == P - 1 ? 0 : k + 1);
-    const int crep = c / P;
-    const bool valid = col < a.C;
-    const bool odd = (k & 1) != 0;
+    const int k = col % PT; // slice (dead column if k >= P)
+    const int cl = c - k + (k == 0 ? P - 1 : k - 1), cr = k < P ? c - k + (k == P - 1 ? 0 : k + 1) : c;
+    const int crep = c / PT;
+    const bool valid = col < a.C && k < P;
+    const bool oddP = (P & 1) != 0 && P > 1; // odd ring: slice P-1 neighbours slice 0 and is visited alone, last
+    const bool lastodd = oddP && k == P - 1;
+    const bool odd = (k & 1) != 0 && !lastodd, even = (k & 1) == 0 && !lastodd;
     const float sc = a.nl2e_over_t, bco = a.bcoef, jp2 = a.jperp2;
     const bool trotter = a.trotter != 0 && P > 1, glob = a.global_moves != 0;
     const unsigned segmask = PT >= 32 ? 0xffffffffu : (((1u << (PT & 31)) - 1u) << ((tid & 31) & ~(PT - 1)));
@@ -340,10 +346,15 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
                 if (trotter) { // even slices, then odd slices (P is even); neighbours by shuffle
                     float nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
                     float dE = s * fmaf(jp2, nb, bf);
-                    s = ((!odd) & MCS_ACCEPT(dE, lu[j])) ? -s : s;
+                    s = (even & MCS_ACCEPT(dE, lu[j])) ? -s : s;
                     nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
                     dE = s * fmaf(jp2, nb, bf);
                     s = (odd & MCS_ACCEPT(dE, lu[j])) ? -s : s;
+                    if (oddP) { // warp-uniform
+                        nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                        dE = s * fmaf(jp2, nb, bf);
+                        s = (lastodd & MCS_ACCEPT(dE, lu[j])) ? -s : s;
+                    }
                 } else {
                     const float dE = s * bf;
                     s = MCS_ACCEPT(dE, lu[j]) ? -s : s;
@@ -352,7 +363,7 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
                     // sum over the replica's lanes in fixed point with one redux.sync instead of log2(P)
                     // dependent shuffles (the scale is chosen per launch from the instance's largest possible
                     // field: resolution P |dE|_max 2^-30, finer than the fp32 butterfly it replaces)
-                    const int part = __float2int_rn(s * bf * a.gscale);
+                    const int part = valid ? __float2int_rn(s * bf * a.gscale) : 0;
                     const float dE = (float)__reduce_add_sync(segmask, part) * a.ginv;
                     s = MCS_ACCEPT(dE, ug[j]) ? -s : s;
                 }
@@ -400,7 +411,7 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
 __device__ __forceinline__ void dense_phase_b_dispatch(const DensePass &a, float *Hb, unsigned char *scr,
                                                        float *uglob, int col0)
 {
-    switch (a.P) {
+    switch (a.PS) {
     case 1: dense_phase_b_strips<1>(a, Hb, scr, uglob, col0); break;
     case 2: dense_phase_b_strips<2>(a, Hb, scr, uglob, col0); break;
     case 4: dense_phase_b_strips<4>(a, Hb, scr, uglob, col0); break;
@@ -652,21 +663,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 // W[N][Rpad] (bit k = slice k) -> S[(r P + k)][site]
 __global__ void dense_expand_piqmc_kernel(const uint64_t *__restrict__ W, __nv_bfloat16 *__restrict__ S, int N,
-                                          int Npad, long long R, long long Rpad, int P, long long Cpad)
+                                          int Npad, long long R, long long Rpad, int P, int PS, long long Cpad)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Cpad * Npad) return;
     const long long col = t / Npad;
     const int i = (int)(t % Npad);
-    const long long r = col / P;
-    const int k = (int)(col % P);
+    const long long r = col / PS;
+    const int k = (int)(col % PS);
     float v = 1.0f;
-    if (i < N && r < R) v = ((W[(long long)i * Rpad + r] >> k) & 1ull) ? -1.0f : 1.0f;
+    if (i < N && r < R && k < P) v = ((W[(long long)i * Rpad + r] >> k) & 1ull) ? -1.0f : 1.0f;
     S[t] = __float2bfloat16(v);
 }
 
 __global__ void dense_compress_piqmc_kernel(const __nv_bfloat16 *__restrict__ S, uint64_t *__restrict__ W, int N,
-                                            int Npad, long long R, long long Rpad, int P)
+                                            int Npad, long long R, long long Rpad, int P, int PS)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)N * R) return;
@@ -674,7 +685,7 @@ __global__ void dense_compress_piqmc_kernel(const __nv_bfloat16 *__restrict__ S,
     const int i = (int)(t % N);
     uint64_t w = 0;
     for (int k = 0; k < P; ++k)
-        w |= (uint64_t)(__bfloat162float(S[(r * P + k) * Npad + i]) < 0.0f) << k;
+        w |= (uint64_t)(__bfloat162float(S[(r * PS + k) * Npad + i]) < 0.0f) << k;
     W[(long long)i * Rpad + r] = w;
 }
 
@@ -759,7 +770,7 @@ static void launch_dense_tc(unsigned grid, cudaStream_t stream, const DensePass 
 bool mcs_dense_supported(const mcs_instance *inst, int P)
 {
     if (!inst->dense || inst->nsteps != 1) return false;
-    return P == 1 || (P <= kTC && (kTC % P) == 0);
+    return P >= 1 && P <= kTC; // any number of slices: a replica takes the next power of two (or 64) columns
 }
 
 // kind: MCS_KIND_PIQMC (A, B schedules) or MCS_KIND_SA (A = temperature schedule, B unused)
@@ -770,7 +781,9 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     mcs_instance *inst = st->inst;
     MCS_CUDA(cudaSetDevice(inst->device));
     const int P = (int)st->P;
-    const long long C = st->R * P;
+    int PS = 1; // columns per replica
+    while (PS < P) PS *= 2;
+    const long long C = st->R * PS;
     const long long Cpad = (C + kTC - 1) / kTC * kTC;
     const int Npad = (int)inst->Npad;
     if (!st->d_S16 || st->S16_cols != Cpad) {
@@ -802,7 +815,7 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     const long long nexp = Cpad * Npad;
     if (kind == MCS_KIND_PIQMC)
         dense_expand_piqmc_kernel<<<(unsigned)((nexp + 255) / 256), 256, 0, inst->stream>>>(
-            st->d_W, S16, (int)inst->N, Npad, st->R, st->Rpad, P, Cpad);
+            st->d_W, S16, (int)inst->N, Npad, st->R, st->Rpad, P, PS, Cpad);
     else
         dense_expand_sa_kernel<<<(unsigned)((nexp + 255) / 256), 256, 0, inst->stream>>>(st->d_V, S16, (int)inst->N,
                                                                                         Npad, st->R, st->G, Cpad);
@@ -818,6 +831,7 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     a.N = (int)inst->N;
     a.C = (int)C;
     a.P = P;
+    a.PS = PS;
     a.trotter = kind == MCS_KIND_PIQMC ? 1 : 0;
     a.keys = mcs_philox_expand(seed);
     a.replica_offset = (uint32_t)replica_offset;
@@ -858,7 +872,7 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     if (kind == MCS_KIND_PIQMC) {
         const long long n = inst->N * st->R;
         dense_compress_piqmc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(
-            S16, st->d_W, (int)inst->N, Npad, st->R, st->Rpad, P);
+            S16, st->d_W, (int)inst->N, Npad, st->R, st->Rpad, P, PS);
     } else {
         const long long n = inst->N * st->G;
         dense_compress_sa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(S16, st->d_V, (int)inst->N, Npad,
