@@ -17,6 +17,7 @@
 // forest in L[node][replica] (replica fastest, like W).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "mcs_common.cuh"
 
@@ -29,7 +30,8 @@ struct ClusterArgs {
     const int32_t *ell_idx;
     const float *ell_J;
     const float *h;
-    long long N, R, Rpad, G, Rl;
+    long long N, R, Rpad, G, Rl; // R: replicas of this chunk, Rl: label stride (replicas per chunk, padded)
+    long long r0;                // first replica of the chunk (the label array holds one chunk at a time)
     int P, dpad;
     float kin;   // in-plane factor:  K_ij = kin * J_ij   (= -B/teff, or -1/T for SA)
     float kperp; // Trotter coupling  J_perp / teff
@@ -72,6 +74,7 @@ __device__ __forceinline__ void uf_union(int32_t *L, long long stride, long long
 // spin word of (site, replica) as a 64-bit mask over slices (SA: one bit)
 __device__ __forceinline__ uint64_t load_word(const ClusterArgs &a, long long i, long long r)
 {
+    r += a.r0;
     if (a.W) return a.W[i * a.Rpad + r];
     return (uint64_t)((a.V[i * a.G + (r >> 5)] >> (r & 31)) & 1u);
 }
@@ -115,7 +118,7 @@ __global__ void cluster_union_kernel(const __grid_constant__ ClusterArgs a)
     const int P = a.P;
     const uint64_t pmask = P == 64 ? ~0ull : ((1ull << P) - 1ull);
     const uint64_t w = load_word(a, i, r);
-    const uint32_t c0 = a.replica_offset + (uint32_t)r;
+    const uint32_t c0 = a.replica_offset + (uint32_t)(a.r0 + r);
     const int32_t ghost = (int32_t)(a.N * P);
     // in-plane bonds, each taken once from the row of its smaller endpoint
     for (int s = 0; s < a.dpad; ++s) {
@@ -183,7 +186,7 @@ __global__ void cluster_flip_kernel(const __grid_constant__ ClusterArgs a)
     if (r >= a.R) return;
     const int P = a.P;
     const int32_t groot = uf_find(a.L, a.Rl, r, (int32_t)(a.N * P));
-    const uint32_t c0 = a.replica_offset + (uint32_t)r;
+    const uint32_t c0 = a.replica_offset + (uint32_t)(a.r0 + r);
     uint64_t flip = 0;
     for (int k = 0; k < P; ++k) {
         const int32_t root = uf_find(a.L, a.Rl, r, (int32_t)(i * P + k));
@@ -193,10 +196,11 @@ __global__ void cluster_flip_kernel(const __grid_constant__ ClusterArgs a)
         if (rnd[0] & 1u) flip |= 1ull << k;
     }
     if (!flip) return;
+    const long long rg = a.r0 + r;
     if (a.W) {
-        a.W[i * a.Rpad + r] ^= flip;
+        a.W[i * a.Rpad + rg] ^= flip;
     } else {
-        atomicXor(&a.V[i * a.G + (r >> 5)], 1u << (r & 31)); // 32 replicas share a word
+        atomicXor(&a.V[i * a.G + (rg >> 5)], 1u << (rg & 31)); // 32 replicas share a word
     }
 }
 
@@ -213,7 +217,13 @@ int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double
     const int P = (int)st->P;
     const long long nodes = inst->N * P + 1;
     MCS_REQUIRE(nodes < (1ll << 31), MCS_EUNSUPPORTED, "cluster moves: N*P too large for 32-bit labels");
-    const long long Rl = st->kind == MCS_KIND_PIQMC ? st->Rpad : st->R;
+    // labels [(N P + 1)][Rl]: one forest per replica.  The batch is labelled in chunks of Rl replicas so that the
+    // array stays below 512 MB whatever the batch (80x80, P = 64: 1.6 MB per replica -> 320 replicas per chunk;
+    // all 4096 at once would be 6.7 GB)
+    const long long Rall = st->kind == MCS_KIND_PIQMC ? st->Rpad : st->R;
+    long long cap = std::max(32ll, ((512ll << 20) / (nodes * 4)) / 32 * 32);
+    if (const char *e = getenv("MCS_CLUSTER_CHUNK")) cap = std::max(32ll, atoll(e) / 32 * 32); // tests
+    const long long Rl = std::min(Rall, cap);
     const size_t bytes = (size_t)nodes * Rl * sizeof(int32_t);
     if (st->labels_bytes < bytes) {
         if (st->d_labels) MCS_CUDA(cudaFree(st->d_labels));
@@ -231,6 +241,7 @@ int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double
     a.h = inst->d_h;
     a.N = inst->N;
     a.R = st->R;
+    a.r0 = 0;
     a.Rpad = st->Rpad;
     a.G = st->G;
     a.Rl = Rl;
@@ -269,10 +280,14 @@ int mcs_launch_cluster_moves(mcs_state *st, double coef_a, double coef_b, double
         const uint64_t sweep = sweep_offset + (uint64_t)mv;
         a.sweep_lo = (uint32_t)sweep;
         a.sweep_hi = (uint32_t)(sweep >> 32);
-        cluster_init_kernel<<<(unsigned)((nodes * Rl + 255) / 256), 256, 0, inst->stream>>>(a.L, nodes, Rl);
-        cluster_union_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, inst->stream>>>(a);
-        cluster_flip_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, inst->stream>>>(a);
-        inst->launches += 3;
+        for (long long r0 = 0; r0 < st->R; r0 += Rl) { // replicas are independent: chunk after chunk
+            a.r0 = r0;
+            a.R = std::min(Rl, st->R - r0);
+            cluster_init_kernel<<<(unsigned)((nodes * Rl + 255) / 256), 256, 0, inst->stream>>>(a.L, nodes, Rl);
+            cluster_union_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, inst->stream>>>(a);
+            cluster_flip_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, inst->stream>>>(a);
+            inst->launches += 3;
+        }
     }
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;

@@ -278,6 +278,36 @@ inline cudaError_t mcs_launch_pdl(Kernel kernel, dim3 grid, dim3 block, cudaStre
     return mcs_note_launch(cudaLaunchKernelEx(&cfg, kernel, args));
 }
 
+// ---- grid-wide barrier of the persistent small-batch kernels (cooperative launch: every CTA is resident) ----
+// sync[0] counts arrivals (monotonic; zeroed before the launch), sync[1] is an error flag.  One thread per CTA
+// arrives and spins until all CTAs of this epoch have; state loads after the barrier bypass L1 (__ldcg).  The spin is bounded: a barrier that cannot complete (it cannot, under a cooperative
+// launch) raises the flag instead of hanging the device.
+// Split in two so that work that does not depend on the other CTAs (the next pass's couplings and threshold table)
+// runs between arriving and waiting.  One fence by the arriving thread after the CTA barrier publishes every
+// thread's stores (fence cumulativity, the pattern of cooperative-groups grid.sync).
+__device__ __forceinline__ void mcs_grid_arrive(unsigned *sync)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&sync[0], 1u);
+    }
+}
+__device__ __forceinline__ void mcs_grid_wait(unsigned *sync, unsigned target)
+{
+    if (threadIdx.x == 0) {
+        unsigned v, spins = 0;
+        for (;;) { // relaxed polls with a short back-off (hundreds of pollers on one L2 line starve the arrivals)
+            asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
+            if ((int)(v - target) >= 0 || ++spins >= (1u << 24)) break;
+            __nanosleep(40);
+        }
+        if ((int)(v - target) < 0) atomicExch(&sync[1], 1u);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 // ---- building blocks shared by the bit-packed sweep kernels (mcs_piqmc.cu, mcs_sa.cu) ---------------
 // Instruction budget, measured on B200 (benchmarks/micro/pipe_rates.cu): ALU-pipe instructions (LOP3, PRMT,
 // IADD3, SHF, ISETP, VIADDMNMX) and FMA-pipe IMAD take 2 issue cycles per warp each and overlap with each

@@ -182,3 +182,28 @@ def test_sw_moves_sa_state_and_critical_ferromagnet(mcs):
     conf = (2 * np.random.RandomState(0).randint(2, size=(32, 36, P)) - 1).astype(np.int8)
     e = mcs.qmc.QuantumAnnealWCL(np.linspace(2.5, 1e-3, 60), np.ones(60), 1, 0.5 / P, conf, nt, seed=4, energies=True)
     assert np.all(e.min(axis=1) == -72.0)
+
+
+def test_cluster_labels_are_built_chunk_by_chunk_without_changing_the_move(mcs):
+    """The union-find forests take 4 (N P + 1) bytes per replica; batches are labelled in chunks that keep the array
+    below 512 MB (80x80, P = 64: 320 replicas at a time instead of 6.7 GB for 4096).  Chunking must not change a
+    single flip (Philox counters carry the global replica index): forced 32-replica chunks == one chunk."""
+    import os
+    _, nbs = inst.torus(8, seed=4, fields=True)
+    P, R = 12, 200
+    lut = 0.2 * (np.pi / (P * np.sin(np.pi * np.arange(1, P) / P))) ** 2
+    I = mcs.Instance(nbs)
+    out = []
+    for chunk in (None, "32"):
+        if chunk:
+            os.environ["MCS_CLUSTER_CHUNK"] = chunk
+        try:
+            st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+            st.init_random(2)
+            for t in range(5):
+                st.cluster_moves(1.0, 0.8, 1.0 / P, 1, seed=9, sweep_offset=t, lookuptable=lut if t % 2 else None)
+            out.append(st.download_spins())
+            st.close()
+        finally:
+            os.environ.pop("MCS_CLUSTER_CHUNK", None)
+    assert np.array_equal(out[0], out[1])
