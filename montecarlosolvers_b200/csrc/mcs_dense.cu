@@ -52,6 +52,11 @@ struct DensePass {
     int global_moves;
     float gscale, ginv; // world-line sums in fixed point: 2^K and 2^-K, K such that P |dE|_max 2^K < 2^30
     unsigned long long *trace; // MCS_DENSE_TRACE=1: phase timestamps of CTA 0 (ns), else nullptr
+    // tcgen05 variant: block kernels of consecutive steps overlap.  ver[c] = number of steps column group c has
+    // completed in this call (its spins written back); ver[groups] is an error flag (a wait that timed out)
+    unsigned *ver;
+    unsigned step;   // index of this launch within the call: sweep * blocks + block
+    int nblocks;     // blocks per sweep
 };
 
 __device__ __forceinline__ void dense_stamp(const DensePass &a, int slot)
@@ -272,7 +277,7 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
 #pragma unroll
         for (int q = 0; q < kBS * kTC / 8 / kThreads; ++q) {
             const int e = tid + q * kThreads, cc = e / (kBS / 8), m8 = (e % (kBS / 8)) * 8;
-            v[q] = __ldg(reinterpret_cast<const uint4 *>(a.S + (long long)(col0 + cc) * ld + i0 + m8));
+            v[q] = __ldcg(reinterpret_cast<const uint4 *>(a.S + (long long)(col0 + cc) * ld + i0 + m8));
         }
 #pragma unroll
         for (int q = 0; q < kBS * kTC / 8 / kThreads; ++q) {
@@ -588,18 +593,38 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = a.Npad / kBK;
-    mcs_pdl_wait(); // S (and nothing else read from here on) is written by the previous block's kernel
 
+    // K order: the block's field needs every spin of its columns, but the spins of block j were last written by
+    // the step that visited block j.  Cyclic order starting at the own block = oldest writer first: everything up to
+    // the last few blocks is long final, and only the tiles of the block just before this one have to wait for the
+    // previous step of this column group -- which is running on another SM right now (the kernels of consecutive
+    // blocks overlap: no griddepcontrol.wait), so this step's GEMM hides behind that step's decision chain.
+    const int b0 = a.i0 / kBS;
+    const int tpb = kBS / kBK; // K tiles per block
     if (warp == 0 && lane == 0) {
         // ---- TMA producer
+        unsigned seen = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % kStages;
+            const int q = kb / tpb;                         // cyclic position of the tile's block
+            const int kbe = (b0 * tpb + kb) % nkb;          // the tile
+            const long long need = (long long)a.step - (a.nblocks - 1 - q); // steps that must be complete
+            if (need > (long long)seen) {
+                unsigned spins = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(a.ver + blockIdx.x) : "memory");
+                    if ((long long)seen >= need) break;
+                    __nanosleep(100);
+                } while (++spins < (1u << 24));
+                if ((long long)seen < need) atomicExch(a.ver + gridDim.x, 1u); // cannot happen: the producer runs
+                asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes -> the TMA reads below
+            }
             mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
             unsigned char *st = ring + s * kStageBytes;
             mbar_expect_tx(&full[s], kStageBytes);
-            tma_load_2d(st, maps.jhi, kb * kBK, a.i0, &full[s]);
-            tma_load_2d(st + kStageA, maps.jlo, kb * kBK, a.i0, &full[s]);
-            tma_load_2d(st + 2 * kStageA, maps.s, kb * kBK, col0, &full[s]);
+            tma_load_2d(st, maps.jhi, kbe * kBK, a.i0, &full[s]);
+            tma_load_2d(st + kStageA, maps.jlo, kbe * kBK, a.i0, &full[s]);
+            tma_load_2d(st + 2 * kStageA, maps.s, kbe * kBK, col0, &full[s]);
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer: D[128 x 64] (+)= Ahi . B^T + Alo . B^T
@@ -659,6 +684,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     // phase B scratch lives in the (now idle) ring, the world-line uniforms behind the barriers
     dense_phase_b_dispatch(a, Hb, ring, reinterpret_cast<float *>(ring + kRingBytes + kHbBytes + 128), col0);
     dense_stamp(a, 6);
+    // this column group has completed step a.step: its spins are written back (all threads), publish
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(a.ver + blockIdx.x), "r"(a.step + 1u) : "memory");
+    }
 }
 
 // W[N][Rpad] (bit k = slice k) -> S[(r P + k)][site]
@@ -838,6 +869,14 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     a.global_moves = (kind == MCS_KIND_PIQMC && global_moves) ? 1 : 0;
     a.gscale = a.ginv = 1.0f;
     a.trace = nullptr;
+    a.ver = nullptr;
+    a.step = 0;
+    a.nblocks = (int)((inst->N + kBS - 1) / kBS);
+    const unsigned groups = (unsigned)(Cpad / kTC);
+    if (use_tc) {
+        MCS_CUDA(cudaMallocAsync((void **)&a.ver, (groups + 1) * sizeof(unsigned), inst->stream));
+        MCS_CUDA(cudaMemsetAsync(a.ver, 0, (groups + 1) * sizeof(unsigned), inst->stream));
+    }
     if (getenv("MCS_DENSE_TRACE")) MCS_CUDA(cudaMalloc((void **)&a.trace, 8 * sizeof(unsigned long long)));
     const double teff = (double)temp * (double)P;
     uint64_t sweep = sweep_offset;
@@ -861,8 +900,10 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
             a.sweep_hi = (uint32_t)(sweep >> 32);
             for (int i0 = 0; i0 < (int)inst->N; i0 += kBS) {
                 a.i0 = i0;
-                if (use_tc)
-                    launch_dense_tc((unsigned)(Cpad / kTC), inst->stream, a, maps);
+                if (use_tc) {
+                    launch_dense_tc(groups, inst->stream, a, maps);
+                    a.step++;
+                }
                 else
                     dense_block_kernel<<<(unsigned)(Cpad / kTC), kThreads, kSmemBytes, inst->stream>>>(a);
                 inst->launches++;
@@ -881,6 +922,17 @@ int mcs_launch_dense_sweeps(mcs_state *st, int kind, const double *A, const doub
     inst->launches++;
     MCS_CUDA(mcs_take_launch_error());
     MCS_CUDA(cudaGetLastError());
+    if (a.ver) {
+        if (getenv("MCS_DENSE_CHECK")) { // tests: surface the (impossible) wait time-out
+            unsigned flag = 0;
+            MCS_CUDA(cudaMemcpyAsync(&flag, a.ver + groups, sizeof(flag), cudaMemcpyDeviceToHost, inst->stream));
+            MCS_CUDA(cudaStreamSynchronize(inst->stream));
+            MCS_CUDA(cudaFreeAsync(a.ver, inst->stream));
+            MCS_REQUIRE(flag == 0, MCS_ENODEVICE, "dense sweeps: a wait on the previous block's step timed out");
+        } else {
+            MCS_CUDA(cudaFreeAsync(a.ver, inst->stream));
+        }
+    }
     if (a.trace) { // timestamps of the last block launch: start, GEMM done, prologue done, first strip decided,
                    // first strip applied, all strips done, spins written back
         unsigned long long t[8];

@@ -13,8 +13,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def mcs():
+    import os
     import montecarlosolvers_b200 as m
     m._lib.require_device()
+    os.environ["MCS_DENSE_CHECK"] = "1"  # surface a timed-out wait between overlapping block kernels as an error
     return m
 
 
