@@ -420,8 +420,8 @@ def run_configs(mcs, inst, peaks, which):
         out["cfg1"] = {"workload": "examples/santoro80.py protocol: 80x80 PIQMC P=20 with world-line moves "
                                    "(QuantumAnnealGlobal), tau=354, %d anneals" % R, "value": v, "unit": UNIT,
                        "ms": ms, "gpu_launches": (inst.launches - l0) // 3,
-                       "roofline": hbm_roofline(v, 0.25, peaks, "piqmc_lut_pass_kernel<4,4,false,0,true> (two replicas "
-                                                "per thread)", ms / (2 * tau))}
+                       "roofline": hbm_roofline(v, 0.25, peaks, "piqmc_lut_pass_kernel<4,4,false,0,MODE_PACK> (three "
+                                                "20-slice world lines per working word)", ms / (2 * tau))}
         st.close()
     if "cfg2" in which:  # sa.Anneal, 1024 restarts
         tau, R = 1000, 1024
@@ -433,8 +433,10 @@ def run_configs(mcs, inst, peaks, which):
         out["cfg2"] = {"workload": "sa.Anneal on 80x80 Santoro, %d restarts, linspace(3,0,1000), 1 sweep each" % R,
                        "value": v, "unit": UNIT, "ms": ms,
                        "roofline": hbm_roofline(v, 0.25, peaks, "sa_lut_pass_kernel<4,*,0>", ms / (2 * tau),
-                                                "latency bound at this batch size: one colour pass of 1024 restarts "
-                                                "is a single wave of 100 warps")}
+                                                "latency bound at this batch size: a colour pass is 3200 warps (one "
+                                                "wave): 2.1 us of SM-bound work + 2.3 us kernel-boundary latency per "
+                                                "pass (profiles/r02_small_batch.log; a cooperative persistent kernel "
+                                                "with a grid barrier measured 4.6 us per pass, MCS_PERSIST=1)")}
         st.close()
     if "refdyn" in which:  # cfg3 shape, the reference's own visiting order in distribution
         P, R, S = 64, 4096, 4
@@ -456,20 +458,25 @@ def run_configs(mcs, inst, peaks, which):
         finally:
             inst.set_dynamics("colored")
     if "exact" in which:  # bit-exact sequential replay of the reference (glibc rand stream, fp64)
-        P, R, S = 64, 4096, 2
+        P, R, S = 64, 4096, 4
         confs = np.repeat((2 * np.random.RandomState(0).randint(2, size=(R, NSPINS, 1)) - 1).astype(np.int8), P, axis=2)
         A, B = np.linspace(3.0, 1e-8, SCHED)[_strided(SCHED, S)].copy(), np.ones(S)
-        t0 = time.perf_counter()
-        mcs.qmc.QuantumAnneal(A, B, 1, 1.0 / P, confs, inst, 1, exact=True, libc_seed=1000)
-        dt = time.perf_counter() - t0
+        dt = 1e30
+        for rep in range(2):  # the first call also pays for the page faults of the 1.7 GB host buffer
+            t0 = time.perf_counter()
+            mcs.qmc.QuantumAnneal(A, B, 1, 1.0 / P, confs, inst, 1, exact=True, libc_seed=1000)
+            dt = min(dt, time.perf_counter() - t0)
         out["cfg3_exact_replay"] = {
             "workload": "80x80 PIQMC P=64, %d anneals, %d sweeps, exact=True: bit-exact replay of the reference's "
-                        "trajectories (Fisher-Yates from glibc rand(), sequential fp64 visits); wall clock of the "
-                        "C-ABI call incl. host copies" % (R, S),
+                        "trajectories (Fisher-Yates from glibc rand(), sequential fp64 visits) -- one warp per anneal, "
+                        "state in shared memory, rand() stream 31 values per step, shuffle iterations and visits in "
+                        "conflict-free windows; wall clock of the C-ABI call incl. 1.7 GB of host copies each way "
+                        "(the kernel alone: 7.8e9 attempts/s, profiles/r02_exact_probe.log)" % (R, S),
             "value": R * S * P * NSPINS / dt, "unit": UNIT, "ms": dt * 1e3,
             "roofline": {"bound": "latency", "note": "one sequential chain per anneal by construction (the rand() "
-                                                     "stream and the visiting order are serial): parity tier (b), "
-                                                     "not a throughput path"}}
+                                                     "stream and the visiting order are serial): about 490 "
+                                                     "dependent windows of ~1700 cycles per slice sweep, 3 warps "
+                                                     "per SM (shared memory); parity tier (b), not a throughput path"}}
         del confs
     if "cfg4" in which:  # SVMC on Chimera C16, 2048 reads
         cn = chimera_instance(16)
@@ -480,9 +487,19 @@ def run_configs(mcs, inst, peaks, which):
         st.init_random(0)
         ms = timed(ci, lambda: st.svmc_sweeps(A4, B4, 1, 0.1, tf=False, seed=5), reps=3)
         v = 2048 * 1000 * 2048 / (ms * 1e-3)
+        ci.set_dynamics("reference")  # the reference's visiting order in distribution (svmc.pyx:83-91)
+        try:
+            st.init_random(0)
+            sel = _strided(1000, 50)
+            ms_rd = timed(ci, lambda: st.svmc_sweeps(A4[sel].copy(), B4[sel].copy(), 1, 0.1, tf=False, seed=5), reps=2)
+            v_rd = 2048 * 50 * 2048 / (ms_rd * 1e-3)
+        finally:
+            ci.set_dynamics("colored")
         out["cfg4"] = {"workload": "svmc.SpinVectorMonteCarloCompact on Chimera C16 (2048 rotors, %d colours), 2048 "
                                    "reads, A=3(1-s), B=s, s=linspace(1e-3,1,1000), T=0.1" % ci.ncolors,
                        "value": v, "unit": UNIT, "ms": ms,
+                       "reference_dynamics": {"value": v_rd, "unit": UNIT, "ms": ms_rd, "sweeps": 50,
+                                              "kernel": "refdyn_svmc_kernel (dependency waves, one CTA per read)"},
                        "roofline": hbm_roofline(v, 8.0, peaks, "svmc_pass_kernel", ms / (1000 * ci.ncolors),
                                                 "SURVEY 8d: 8 B per attempt (theta and cos theta, fp32, read + write); "
                                                 "the 33.5 MB state is L2 resident, the kernel is bound by the latency "
