@@ -143,7 +143,7 @@ def roofline(achieved, peak, have_peaks, R, ms_per_launch, bytes_per_launch, n_p
             continue
     attempts_per_launch = bytes_per_launch / 0.25
     out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-           "traffic": args.traffic, "kernel": "piqmc_lut_pass_kernel<4,4,true,0,false>", "ms_per_launch": ms_per_launch,
+           "traffic": args.traffic, "kernel": "piqmc_lut_pass_kernel<4,4,true,0,MODE_PLAIN>", "ms_per_launch": ms_per_launch,
            "algorithmic_bytes_per_launch": bytes_per_launch,
            "algorithmic_bytes_per_attempt": 0.25,
            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if have_peaks else "fallback 6650 GB/s",
