@@ -32,9 +32,9 @@ def _nvcc():
 def _sha(paths, extra=""):
     import hashlib
     h = hashlib.sha256(extra.encode())
-    for p in paths:
+    for p in paths:  # names, not absolute paths: the tree is copied to another directory on the GPU box
         with open(p, "rb") as f:
-            h.update(p.encode() + b"\0" + f.read())
+            h.update(os.path.basename(p).encode() + b"\0" + f.read())
     return h.hexdigest()
 
 
@@ -80,6 +80,21 @@ def build(force=False, verbose=False, ptxas_info=False):
         return OUT
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
+    # one builder at a time (several ranks of a torchrun launch may get here together): the others wait for the
+    # lock and then find the library up to date
+    import fcntl
+    lock = open(os.path.join(OBJ, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not ptxas_info and up_to_date():
+            return OUT
+        return _build_locked(nvcc, force, verbose, ptxas_info)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc, force, verbose, ptxas_info):
     objs = []
     procs = []
     for src in SOURCES:
