@@ -870,6 +870,9 @@ __global__ void piqmc_init_kernel(uint64_t *W, long long N, long long R, long lo
 // Fixed-order fp64 classical energy per (replica, slice), bit-identical to the oracle's
 // mcs_oracle_ising_energy (definition of tools.ClassicalIsingEnergy, tools.pyx:99-118, with the
 // BLAS-order ambiguity removed): rows in site order, entries in table order, no FMA.
+// MB > 0: rows of at most MB entries; the row of site i + 1 and the MB neighbour words of site i are requested
+// together, ahead of the arithmetic (the loop is a chain of dependent L2 loads otherwise: 1.2 us per site).
+template <int MB>
 __global__ void piqmc_energy_kernel(const uint64_t *__restrict__ W, const int32_t *__restrict__ tab_idx,
                                     const double *__restrict__ tab_J, double *__restrict__ out, long long N,
                                     int maxnb, long long R, long long Rpad, int P)
@@ -882,27 +885,83 @@ __global__ void piqmc_energy_kernel(const uint64_t *__restrict__ W, const int32_
     double e[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) e[q] = 0.0;
-    for (long long i = 0; i < N; ++i) {
-        double pair[8], field = 0.0;
+    if (MB > 0) {
+        // software pipeline, two sites deep: while site i is summed, the words of site i + 1 and the table row of
+        // site i + 2 are in flight (the batch does not fit the L2: a word costs a DRAM round trip)
+        constexpr int M = MB > 0 ? MB : 1;
+        int j1[M], j2[M];      // rows of sites i + 1, i + 2
+        double v1[M], v2[M];
+        uint32_t b1[M], w1;    // words of site i + 1
+        auto load_row = [&](long long i, int (&j)[M], double (&v)[M]) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) pair[q] = 0.0;
-        for (int s = 0; s < maxnb; ++s) {
-            const int j = __ldg(&tab_idx[i * maxnb + s]);
-            const double jv = __ldg(&tab_J[i * maxnb + s]);
-            if (j == i) {
-                field = __dadd_rn(field, jv);
-            } else {
-                const uint32_t bits = (uint32_t)(W[(long long)j * Rpad + r] >> k0);
-                const double njv = -jv;
+            for (int s = 0; s < M; ++s) {
+                const bool in = s < maxnb && i < N;
+                j[s] = in ? __ldg(&tab_idx[i * maxnb + s]) : 0;
+                v[s] = in ? __ldg(&tab_J[i * maxnb + s]) : 0.0;
+            }
+        };
+        auto load_words = [&](long long i, const int (&j)[M], uint32_t (&b)[M], uint32_t &w) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) pair[q] = __dadd_rn(pair[q], ((bits >> q) & 1u) ? njv : jv); // jv * s_j
+            for (int s = 0; s < M; ++s) b[s] = (uint32_t)(__ldg(&W[(long long)j[s] * Rpad + r]) >> k0);
+            w = (uint32_t)(__ldg(&W[(i < N ? i : 0) * Rpad + r]) >> k0);
+        };
+        load_row(0, j1, v1);
+        load_words(0, j1, b1, w1);
+        load_row(1, j2, v2);
+        for (long long i = 0; i < N; ++i) {
+            int j[M];
+            double jv[M];
+            uint32_t bits[M];
+            const uint32_t wi = w1;
+#pragma unroll
+            for (int s = 0; s < M; ++s) j[s] = j1[s], jv[s] = v1[s], bits[s] = b1[s];
+#pragma unroll
+            for (int s = 0; s < M; ++s) j1[s] = j2[s], v1[s] = v2[s];
+            load_words(i + 1, j1, b1, w1);
+            load_row(i + 2, j2, v2);
+            double pair[8], field = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pair[q] = 0.0;
+#pragma unroll
+            for (int s = 0; s < M; ++s) {
+                if (s >= maxnb) break;
+                if (j[s] == (int)i) {
+                    field = __dadd_rn(field, jv[s]);
+                } else {
+                    const double njv = -jv[s];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pair[q] = __dadd_rn(pair[q], ((bits[s] >> q) & 1u) ? njv : jv[s]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double t = __dadd_rn(__dmul_rn(0.5, pair[q]), field);
+                e[q] = __dadd_rn(e[q], ((wi >> q) & 1u) ? -t : t); // s_i * (0.5 pair + field)
             }
         }
-        const uint32_t wi = (uint32_t)(W[i * Rpad + r] >> k0);
+    } else {
+        for (long long i = 0; i < N; ++i) {
+            double pair[8], field = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const double t = __dadd_rn(__dmul_rn(0.5, pair[q]), field);
-            e[q] = __dadd_rn(e[q], ((wi >> q) & 1u) ? -t : t); // s_i * (0.5 pair + field)
+            for (int q = 0; q < 8; ++q) pair[q] = 0.0;
+            for (int s = 0; s < maxnb; ++s) {
+                const int j = __ldg(&tab_idx[i * maxnb + s]);
+                const double jv = __ldg(&tab_J[i * maxnb + s]);
+                if (j == i) {
+                    field = __dadd_rn(field, jv);
+                } else {
+                    const uint32_t bits = (uint32_t)(W[(long long)j * Rpad + r] >> k0);
+                    const double njv = -jv;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pair[q] = __dadd_rn(pair[q], ((bits >> q) & 1u) ? njv : jv); // jv * s_j
+                }
+            }
+            const uint32_t wi = (uint32_t)(W[i * Rpad + r] >> k0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double t = __dadd_rn(__dmul_rn(0.5, pair[q]), field);
+                e[q] = __dadd_rn(e[q], ((wi >> q) & 1u) ? -t : t); // s_i * (0.5 pair + field)
+            }
         }
     }
 #pragma unroll
@@ -1170,8 +1229,17 @@ int mcs_piqmc_energy(mcs_state *st, double *d_out)
     mcs_instance *inst = st->inst;
     const int kgroups = (int)((st->P + 7) / 8);
     dim3 grid((unsigned)((st->R + 31) / 32), (unsigned)((kgroups + 3) / 4));
-    piqmc_energy_kernel<<<grid, dim3(32, 4), 0, inst->stream>>>(st->d_W, inst->tab_idx_at(inst->nsteps - 1), inst->tab_J_at(inst->nsteps - 1), d_out, inst->N,
-                                                      (int)inst->maxnb, st->R, st->Rpad, (int)st->P);
+    const int32_t *ti = inst->tab_idx_at(inst->nsteps - 1);
+    const double *tj = inst->tab_J_at(inst->nsteps - 1);
+    if (inst->maxnb <= 4)
+        piqmc_energy_kernel<4><<<grid, dim3(32, 4), 0, inst->stream>>>(st->d_W, ti, tj, d_out, inst->N, (int)inst->maxnb,
+                                                                        st->R, st->Rpad, (int)st->P);
+    else if (inst->maxnb <= 8)
+        piqmc_energy_kernel<8><<<grid, dim3(32, 4), 0, inst->stream>>>(st->d_W, ti, tj, d_out, inst->N, (int)inst->maxnb,
+                                                                        st->R, st->Rpad, (int)st->P);
+    else
+        piqmc_energy_kernel<0><<<grid, dim3(32, 4), 0, inst->stream>>>(st->d_W, ti, tj, d_out, inst->N, (int)inst->maxnb,
+                                                                        st->R, st->Rpad, (int)st->P);
     inst->launches++;
     MCS_CUDA(cudaGetLastError());
     return MCS_OK;
