@@ -132,6 +132,9 @@ int mcs_instance_scratch_state(mcs_instance *inst, int kind, int64_t R, int64_t 
 // (uniform over the launch); counter = (replica or word index, site, sweep, call tag), so a
 // replica's stream does not depend on launch geometry or on how replicas are sharded over GPUs.
 // ------------------------------------------------------------------------------------------
+#ifndef MCS_BYTES_BY_PRMT
+#define MCS_BYTES_BY_PRMT 0 // index bytes of a decision call: 0 = all eight through the LSU, 1 = four, 2 = none (PRMT)
+#endif
 #ifndef MCS_PHILOX_ROUNDS
 #define MCS_PHILOX_ROUNDS 7
 #endif
@@ -308,6 +311,12 @@ __device__ __forceinline__ void mcs_grid_wait(unsigned *sync, unsigned target)
     __syncthreads();
 }
 
+// u <= T with T == 0 meaning NEVER: mcs_accept_threshold returns 0 exactly when exp(-dE/teff) 2^32 < 1 (underflow,
+// T = 0 in the schedule, NaN energies) -- the reference never accepts there (it compares 0 > rand()/RAND_MAX,
+// qmc.pyx:142).  In the table kernels the pair (u, T) = (0, 0) always looks like a tie, so the rule lives in the
+// refinement path at no cost to the hot loop.
+__device__ __forceinline__ bool mcs_accepts(uint32_t u, uint32_t T) { return (u <= T) & (T != 0u); }
+
 // ---- building blocks shared by the bit-packed sweep kernels (mcs_piqmc.cu, mcs_sa.cu) ---------------
 // Instruction budget, measured on B200 (benchmarks/micro/pipe_rates.cu): ALU-pipe instructions (LOP3, PRMT,
 // IADD3, SHF, ISETP, VIADDMNMX) and FMA-pipe IMAD take 2 issue cycles per warp each and overlap with each
@@ -389,12 +398,24 @@ __device__ __forceinline__ void mcs_decide_call(uint32_t &chA, uint32_t &chB, ui
     chB = 0;
     uint32_t smin = 0xFFFFFFFFu;
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(slot);
+#if MCS_BYTES_BY_PRMT == 1
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(accA) : "memory");
+#elif MCS_BYTES_BY_PRMT == 0
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(accA), "r"(accB) : "memory");
+#endif
 #pragma unroll
     for (int i = 3; i >= 0; --i) {
         uint32_t oA, oB;
+#if MCS_BYTES_BY_PRMT == 2
+        oA = mcs_prmt_byte(accA, i);
+        oB = mcs_prmt_byte(accB, i);
+#elif MCS_BYTES_BY_PRMT == 1
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oA) : "r"(saddr + i) : "memory");
+        oB = mcs_prmt_byte(accB, i);
+#else
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oA) : "r"(saddr + i) : "memory");
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oB) : "r"(saddr + 4 + i) : "memory");
+#endif
         chA = mcs_horner_reject(chA, pow2.up[8], mcs_lut_at<SH>(lut, oA), x[i], smin);
         chB = mcs_horner_reject(chB, pow2.up[8], mcs_lut_at<SH>(lut, oB), x[i] * pow2.up[16], smin);
     }
@@ -417,8 +438,8 @@ __device__ __noinline__ uint2 mcs_refine_call(uint32_t accA, uint32_t accB, cons
         const uint32_t TB = ~mcs_lut_at<SH>(lut, (accB >> (8 * i)) & 0xFFu);
         const uint32_t uA = (x[i] & 0xFFFF0000u) | (f[i] >> 16);
         const uint32_t uB = (x[i] << 16) | (f[i] & 0xFFFFu);
-        chA |= (uA > TA ? 1u : 0u) << (8 * i);
-        chB |= (uB > TB ? 1u : 0u) << (8 * i);
+        chA |= (mcs_accepts(uA, TA) ? 0u : 1u) << (8 * i);
+        chB |= (mcs_accepts(uB, TB) ? 0u : 1u) << (8 * i);
     }
     return make_uint2(chA, chB);
 }
@@ -470,7 +491,7 @@ static __device__ __noinline__ uint4 mcs_refine_call16(uint32_t a0, uint32_t a1,
             const uint32_t T = ~mcs_lut_at<2>(lut, (acc[w] >> (16 * i)) & 0xFFFFu);
             const uint32_t xi = x[2 * (w & 1) + i], fi = f[2 * (w & 1) + i];
             const uint32_t u = w < 2 ? ((xi & 0xFFFF0000u) | (fi >> 16)) : ((xi << 16) | (fi & 0xFFFFu));
-            ch[w] |= (u > T ? 1u : 0u) << (16 * i);
+            ch[w] |= (mcs_accepts(u, T) ? 0u : 1u) << (16 * i);
         }
     return make_uint4(ch[0], ch[1], ch[2], ch[3]);
 }
@@ -482,7 +503,7 @@ inline uint32_t mcs_tie_threshold()
 }
 
 // Metropolis acceptance threshold: the move is accepted iff a uniform 32-bit draw u satisfies
-// u <= T.  dE <= 0 -> always (qmc.pyx:140-141); otherwise P(accept) = ceil(p 2^32)/2^32 with
+// u <= T (mcs_accepts).  dE <= 0 -> always (qmc.pyx:140-141); otherwise P(accept) = ceil(p 2^32)/2^32 with
 // p = exp(-dE/teff) (qmc.pyx:142), floored at 2^-32 (the reference's own floor is 2^-31: it
 // compares exp(..) > rand()/RAND_MAX and rand() returns 0 once in 2^31 draws).
 // nl2e_over_t = -log2(e)/teff.  NaN dE (inf - inf at A = 0) -> never, like the reference.

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
             idx |= (uint32_t)((tr >> k) & 1ull) << (NPL + 1);
             uint32_t rnd[4];
             mcs_philox4x32_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
-            if (rnd[0] <= ~lut[idx]) w ^= 1ull << k;
+            if (mcs_accepts(rnd[0], ~lut[idx])) w ^= 1ull << k;
         }
     }
 
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
                 for (int j = 0; j < NPL; ++j)
                     dE += c[j] * (float)(P - 2 * __popcll((j < NQ ? pl[j] ^ flips : w) & seg));
                 const uint32_t u = (m & 3) == 0 ? rnd[0] : (m & 3) == 1 ? rnd[1] : (m & 3) == 2 ? rnd[2] : rnd[3];
-                if (u <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= seg;
+                if (mcs_accepts(u, mcs_accept_threshold(dE, a.nl2e_over_t))) w ^= seg;
             }
         } else {
             float dE[2] = {0.0f, 0.0f};
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
             for (int hh = 0; hh < (FUSE ? 2 : 1); ++hh) {
                 uint32_t rnd[4];
                 mcs_philox4x32_rk(c0h[hh], c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
-                if (rnd[0] <= mcs_accept_threshold(dE[hh], a.nl2e_over_t)) w ^= FUSE ? (pm1 << (32 * hh)) : pm1;
+                if (mcs_accepts(rnd[0], mcs_accept_threshold(dE[hh], a.nl2e_over_t))) w ^= FUSE ? (pm1 << (32 * hh)) : pm1;
             }
         }
     }
@@ -539,7 +539,7 @@ __device__ __forceinline__ uint64_t phase_direct(const PiqmcPass &a, int site, l
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int q = 4 * q4 + i;
-            if (rnd[i] <= mcs_accept_threshold(e[q], a.nl2e_over_t)) flip |= 1ull << (2 * q + PARITY);
+            if (mcs_accepts(rnd[i], mcs_accept_threshold(e[q], a.nl2e_over_t))) flip |= 1ull << (2 * q + PARITY);
         }
     }
     return flip & allowed;
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_direct_pass_kernel(const __
         }
         uint32_t rnd[4];
         mcs_philox4x32_rk(c0, c1, c2, c3hi | MCS_TAG_LAST_SLICE, a.keys, rnd);
-        if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= 1ull << k;
+        if (mcs_accepts(rnd[0], mcs_accept_threshold(dE, a.nl2e_over_t))) w ^= 1ull << k;
     }
     if (a.global_moves) {
         float dE = hc * (float)(P - 2 * __popcll(w & pmask));
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_direct_pass_kernel(const __
         }
         uint32_t rnd[4];
         mcs_philox4x32_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
-        if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
+        if (mcs_accepts(rnd[0], mcs_accept_threshold(dE, a.nl2e_over_t))) w ^= pmask;
     }
     a.W[(long long)site * a.Rpad + r] = w;
 }
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __gr
         for (int b = 0; b < nbytes; ++b) wsum += s_tab[b][(uint32_t)(y >> (8 * b)) & 255u];
         dE += bath.c0 - wsum;
         const uint32_t u = (k & 3) == 0 ? rnd[0] : (k & 3) == 1 ? rnd[1] : (k & 3) == 2 ? rnd[2] : rnd[3];
-        if (u <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= 1ull << k;
+        if (mcs_accepts(u, mcs_accept_threshold(dE, a.nl2e_over_t))) w ^= 1ull << k;
     }
     if (a.global_moves) { // a world-line flip leaves every s_k s_k' invariant: no bath term (qmc.pyx:575-609)
         float dE = 0.0f;
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __gr
             }
         }
         mcs_philox4x32_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
-        if (rnd[0] <= mcs_accept_threshold(dE, a.nl2e_over_t)) w ^= pmask;
+        if (mcs_accepts(rnd[0], mcs_accept_threshold(dE, a.nl2e_over_t))) w ^= pmask;
     }
     a.W[(long long)site * a.Rpad + r] = w;
 }

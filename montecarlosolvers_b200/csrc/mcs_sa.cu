@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kWarps * 32) sa_direct_pass_kernel(const __gri
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int b = 8 * i + 7 - q;
-            if (rnd[i] <= mcs_accept_threshold(e[b], a.nl2e_over_t)) flip |= 1u << b;
+            if (mcs_accepts(rnd[i], mcs_accept_threshold(e[b], a.nl2e_over_t))) flip |= 1u << b;
         }
     }
     a.V[(long long)site * a.G + g] = v ^ flip;

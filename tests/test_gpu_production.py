@@ -771,3 +771,29 @@ def test_persistent_small_batch_sa_equals_the_multi_launch_path(mcs, case):
     assert out[0][1] == 2 and out[1][1] >= 2 * S * 2  # two cooperative launches vs one launch per colour pass
     assert not np.array_equal(out[0][0], s0)
     assert np.array_equal(out[0][0], out[1][0])
+
+
+def test_zero_temperature_never_accepts_an_uphill_move(mcs):
+    """T = 0 (the tail of the example's classical schedule, santoro80.py:260): the reference compares
+    0 > rand()/RAND_MAX -- never.  A threshold of 0 means NEVER here too (mcs_accepts), not "once in 2^32": after a
+    quench into local minima, 2.6e9 further T = 0 attempts (about 0.6 spurious flips expected under the old u <= T rule)
+    change nothing, and the same holds through the always-refine path."""
+    from bench import load_instance
+    nbs, _ = load_instance()
+    I = mcs.Instance(nbs)
+    R = 4096
+    st = mcs.State(I, mcs._lib.KIND_SA, R, 1)
+    st.init_random(3)
+    st.sa_sweeps(np.zeros(60), 1, seed=4)
+    e0, s0 = st.energies(), st.download_spins()
+    st.sa_sweeps(np.zeros(100), 1, seed=4, sweep_offset=60)
+    assert np.array_equal(st.download_spins(), s0)
+    assert np.array_equal(st.energies(), e0)
+    de = orc.sa_delta_e(s0[7].astype(np.int64), nbs)
+    assert de.min() > 0.0  # a strict local minimum: every move is uphill
+    os.environ["MCS_ALWAYS_REFINE"] = "1"
+    try:
+        st.sa_sweeps(np.zeros(3), 1, seed=4, sweep_offset=160)
+    finally:
+        os.environ.pop("MCS_ALWAYS_REFINE", None)
+    assert np.array_equal(st.download_spins(), s0)
