@@ -413,6 +413,219 @@ __device__ __forceinline__ void dense_phase_b_strips(const DensePass &a, float *
     }
 }
 
+// ---- phase B, pipelined (tcgen05 variant, P <= 32) ---------------------------------------------------------------
+// Same decisions as dense_phase_b_strips, with everything that is not the decision chain moved off it.  Scratch
+// that does NOT alias the TMA ring, so the state-independent part of the prologue runs while the GEMM streams:
+//   Js   [3][128][16]  the strip's J columns: J[block rows r0.., strip columns]  (cp.async, one strip ahead; three
+//                      buffers: the strip being decided, the previous one still being applied, the next one arriving)
+//   ul   [2][16][64]   log2 of the strip's local uniforms, ug [2][16][32] of its world-line uniforms
+//   ds   [2][16][64]   spin changes of a strip
+//   sb   [128][64]     spins of the block, hb [128] fields
+// During the decisions of strip r0 (two warps) the other six warps (a) apply the PREVIOUS strip's rank-16 correction
+// to the rows beyond the current strip's successor, (b) write the previous strip's final spins back, (c) fetch the
+// next strip's J columns and draw its uniforms.  After the decisions only the next strip's 16 rows get this strip's
+// correction before the chain continues.
+constexpr int kS2Js = 0;                                  // float [3][kBS][kSB]
+constexpr int kS2Ul = kS2Js + 3 * kBS * kSB * 4;          // float [2][kSB][kTC]
+constexpr int kS2Ug = kS2Ul + 2 * kSB * kTC * 4;          // float [2][kSB][kTC/2]
+constexpr int kS2Ds = kS2Ug + 2 * kSB * (kTC / 2) * 4;    // float [2][kSB][kTC]
+constexpr int kS2Sb = kS2Ds + 2 * kSB * kTC * 4;          // int8  [kBS][kTC]
+constexpr int kS2Hb = kS2Sb + kBS * kTC;                  // float [kBS]
+constexpr int kS2Bytes = kS2Hb + kBS * 4;
+
+struct Strips2 {
+    float *Js, *ul, *ug, *ds, *hb;
+    signed char *sb;
+    __device__ explicit Strips2(unsigned char *scr)
+        : Js(reinterpret_cast<float *>(scr + kS2Js)), ul(reinterpret_cast<float *>(scr + kS2Ul)),
+          ug(reinterpret_cast<float *>(scr + kS2Ug)), ds(reinterpret_cast<float *>(scr + kS2Ds)),
+          hb(reinterpret_cast<float *>(scr + kS2Hb)), sb(reinterpret_cast<signed char *>(scr + kS2Sb))
+    {
+    }
+};
+
+// J columns of strip r0 (rows r0 .. 127 of the block, 16 columns): t = this thread's index among nt helpers
+__device__ __forceinline__ void strips2_fetch_J(const DensePass &a, const Strips2 &z, int r0, int t, int nt)
+{
+    float *dst = z.Js + ((r0 / kSB) % 3) * kBS * kSB;
+    const long long ld = a.Npad;
+    for (int e = t; e < (kBS - r0) * (kSB / 4); e += nt) {
+        const int lr = e / (kSB / 4), c4 = (e % (kSB / 4)) * 4;
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + lr * kSB + c4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d),
+                     "l"(a.Jf + (long long)(a.i0 + r0 + lr) * ld + a.i0 + r0 + c4)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// uniforms of strip r0 (same Philox counters as the unpipelined scheme)
+template <int PT>
+__device__ __forceinline__ void strips2_draw(const DensePass &a, const Strips2 &z, int r0, int col0, int t, int nt)
+{
+    constexpr int G4 = (PT + 3) / 4, NREP = kTC / PT;
+    float *ul = z.ul + ((r0 / kSB) & 1) * kSB * kTC, *ug = z.ug + ((r0 / kSB) & 1) * kSB * (kTC / 2);
+    for (int e = t; e < kSB * NREP * G4; e += nt) {
+        const int j = e / (NREP * G4), rr = (e / G4) % NREP, g = e % G4;
+        const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * PT) / PT);
+        uint32_t rnd[4];
+        mcs_philox4x32_rk(rep, (uint32_t)(a.i0 + r0 + j), a.sweep_lo, (a.sweep_hi << 8) | (uint32_t)g, a.keys, rnd);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (4 * g + q < PT) ul[j * kTC + rr * PT + 4 * g + q] = __log2f((float)rnd[q] + 1.0f) - 32.0f;
+    }
+    if (a.global_moves) {
+        for (int e = t; e < kSB * NREP; e += nt) {
+            const int j = e / NREP, rr = e % NREP;
+            const uint32_t rep = a.replica_offset + (uint32_t)((col0 + rr * PT) / PT);
+            uint32_t rnd[4];
+            mcs_philox4x32_rk(rep, (uint32_t)(a.i0 + r0 + j), a.sweep_lo, (a.sweep_hi << 8) | MCS_TAG_GLOBAL, a.keys, rnd);
+            ug[j * (kTC / 2) + rr] = __log2f((float)rnd[0] + 1.0f) - 32.0f;
+        }
+    }
+}
+
+// Hb[rows lo .. hi) += J[row, strip rs columns] . deltas of strip rs
+__device__ __forceinline__ void strips2_update(const Strips2 &z, float *Hb, int rs, int lo, int hi, int t, int nt)
+{
+    const float *Js = z.Js + ((rs / kSB) % 3) * kBS * kSB, *ds = z.ds + ((rs / kSB) & 1) * kSB * kTC;
+    for (int it = t; it < (hi - lo) * (kTC / 4); it += nt) {
+        const int row = lo + it / (kTC / 4), c4 = (it % (kTC / 4)) * 4;
+        float4 h = *reinterpret_cast<const float4 *>(Hb + row * kHld + c4);
+        const float *jr = Js + (row - rs) * kSB;
+#pragma unroll
+        for (int j = 0; j < kSB; ++j) {
+            const float jv = jr[j];
+            const float4 dd = *reinterpret_cast<const float4 *>(ds + j * kTC + c4);
+            h.x = fmaf(jv, dd.x, h.x);
+            h.y = fmaf(jv, dd.y, h.y);
+            h.z = fmaf(jv, dd.z, h.z);
+            h.w = fmaf(jv, dd.w, h.w);
+        }
+        *reinterpret_cast<float4 *>(Hb + row * kHld + c4) = h;
+    }
+}
+
+// final spins of strip rs -> S
+__device__ __forceinline__ void strips2_writeback(const DensePass &a, const Strips2 &z, int rs, int col0, int t, int nt)
+{
+    const long long ld = a.Npad;
+    for (int e = t; e < kSB * kTC; e += nt) {
+        const int cc = e / kSB, j = e % kSB;
+        a.S[(long long)(col0 + cc) * ld + a.i0 + rs + j] = __float2bfloat16((float)z.sb[(rs + j) * kTC + cc]);
+    }
+}
+
+// everything that does not depend on the GEMM (run by warps 4-7 while it streams): fields, own-block spins,
+// J columns and uniforms of strip 0
+template <int PT>
+__device__ __forceinline__ void strips2_early(const DensePass &a, unsigned char *scr, int col0, int t, int nt)
+{
+    const Strips2 z(scr);
+    const long long ld = a.Npad;
+    strips2_fetch_J(a, z, 0, t, nt);
+    for (int e = t; e < kBS; e += nt) z.hb[e] = __ldg(&a.h[a.i0 + e]);
+    // spins: item = (column, 8 consecutive sites) = one 16-byte load of bf16, stored transposed as int8.  The own
+    // block's spins were written by this column group's step `step - nblocks` (the caller has waited for it).
+    for (int e = t; e < kBS * kTC / 8; e += nt) {
+        const int cc = e / (kBS / 8), m8 = (e % (kBS / 8)) * 8;
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(a.S + (long long)(col0 + cc) * ld + a.i0 + m8));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) z.sb[(m8 + q) * kTC + cc] = ((w[q >> 1] >> (16 * (q & 1) + 15)) & 1u) ? -1 : 1;
+    }
+    strips2_draw<PT>(a, z, 0, col0, t, nt);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int PT>
+__device__ __forceinline__ void dense_phase_b_strips2(const DensePass &a, float *Hb, unsigned char *scr, int col0)
+{
+    const Strips2 z(scr);
+    const int tid = threadIdx.x;
+    const int P = a.P;
+    const int c = tid & (kTC - 1);
+    const int col = col0 + c;
+    const int k = col % PT;
+    const int cl = c - k + (k == 0 ? P - 1 : k - 1), cr = k < P ? c - k + (k == P - 1 ? 0 : k + 1) : c;
+    const int crep = c / PT;
+    const bool valid = col < a.C && k < P;
+    const bool oddP = (P & 1) != 0 && P > 1;
+    const bool lastodd = oddP && k == P - 1;
+    const bool odd = (k & 1) != 0 && !lastodd, even = (k & 1) == 0 && !lastodd;
+    const float sc = a.nl2e_over_t, bco = a.bcoef, jp2 = a.jperp2;
+    const bool trotter = a.trotter != 0 && P > 1, glob = a.global_moves != 0;
+    const unsigned segmask = PT >= 32 ? 0xffffffffu : (((1u << (PT & 31)) - 1u) << ((tid & 31) & ~(PT - 1)));
+    constexpr int NH = kThreads - kTC; // helper threads
+    dense_stamp(a, 2);
+#define MCS_ACCEPT(dE, lg) (valid & (((dE) <= 0.0f) | ((dE) * sc >= (lg))))
+#pragma unroll 1
+    for (int r0 = 0; r0 < kBS; r0 += kSB) {
+        const int b = (r0 / kSB) & 1;
+        if (tid < kTC) {
+            const float *Js = z.Js + ((r0 / kSB) % 3) * kBS * kSB, *ul = z.ul + b * kSB * kTC, *ug = z.ug + b * kSB * (kTC / 2);
+            float *ds = z.ds + b * kSB * kTC;
+            float f[kSB], lu[kSB], hb[kSB], s0[kSB], gu[kSB];
+#pragma unroll
+            for (int j = 0; j < kSB; ++j) {
+                f[j] = Hb[(r0 + j) * kHld + c];
+                lu[j] = ul[j * kTC + c];
+                hb[j] = z.hb[r0 + j];
+                s0[j] = (float)z.sb[(r0 + j) * kTC + c];
+                gu[j] = glob ? ug[j * (kTC / 2) + crep] : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < kSB; ++j) {
+                const float bf = bco * (f[j] + hb[j]); // -2B * local field
+                float s = s0[j];
+                if (trotter) {
+                    float nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                    float dE = s * fmaf(jp2, nb, bf);
+                    s = (even & MCS_ACCEPT(dE, lu[j])) ? -s : s;
+                    nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                    dE = s * fmaf(jp2, nb, bf);
+                    s = (odd & MCS_ACCEPT(dE, lu[j])) ? -s : s;
+                    if (oddP) { // warp-uniform
+                        nb = __shfl_sync(0xffffffffu, s, cl & 31) + __shfl_sync(0xffffffffu, s, cr & 31);
+                        dE = s * fmaf(jp2, nb, bf);
+                        s = (lastodd & MCS_ACCEPT(dE, lu[j])) ? -s : s;
+                    }
+                } else {
+                    const float dE = s * bf;
+                    s = MCS_ACCEPT(dE, lu[j]) ? -s : s;
+                }
+                if (glob) {
+                    const int part = valid ? __float2int_rn(s * bf * a.gscale) : 0;
+                    const float dE = (float)__reduce_add_sync(segmask, part) * a.ginv;
+                    s = MCS_ACCEPT(dE, gu[j]) ? -s : s;
+                }
+                z.sb[(r0 + j) * kTC + c] = (signed char)s;
+                const float d = s - s0[j];
+#pragma unroll
+                for (int j2 = j + 1; j2 < kSB; ++j2) f[j2] = fmaf(Js[j2 * kSB + j], d, f[j2]); // local row j2, column j
+                ds[j * kTC + c] = d;
+            }
+        } else {
+            const int t = tid - kTC;
+            if (r0 + kSB < kBS) strips2_fetch_J(a, z, r0 + kSB, t, NH); // next strip's J columns
+            if (r0 > 0) {
+                strips2_update(z, Hb, r0 - kSB, r0 + kSB, kBS, t, NH);      // previous strip -> rows beyond the next one
+                strips2_writeback(a, z, r0 - kSB, col0, t, NH);
+            }
+            if (r0 + kSB < kBS) strips2_draw<PT>(a, z, r0 + kSB, col0, t, NH);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (r0 == 0) dense_stamp(a, 3);
+        if (r0 + kSB < kBS) strips2_update(z, Hb, r0, r0 + kSB, r0 + 2 * kSB, tid, kThreads); // this strip -> the next strip's rows
+        __syncthreads();
+        if (r0 == 0) dense_stamp(a, 4);
+    }
+#undef MCS_ACCEPT
+    dense_stamp(a, 5);
+    strips2_writeback(a, z, kBS - kSB, col0, tid, kThreads);
+}
+
 __device__ __forceinline__ void dense_phase_b_dispatch(const DensePass &a, float *Hb, unsigned char *scr,
                                                        float *uglob, int col0)
 {
@@ -570,6 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint64_t *empty = full + kStages;
     uint64_t *accum_full = empty + kStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+    unsigned char *scr2 = ring + kRingBytes + kHbBytes + 128 + kUglobBytes; // pipelined phase B (16-byte aligned)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int col0 = blockIdx.x * kTC;
 
@@ -646,6 +860,28 @@ __global__ void __launch_bounds__(kThreads, 1)
             umma_commit(&empty[s]); // stage reusable once these MMAs have read it
         }
         umma_commit(accum_full);
+    } else if (warp >= 4 && a.PS <= 32) {
+        // ---- warps 4-7: the part of phase B's prologue that does not need the fields, under the GEMM.  The own
+        // block's spins were last written by this column group's step `step - nblocks`.
+        if (tid == 128) {
+            const long long need = (long long)a.step - a.nblocks + 1;
+            unsigned seen = 0, spins = 0;
+            while (need > 0) {
+                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(a.ver + blockIdx.x) : "memory");
+                if ((long long)seen >= need || ++spins >= (1u << 24)) break;
+                __nanosleep(100);
+            }
+            if (need > 0 && (long long)seen < need) atomicExch(a.ver + gridDim.x, 1u);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        switch (a.PS) {
+        case 1: strips2_early<1>(a, scr2, col0, tid - 128, 128); break;
+        case 2: strips2_early<2>(a, scr2, col0, tid - 128, 128); break;
+        case 4: strips2_early<4>(a, scr2, col0, tid - 128, 128); break;
+        case 8: strips2_early<8>(a, scr2, col0, tid - 128, 128); break;
+        case 16: strips2_early<16>(a, scr2, col0, tid - 128, 128); break;
+        default: strips2_early<32>(a, scr2, col0, tid - 128, 128); break;
+        }
     }
     __syncwarp();
     if (warp < 4) {
@@ -681,8 +917,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
     dense_stamp(a, 1);
-    // phase B scratch lives in the (now idle) ring, the world-line uniforms behind the barriers
-    dense_phase_b_dispatch(a, Hb, ring, reinterpret_cast<float *>(ring + kRingBytes + kHbBytes + 128), col0);
+    if (a.PS <= 32) { // pipelined phase B on its own scratch (its early part ran under the GEMM)
+        switch (a.PS) {
+        case 1: dense_phase_b_strips2<1>(a, Hb, scr2, col0); break;
+        case 2: dense_phase_b_strips2<2>(a, Hb, scr2, col0); break;
+        case 4: dense_phase_b_strips2<4>(a, Hb, scr2, col0); break;
+        case 8: dense_phase_b_strips2<8>(a, Hb, scr2, col0); break;
+        case 16: dense_phase_b_strips2<16>(a, Hb, scr2, col0); break;
+        default: dense_phase_b_strips2<32>(a, Hb, scr2, col0); break;
+        }
+    } else { // P > 32: row-by-row scheme; its scratch lives in the (now idle) ring
+        dense_phase_b_dispatch(a, Hb, ring, reinterpret_cast<float *>(ring + kRingBytes + kHbBytes + 128), col0);
+    }
     dense_stamp(a, 6);
     // this column group has completed step a.step: its spins are written back (all threads), publish
     __syncthreads();
@@ -749,8 +995,9 @@ __global__ void dense_compress_sa_kernel(const __nv_bfloat16 *__restrict__ S, ui
 }
 
 constexpr size_t kSmemBytes = kBS * kHld * 4 + kScrBytes + kUglobBytes;
-constexpr size_t kSmemBytesTc = kRingBytes + kHbBytes + 128 + kUglobBytes + 1024; // + barriers + world-line uniforms
-                                                                                  // + slack for 1024-byte alignment
+constexpr size_t kSmemBytesTc = kRingBytes + kHbBytes + 128 + kUglobBytes + kS2Bytes + 1024; // + barriers + world-line
+                                                                 // uniforms (P > 32) + pipelined phase B + alignment slack
+static_assert(kSmemBytesTc <= 227 * 1024, "dense_block_kernel_tc: shared memory");
 static_assert(kScrBytes <= kRingBytes, "phase B scratch must fit the ring");
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
