@@ -101,3 +101,34 @@ def test_shard_covers_replicas_exactly_once():
             a = [parallel.shard_aligned(R, r, world) for r in range(world)]
             assert a[0][0] == 0 and a[-1][1] == R and all(l % 32 == 0 for l, h in a if h > l)
             assert sum(h - l for l, h in a) == R
+
+
+def test_build_stamp_is_a_content_hash_that_survives_copying_the_tree(tmp_path):
+    """The GPU box runs a COPY of the tree at another path with fresh mtimes: the library must count as up to date
+    there (every rank of a torchrun launch would otherwise rebuild it at once), and must stop counting as up to date
+    as soon as a source changes."""
+    import shutil
+    import subprocess
+    import sys
+    from montecarlosolvers_b200 import build
+    if not os.path.isfile(build.OUT):
+        pytest.skip("library not built")
+    assert build.up_to_date()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(build.__file__)))
+    dst = tmp_path / "copy"
+    (dst / "montecarlosolvers_b200").mkdir(parents=True)
+    shutil.copytree(os.path.join(root, "include"), dst / "include")
+    for name in os.listdir(os.path.join(root, "montecarlosolvers_b200")):
+        src = os.path.join(root, "montecarlosolvers_b200", name)
+        if name == "csrc":
+            shutil.copytree(src, dst / "montecarlosolvers_b200" / "csrc")
+        elif os.path.isfile(src) and (name.endswith(".py") or name.endswith(".srchash")):
+            shutil.copy(src, dst / "montecarlosolvers_b200" / name)
+    (dst / "montecarlosolvers_b200" / "libmcs_b200.so").write_bytes(b"")  # presence is enough for the check
+    code = "from montecarlosolvers_b200 import build; print(build.up_to_date())"
+    run = lambda: subprocess.run([sys.executable, "-c", code], cwd=str(dst), stdout=subprocess.PIPE, text=True,
+                                 env=dict(os.environ, PYTHONPATH=str(dst))).stdout.strip()
+    assert run() == "True"
+    with open(dst / "montecarlosolvers_b200" / "csrc" / "mcs_sa.cu", "a") as f:
+        f.write("// touched\n")
+    assert run() == "False"
