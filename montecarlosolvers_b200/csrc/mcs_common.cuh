@@ -46,6 +46,8 @@ struct mcs_instance {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr; // copy streams of the pipelined one-shot calls (lazy)
+    cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr}; // extra launch streams: replica chunks pass-interleaved (lazy)
+    cudaEvent_t ev_aux0 = nullptr, ev_aux1[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_up[16] = {}, ev_done[16] = {}, ev_t0 = nullptr;
     int64_t N = 0, maxnb = 0;
     int64_t nsteps = 1;  // > 1: time-dependent couplings, one table per schedule step (Noisy* functions)

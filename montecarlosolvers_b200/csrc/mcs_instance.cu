@@ -365,6 +365,11 @@ extern "C" void mcs_instance_destroy(mcs_instance *inst)
     }
     if (inst->s_in) cudaStreamDestroy(inst->s_in);
     if (inst->s_out) cudaStreamDestroy(inst->s_out);
+    for (int q = 0; q < 3; ++q) {
+        if (inst->s_aux[q]) cudaStreamDestroy(inst->s_aux[q]);
+        if (inst->ev_aux1[q]) cudaEventDestroy(inst->ev_aux1[q]);
+    }
+    if (inst->ev_aux0) cudaEventDestroy(inst->ev_aux0);
     if (inst->ev0) cudaEventDestroy(inst->ev0);
     if (inst->ev1) cudaEventDestroy(inst->ev1);
     if (inst->stream) cudaStreamDestroy(inst->stream);

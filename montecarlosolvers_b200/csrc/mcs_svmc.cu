@@ -9,6 +9,7 @@
 // line of cos(theta_j).  Colour classes are launched one after another; neighbours are frozen.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "mcs_common.cuh"
 
@@ -227,6 +228,30 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
     MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
                 "time-dependent instance has %lld tables but the schedule has %lld steps", (long long)inst->nsteps,
                 (long long)S);
+    // Mid-size batches (BASELINE cfg4: 2048 reads): a colour pass is 5 us of work behind 4.4 us of kernel-boundary
+    // latency.  Replicas are independent, so the batch is cut into two chunks whose passes alternate on two
+    // streams: one chunk computes while the other sits in its launch gap (+16 %; with three or four chunks the host
+    // cannot issue the launches fast enough: 2.3e11 / 1.7e11 attempts/s against 2.6e11 with two; MCS_STREAMS=n).
+    const long long groups = st->Rpad / 128;
+    long long max_sites = 0;
+    for (int c = 0; c < inst->ncolors; ++c)
+        max_sites = std::max(max_sites, (long long)(inst->color_start[c + 1] - inst->color_start[c]));
+    int nchunk = 1;
+    if (groups * max_sites <= 65536 && !getenv("MCS_ONE_STREAM")) nchunk = (int)std::max(1ll, std::min(2ll, groups / 2));
+    if (const char *e = getenv("MCS_STREAMS")) nchunk = (int)std::max(1ll, std::min(std::min(4ll, groups), atoll(e)));
+    if (nchunk > 1 && !inst->ev_aux0) MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_aux0, cudaEventDisableTiming));
+    for (int q = 0; q + 1 < nchunk; ++q) {
+        if (!inst->s_aux[q]) {
+            MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_aux[q], cudaStreamNonBlocking));
+            MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_aux1[q], cudaEventDisableTiming));
+        }
+    }
+    if (nchunk > 1) {
+        MCS_CUDA(cudaEventRecord(inst->ev_aux0, inst->stream));
+        for (int q = 0; q + 1 < nchunk; ++q) MCS_CUDA(cudaStreamWaitEvent(inst->s_aux[q], inst->ev_aux0, 0));
+    }
+    float *const theta0 = a.theta, *const cosz0 = a.cosz;
+    const uint32_t roff0 = a.replica_offset;
     for (int64_t f = 0; f < S; ++f) {
         a.ell_J = inst->ell_J_at(f); // svmc.NoisySVMC: nbs[ifield] (svmc.pyx:317-319)
         a.h = inst->h_at(f);
@@ -241,14 +266,25 @@ int mcs_launch_svmc_sweeps(mcs_state *st, const double *A, const double *B, int6
                 a.sites = inst->d_order + inst->color_start[c];
                 a.nsites = inst->color_start[c + 1] - inst->color_start[c];
                 if (a.nsites == 0) continue;
-                const long long ctas = (long long)((a.nsites + kWarps - 1) / kWarps) * (a.Rpad / 128);
-                if (cache)
-                    mcs_launch_pdl(svmc_pass_kernel<true>, dim3((unsigned)ctas), dim3(kWarps * 32), inst->stream, a);
-                else
-                    mcs_launch_pdl(svmc_pass_kernel<false>, dim3((unsigned)ctas), dim3(kWarps * 32), inst->stream, a);
-                inst->launches++;
+                for (int q = 0; q < nchunk; ++q) {
+                    const long long g0 = groups * q / nchunk, ng = groups * (q + 1) / nchunk - g0;
+                    a.theta = theta0 + g0 * 128; // replica is the fastest axis: a chunk is a column offset
+                    a.cosz = cosz0 + g0 * 128;
+                    a.replica_offset = roff0 + (uint32_t)(g0 * 128);
+                    cudaStream_t s = q ? inst->s_aux[q - 1] : inst->stream;
+                    const long long ctas = (long long)((a.nsites + kWarps - 1) / kWarps) * ng;
+                    if (cache)
+                        mcs_launch_pdl(svmc_pass_kernel<true>, dim3((unsigned)ctas), dim3(kWarps * 32), s, a);
+                    else
+                        mcs_launch_pdl(svmc_pass_kernel<false>, dim3((unsigned)ctas), dim3(kWarps * 32), s, a);
+                    inst->launches++;
+                }
             }
         }
+    }
+    for (int q = 0; q + 1 < nchunk; ++q) {
+        MCS_CUDA(cudaEventRecord(inst->ev_aux1[q], inst->s_aux[q]));
+        MCS_CUDA(cudaStreamWaitEvent(inst->stream, inst->ev_aux1[q], 0));
     }
     MCS_CUDA(mcs_take_launch_error());
     MCS_CUDA(cudaGetLastError());
