@@ -87,6 +87,7 @@ struct mcs_instance {
     const int32_t *tab_idx_at(int64_t f) const { return d_tab_idx + (nsteps > 1 ? (size_t)f * N * maxnb : 0); }
     const double *tab_J_at(int64_t f) const { return d_tab_J + (nsteps > 1 ? (size_t)f * N * maxnb : 0); }
     int32_t *d_order = nullptr;   // [N]
+    int32_t *d_pos = nullptr;     // [N] inverse of order: position of a site in the colour-sorted list
     void *d_Jhi = nullptr, *d_Jlo = nullptr; // dense only: [Npad][Npad] bf16 split J = hi + lo
     float *d_Jf = nullptr;                   // dense only: [Npad][Npad] fp32
     float *d_hpad = nullptr;                 // dense only: [Npad]
@@ -445,6 +446,91 @@ __device__ __noinline__ uint2 mcs_refine_call(uint32_t accA, uint32_t accB, cons
     }
     return make_uint2(chA, chB);
 }
+
+// ---- column tables of the cluster-resident kernels (mcs_sa.cu: sa_cluster_kernel) -------------------------
+// There the 32 lanes of a warp are 32 different SITES, each with its own threshold table.  Entry e of local site
+// l sits at word e * stride + l (stride a multiple of 32): the bank of a lookup is the lane's site, whatever the
+// pattern, so the random lookups of a warp never conflict.  `col` points at the site's column, `off` is the
+// pattern index * 4 as in mcs_lut_at<2>: the address is one IMAD (FMA pipe) instead of an add on the ALU pipe.
+__device__ __forceinline__ uint32_t mcs_lut_col(const uint32_t *col, uint32_t off, uint32_t stride)
+{
+    return *(const uint32_t *)((const char *)col + off * stride);
+}
+
+// mcs_decide_call / mcs_refine_call on a column table: same Philox call, same uniforms, same decisions
+__device__ __forceinline__ void mcs_decide_call_col(uint32_t &chA, uint32_t &chB, uint32_t &flags, uint32_t accA,
+                                                    uint32_t accB, const uint32_t *col, uint32_t stride, uint32_t c0,
+                                                    uint32_t c1, uint32_t c2, uint32_t c3,
+                                                    const mcs_philox_keys &keys, const mcs_pow2_table &pow2,
+                                                    uint32_t tie_thr, uint2 *slot)
+{
+    uint32_t x[4];
+    mcs_philox4x32_rk(c0, c1, c2, c3, keys, x);
+    chA = 0;
+    chB = 0;
+    uint32_t smin = 0xFFFFFFFFu;
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(slot);
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(accA), "r"(accB) : "memory");
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+        uint32_t oA, oB;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oA) : "r"(saddr + i) : "memory");
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(oB) : "r"(saddr + 4 + i) : "memory");
+        chA = mcs_horner_reject(chA, pow2.up[8], mcs_lut_col(col, oA, stride), x[i], smin);
+        chB = mcs_horner_reject(chB, pow2.up[8], mcs_lut_col(col, oB, stride), x[i] * pow2.up[16], smin);
+    }
+    mcs_horner_flag(flags, smin, tie_thr, pow2.up[1]);
+}
+
+static __device__ __noinline__ uint2 mcs_refine_call_col(uint32_t accA, uint32_t accB, const uint32_t *col,
+                                                         uint32_t stride, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                         uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    uint32_t x[4], f[4];
+    mcs_philox4x32(c0, c1, c2, c3, k0, k1, x);
+    mcs_philox4x32(c0, c1, c2, c3 | MCS_TAG_REFINE, k0, k1, f);
+    uint32_t chA = 0, chB = 0; // reject bit of byte i at bit 8 i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t TA = ~mcs_lut_col(col, (accA >> (8 * i)) & 0xFFu, stride);
+        const uint32_t TB = ~mcs_lut_col(col, (accB >> (8 * i)) & 0xFFu, stride);
+        const uint32_t uA = (x[i] & 0xFFFF0000u) | (f[i] >> 16);
+        const uint32_t uB = (x[i] << 16) | (f[i] & 0xFFFFu);
+        chA |= (mcs_accepts(uA, TA) ? 0u : 1u) << (8 * i);
+        chB |= (mcs_accepts(uB, TB) ? 0u : 1u) << (8 * i);
+    }
+    return make_uint2(chA, chB);
+}
+
+// ---- thread-block clusters: distributed shared memory and the cluster barrier (sm_90+) --------------------
+__device__ __forceinline__ uint32_t mcs_cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA's layout) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mcs_mapa(uint32_t saddr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t mcs_ld_cluster_u32(uint32_t caddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(caddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t mcs_ld_cluster_u64(uint32_t caddr)
+{
+    uint64_t v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(caddr) : "memory");
+    return v;
+}
+// split barrier: every thread of every CTA of the cluster arrives (release) and later waits (acquire)
+__device__ __forceinline__ void mcs_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mcs_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // ---- wide index fields (9 or 10 planes: degree + field of 7 or 8 in the PIQMC kernel) --------------------
 // The pattern index no longer fits a byte, so an index word holds TWO 16-bit fields (index * 4) and one Philox

@@ -258,6 +258,11 @@ extern "C" int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int6
         (rc = upload(&inst->d_ell_idx, ell_idx)) || (rc = upload(&inst->d_ell_J, ell_J)) ||
         (rc = upload(&inst->d_h, hf)) || (rc = upload(&inst->d_order, inst->order)))
         return fail(rc);
+    {
+        std::vector<int32_t> pos((size_t)nspins);
+        for (int64_t q = 0; q < nspins; ++q) pos[(size_t)inst->order[(size_t)q]] = (int32_t)q;
+        if ((rc = upload(&inst->d_pos, pos))) return fail(rc);
+    }
     // dense instances (SK-like): the coupling matrix itself, fp32 and split into two bf16 halves.  Decided from the
     // DENSITY of the graph (at least a quarter of all pairs coupled), not from one hub: a sparse graph with a few
     // high-degree sites stays with the coloured kernels.  The blocked path needs 8 Npad^2 bytes on the device.
@@ -355,6 +360,7 @@ extern "C" void mcs_instance_destroy(mcs_instance *inst)
     cudaFree(inst->d_ell_J);
     cudaFree(inst->d_h);
     cudaFree(inst->d_order);
+    cudaFree(inst->d_pos);
     cudaFree(inst->d_Jhi);
     cudaFree(inst->d_Jlo);
     cudaFree(inst->d_Jf);

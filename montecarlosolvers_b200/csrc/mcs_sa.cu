@@ -446,6 +446,267 @@ const void *sa_persistent_fn(int npl, int field)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Small batches, cluster-resident: the whole schedule in ONE launch without a grid barrier.  Restarts are
+// independent, so the batch is cut into groups of Wc words (32 Wc restarts) and each group is owned by one
+// thread-block CLUSTER for the whole schedule: CTA r of the cluster keeps a contiguous slice of every colour class
+// (all Wc words of those sites) in its shared memory, reads the neighbour words that live in the other CTAs through
+// distributed shared memory, and the colour passes are separated by the hardware cluster barrier (~0.2 us) instead of
+// a kernel boundary or a grid barrier (~2.3 us).  The lanes of a warp are 32 SITES of one word here, so every site
+// has its own threshold table, kept column-wise (mcs_lut_col: conflict-free) and rebuilt per schedule step between
+// arriving at the barrier and waiting on it; a pattern and its complement have opposite energy differences, so half
+// the entries need no exponential.  Same Philox counters (global word, site, sweep), same thresholds, same decision
+// code as sa_lut_pass_kernel: bit-identical to the multi-launch path (tests).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kClMaxColors = 16;
+
+struct SaCluster {
+    uint32_t *V;
+    const int32_t *ell_idx;
+    const float *ell_J; // [nsteps][N][dpad]
+    const float *h;     // [nsteps][N]
+    long long ellJ_stride, h_stride;
+    const int32_t *order; // sites sorted by colour
+    const int32_t *pos;   // inverse of order
+    const float *nl2e;    // [S]: -log2(e) / sched[t]
+    long long *prof;      // MCS_CLUSTER_PROF=1: cycles of thread 0 of CTA 0 in {items, arrive + tables, wait}
+    int color_start[kClMaxColors + 1];
+    int per[kClMaxColors];          // sites of the colour per CTA = ceil(n_c / C)
+    int loc_base[kClMaxColors + 1]; // local index of a CTA's first site of the colour
+    int ncolors, dpad, S, mcsteps, Wc, nloc_pad, csize, prof_cta;
+    long long G;
+    uint64_t sweep_offset;
+    mcs_philox_keys keys;
+    mcs_pow2_table pow2;
+    uint32_t word_offset, tie_thr;
+};
+
+// x / d and x % d for 0 <= x < 2^22, d >= 1 (rcp = 1.0f / d): no integer division in the pass loop
+__device__ __forceinline__ void sa_divmod(int x, int d, float rcp, int &q, int &r)
+{
+    q = __float2int_rz(__int2float_rn(x) * rcp);
+    r = x - q * d;
+    if (r < 0) r += d, --q;
+    if (r >= d) r -= d, ++q;
+}
+
+template <int NPL, int FLD>
+__global__ void __launch_bounds__(1024, 1) sa_cluster_kernel(const __grid_constant__ SaCluster a)
+{
+    constexpr int ENT = 1 << NPL, NQ = NPL - FLD;
+    static_assert(NPL <= 6, "byte index fields hold pattern * 4");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const uint32_t NP = (uint32_t)a.nloc_pad;
+    uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw);        // [ENT][NP]
+    uint32_t *s_V = s_lut + (size_t)ENT * NP;                       // [Wc][NP]
+    uint32_t *s_nba = s_V + (size_t)a.Wc * NP;                      // [NQ][NP] shared::cluster address of word 0
+    float *s_c = reinterpret_cast<float *>(s_nba + (size_t)NQ * NP); // [NPL][NP] -2 J, -2 h (static instances)
+    int32_t *s_site = reinterpret_cast<int32_t *>(s_c + (size_t)NPL * NP); // [NP] global site, -1: none
+    uint2 *s_bounce = reinterpret_cast<uint2 *>(s_site + NP);       // [4][T]
+    const uint32_t rank = mcs_cluster_ctarank();
+    const uint32_t cid = blockIdx.x / (uint32_t)a.csize;
+    const uint32_t w0 = cid * (uint32_t)a.Wc;
+    const uint32_t G32 = (uint32_t)a.G;
+    const int nw = (int)min((uint32_t)a.Wc, G32 - w0);
+    const bool fixed = a.ellJ_stride == 0 && a.h_stride == 0;
+    const int nloc = a.loc_base[a.ncolors];
+
+    // ---- resident data: sites, neighbour addresses, couplings, state ----
+    for (int loc = tid; loc < (int)NP; loc += T) {
+        int site = -1;
+        if (loc < nloc) {
+            int c = 0;
+            while (c + 1 < a.ncolors && loc >= a.loc_base[c + 1]) ++c;
+            const int q = (int)rank * a.per[c] + (loc - a.loc_base[c]);
+            if (q < a.color_start[c + 1] - a.color_start[c]) site = __ldg(&a.order[a.color_start[c] + q]);
+        }
+        s_site[loc] = site;
+        if (site < 0) {
+            for (int w = 0; w < a.Wc; ++w) s_V[(uint32_t)w * NP + loc] = 0u;
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            if (j < NQ) {
+                const int nbs = __ldg(&a.ell_idx[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j]);
+                const int p = __ldg(&a.pos[nbs]);
+                int c = 0;
+                while (c + 1 < a.ncolors && p >= a.color_start[c + 1]) ++c;
+                const int q = p - a.color_start[c];
+                const int r = q / a.per[c];
+                const int l = a.loc_base[c] + (q - r * a.per[c]);
+                s_nba[(uint32_t)j * NP + loc] =
+                    mcs_mapa((uint32_t)__cvta_generic_to_shared(s_V + l), (uint32_t)r);
+                s_c[(uint32_t)j * NP + loc] = -2.0f * __ldg(&a.ell_J[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j]);
+            } else {
+                s_c[(uint32_t)j * NP + loc] = -2.0f * __ldg(&a.h[site]);
+            }
+        }
+        for (int w = 0; w < a.Wc; ++w)
+            s_V[(uint32_t)w * NP + loc] = w < nw ? a.V[(uint64_t)(uint32_t)site * G32 + w0 + w] : 0u;
+    }
+    __syncthreads();
+
+    // Threshold tables of this CTA's colour-`col` sites at schedule step t, spread over threads [first, first + nthr):
+    // one work item = (site, pattern e with its top bit clear) fills the entries of e and of its complement, whose
+    // energy difference is the exact negation (same terms, same order, opposite signs): one exponential per pair.
+    auto build_tables = [&](int col, int t, int first, int nthr) {
+        const int nc = a.color_start[col + 1] - a.color_start[col];
+        const int pv = max(0, min(a.per[col], nc - (int)rank * a.per[col]));
+        const int work = pv * (ENT / 2);
+        if (tid < first || work == 0) return;
+        const float rcp = 1.0f / (float)pv;
+        const float nl2e = __ldg(&a.nl2e[t]);
+        const float *ellJ = a.ell_J + (size_t)t * a.ellJ_stride;
+        const float *hrow = a.h + (size_t)t * a.h_stride;
+        for (int idx = tid - first; idx < work; idx += nthr) {
+            int e, q;
+            sa_divmod(idx, pv, rcp, e, q);
+            const int loc = a.loc_base[col] + q;
+            float dE = 0.0f;
+            if (fixed) {
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    const float cj = s_c[(uint32_t)j * NP + loc];
+                    dE += ((e >> j) & 1) ? -cj : cj;
+                }
+            } else {
+                const int site = s_site[loc];
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    const float cj = -2.0f * (j < NQ ? __ldg(&ellJ[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j])
+                                                     : __ldg(&hrow[site]));
+                    dE += ((e >> j) & 1) ? -cj : cj;
+                }
+            }
+            const uint32_t nthr_ = ~mcs_accept_threshold(fabsf(dE), nl2e); // dE == 0: always; NaN: never, both ways
+            s_lut[(uint32_t)e * NP + loc] = !(dE <= 0.0f) ? nthr_ : 0u;
+            s_lut[(uint32_t)(ENT - 1 - e) * NP + loc] = !(dE >= 0.0f) ? nthr_ : 0u;
+        }
+    };
+    auto items_of = [&](int col) {
+        const int nc = a.color_start[col + 1] - a.color_start[col];
+        return max(0, min(a.per[col], nc - (int)rank * a.per[col])) * nw;
+    };
+
+    const long long npass = (long long)a.S * a.mcsteps * a.ncolors;
+    build_tables(0, 0, 0, T);
+    mcs_cluster_arrive(); // every CTA's state is in place before the first remote read
+    __syncthreads();
+    mcs_cluster_wait();
+
+    uint2 *bounce = s_bounce + tid;
+    long long pf[4] = {0, 0, 0, 0}, tq = clock64();
+    int col = 0, step_in = 0, t = 0; // pass p = ((t * mcsteps) + step_in) * ncolors + col
+    uint64_t sweep = a.sweep_offset;
+    for (long long p = 0; p < npass; ++p) {
+        const int nc = a.color_start[col + 1] - a.color_start[col];
+        const int pv = max(0, min(a.per[col], nc - (int)rank * a.per[col]));
+        const int items = pv * nw;
+        const uint32_t c2 = (uint32_t)sweep, c3hi = (uint32_t)(sweep >> 32) << 8;
+        const float rcp = pv > 0 ? 1.0f / (float)pv : 0.0f;
+        // Tables of the NEXT pass (another colour: nobody reads those columns during this pass).  With enough
+        // threads left over after the items (at least a quarter of the CTA) they build them now, under the decisions;
+        // otherwise every thread takes a share between arriving at the barrier and waiting on it.
+        int ncol = col + 1, nstep = step_in, nt = t;
+        if (ncol == a.ncolors) {
+            ncol = 0;
+            if (++nstep == a.mcsteps) nstep = 0, ++nt;
+        }
+        const bool need_tables = p + 1 < npass && nstep == 0 && (ncol != col || items == 0);
+        const bool tables_now = need_tables && a.ncolors > 1 && 4 * (T - items) >= T;
+        if (tables_now) build_tables(ncol, nt, items, T - items);
+        for (int item = tid; item < items; item += T) {
+            int w, q;
+            sa_divmod(item, pv, rcp, w, q);
+            const uint32_t loc = (uint32_t)(a.loc_base[col] + q);
+            uint32_t *own = s_V + (uint32_t)w * NP + loc;
+            const uint32_t v = *own;
+            uint32_t pl[NPL];
+#pragma unroll
+            for (int j = 0; j < NPL; ++j)
+                pl[j] = j < NQ ? v ^ mcs_ld_cluster_u32(s_nba[(uint32_t)j * NP + loc] + (uint32_t)w * NP * 4u) : v;
+            const uint32_t *lcol = s_lut + loc;
+            const uint32_t c0 = a.word_offset + w0 + (uint32_t)w, c1 = (uint32_t)s_site[loc];
+            uint32_t rej = 0, flags = 0;
+#define MCS_SA_CALL(qq)                                                                                       \
+    {                                                                                                         \
+        uint32_t chA, chB;                                                                                    \
+        mcs_decide_call_col(chA, chB, flags, sa_gather_index<NPL, 2 * (qq)>(pl, a.pow2),                      \
+                            sa_gather_index<NPL, 2 * (qq) + 1>(pl, a.pow2), lcol, NP, c0, c1, c2,             \
+                            c3hi | (uint32_t)(2 * (qq)), a.keys, a.pow2, a.tie_thr, bounce + (qq) * T);       \
+        rej = chA * a.pow2.up[7 - 2 * (qq)] + rej;                                                            \
+        rej = chB * a.pow2.up[6 - 2 * (qq)] + rej;                                                            \
+    }
+            MCS_SA_CALL(0) MCS_SA_CALL(1) MCS_SA_CALL(2) MCS_SA_CALL(3)
+#undef MCS_SA_CALL
+            if (flags) {
+#define MCS_SA_REFINE(qq)                                                                                     \
+    if (flags & (8u >> (qq))) {                                                                               \
+        const uint2 ch = mcs_refine_call_col(sa_gather_index<NPL, 2 * (qq)>(pl, a.pow2),                      \
+                                             sa_gather_index<NPL, 2 * (qq) + 1>(pl, a.pow2), lcol, NP, c0, c1,\
+                                             c2, c3hi | (uint32_t)(2 * (qq)), a.keys.rk[0], a.keys.rk[1]);    \
+        rej = (rej & ~(0x03030303u << (6 - 2 * (qq)))) | (ch.x << (7 - 2 * (qq))) | (ch.y << (6 - 2 * (qq))); \
+    }
+                MCS_SA_REFINE(0) MCS_SA_REFINE(1) MCS_SA_REFINE(2) MCS_SA_REFINE(3)
+#undef MCS_SA_REFINE
+            }
+            *own = v ^ ~rej;
+        }
+        // next pass
+        if (++col == a.ncolors) {
+            col = 0;
+            ++sweep;
+            if (++step_in == a.mcsteps) step_in = 0, ++t;
+        }
+        long long tn = clock64();
+        pf[0] += tn - tq, tq = tn;
+        mcs_cluster_arrive();
+        // the tables of the next colour are not in use by anyone (their last readers passed a cluster barrier); a
+        // single-colour instance rebuilds its only table here, after the CTA's readers are done
+        if (p + 1 < npass && step_in == 0 && !tables_now) {
+            if (a.ncolors == 1) __syncthreads();
+            build_tables(col, t, 0, T);
+        }
+        tn = clock64();
+        pf[1] += tn - tq, tq = tn;
+        __syncthreads();
+        tn = clock64();
+        pf[2] += tn - tq, tq = tn;
+        mcs_cluster_wait();
+        tn = clock64();
+        pf[3] += tn - tq, tq = tn;
+    }
+    if (a.prof && blockIdx.x == (unsigned)a.prof_cta && tid == 0)
+        for (int q = 0; q < 4; ++q) a.prof[q] = pf[q];
+    // no remote read is in flight after the last barrier: write the state back
+    for (int loc = tid; loc < nloc; loc += T) {
+        const int site = s_site[loc];
+        if (site < 0) continue;
+        for (int w = 0; w < nw; ++w) a.V[(uint64_t)(uint32_t)site * G32 + w0 + w] = s_V[(uint32_t)w * NP + loc];
+    }
+}
+
+template <int NPL>
+const void *sa_cluster_fn(int field)
+{
+    return field ? (const void *)sa_cluster_kernel<NPL, 1> : (const void *)sa_cluster_kernel<NPL, 0>;
+}
+
+const void *sa_cluster_fn(int npl, int field)
+{
+    switch (npl) {
+    case 1: return sa_cluster_fn<1>(field);
+    case 2: return sa_cluster_fn<2>(field);
+    case 3: return sa_cluster_fn<3>(field);
+    case 4: return sa_cluster_fn<4>(field);
+    case 5: return sa_cluster_fn<5>(field);
+    default: return sa_cluster_fn<6>(field);
+    }
+}
+
 template <int NPL, int FLD>
 void launch_lut_wf(int warps, cudaStream_t s, const SaPass &a)
 {
@@ -481,6 +742,144 @@ void launch_lut(int npl, int warps, cudaStream_t s, const SaPass &a)
     case 7: launch_lut_w<7>(warps, s, a); break;
     default: launch_lut_w<8>(warps, s, a); break;
     }
+}
+
+
+// Cluster-resident schedule (sa_cluster_kernel) when the batch is small enough for every cluster to be resident at
+// once; returns MCS_OK with *done = false when the shape does not qualify (the caller takes the multi-launch path).
+int sa_try_cluster(mcs_state *st, const double *sched, int64_t S, int mcsteps, uint64_t sweep_offset, int npl,
+                   const SaPass &a, bool *done)
+{
+    *done = false;
+    mcs_instance *inst = st->inst;
+    const char *env = getenv("MCS_CLUSTER");
+    if (env && env[0] == '0') return MCS_OK;
+    const bool forced = env && env[0] == '1';
+    const long long passes = (long long)S * mcsteps * inst->ncolors;
+    if (npl > 6 || inst->ncolors > kClMaxColors || passes < 8 || st->G <= 0) return MCS_OK;
+    int csize = 16; // measured on B200 (benchmarks/sa_cluster_probe.py): 16 beats 8 and 4 at every batch size
+    if (const char *e = getenv("MCS_CLUSTER_SIZE")) csize = atoi(e);
+    if (csize != 1 && csize != 2 && csize != 4 && csize != 8 && csize != 16) return MCS_OK;
+    SaCluster c;
+    int max_per = 0;
+    c.loc_base[0] = 0;
+    for (int k = 0; k < inst->ncolors; ++k) {
+        const int nc = inst->color_start[k + 1] - inst->color_start[k];
+        c.color_start[k] = inst->color_start[k];
+        c.per[k] = std::max(1, (nc + csize - 1) / csize);
+        c.loc_base[k + 1] = c.loc_base[k] + c.per[k];
+        max_per = std::max(max_per, c.per[k]);
+    }
+    c.color_start[inst->ncolors] = inst->color_start[inst->ncolors];
+    const int nloc = c.loc_base[inst->ncolors];
+    c.nloc_pad = (nloc + 31) / 32 * 32;
+    if (max_per > 1024) return MCS_OK;
+    const void *fn = sa_cluster_fn(npl, a.field);
+    const int ent = 1 << npl, nq = npl - a.field;
+    auto smem_for = [&](int wc, int threads) {
+        return (size_t)c.nloc_pad * 4u * (size_t)(ent + wc + nq + npl + 1) + (size_t)threads * 32u;
+    };
+    // 1024 threads whatever the item count: the threads without an item build the next pass's tables meanwhile
+    auto threads_for = [&](int wc) { return wc >= 0 ? 1024 : 0; };
+    int smem_max = 0;
+    MCS_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, inst->device));
+    if (smem_for(1, threads_for(1)) > (size_t)smem_max) return MCS_OK;
+    MCS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    if (csize > 8) MCS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    // how many clusters are resident together (one CTA per SM: 1024 threads x 64 registers)
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.stream = inst->stream;
+    // words per cluster: as few as keep every cluster resident at once (more clusters = more SMs at work), at most
+    // what one CTA's threads (one item per thread and pass) and shared memory hold
+    int wc_max = std::max(1, 1024 / max_per);
+    while (wc_max > 1 && smem_for(wc_max, threads_for(wc_max)) > (size_t)smem_max) --wc_max;
+    int wc = 0, resident = 0;
+    for (int w = 1; w <= wc_max; ++w) {
+        cfg.gridDim = dim3((unsigned)csize);
+        cfg.blockDim = dim3((unsigned)threads_for(w));
+        cfg.dynamicSmemBytes = smem_for(w, threads_for(w));
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            return MCS_OK;
+        }
+        resident = ncl;
+        if ((st->G + w - 1) / w <= ncl) {
+            wc = w;
+            break;
+        }
+    }
+    // Measured on B200 (80 x 80 torus, profiles/r02_sa_cluster.log): per SM the cluster kernel decides as fast as the
+    // pass kernels, but only the 7 x 16 SMs that hold resident clusters work: 2.6 us per pass up to 224 restarts, 3.2 at
+    // 448, 4.1 at 896, 4.45 at 1024 (cfg2) against 4.4-4.5 us for one launch per pass at any of these sizes -- and ONE
+    // launch instead of thousands on the host.  Batches whose clusters do not all fit at once take the pass kernels.
+    if (const char *e = getenv("MCS_CLUSTER_WORDS")) {
+        const int w = atoi(e);
+        if (w >= 1 && w <= wc_max) wc = w;
+    }
+    if (wc == 0) {
+        if (!forced) return MCS_OK; // more clusters than fit at once: the batch is large, one launch per pass is faster
+        wc = wc_max;
+    }
+    const long long nclusters = (st->G + wc - 1) / wc;
+    const int threads = threads_for(wc);
+    std::vector<float> nl((size_t)S);
+    for (int64_t t = 0; t < S; ++t) nl[(size_t)t] = (float)(-1.4426950408889634 / sched[t]); // sa.pyx:98
+    float *d_nl = nullptr;
+    MCS_CUDA(cudaMallocAsync((void **)&d_nl, (size_t)S * sizeof(float) + 64, inst->stream));
+    MCS_CUDA(cudaMemcpyAsync(d_nl, nl.data(), (size_t)S * sizeof(float), cudaMemcpyHostToDevice, inst->stream));
+    c.V = st->d_V;
+    c.ell_idx = inst->d_ell_idx;
+    c.ell_J = inst->d_ell_J;
+    c.h = inst->d_h;
+    c.ellJ_stride = inst->nsteps > 1 ? (long long)inst->N * inst->dpad : 0;
+    c.h_stride = inst->nsteps > 1 ? (long long)inst->N : 0;
+    c.order = inst->d_order;
+    c.pos = inst->d_pos;
+    c.nl2e = d_nl;
+    c.prof = getenv("MCS_CLUSTER_PROF") ? reinterpret_cast<long long *>(d_nl + ((S + 1) / 2) * 2) : nullptr;
+    c.prof_cta = c.prof ? atoi(getenv("MCS_CLUSTER_PROF")) : 0;
+    c.ncolors = inst->ncolors;
+    c.dpad = inst->dpad;
+    c.S = (int)S;
+    c.mcsteps = mcsteps;
+    c.Wc = wc;
+    c.csize = csize;
+    c.G = st->G;
+    c.sweep_offset = sweep_offset;
+    c.keys = a.keys;
+    c.pow2 = a.pow2;
+    c.word_offset = a.word_offset;
+    c.tie_thr = a.tie_thr;
+    cfg.gridDim = dim3((unsigned)(nclusters * csize));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem_for(wc, threads);
+    void *args[] = {&c};
+    // the host copy of the schedule must outlive the asynchronous upload: pageable memory is staged by the runtime
+    // before cudaMemcpyAsync returns
+    const cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
+    inst->launches++;
+    if (c.prof && le == cudaSuccess) {
+        long long hp[4] = {0, 0, 0, 0};
+        MCS_CUDA(cudaMemcpyAsync(hp, c.prof, sizeof(hp), cudaMemcpyDeviceToHost, inst->stream));
+        MCS_CUDA(cudaStreamSynchronize(inst->stream));
+        fprintf(stderr, "[mcs cluster] per pass: %.0f cycles item, %.0f arrive + tables, %.0f CTA barrier, %.0f cluster wait\n",
+                (double)hp[0] / passes, (double)hp[1] / passes, (double)hp[2] / passes, (double)hp[3] / passes);
+    }
+    MCS_CUDA(cudaFreeAsync(d_nl, inst->stream));
+    MCS_CUDA(le);
+    if (getenv("MCS_CLUSTER_VERBOSE"))
+        fprintf(stderr, "[mcs cluster] %lld clusters (%d resident) of %d CTAs x %d threads, %d words per cluster, %zu B smem, %lld passes\n",
+                nclusters, resident, csize, threads, wc, (size_t)cfg.dynamicSmemBytes, passes);
+    *done = true;
+    return MCS_OK;
 }
 
 } // namespace
@@ -519,6 +918,12 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
     MCS_REQUIRE(inst->nsteps == 1 || S <= inst->nsteps, MCS_EINVAL,
                 "time-dependent instance has %lld tables but the schedule has %lld steps", (long long)inst->nsteps,
                 (long long)S);
+    // ---- small batches: the whole schedule resident in thread-block clusters (sa_cluster_kernel) ----
+    if (lut) {
+        bool done = false;
+        MCS_TRY(sa_try_cluster(st, sched, S, mcsteps, sweep_offset, npl, a, &done));
+        if (done) return MCS_OK;
+    }
     // ---- small batches: one cooperative launch for the whole schedule (sa_persistent_kernel) ----
     long long max_items = 0;
     for (int c = 0; c < inst->ncolors; ++c)
