@@ -88,6 +88,9 @@ struct mcs_instance {
     const double *tab_J_at(int64_t f) const { return d_tab_J + (nsteps > 1 ? (size_t)f * N * maxnb : 0); }
     int32_t *d_order = nullptr;   // [N]
     int32_t *d_pos = nullptr;     // [N] inverse of order: position of a site in the colour-sorted list
+    int max_offdiag = 0;          // most table entries with j != i in one row (padding included)
+    double *d_etab = nullptr;     // [N][16] fixed-order energy terms per neighbour sign pattern (lazy, mcs_energy_tables)
+    int32_t *d_etab_j = nullptr;  // [N][4]  the row's off-diagonal neighbours in table order, -1 padded
     void *d_Jhi = nullptr, *d_Jlo = nullptr; // dense only: [Npad][Npad] bf16 split J = hi + lo
     float *d_Jf = nullptr;                   // dense only: [Npad][Npad] fp32
     float *d_hpad = nullptr;                 // dense only: [Npad]
@@ -603,6 +606,10 @@ __device__ __forceinline__ uint32_t mcs_accept_threshold(float dE, float nl2e_ov
     if (t >= 4294967296.0f) return 0xFFFFFFFFu;
     return (uint32_t)t - 1u;
 }
+
+// Fixed-order energy by table (rows with at most four off-diagonal entries): builds the instance's tables on first
+// use (mcs_piqmc.cu).  Returns false when the instance does not qualify.
+bool mcs_energy_tables(mcs_instance *inst);
 
 // kernels launchers implemented in the other translation units
 int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,

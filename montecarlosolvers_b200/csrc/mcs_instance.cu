@@ -164,9 +164,13 @@ extern "C" int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int6
     std::vector<std::vector<std::map<int32_t, double>>> quad(nsteps, std::vector<std::map<int32_t, double>>(nspins));
     std::vector<double> h((size_t)nspins * nsteps, 0.0);
     bool has_field = false;
+    int max_offdiag = 0;
     for (int64_t t = 0; t < nsteps; ++t) {
         const double *tab = nbs + (size_t)t * tab_n * 2;
         for (int64_t i = 0; i < nspins; ++i) {
+            int offdiag = 0;
+            for (int64_t s = 0; s < maxnb; ++s) offdiag += (int64_t)tab[(i * maxnb + s) * 2] != i;
+            max_offdiag = std::max(max_offdiag, offdiag);
             for (int64_t s = 0; s < maxnb; ++s) {
                 double fi = tab[(i * maxnb + s) * 2];
                 double jv = tab[(i * maxnb + s) * 2 + 1];
@@ -202,6 +206,7 @@ extern "C" int mcs_instance_create_steps(const double *nbs, int64_t nsteps, int6
         }
 
     mcs_instance *inst = new mcs_instance();
+    inst->max_offdiag = max_offdiag;
     inst->device = device;
     inst->N = nspins;
     inst->maxnb = maxnb;
@@ -361,6 +366,8 @@ extern "C" void mcs_instance_destroy(mcs_instance *inst)
     cudaFree(inst->d_h);
     cudaFree(inst->d_order);
     cudaFree(inst->d_pos);
+    cudaFree(inst->d_etab);
+    cudaFree(inst->d_etab_j);
     cudaFree(inst->d_Jhi);
     cudaFree(inst->d_Jlo);
     cudaFree(inst->d_Jf);

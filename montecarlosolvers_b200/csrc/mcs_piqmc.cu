@@ -969,6 +969,129 @@ __global__ void piqmc_energy_kernel(const uint64_t *__restrict__ W, const int32_
         if (k0 + q < P) out[r * P + k0 + q] = e[q];
 }
 
+
+// ---- fixed-order energy by table ---------------------------------------------------------------------------
+// The chain kernel above spends seven fp64 operations per (replica, slice, site) on a chain of dependent loads:
+// 3.7 ms at 4096 anneals and 2.4 ms however small the batch (the fixed cost that capped the 8-GPU end-to-end
+// efficiency).  For a row with at most four off-diagonal entries the term s_i (0.5 pair + field) takes 2 x 16 values: the
+// sixteen t0[b] = 0.5 pair(b) + field, pair(b) accumulated in table order with the signs of pattern b, are computed
+// ONCE per instance by exactly the operations of the chain kernel; an accumulator then looks its term up and spends
+// one addition per site.  Same values, same order of additions: bit-identical (tests).
+__global__ void energy_table_kernel(const int32_t *__restrict__ tab_idx, const double *__restrict__ tab_J,
+                                    double *__restrict__ etab, int32_t *__restrict__ etab_j, long long N, int maxnb)
+{
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= N * 16) return;
+    const long long i = x >> 4;
+    const int b = (int)(x & 15);
+    double pair = 0.0, field = 0.0;
+    int slot = 0;
+    for (int s = 0; s < maxnb; ++s) {
+        const int j = tab_idx[i * maxnb + s];
+        const double jv = tab_J[i * maxnb + s];
+        if (j == i) {
+            field = __dadd_rn(field, jv);
+        } else {
+            pair = __dadd_rn(pair, ((b >> slot) & 1) ? -jv : jv); // jv * s_j
+            if (b == 0) etab_j[i * 4 + slot] = j;
+            ++slot;
+        }
+    }
+    if (b == 0)
+        for (; slot < 4; ++slot) etab_j[i * 4 + slot] = (int32_t)i; // unused pattern bits are never looked at
+    etab[x] = __dadd_rn(__dmul_rn(0.5, pair), field);
+}
+
+// bit q of a byte -> bit 4 q
+__host__ __device__ constexpr uint32_t spread_nibbles(uint32_t v)
+{
+    uint32_t r = 0;
+    for (int q = 0; q < 8; ++q) r |= ((v >> q) & 1u) << (4 * q);
+    return r;
+}
+
+constexpr int kLTile = 128;
+// thread = (replica, group of 8 consecutive slices); CTA = 32 replicas x blockDim.y slice groups
+template <int CH>
+__global__ void __launch_bounds__(256) piqmc_energy_lut_kernel(const uint64_t *__restrict__ W,
+                                                               const double *__restrict__ etab,
+                                                               const int32_t *__restrict__ etab_j,
+                                                               double *__restrict__ out, long long N, long long R,
+                                                               long long Rpad, int P)
+{
+    __shared__ __align__(16) double s_t[kLTile][16];
+    __shared__ __align__(16) int32_t s_j[kLTile][4];
+    __shared__ uint32_t s_spread[256];
+    const int tid = threadIdx.y * 32 + threadIdx.x, nthr = blockDim.y * 32;
+    const long long r = (long long)blockIdx.x * 32 + threadIdx.x; // < Rpad
+    const int k0 = (blockIdx.y * blockDim.y + threadIdx.y) * 8;
+    // the eight slices of this thread sit in one 32-bit half of the word; raw halves are kept in registers and
+    // shifted at use, and every load is unconditional (a conditional load is consumed inside its branch: the loads
+    // of a chunk would then wait for each other)
+    const uint32_t *Wr = reinterpret_cast<const uint32_t *>(W + r) + (k0 >> 5);
+    const int sh = k0 & 31;
+    const long long rstride = 2 * Rpad;
+    for (int v = tid; v < 256; v += nthr) s_spread[v] = spread_nibbles((uint32_t)v);
+    double e[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) e[q] = 0.0;
+    for (long long tile0 = 0; tile0 < N; tile0 += kLTile) {
+        const int nt = (int)min((long long)kLTile, N - tile0);
+        __syncthreads();
+        {
+            const double2 *src = reinterpret_cast<const double2 *>(etab + tile0 * 16);
+            double2 *dst = reinterpret_cast<double2 *>(&s_t[0][0]);
+#pragma unroll 8
+            for (int x = tid; x < nt * 8; x += nthr) dst[x] = __ldg(&src[x]);
+        }
+        for (int x = tid; x < nt * 4; x += nthr) (&s_j[0][0])[x] = __ldg(&etab_j[tile0 * 4 + x]);
+        __syncthreads();
+        uint32_t b[2][CH][4], w[2][CH];
+        auto load_chunk = [&](int c0, uint32_t (&bb)[CH][4], uint32_t (&ww)[CH]) {
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int i = min(c0 + u, nt - 1); // past the tile: a valid row, never summed
+                const int4 j = *reinterpret_cast<const int4 *>(s_j[i]);
+                bb[u][0] = __ldg(&Wr[(long long)j.x * rstride]);
+                bb[u][1] = __ldg(&Wr[(long long)j.y * rstride]);
+                bb[u][2] = __ldg(&Wr[(long long)j.z * rstride]);
+                bb[u][3] = __ldg(&Wr[(long long)j.w * rstride]);
+                ww[u] = __ldg(&Wr[(tile0 + i) * rstride]);
+            }
+        };
+        auto sum_chunk = [&](int c0, const uint32_t (&bb)[CH][4], const uint32_t (&ww)[CH]) {
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int i = c0 + u;
+                if (i < nt) {
+                    // anti-alignment pattern of slice k0 + q in nibble q (bit s: neighbour s is -1)
+                    const uint32_t packed = s_spread[(bb[u][0] >> sh) & 0xFFu] | (s_spread[(bb[u][1] >> sh) & 0xFFu] << 1) |
+                                            (s_spread[(bb[u][2] >> sh) & 0xFFu] << 2) |
+                                            (s_spread[(bb[u][3] >> sh) & 0xFFu] << 3);
+                    const uint32_t wi = ww[u] >> sh;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const double t = s_t[i][(packed >> (4 * q)) & 15u];
+                        e[q] = __dadd_rn(e[q], ((wi >> q) & 1u) ? -t : t); // s_i * (0.5 pair + field)
+                    }
+                }
+            }
+        };
+        load_chunk(0, b[0], w[0]);
+        for (int c0 = 0; c0 < nt; c0 += 2 * CH) {
+            load_chunk(c0 + CH, b[1], w[1]);
+            sum_chunk(c0, b[0], w[0]);
+            load_chunk(c0 + 2 * CH, b[0], w[0]);
+            sum_chunk(c0 + CH, b[1], w[1]);
+        }
+    }
+    if (r < R) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (k0 + q < P) out[r * P + k0 + q] = e[q];
+    }
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1224,6 +1347,27 @@ int mcs_piqmc_init(mcs_state *st, uint64_t seed, uint64_t replica_offset)
     return MCS_OK;
 }
 
+bool mcs_energy_tables(mcs_instance *inst)
+{
+    if (inst->max_offdiag > 4 || inst->N <= 0) return false;
+    if (inst->d_etab) return true;
+    double *et = nullptr;
+    int32_t *ej = nullptr;
+    if (cudaMalloc((void **)&et, (size_t)inst->N * 16 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&ej, (size_t)inst->N * 4 * sizeof(int32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(et);
+        return false;
+    }
+    const long long n = inst->N * 16;
+    energy_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(
+        inst->tab_idx_at(inst->nsteps - 1), inst->tab_J_at(inst->nsteps - 1), et, ej, inst->N, (int)inst->maxnb);
+    inst->launches++;
+    inst->d_etab = et;
+    inst->d_etab_j = ej;
+    return true;
+}
+
 int mcs_piqmc_energy(mcs_state *st, double *d_out)
 {
     mcs_instance *inst = st->inst;
@@ -1231,6 +1375,20 @@ int mcs_piqmc_energy(mcs_state *st, double *d_out)
     dim3 grid((unsigned)((st->R + 31) / 32), (unsigned)((kgroups + 3) / 4));
     const int32_t *ti = inst->tab_idx_at(inst->nsteps - 1);
     const double *tj = inst->tab_J_at(inst->nsteps - 1);
+    const char *chain = getenv("MCS_ENERGY_CHAIN"); // tests: the chain kernel
+    if (!chain && mcs_energy_tables(inst)) {
+        // enough CTAs for every SM when the batch is small: a CTA takes as few slice groups as that needs
+        const long long warps = st->Rpad / 32 * kgroups;
+        int wpc = kgroups;
+        while (wpc > 1 && (wpc % 2 == 0) && warps / wpc < 296) wpc /= 2;
+        if (kgroups % wpc != 0) wpc = 1;
+        const dim3 lgrid((unsigned)(st->Rpad / 32), (unsigned)(kgroups / wpc)), lblock(32, (unsigned)wpc);
+        piqmc_energy_lut_kernel<8><<<lgrid, lblock, 0, inst->stream>>>(st->d_W, inst->d_etab, inst->d_etab_j, d_out,
+                                                                      inst->N, st->R, st->Rpad, (int)st->P);
+        inst->launches++;
+        MCS_CUDA(cudaGetLastError());
+        return MCS_OK;
+    }
     if (inst->maxnb <= 4)
         piqmc_energy_kernel<4><<<grid, dim3(32, 4), 0, inst->stream>>>(st->d_W, ti, tj, d_out, inst->N, (int)inst->maxnb,
                                                                         st->R, st->Rpad, (int)st->P);

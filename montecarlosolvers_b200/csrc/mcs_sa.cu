@@ -244,6 +244,71 @@ __global__ void sa_energy_kernel(const uint32_t *__restrict__ V, const int32_t *
     out[r] = e;
 }
 
+// Fixed-order energy by table (mcs_energy_tables, see mcs_piqmc.cu): one fp64 addition per site and restart.
+constexpr int kSaLTile = 128;
+template <int CH>
+__global__ void __launch_bounds__(128) sa_energy_lut_kernel(const uint32_t *__restrict__ V,
+                                                            const double *__restrict__ etab,
+                                                            const int32_t *__restrict__ etab_j,
+                                                            double *__restrict__ out, long long N, long long R,
+                                                            long long G)
+{
+    __shared__ __align__(16) double s_t[kSaLTile][16];
+    __shared__ __align__(16) int32_t s_j[kSaLTile][4];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const long long r = (long long)blockIdx.x * blockDim.x + tid;
+    const long long g = min(r >> 5, G - 1);
+    const int bit = (int)(r & 31);
+    const uint32_t *Vg = V + g;
+    double e = 0.0;
+    for (long long tile0 = 0; tile0 < N; tile0 += kSaLTile) {
+        const int nt = (int)min((long long)kSaLTile, N - tile0);
+        __syncthreads();
+        {
+            const double2 *src = reinterpret_cast<const double2 *>(etab + tile0 * 16);
+            double2 *dst = reinterpret_cast<double2 *>(&s_t[0][0]);
+#pragma unroll 8
+            for (int x = tid; x < nt * 8; x += nthr) dst[x] = __ldg(&src[x]);
+        }
+        for (int x = tid; x < nt * 4; x += nthr) (&s_j[0][0])[x] = __ldg(&etab_j[tile0 * 4 + x]);
+        __syncthreads();
+        uint32_t b[2][CH][4], w[2][CH];
+        // every load unconditional, raw words kept and shifted at use (see piqmc_energy_lut_kernel)
+        auto load_chunk = [&](int c0, uint32_t (&bb)[CH][4], uint32_t (&ww)[CH]) {
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int i = min(c0 + u, nt - 1);
+                const int4 j = *reinterpret_cast<const int4 *>(s_j[i]);
+                bb[u][0] = __ldg(&Vg[(long long)j.x * G]);
+                bb[u][1] = __ldg(&Vg[(long long)j.y * G]);
+                bb[u][2] = __ldg(&Vg[(long long)j.z * G]);
+                bb[u][3] = __ldg(&Vg[(long long)j.w * G]);
+                ww[u] = __ldg(&Vg[(tile0 + i) * G]);
+            }
+        };
+        auto sum_chunk = [&](int c0, const uint32_t (&bb)[CH][4], const uint32_t (&ww)[CH]) {
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int i = c0 + u;
+                if (i < nt) {
+                    const uint32_t idx = ((bb[u][0] >> bit) & 1u) | (((bb[u][1] >> bit) & 1u) << 1) |
+                                         (((bb[u][2] >> bit) & 1u) << 2) | (((bb[u][3] >> bit) & 1u) << 3);
+                    const double t = s_t[i][idx];
+                    e = __dadd_rn(e, ((ww[u] >> bit) & 1u) ? -t : t);
+                }
+            }
+        };
+        load_chunk(0, b[0], w[0]);
+        for (int c0 = 0; c0 < nt; c0 += 2 * CH) {
+            load_chunk(c0 + CH, b[1], w[1]);
+            sum_chunk(c0, b[0], w[0]);
+            load_chunk(c0 + 2 * CH, b[0], w[0]);
+            sum_chunk(c0 + CH, b[1], w[1]);
+        }
+    }
+    if (r < R) out[r] = e;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Small batches: the whole schedule in ONE cooperative launch.  A colour pass of 1024 restarts is a single wave of
 // 3200 warps that lasts about a microsecond; as separate launches the passes are spaced by the kernel-boundary
@@ -1060,6 +1125,15 @@ int mcs_sa_init(mcs_state *st, uint64_t seed, uint64_t replica_offset)
 int mcs_sa_energy(mcs_state *st, double *d_out)
 {
     mcs_instance *inst = st->inst;
+    const char *chain = getenv("MCS_ENERGY_CHAIN"); // tests: the chain kernel
+    if (!chain && mcs_energy_tables(inst)) {
+        const int threads = st->R >= 128 * 296 ? 128 : (st->R >= 64 * 296 ? 64 : 32);
+        sa_energy_lut_kernel<8><<<(unsigned)((st->R + threads - 1) / threads), threads, 0, inst->stream>>>(
+            st->d_V, inst->d_etab, inst->d_etab_j, d_out, inst->N, st->R, st->G);
+        inst->launches++;
+        MCS_CUDA(cudaGetLastError());
+        return MCS_OK;
+    }
     sa_energy_kernel<<<(unsigned)((st->R + 63) / 64), 64, 0, inst->stream>>>(
         st->d_V, inst->tab_idx_at(inst->nsteps - 1), inst->tab_J_at(inst->nsteps - 1), d_out, inst->N, (int)inst->maxnb, st->R, st->G);
     inst->launches++;

@@ -62,6 +62,51 @@ def test_state_energies_bit_exact_and_roundtrip(mcs):
         assert e[r] == orc.ising_energy(s[r].astype(np.int64), nbs)
 
 
+@pytest.mark.parametrize("case", ["torus19", "torus18_fields", "circulant300_deg6"])
+def test_tiled_energy_kernels_bit_exact(mcs, case):
+    """The fixed-order energy kernels -- by table (rows with at most four off-diagonal entries: sixteen precomputed
+    terms per site, one fp64 addition per site and accumulator) and the chain kernel -- perform the same additions in
+    the same order as the oracle: several tiles, a ragged last tile and chunk, rows of 4 / 5 / 7 entries (the
+    last: chain kernel only), fields, ragged replica counts."""
+    if case == "torus19":
+        nbs = inst.torus(19, seed=2)[1]
+    elif case == "torus18_fields":
+        nbs = inst.torus(18, seed=3, fields=True)[1]
+    else:
+        nbs = inst.circulant(300, (1, 2, 3), seed=4, fields=True)[1]
+    n = nbs.shape[0]
+    I = mcs.Instance(nbs)
+    for P, R in ((64, 37), (20, 70), (3, 5)):
+        c = (2 * np.random.RandomState(P).randint(2, size=(R, n, P)) - 1).astype(np.int8)
+        st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+        st.upload_spins(c)
+        e = st.energies()
+        for mode in ("1",):
+            os.environ["MCS_ENERGY_CHAIN"] = mode
+            try:
+                assert np.array_equal(e, st.energies()), mode
+            finally:
+                os.environ.pop("MCS_ENERGY_CHAIN", None)
+        for r in (0, R // 2, R - 1):
+            for k in (0, P // 2, P - 1):
+                assert e[r, k] == orc.ising_energy(c[r, :, k].astype(np.int64), nbs)
+        st.close()
+    R = 200
+    s = (2 * np.random.RandomState(1).randint(2, size=(R, n)) - 1).astype(np.int8)
+    st = mcs.State(I, mcs._lib.KIND_SA, R, 1)
+    st.upload_spins(s)
+    e = st.energies()
+    for mode in ("1",):
+        os.environ["MCS_ENERGY_CHAIN"] = mode
+        try:
+            assert np.array_equal(e, st.energies()), mode
+        finally:
+            os.environ.pop("MCS_ENERGY_CHAIN", None)
+    for r in (0, 31, 32, 127, 128, R - 1):
+        assert e[r] == orc.ising_energy(s[r].astype(np.int64), nbs)
+    st.close()
+
+
 def test_exact_qmc_golden(mcs):
     d = np.load(os.path.join(G, "traj_qmc_torus6.npz"))
     for P in (2, 3, 8, 20):
