@@ -823,6 +823,34 @@ def test_cluster_resident_sa_equals_the_multi_launch_path(mcs, case, csize):
     assert np.array_equal(out[0][0], out[1][0])
 
 
+@pytest.mark.parametrize("P,glob", [(64, 0), (32, 1), (24, 0), (7, 1)])
+def test_piqmc_two_stream_chunks_equal_one_stream(mcs, P, glob):
+    """Mid-size PIQMC batches are cut into replica chunks whose colour passes alternate on two streams (the tail of
+    one chunk's pass runs under the other's).  Chunks are windows of whole 256-replica blocks: the state after a
+    schedule is bit-identical with one, two and three streams (plain, fused and odd-P kernels, world-line moves)."""
+    nbs = inst.torus(8, seed=5, fields=(P == 24))[1]
+    I = mcs.Instance(nbs)
+    R, S = 768, 12
+    A, B = np.linspace(2.5, 0.05, S), np.linspace(0.3, 1.0, S)
+    out = []
+    for streams in ("1", None, "3"):
+        os.environ.pop("MCS_STREAMS", None)
+        if streams:
+            os.environ["MCS_STREAMS"] = streams
+        try:
+            st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+            st.init_random(9)
+            l0 = I.launches
+            st.piqmc_sweeps(A, B, 2, 0.05, global_moves=bool(glob), seed=77)
+            nl = I.launches - l0
+            out.append((st.download_spins(), nl))
+            st.close()
+        finally:
+            os.environ.pop("MCS_STREAMS", None)
+    assert out[1][1] == 2 * out[0][1] and out[2][1] == 3 * out[0][1]  # launches per pass = chunks
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][0], out[2][0])
+
+
 def test_zero_temperature_never_accepts_an_uphill_move(mcs):
     """T = 0 (the tail of the example's classical schedule, santoro80.py:260): the reference compares
     0 > rand()/RAND_MAX -- never.  A threshold of 0 means NEVER here too (mcs_accepts), not "once in 2^32": after a
