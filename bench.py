@@ -435,8 +435,29 @@ def run_configs(mcs, inst, peaks, which):
                        "roofline": hbm_roofline(v, 0.25, peaks, "sa_lut_pass_kernel<4,*,0>", ms / (2 * tau),
                                                 "latency bound at this batch size: a colour pass is 3200 warps (one "
                                                 "wave): 2.1 us of SM-bound work + 2.3 us kernel-boundary latency per "
-                                                "pass (profiles/r02_small_batch.log; a cooperative persistent kernel "
-                                                "with a grid barrier measured 4.6 us per pass, MCS_PERSIST=1)")}
+                                                "pass; the cluster-resident kernel (sa_cluster_kernel: state and "
+                                                "threshold tables in distributed shared memory, hardware cluster "
+                                                "barrier between passes) ties at this size because only 7 x 16 SMs "
+                                                "hold resident clusters, and wins below it "
+                                                "(profiles/r02_sa_cluster.log)")}
+        st.close()
+        # the latency regime proper: 224 restarts, whole schedule in one launch of 7 clusters x 16 CTAs
+        Rs = 224
+        st = mcs.State(inst, K.KIND_SA, Rs, 1)
+        st.init_random(1)
+        l0 = inst.launches
+        ms_c = timed(inst, lambda: st.sa_sweeps(sched, 1, seed=2), reps=3)
+        nl = (inst.launches - l0) // 4
+        os.environ["MCS_CLUSTER"] = "0"
+        try:
+            ms_m = timed(inst, lambda: st.sa_sweeps(sched, 1, seed=2), reps=3)
+        finally:
+            os.environ.pop("MCS_CLUSTER", None)
+        out["cfg2"]["small_batch"] = {
+            "workload": "the same anneal with %d restarts (latency regime)" % Rs, "launches_per_anneal": nl,
+            "cluster_resident": {"value": Rs * tau * NSPINS / (ms_c * 1e-3), "us_per_colour_pass": 1e3 * ms_c / (2 * tau)},
+            "one_launch_per_pass": {"value": Rs * tau * NSPINS / (ms_m * 1e-3), "us_per_colour_pass": 1e3 * ms_m / (2 * tau)},
+            "unit": UNIT}
         st.close()
     if "refdyn" in which:  # cfg3 shape, the reference's own visiting order in distribution
         P, R, S = 64, 4096, 4

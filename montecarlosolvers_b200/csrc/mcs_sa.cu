@@ -883,8 +883,10 @@ int sa_try_cluster(mcs_state *st, const double *sched, int64_t S, int mcsteps, u
     }
     // Measured on B200 (80 x 80 torus, profiles/r02_sa_cluster.log): per SM the cluster kernel decides as fast as the
     // pass kernels, but only the 7 x 16 SMs that hold resident clusters work: 2.6 us per pass up to 224 restarts, 3.2 at
-    // 448, 4.1 at 896, 4.45 at 1024 (cfg2) against 4.4-4.5 us for one launch per pass at any of these sizes -- and ONE
-    // launch instead of thousands on the host.  Batches whose clusters do not all fit at once take the pass kernels.
+    // 448, 4.1 at 896 against 4.4-4.5 us for one launch per pass at any of these sizes (and ONE launch instead of
+    // thousands on the host); at 1000 items per CTA (1024 restarts, cfg2) the two tie, so the pass kernels keep it.
+    // Batches whose clusters do not all fit at once take the pass kernels too.
+    if (!forced && wc > 0 && (long long)max_per * wc > 800) wc = 0;
     if (const char *e = getenv("MCS_CLUSTER_WORDS")) {
         const int w = atoi(e);
         if (w >= 1 && w <= wc_max) wc = w;
