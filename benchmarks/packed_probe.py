@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Packed mode (even P <= 20): packed words resident in HBM for the duration of a sweep call (default) against
+gathering the members in every pass (MCS_PACK_GATHER=1); cfg1 shape (80x80, tau = 354, world-line moves)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import montecarlosolvers_b200 as mcs  # noqa: E402
+from bench import load_instance  # noqa: E402
+
+nbs, _ = load_instance()
+inst = mcs.Instance(nbs)
+N = inst.nspins
+tau = 354
+A, B = np.linspace(3.0, 1e-8, tau), np.ones(tau)
+for P, glob in ((20, True), (20, False), (16, False), (10, False)):
+    for R in (4096, 512):
+        row = {"P": P, "R": R, "global_moves": glob}
+        for name, env in (("gather", {"MCS_PACK_GATHER": "1"}), ("resident_1stream", {"MCS_STREAMS": "1"}), ("resident", {})):
+            os.environ.update(env)
+            st = mcs.State(inst, mcs._lib.KIND_PIQMC, R, P)
+            st.init_random(1)
+            st.piqmc_sweeps(A, B, 1, 1.0 / P, global_moves=glob, seed=3)
+            inst.synchronize()
+            best = 1e9
+            for rep in range(2):
+                inst.timer_start()
+                st.piqmc_sweeps(A, B, 1, 1.0 / P, global_moves=glob, seed=3)
+                best = min(best, inst.timer_stop())
+            row[name] = float("%.4g" % (R * tau * P * N / (best * 1e-3)))
+            st.close()
+            for k in env:
+                os.environ.pop(k, None)
+        print(json.dumps(row), flush=True)

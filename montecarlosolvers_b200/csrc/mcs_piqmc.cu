@@ -62,6 +62,11 @@ struct PiqmcPass {
     long long group0;      // global index of the block warp 0 owns
     long long nvalid;      // replicas of this window that exist (members outside [0, nvalid) are skipped)
     uint64_t seg_lsb;      // bit 0 of every segment
+    long long gw_lo, gw_n; // packed mode: this launch covers the group warps [gw_lo, gw_lo + gw_n) of the window
+    // MODE_PACKN: the packed working words themselves, [N][gp] (gp = 32 x group warps of the window), built once per
+    // sweep call from W and unpacked at its end: one 64-bit load per row instead of pk guarded loads and shifts
+    uint64_t *Wp;
+    long long gp;
 };
 
 __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
@@ -101,7 +106,7 @@ __device__ __forceinline__ uint64_t rotr_seg(uint64_t w, int P, uint64_t lsb)
 }
 
 // how the working word of a thread is made up
-enum { MODE_PLAIN = 0, MODE_FUSE = 1, MODE_PACK = 2 };
+enum { MODE_PLAIN = 0, MODE_FUSE = 1, MODE_PACK = 2, MODE_PACKN = 3 }; // PACKN: packed words resident in HBM
 
 // Pattern-index bits live at bit positions SH .. SH+NPL+1 of a field of an index word: one BYTE per slice up to
 // 8 planes, one HALF WORD per slice for 9 and 10 planes (FW = field width).  Where it fits (up to 6 planes, and
@@ -251,9 +256,9 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
     constexpr int NPP = LutGeom<NPL>::NPP, NPAIR = LutGeom<NPL>::NPAIR;
     constexpr bool FUSE = MODE == MODE_FUSE;
     // bit k: slice k anti-aligned with slice k-1 / k+1
-    const uint64_t tl = w ^ (MODE == MODE_PACK ? rotl_seg(w, P, seg_lsb)
+    const uint64_t tl = w ^ (MODE >= MODE_PACK ? rotl_seg(w, P, seg_lsb)
                                                : (FUSE ? rotl_ring2(w, P, pmask) : rotl_ring(w, P, pmask)));
-    const uint64_t tr = w ^ (MODE == MODE_PACK ? rotr_seg(w, P, seg_lsb)
+    const uint64_t tr = w ^ (MODE >= MODE_PACK ? rotr_seg(w, P, seg_lsb)
                                                : (FUSE ? rotr_ring2(w, P, pmask) : rotr_ring(w, P, pmask)));
     const uint32_t c0 = c0h[0];
     uint32_t m[2][NPAIR];
@@ -344,7 +349,7 @@ template <int NPL, int WARPS, bool FULL, int FLD, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
     static_assert(!(FULL && MODE != MODE_PLAIN), "fused / packed modes are for P <= 32");
-    constexpr bool FUSE = MODE == MODE_FUSE, PACK = MODE == MODE_PACK;
+    constexpr bool FUSE = MODE == MODE_FUSE, PACK = MODE >= MODE_PACK, NATIVE = MODE == MODE_PACKN;
     constexpr int ENT = LutGeom<NPL>::ENT, NQ = NPL - FLD;
     __shared__ uint32_t s_lut[ENT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -384,15 +389,19 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     // row offsets as one IMAD.WIDE.U32 each (site indices and Rpad are below 2^32)
     const uint32_t rpad = (uint32_t)a.Rpad;
     // PACK: member m of this thread is local replica first + 32 m (global index (group0 + warp) 32 pk + 32 m + lane)
-    const long long gwarp = (long long)blockIdx.x * WARPS + warp;
+    const long long gwarp = (PACK ? a.gw_lo : 0) + (long long)blockIdx.x * WARPS + warp;
+    const bool gw_ok = !PACK || gwarp < a.gw_lo + a.gw_n; // the last CTA of a packed launch may have spare warps
     const long long first = PACK ? (a.group0 + gwarp) * 32 * pk + lane - (long long)a.replica_offset : r;
     const uint64_t *Wr = a.W + first, *Wr2 = Wr + (FUSE ? a.half : 0);
+    uint64_t *Wn = NATIVE ? a.Wp + (gw_ok ? gwarp * 32 + lane : 0) : nullptr;
+    const uint32_t gp = NATIVE ? (uint32_t)a.gp : 0u;
     uint32_t present = 0; // PACK: members that exist in this window
-    if (PACK)
+    if (PACK && !NATIVE && gw_ok)
         for (int m = 0; m < pk; ++m)
             if (first + 32 * m >= 0 && first + 32 * m < a.nvalid) present |= 1u << m;
     mcs_pdl_wait(); // everything above depends on the instance and the schedule only
     auto load = [&](int row) -> uint64_t {
+        if (NATIVE) return gw_ok ? Wn[(uint64_t)(uint32_t)row * gp] : 0ull;
         if (PACK) {
             uint64_t v = 0;
 #pragma unroll
@@ -486,7 +495,9 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
             }
         }
     }
-    if (PACK) {
+    if (NATIVE) {
+        if (gw_ok) Wn[(uint64_t)(uint32_t)site * gp] = w;
+    } else if (PACK) {
 #pragma unroll
         for (int m = 0; m < 6; ++m)
             if ((present >> m) & 1u) a.W[(uint64_t)(uint32_t)site * rpad + first + 32 * m] = (w >> (m * P)) & pm1;
@@ -729,6 +740,31 @@ __device__ __forceinline__ uint32_t nibble_spins(uint32_t n)
 {
     const uint32_t b = (n * 0x00204081u) & 0x01010101u;
     return 0x01010101u | (b * 0xFEu);
+}
+
+// W <-> packed working words (MODE_PACKN): thread = (site, group warp, lane); member m of the word is the window's
+// column first + 32 m, first = (group0 + g) 32 pk + lane - replica_offset, where it exists
+__global__ void piqmc_words_pack_kernel(const uint64_t *__restrict__ W, uint64_t *__restrict__ Wp, long long N,
+                                        long long rpad, long long gw, long long group0, long long roff,
+                                        long long nvalid, int pk, int P, int unpack)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * gw * 32) return;
+    const long long i = t / (gw * 32), x = t % (gw * 32), g = x >> 5;
+    const int lane = (int)(x & 31);
+    const long long first = (group0 + g) * 32 * pk + lane - roff;
+    const uint64_t pm1 = (1ull << P) - 1ull;
+    uint64_t *Wi = const_cast<uint64_t *>(W) + i * rpad;
+    if (unpack) {
+        const uint64_t v = Wp[t];
+        for (int m = 0; m < pk; ++m)
+            if (first + 32 * m >= 0 && first + 32 * m < nvalid) Wi[first + 32 * m] = (v >> (m * P)) & pm1;
+    } else {
+        uint64_t v = 0;
+        for (int m = 0; m < pk; ++m)
+            if (first + 32 * m >= 0 && first + 32 * m < nvalid) v |= (Wi[first + 32 * m] & pm1) << (m * P);
+        Wp[t] = v;
+    }
 }
 
 __global__ void __launch_bounds__(1024) piqmc_pack_kernel(const int8_t *__restrict__ in, uint64_t *__restrict__ W,
@@ -1110,18 +1146,30 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
         a.pk = std::min(64 / a.P, 6);
         const long long blk = 32ll * a.pk; // replicas per warp
         a.group0 = (long long)a.replica_offset / blk;
-        const long long gw = ((long long)a.replica_offset + a.nvalid - 1) / blk - a.group0 + 1; // warps
+        long long gw = ((long long)a.replica_offset + a.nvalid - 1) / blk - a.group0 + 1; // warps
+        if (a.gw_n > 0)
+            gw = a.gw_n; // a chunk of the window's group warps (two-stream sweeps)
+        else
+            a.gw_lo = 0, a.gw_n = gw;
         const int wf = gw >= 4 ? 4 : (gw >= 2 ? 2 : 1);
         a.seg_lsb = 0;
         for (int m = 0; m < a.pk; ++m) a.seg_lsb |= 1ull << (m * a.P);
         a.half = 0;
         const dim3 grid((unsigned)((gw + wf - 1) / wf), ny, nz);
-        if (wf == 4)
-            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN>, grid, dim3(128), s, a);
+        constexpr int MP = LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN, MN = LutGeom<NPL>::FW == 8 ? MODE_PACKN : MODE_PLAIN;
+        if (a.Wp) {
+            if (wf == 4)
+                mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, MN>, grid, dim3(128), s, a);
+            else if (wf == 2)
+                mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, MN>, grid, dim3(64), s, a);
+            else
+                mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, MN>, grid, dim3(32), s, a);
+        } else if (wf == 4)
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, MP>, grid, dim3(128), s, a);
         else if (wf == 2)
-            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN>, grid, dim3(64), s, a);
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 2, false, FLD, MP>, grid, dim3(64), s, a);
         else
-            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN>, grid, dim3(32), s, a);
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, MP>, grid, dim3(32), s, a);
         return;
     }
     a.pk = 0;
@@ -1245,6 +1293,10 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     a.group0 = 0;
     a.nvalid = st->win_valid();
     a.seg_lsb = 0;
+    a.gw_lo = 0;
+    a.gw_n = 0;
+    a.Wp = nullptr;
+    a.gp = 0;
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;
@@ -1256,10 +1308,32 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     // its last, partial wave plus the kernel boundary leave SMs idle (56.0 us per pass against 8 x 54.6 for eight
     // times the batch).  Replicas are independent, so the window is cut into two chunks of whole 128- / 256-replica blocks
     // whose passes alternate on two streams: the tail of one chunk's pass runs under the body of the other's.
-    // Windows already guarantee that results do not depend on how replicas are grouped (tests); the packed mode
-    // (groups on global indices) keeps one stream.
+    // Windows already guarantee that results do not depend on how replicas are grouped (tests); in the packed mode a
+    // chunk is a range of the window's group warps.
     const long long G0 = a.G;
     const bool packed_mode = P <= 20 && (P & 1) == 0 && !getenv("MCS_NO_FUSE") && !getenv("MCS_NO_PACK");
+    // Packed mode (even P <= 20): the working words (pk world lines each) are built ONCE per call into a scratch array
+    // and the passes run on them -- one 64-bit load per table row instead of pk guarded loads and shifts -- then
+    // unpacked (MCS_PACK_GATHER=1: gather the members in every pass, the round-1/2 kernel; same decisions)
+    uint64_t *d_Wp = nullptr;
+    long long pk_gw = 0, pk_group0 = 0;
+    int pk_n = 0;
+    const bool lut_path = !lookuptable && inst->lut_ok && !force_direct;
+    if (packed_mode && lut_path && npl + 2 <= 8 && a.nvalid > 0) {
+        pk_n = std::min(64 / P, 6);
+        const long long blk = 32ll * pk_n;
+        pk_group0 = (long long)a.replica_offset / blk;
+        pk_gw = ((long long)a.replica_offset + a.nvalid - 1) / blk - pk_group0 + 1;
+        if (!getenv("MCS_PACK_GATHER") && (long long)S * mcsteps * inst->ncolors >= 4) {
+            const long long n = inst->N * pk_gw * 32;
+            MCS_CUDA(cudaMallocAsync((void **)&d_Wp, (size_t)n * sizeof(uint64_t), inst->stream));
+            piqmc_words_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(
+                a.W, d_Wp, inst->N, st->Rpad, pk_gw, pk_group0, (long long)a.replica_offset, a.nvalid, pk_n, P, 0);
+            inst->launches++;
+            a.Wp = d_Wp;
+            a.gp = pk_gw * 32;
+        }
+    }
     long long max_sites = 0;
     for (int c = 0; c < inst->ncolors; ++c)
         max_sites = std::max(max_sites, (long long)(inst->color_start[c + 1] - inst->color_start[c]));
@@ -1267,10 +1341,11 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     // at 512: the per-GPU rate of the 8-GPU run equals the 1-GPU rate), nothing more with three streams
     const long long gran = P <= 32 ? 8 : 4; // groups of 32 replicas per block: four-warp CTAs, two replicas per thread
     int nchunk = 1;
-    const bool can_chunk = !lookuptable && inst->lut_ok && !force_direct && !packed_mode && G0 % gran == 0;
-    if (can_chunk && G0 >= 2 * gran && G0 * max_sites <= (long long)1 << 20 && !getenv("MCS_ONE_STREAM")) nchunk = 2;
+    const bool can_chunk = lut_path && (packed_mode ? (d_Wp != nullptr && pk_gw >= 8) : G0 % gran == 0);
+    if (can_chunk && (packed_mode || G0 >= 2 * gran) && G0 * max_sites <= (long long)1 << 20 && !getenv("MCS_ONE_STREAM"))
+        nchunk = 2;
     if (const char *e = getenv("MCS_STREAMS"))
-        if (can_chunk) nchunk = (int)std::max(1ll, std::min(std::min(4ll, G0 / gran), atoll(e)));
+        if (can_chunk) nchunk = (int)std::max(1ll, std::min(std::min(4ll, packed_mode ? pk_gw / 4 : G0 / gran), atoll(e)));
     if (nchunk > 1 && !inst->ev_aux0) MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_aux0, cudaEventDisableTiming));
     for (int q = 0; q + 1 < nchunk; ++q) {
         if (!inst->s_aux[q]) {
@@ -1299,6 +1374,19 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
                 a.sites = inst->d_order + inst->color_start[c];
                 a.nsites = inst->color_start[c + 1] - inst->color_start[c];
                 if (a.nsites == 0) continue;
+                if (nchunk > 1 && packed_mode) { // chunks of the window's group warps (whole four-warp CTAs)
+                    for (int q = 0; q < nchunk; ++q) {
+                        const long long g0 = (pk_gw / 4 * q / nchunk) * 4;
+                        const long long g1 = q + 1 == nchunk ? pk_gw : (pk_gw / 4 * (q + 1) / nchunk) * 4;
+                        a.gw_lo = g0;
+                        a.gw_n = g1 - g0;
+                        launch_lut(npl, 4, q ? inst->s_aux[q - 1] : inst->stream, a);
+                        inst->launches++;
+                    }
+                    a.gw_lo = 0;
+                    a.gw_n = 0;
+                    continue;
+                }
                 if (nchunk > 1) {
                     for (int q = 0; q < nchunk; ++q) {
                         const long long g0 = (G0 / gran * q / nchunk) * gran, g1 = (G0 / gran * (q + 1) / nchunk) * gran;
@@ -1326,6 +1414,13 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     for (int q = 0; q + 1 < nchunk; ++q) {
         MCS_CUDA(cudaEventRecord(inst->ev_aux1[q], inst->s_aux[q]));
         MCS_CUDA(cudaStreamWaitEvent(inst->stream, inst->ev_aux1[q], 0));
+    }
+    if (d_Wp) {
+        const long long n = inst->N * pk_gw * 32;
+        piqmc_words_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(
+            W0, d_Wp, inst->N, st->Rpad, pk_gw, pk_group0, (long long)roff0, valid0, pk_n, P, 1);
+        inst->launches++;
+        MCS_CUDA(cudaFreeAsync(d_Wp, inst->stream));
     }
     if (d_lut4) MCS_CUDA(cudaFreeAsync(d_lut4, inst->stream));
     MCS_CUDA(mcs_take_launch_error());

@@ -851,6 +851,34 @@ def test_piqmc_two_stream_chunks_equal_one_stream(mcs, P, glob):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][0], out[2][0])
 
 
+@pytest.mark.parametrize("P,R,roff,glob", [(20, 4096, 0, 1), (20, 333, 77, 1), (10, 1000, 64, 0), (16, 130, 5, 1), (2, 70, 0, 0)])
+def test_packed_words_resident_in_hbm_equal_the_gathering_kernel(mcs, P, R, roff, glob):
+    """Even P <= 20: the packed working words (floor(64 / P) world lines each, groups on GLOBAL replica indices) are
+    built once per sweep call and the passes run on them (MODE_PACKN: one load per table row); MCS_PACK_GATHER=1
+    gathers the members in every pass as before.  Same words, same counters, same decisions: bit-identical states,
+    with ragged counts, replica offsets inside a group, split schedules, and on one or two streams."""
+    nbs = inst.torus(8, seed=5)[1]
+    I = mcs.Instance(nbs)
+    S = 10
+    A, B = np.linspace(2.5, 0.05, S), np.linspace(0.3, 1.0, S)
+    out = []
+    for env in ({"MCS_PACK_GATHER": "1"}, {}, {"MCS_STREAMS": "1"}, {"MCS_STREAMS": "3"}):
+        os.environ.update(env)
+        try:
+            st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+            st.init_random(9)
+            st.piqmc_sweeps(A[:4], B[:4], 2, 0.05, global_moves=bool(glob), seed=77, replica_offset=roff)
+            st.piqmc_sweeps(A[4:], B[4:], 2, 0.05, global_moves=bool(glob), seed=77, replica_offset=roff, sweep_offset=8)
+            out.append(st.download_spins())
+            st.close()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    assert not np.array_equal(out[0][:, :, 0], out[0][:, :, 1]) or P == 2
+    for o in out[1:]:
+        assert np.array_equal(out[0], o)
+
+
 def test_zero_temperature_never_accepts_an_uphill_move(mcs):
     """T = 0 (the tail of the example's classical schedule, santoro80.py:260): the reference compares
     0 > rand()/RAND_MAX -- never.  A threshold of 0 means NEVER here too (mcs_accepts), not "once in 2^32": after a
