@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Packed mode (even P <= 20): packed words resident in HBM for the duration of a sweep call (default) against
-gathering the members in every pass (MCS_PACK_GATHER=1); cfg1 shape (80x80, tau = 354, world-line moves)."""
+"""Packed mode (even P <= 20, odd P 3 .. 21): packed words resident in HBM for the duration of a sweep call (default)
+against gathering the members in every pass (MCS_PACK_GATHER=1) and against two world lines per word (MCS_NO_PACK=1);
+cfg1 shape (80x80, tau = 354)."""
 import json
 import os
 import sys
@@ -16,10 +17,10 @@ inst = mcs.Instance(nbs)
 N = inst.nspins
 tau = 354
 A, B = np.linspace(3.0, 1e-8, tau), np.ones(tau)
-for P, glob in ((20, True), (20, False), (16, False), (10, False)):
+for P, glob in ((20, True), (5, True), (21, False), (7, False)):
     for R in (4096, 512):
         row = {"P": P, "R": R, "global_moves": glob}
-        for name, env in (("gather", {"MCS_PACK_GATHER": "1"}), ("resident_1stream", {"MCS_STREAMS": "1"}), ("resident", {})):
+        for name, env in (("two_per_word", {"MCS_NO_PACK": "1"}), ("gather", {"MCS_PACK_GATHER": "1"}), ("resident", {})):
             os.environ.update(env)
             st = mcs.State(inst, mcs._lib.KIND_PIQMC, R, P)
             st.init_random(1)

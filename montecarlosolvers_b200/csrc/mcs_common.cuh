@@ -243,6 +243,7 @@ enum {
     MCS_TAG_GLOBAL = 17,     // PIQMC world-line move
     MCS_TAG_SVMC = 18,       // SVMC proposal + acceptance
     MCS_TAG_GLOBAL2 = 19,    // PIQMC world-line move, members 4.. of a packed group
+    MCS_TAG_LAST_SLICE2 = 20, // PIQMC odd-P closing slice, members 4.. of a packed group
     MCS_TAG_REFINE = 0x80,   // OR-ed into a group tag: second half of the lazily refined uniforms
     MCS_TAG_INIT = 0x40000000u
 };
@@ -610,6 +611,9 @@ __device__ __forceinline__ uint32_t mcs_accept_threshold(float dE, float nl2e_ov
 // Fixed-order energy by table (rows with at most four off-diagonal entries): builds the instance's tables on first
 // use (mcs_piqmc.cu).  Returns false when the instance does not qualify.
 bool mcs_energy_tables(mcs_instance *inst);
+
+// PIQMC packed mode: floor(64 / P) (at most 6) world lines per working word -- even P up to 20, odd P from 3 to 21
+inline bool mcs_piqmc_packs(int P) { return (P & 1) ? (P >= 3 && P <= 21) : (P >= 2 && P <= 20); }
 
 // kernels launchers implemented in the other translation units
 int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,

@@ -426,11 +426,14 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
                              a.replica_offset + (uint32_t)(r + a.half)};
     const uint32_t c1 = (uint32_t)site, c2 = a.sweep_lo;
     const uint32_t c3hi = a.sweep_hi << 8;
-    const bool oddP = !FULL && !PACK && (P & 1) != 0;
-    const uint64_t last = FUSE ? b0_shift(P) : (1ull << (P - 1)); // slice P-1 of every world line in the word
-    uint64_t even_allowed = 0x5555555555555555ull & pmask;
-    if (oddP) even_allowed &= ~last; // slice P-1 neighbours slice 0: handled alone below
-    const uint64_t odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
+    const bool oddP = !FULL && (P & 1) != 0;
+    // slice P-1 of every world line in the word
+    const uint64_t last = FUSE ? b0_shift(P) : (PACK ? a.seg_lsb << (P - 1) : (1ull << (P - 1)));
+    uint64_t even_allowed = 0x5555555555555555ull & pmask, odd_allowed = 0xAAAAAAAAAAAAAAAAull & pmask;
+    // An odd ring is not 2-colourable: slice P-1 neighbours slice 0 and is handled alone below.  In a packed word the
+    // segments start at bits of either parity (a phase then takes the even slices of one segment and the odd slices
+    // of the next: alternate slices of every ring, which is all that matters), so both masks lose the last slices.
+    if (oddP) even_allowed &= ~last, odd_allowed &= ~last;
 
     // [phase][call][thread]: private slots for the index fields (8 bytes per call, 16 with half-word fields)
     __shared__ __align__(16) uint2 s_bounce[(LutGeom<NPL>::FW == 16 ? 16 : 8) * WARPS * 32];
@@ -440,7 +443,24 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
                                    bounce, WARPS * 32, a.seg_lsb, bits);
     w ^= phase<NPL, 1, FULL, MODE>(pl, w, P, pmask, odd_allowed, lut, c0h, c1, c2, c3hi, a.keys, a.pow2, a.tie_thr,
                                    bounce + 4 * kSlot * WARPS * 32, WARPS * 32, a.seg_lsb, bits);
-    if (oddP) {
+    if (oddP && PACK) { // the closing slices of the pk rings: independent of each other, one Philox call per four
+        const uint64_t tl = w ^ rotl_seg(w, P, a.seg_lsb), tr = w ^ rotr_seg(w, P, a.seg_lsb);
+        uint32_t rnd[4];
+        uint64_t fl = 0;
+        for (int m = 0; m < pk; ++m) {
+            if ((m & 3) == 0)
+                mcs_philox4x32_rk(c0h[0], c1, c2, c3hi | (m == 0 ? MCS_TAG_LAST_SLICE : MCS_TAG_LAST_SLICE2), a.keys, rnd);
+            const int k = m * P + P - 1;
+            uint32_t idx = 0;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) idx |= (uint32_t)((pl[j] >> k) & 1ull) << j;
+            idx |= (uint32_t)((tl >> k) & 1ull) << NPL;
+            idx |= (uint32_t)((tr >> k) & 1ull) << (NPL + 1);
+            const uint32_t u = (m & 3) == 0 ? rnd[0] : (m & 3) == 1 ? rnd[1] : (m & 3) == 2 ? rnd[2] : rnd[3];
+            if (mcs_accepts(u, ~lut[idx])) fl |= 1ull << k;
+        }
+        w ^= fl;
+    } else if (oddP) {
         const uint64_t tl = w ^ (FUSE ? rotl_ring2(w, P, pmask) : rotl_ring(w, P, pmask));
         const uint64_t tr = w ^ (FUSE ? rotr_ring2(w, P, pmask) : rotr_ring(w, P, pmask));
 #pragma unroll
@@ -1141,7 +1161,7 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
     const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
     const bool no_fuse = getenv("MCS_NO_FUSE") != nullptr; // tests: one replica per thread for every P
     const bool no_pack = getenv("MCS_NO_PACK") != nullptr; // tests: at most two replicas per thread
-    if (LutGeom<NPL>::FW == 8 && a.P <= 20 && (a.P & 1) == 0 && !no_fuse && !no_pack) { // pk >= 3
+    if (LutGeom<NPL>::FW == 8 && mcs_piqmc_packs(a.P) && !no_fuse && !no_pack) { // pk >= 3
         // pk = floor(64 / P) replicas per thread (at most 6: loads per thread), blocks of 32 pk GLOBAL replicas per warp
         a.pk = std::min(64 / a.P, 6);
         const long long blk = 32ll * a.pk; // replicas per warp
@@ -1151,7 +1171,14 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
             gw = a.gw_n; // a chunk of the window's group warps (two-stream sweeps)
         else
             a.gw_lo = 0, a.gw_n = gw;
-        const int wf = gw >= 4 ? 4 : (gw >= 2 ? 2 : 1);
+        // warps per CTA (they share the site's table): the largest of 4, 2, 1 that leaves at most a tenth of the
+        // launched warps without a group
+        int wf = 1;
+        for (int cand = 4; cand >= 2; cand /= 2)
+            if (gw >= cand && ((gw + cand - 1) / cand * cand - gw) * 10 <= gw) {
+                wf = cand;
+                break;
+            }
         a.seg_lsb = 0;
         for (int m = 0; m < a.pk; ++m) a.seg_lsb |= 1ull << (m * a.P);
         a.half = 0;
@@ -1311,7 +1338,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     // Windows already guarantee that results do not depend on how replicas are grouped (tests); in the packed mode a
     // chunk is a range of the window's group warps.
     const long long G0 = a.G;
-    const bool packed_mode = P <= 20 && (P & 1) == 0 && !getenv("MCS_NO_FUSE") && !getenv("MCS_NO_PACK");
+    const bool packed_mode = mcs_piqmc_packs(P) && !getenv("MCS_NO_FUSE") && !getenv("MCS_NO_PACK");
     // Packed mode (even P <= 20): the working words (pk world lines each) are built ONCE per call into a scratch array
     // and the passes run on them -- one 64-bit load per table row instead of pk guarded loads and shifts -- then
     // unpacked (MCS_PACK_GATHER=1: gather the members in every pass, the round-1/2 kernel; same decisions)

