@@ -17,4 +17,7 @@ ncu --set full --clock-control none --import-source on -k regex:dense_block_kern
 python benchmarks/refdyn_probe.py 296 1 > gpurun_out/cap_refdyn_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:refdyn_ising_kernel -s 1 -c 1 -f \
     -o gpurun_out/cap_refdyn python benchmarks/refdyn_probe.py 296 1 > gpurun_out/cap_ncu4.log 2>&1
+python benchmarks/sa_cluster_ncu.py > gpurun_out/cap_sa_cluster_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:sa_cluster_kernel -s 2 -c 1 -f \
+    -o gpurun_out/cap_sa_cluster python benchmarks/sa_cluster_ncu.py > gpurun_out/cap_ncu5.log 2>&1
 echo "capture done: $(ls gpurun_out | grep cap_ | tr '\n' ' ')"
