@@ -132,7 +132,7 @@ def hbm_roofline(attempts_per_s, bytes_per_attempt, peaks, kernel, ms_per_launch
 def roofline(achieved, peak, have_peaks, R, ms_per_launch, bytes_per_launch, n_pass, args):
     """The base contract's HBM roofline of the pass kernel, plus what ncu says actually binds it.  The ncu numbers
     come from the newest committed capture profiles/r0*_piqmc_lut_pass_ncu.json (profiles/capture.sh +
-    profiles/summarize_ncu.py), taken at 4096 replicas per GPU; traffic scales linearly with the replicas."""
+    profiles/summarize_ncu.py); traffic scales linearly with the replicas a launch covers."""
     prof, src = None, None
     for rnd in ("r02", "r01"):
         cand = os.path.join("profiles", "%s_piqmc_lut_pass_ncu.json" % rnd)
@@ -150,7 +150,9 @@ def roofline(achieved, peak, have_peaks, R, ms_per_launch, bytes_per_launch, n_p
            "note": "the sweep is instruction bound (Philox multiplies and the per-attempt threshold compare on the "
                    "ALU / FMA pipes), not HBM bound: see binding_unit, profiles/ and DESIGN.md section 4"}
     if prof:
-        scale = R / 4096.0
+        # the profiled launch: grid_size CTAs of 128 threads, one 64-slice word per thread
+        prof_attempts = float(prof.get("grid_size", 102400)) * 128 * 64
+        scale = attempts_per_launch / prof_attempts
         if args.traffic is None:
             out["traffic"] = (prof["dram_bytes_read"] + prof["dram_bytes_write"]) * scale
         out["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum, " + src
@@ -159,7 +161,7 @@ def roofline(achieved, peak, have_peaks, R, ms_per_launch, bytes_per_launch, n_p
             "alu_pipe_inst_pct_of_peak": prof["alu_pipe_inst_pct_of_peak"],
             "fma_pipe_cycles_active_pct": prof["fma_pipe_cycles_active_pct"],
             "issue_slots_busy_pct": prof["issue_slots_busy_pct"],
-            "instructions_per_attempt": prof["warp_instructions"] * 32.0 / (attempts_per_launch / scale),
+            "instructions_per_attempt": prof["warp_instructions"] * 32.0 / prof_attempts,
             "dram_pct_of_peak": prof["dram_pct_of_peak"], "source": "ncu --set full, " + src}
     return out
 
@@ -707,9 +709,11 @@ def run_ours(args, out):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # dominant kernel: piqmc_lut_pass_kernel, one launch per colour class per sweep.
         # algorithmic bytes: 0.25 B per attempt (read + write of one bit-packed spin), DESIGN.md section 4
+        # (a colour pass of a batch of 512+ anneals is TWO launches, one per replica chunk, alternating on two streams:
+        # a launch covers half the batch and consecutive launches overlap; ms_per_launch = step time / launches)
         n_pass = launches - args.steps  # minus the init kernel of each step
         ms_per_launch = ms_dev / max(n_pass, 1)
-        bytes_per_launch = 0.25 * (NSPINS / 2) * R * P_SLICES
+        bytes_per_launch = 0.25 * NSPINS * R * P_SLICES * S * args.steps / max(n_pass, 1)
         achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
