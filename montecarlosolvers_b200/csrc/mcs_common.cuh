@@ -288,36 +288,6 @@ inline cudaError_t mcs_launch_pdl(Kernel kernel, dim3 grid, dim3 block, cudaStre
     return mcs_note_launch(cudaLaunchKernelEx(&cfg, kernel, args));
 }
 
-// ---- grid-wide barrier of the persistent small-batch kernels (cooperative launch: every CTA is resident) ----
-// sync[0] counts arrivals (monotonic; zeroed before the launch), sync[1] is an error flag.  One thread per CTA
-// arrives and spins until all CTAs of this epoch have; state loads after the barrier bypass L1 (__ldcg).  The spin is bounded: a barrier that cannot complete (it cannot, under a cooperative
-// launch) raises the flag instead of hanging the device.
-// Split in two so that work that does not depend on the other CTAs (the next pass's couplings and threshold table)
-// runs between arriving and waiting.  One fence by the arriving thread after the CTA barrier publishes every
-// thread's stores (fence cumulativity, the pattern of cooperative-groups grid.sync).
-__device__ __forceinline__ void mcs_grid_arrive(unsigned *sync)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(&sync[0], 1u);
-    }
-}
-__device__ __forceinline__ void mcs_grid_wait(unsigned *sync, unsigned target)
-{
-    if (threadIdx.x == 0) {
-        unsigned v, spins = 0;
-        for (;;) { // relaxed polls with a short back-off (hundreds of pollers on one L2 line starve the arrivals)
-            asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
-            if ((int)(v - target) >= 0 || ++spins >= (1u << 24)) break;
-            __nanosleep(40);
-        }
-        if ((int)(v - target) < 0) atomicExch(&sync[1], 1u);
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 // u <= T with T == 0 meaning NEVER: mcs_accept_threshold returns 0 exactly when exp(-dE/teff) 2^32 < 1 (underflow,
 // T = 0 in the schedule, NaN energies) -- the reference never accepts there (it compares 0 > rand()/RAND_MAX,
 // qmc.pyx:142).  In the table kernels the pair (u, T) = (0, 0) always looks like a tie, so the rule lives in the

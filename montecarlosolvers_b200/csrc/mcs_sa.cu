@@ -310,209 +310,6 @@ __global__ void __launch_bounds__(128) sa_energy_lut_kernel(const uint32_t *__re
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Small batches: the whole schedule in ONE cooperative launch.  A colour pass of 1024 restarts is a single wave of
-// 3200 warps that lasts about a microsecond; as separate launches the passes are spaced by the kernel-boundary
-// latency (4.4 us per pass however small the batch: benchmarks/small_batch_probe.py).  Here a warp takes the
-// (site, 32 words) items of a pass in a grid-stride loop -- its own copy of the site's threshold table in shared
-// memory -- and the passes are separated by mcs_grid_sync.  Same Philox counters, same thresholds, same decision
-// code as sa_lut_pass_kernel: the result is bit-identical to the multi-launch path (tests).
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kPersistWarps = 24;
-
-struct SaPersist {
-    uint32_t *V;
-    const int32_t *ell_idx;
-    const float *ell_J; // [nsteps][N][dpad]
-    const float *h;     // [nsteps][N]
-    long long ellJ_stride, h_stride; // elements between the tables of consecutive schedule steps (0: static)
-    const int32_t *order;       // sites sorted by colour
-    const int32_t *color_start; // device copy, [ncolors + 1]
-    const float *nl2e;          // [S]: -log2(e) / sched[t]
-    unsigned *sync;             // mcs_grid_sync
-    long long *prof;            // MCS_PERSIST_PROF=1: cycles of CTA 0 / thread 0 in {items, arrive + prepare, wait}
-    int ncolors, dpad, chunks, S, mcsteps;
-    long long G;
-    uint64_t sweep_offset;
-    mcs_philox_keys keys;
-    mcs_pow2_table pow2;
-    uint32_t word_offset, tie_thr;
-};
-
-template <int NPL, int FLD>
-__global__ void __launch_bounds__(kPersistWarps * 32, 1) sa_persistent_kernel(const __grid_constant__ SaPersist a)
-{
-    constexpr int ENT = 1 << NPL, NQ = NPL - FLD, SH = NPL <= 6 ? 2 : 0, T = kPersistWarps * 32;
-    __shared__ uint32_t s_lut[kPersistWarps][ENT];
-    __shared__ uint2 s_bounce[4 * T]; // [call][thread]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gwarp = (long long)blockIdx.x * kPersistWarps + warp, nwarps = (long long)gridDim.x * kPersistWarps;
-    const uint32_t G32 = (uint32_t)a.G;
-    uint32_t *lut = s_lut[warp];
-    uint2 *bounce = s_bounce + threadIdx.x;
-    const long long npass = (long long)a.S * a.mcsteps * a.ncolors;
-
-    // Everything of an item that does not depend on the state: site, neighbours, couplings, threshold table.
-    // Done for the warp's FIRST item of the next pass between arriving at the barrier and waiting on it.  With a
-    // static table and at most kStatic colours the warp's first item of a colour is the same in every sweep: its
-    // site, neighbours and couplings are read ONCE into registers, and only the table (one exp2 per entry) is
-    // rebuilt per pass.
-    constexpr int kStatic = 2;
-    const bool fixed = a.ncolors <= kStatic && a.ellJ_stride == 0 && a.h_stride == 0;
-    int site = 0, nb[NPL];
-    float c[NPL];
-    int f_site[kStatic], f_nb[kStatic][NPL];
-    float f_c[kStatic][NPL];
-    long long f_items[kStatic];
-    uint32_t g = 0;
-    long long items = 0;
-    float nl2e = 0.0f;
-    const float *ellJ = a.ell_J, *hrow = a.h;
-    int base = 0;
-    auto load_static = [&](long long item) {
-        site = __ldg(&a.order[base + (int)(item / a.chunks)]);
-        g = (uint32_t)(item % a.chunks) * 32u + (uint32_t)lane;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            if (j < NQ) {
-                nb[j] = __ldg(&a.ell_idx[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j]);
-                c[j] = -2.0f * __ldg(&ellJ[(uint64_t)(uint32_t)site * (uint32_t)a.dpad + j]); // sa.pyx:91-94
-            } else {
-                nb[j] = site;
-                c[j] = -2.0f * __ldg(&hrow[site]);
-            }
-        }
-    };
-    auto build_table = [&]() {
-        for (int e = lane; e < ENT; e += 32) {
-            float dE = 0.0f;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) dE += ((e >> j) & 1) ? -c[j] : c[j];
-            lut[e] = ~mcs_accept_threshold(dE, nl2e);
-        }
-        __syncwarp();
-    };
-    auto prepare = [&](long long item) {
-        load_static(item);
-        build_table();
-    };
-    if (fixed) {
-#pragma unroll
-        for (int col = 0; col < kStatic; ++col) {
-            f_items[col] = 0;
-            if (col < a.ncolors) {
-                base = __ldg(&a.color_start[col]);
-                f_items[col] = (long long)(__ldg(&a.color_start[col + 1]) - base) * a.chunks;
-                if (gwarp < f_items[col]) load_static(gwarp);
-                f_site[col] = site;
-#pragma unroll
-                for (int j = 0; j < NPL; ++j) f_nb[col][j] = nb[j], f_c[col][j] = c[j];
-            }
-        }
-    }
-    auto begin_pass = [&](long long p) { // schedule position of pass p
-        const int col = (int)(p % a.ncolors);
-        const long long sw = p / a.ncolors;
-        const int t = (int)(sw / a.mcsteps);
-        nl2e = __ldg(&a.nl2e[t]);
-        if (fixed) {
-#pragma unroll
-            for (int q = 0; q < kStatic; ++q)
-                if (q == col) {
-                    site = f_site[q];
-                    items = f_items[q];
-#pragma unroll
-                    for (int j = 0; j < NPL; ++j) nb[j] = f_nb[q][j], c[j] = f_c[q][j];
-                }
-            base = __ldg(&a.color_start[col]);
-            g = (uint32_t)(gwarp % a.chunks) * 32u + (uint32_t)lane;
-            if (gwarp < items) build_table();
-            return;
-        }
-        ellJ = a.ell_J + (size_t)t * a.ellJ_stride;
-        hrow = a.h + (size_t)t * a.h_stride;
-        base = __ldg(&a.color_start[col]);
-        items = (long long)(__ldg(&a.color_start[col + 1]) - base) * a.chunks;
-        if (gwarp < items) prepare(gwarp);
-    };
-    begin_pass(0);
-    long long pf[3] = {0, 0, 0}, tq = clock64();
-    for (long long p = 0; p < npass; ++p) {
-        const uint64_t sweep = a.sweep_offset + (uint64_t)(p / a.ncolors);
-        const uint32_t c2 = (uint32_t)sweep, c3hi = (uint32_t)(sweep >> 32) << 8;
-        for (long long item = gwarp; item < items; item += nwarps) {
-            if (item != gwarp) prepare(item); // second item of a pass: not prefetched
-            const bool live = g < G32;
-            uint32_t *Vg = a.V + (live ? g : 0u);
-            const uint32_t v = __ldcg(&Vg[(uint64_t)(uint32_t)site * G32]);
-            uint32_t pl[NPL];
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) pl[j] = j < NQ ? v ^ __ldcg(&Vg[(uint64_t)(uint32_t)nb[j] * G32]) : v;
-            if (live) {
-                const uint32_t c0 = a.word_offset + g, c1 = (uint32_t)site;
-                uint32_t rej = 0, flags = 0;
-#define MCS_SA_CALL(q)                                                                                        \
-    {                                                                                                         \
-        uint32_t chA, chB;                                                                                    \
-        mcs_decide_call<SH>(chA, chB, flags, sa_gather_index<NPL, 2 * (q)>(pl, a.pow2),                       \
-                            sa_gather_index<NPL, 2 * (q) + 1>(pl, a.pow2), lut, c0, c1, c2,                   \
-                            c3hi | (uint32_t)(2 * (q)), a.keys, a.pow2, a.tie_thr, bounce + (q) * T);         \
-        rej = chA * a.pow2.up[7 - 2 * (q)] + rej;                                                             \
-        rej = chB * a.pow2.up[6 - 2 * (q)] + rej;                                                             \
-    }
-                MCS_SA_CALL(0) MCS_SA_CALL(1) MCS_SA_CALL(2) MCS_SA_CALL(3)
-#undef MCS_SA_CALL
-                if (flags) {
-#define MCS_SA_REFINE(q)                                                                                      \
-    if (flags & (8u >> (q))) {                                                                                \
-        const uint2 ch = mcs_refine_call<SH>(sa_gather_index<NPL, 2 * (q)>(pl, a.pow2),                       \
-                                             sa_gather_index<NPL, 2 * (q) + 1>(pl, a.pow2), lut, c0, c1, c2,  \
-                                             c3hi | (uint32_t)(2 * (q)), a.keys.rk[0], a.keys.rk[1]);         \
-        rej = (rej & ~(0x03030303u << (6 - 2 * (q)))) | (ch.x << (7 - 2 * (q))) | (ch.y << (6 - 2 * (q)));    \
-    }
-                    MCS_SA_REFINE(0) MCS_SA_REFINE(1) MCS_SA_REFINE(2) MCS_SA_REFINE(3)
-#undef MCS_SA_REFINE
-                }
-                __stcg(&Vg[(uint64_t)(uint32_t)site * G32], v ^ ~rej);
-            }
-            __syncwarp(); // the table is rewritten by this warp's next item
-        }
-        if (p + 1 == npass) break;
-        long long tn = clock64();
-        pf[0] += tn - tq, tq = tn;
-        mcs_grid_arrive(a.sync);
-        begin_pass(p + 1);
-        tn = clock64();
-        pf[1] += tn - tq, tq = tn;
-        mcs_grid_wait(a.sync, (unsigned)(p + 1) * gridDim.x);
-        tn = clock64();
-        pf[2] += tn - tq, tq = tn;
-    }
-    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0)
-        for (int q = 0; q < 3; ++q) a.prof[q] = pf[q];
-}
-
-template <int NPL>
-const void *sa_persistent_fn(int field)
-{
-    return field ? (const void *)sa_persistent_kernel<NPL, 1> : (const void *)sa_persistent_kernel<NPL, 0>;
-}
-
-const void *sa_persistent_fn(int npl, int field)
-{
-    switch (npl) {
-    case 1: return sa_persistent_fn<1>(field);
-    case 2: return sa_persistent_fn<2>(field);
-    case 3: return sa_persistent_fn<3>(field);
-    case 4: return sa_persistent_fn<4>(field);
-    case 5: return sa_persistent_fn<5>(field);
-    case 6: return sa_persistent_fn<6>(field);
-    case 7: return sa_persistent_fn<7>(field);
-    default: return sa_persistent_fn<8>(field);
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------------------
 // Small batches, cluster-resident: the whole schedule in ONE launch without a grid barrier.  Restarts are
 // independent, so the batch is cut into groups of Wc words (32 Wc restarts) and each group is owned by one
 // thread-block CLUSTER for the whole schedule: CTA r of the cluster keeps a contiguous slice of every colour class
@@ -990,81 +787,6 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
         bool done = false;
         MCS_TRY(sa_try_cluster(st, sched, S, mcsteps, sweep_offset, npl, a, &done));
         if (done) return MCS_OK;
-    }
-    // ---- small batches: one cooperative launch for the whole schedule (sa_persistent_kernel) ----
-    long long max_items = 0;
-    for (int c = 0; c < inst->ncolors; ++c)
-        max_items = std::max(max_items, (long long)(inst->color_start[c + 1] - inst->color_start[c]) * a.chunks);
-    const long long passes = (long long)S * mcsteps * inst->ncolors;
-    // Opt-in (MCS_PERSIST=1).  Measured on B200 at BASELINE cfg2 (1024 restarts, 2000 colour passes): 4.6 us per
-    // pass (2.6 us of SM-bound item work on 134 SMs + 2.0 us of barrier and intra-CTA imbalance) against 4.4 us per
-    // pass for one programmatic-dependent launch per colour pass -- the barrier costs what the kernel boundary it
-    // replaces costs, so the multi-launch path stays the default (profiles/r02_small_batch.log).
-    if (lut && passes >= 8 && max_items > 0 && getenv("MCS_PERSIST")) {
-        const void *fn = sa_persistent_fn(npl, a.field);
-        int per_sm = 0, sms = 0, coop = 0;
-        MCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kPersistWarps * 32, 0));
-        MCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, inst->device));
-        MCS_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, inst->device));
-        const long long capacity = (long long)per_sm * sms; // CTAs that are resident together
-        const long long want = (max_items + kPersistWarps - 1) / kPersistWarps;
-        if (coop && capacity > 0 && want <= 2 * capacity) { // at most two items per warp and pass
-            std::vector<float> nl((size_t)S);
-            for (int64_t t = 0; t < S; ++t) nl[(size_t)t] = (float)(-1.4426950408889634 / sched[t]); // sa.pyx:98
-            const size_t nb_sched = (size_t)S * sizeof(float), nb_col = (size_t)(inst->ncolors + 1) * sizeof(int32_t);
-            unsigned char *d_buf = nullptr; // [nl2e | color_start | sync]
-            MCS_CUDA(cudaMallocAsync((void **)&d_buf, nb_sched + nb_col + 2 * sizeof(unsigned) + 32, inst->stream));
-            MCS_CUDA(cudaMemcpyAsync(d_buf, nl.data(), nb_sched, cudaMemcpyHostToDevice, inst->stream));
-            MCS_CUDA(cudaMemcpyAsync(d_buf + nb_sched, inst->color_start.data(), nb_col, cudaMemcpyHostToDevice,
-                                     inst->stream));
-            MCS_CUDA(cudaMemsetAsync(d_buf + nb_sched + nb_col, 0, 2 * sizeof(unsigned), inst->stream));
-            SaPersist p;
-            p.V = st->d_V;
-            p.ell_idx = inst->d_ell_idx;
-            p.ell_J = inst->d_ell_J;
-            p.h = inst->d_h;
-            p.ellJ_stride = inst->nsteps > 1 ? (long long)inst->N * inst->dpad : 0;
-            p.h_stride = inst->nsteps > 1 ? (long long)inst->N : 0;
-            p.order = inst->d_order;
-            p.nl2e = reinterpret_cast<const float *>(d_buf);
-            p.color_start = reinterpret_cast<const int32_t *>(d_buf + nb_sched);
-            p.sync = reinterpret_cast<unsigned *>(d_buf + nb_sched + nb_col);
-            const size_t prof_off = (nb_sched + nb_col + 2 * sizeof(unsigned) + 7) & ~(size_t)7;
-            p.prof = getenv("MCS_PERSIST_PROF") ? reinterpret_cast<long long *>(d_buf + prof_off) : nullptr;
-            p.ncolors = inst->ncolors;
-            p.dpad = inst->dpad;
-            p.chunks = a.chunks;
-            p.S = (int)S;
-            p.mcsteps = mcsteps;
-            p.G = st->G;
-            p.sweep_offset = sweep_offset;
-            p.keys = a.keys;
-            p.pow2 = a.pow2;
-            p.word_offset = a.word_offset;
-            p.tie_thr = a.tie_thr;
-            void *args[] = {&p};
-            const unsigned grid = (unsigned)std::min(capacity, want);
-            MCS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistWarps * 32), args, 0, inst->stream));
-            inst->launches++;
-            if (p.prof) {
-                long long hp[3] = {0, 0, 0};
-                MCS_CUDA(cudaMemcpyAsync(hp, p.prof, sizeof(hp), cudaMemcpyDeviceToHost, inst->stream));
-                MCS_CUDA(cudaStreamSynchronize(inst->stream));
-                fprintf(stderr, "[mcs persist] %u CTAs x %d threads, %lld passes: per pass %.0f cycles items, %.0f arrive + "
-                                "prepare, %.0f wait\n", grid, kPersistWarps * 32, passes, (double)hp[0] / passes,
-                        (double)hp[1] / passes, (double)hp[2] / passes);
-            }
-            if (getenv("MCS_PERSIST_CHECK")) { // tests: surface the (impossible) barrier time-out
-                unsigned h_sync[2] = {0, 0};
-                MCS_CUDA(cudaMemcpyAsync(h_sync, p.sync, sizeof(h_sync), cudaMemcpyDeviceToHost, inst->stream));
-                MCS_CUDA(cudaStreamSynchronize(inst->stream));
-                MCS_CUDA(cudaFreeAsync(d_buf, inst->stream));
-                MCS_REQUIRE(h_sync[1] == 0, MCS_ENODEVICE, "persistent sweep: a grid barrier timed out");
-                return MCS_OK;
-            }
-            MCS_CUDA(cudaFreeAsync(d_buf, inst->stream));
-            return MCS_OK;
-        }
     }
     for (int64_t t = 0; t < S; ++t) {
         a.ell_J = inst->ell_J_at(t); // sa.NoisyAnneal: nbs[itemp] (sa.pyx:363-365)

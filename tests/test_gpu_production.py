@@ -735,54 +735,6 @@ def test_one_shot_calls_from_several_threads_on_one_instance(mcs):
             assert np.array_equal(threaded[t], serial[t]), (rep, t)
 
 
-@pytest.mark.parametrize("case", ["torus16_R1024", "graph60_fields_R37", "torus6_noisy_R1", "circulant48_8planes_R96"])
-def test_persistent_small_batch_sa_equals_the_multi_launch_path(mcs, case):
-    """Opt-in small-batch mode (MCS_PERSIST=1): the whole schedule in one cooperative launch (sa_persistent_kernel,
-    grid barrier between colour passes).  Same Philox counters, thresholds and decision code: bit-identical to one
-    launch per colour pass -- two and more colours, fields, time-dependent tables, ragged restart counts."""
-    if case == "torus16_R1024":
-        nbs, R, S = inst.torus(16, seed=1)[1], 1024, 60
-    elif case == "graph60_fields_R37":
-        nbs, R, S = inst.random_graph(60, 150, seed=2, fields=True)[1], 37, 40
-    elif case == "torus6_noisy_R1":
-        base = inst.torus(6, seed=3, fields=True)[1]
-        S, R = 25, 1
-        nbs = np.repeat(base[None], S, axis=0).copy()
-        nbs[..., 1] *= np.linspace(0.2, 1.0, S).reshape(S, 1, 1)
-    else:
-        nbs, R, S = inst.circulant(48, (1, 2, 3, 4), seed=6, fields=False)[1], 96, 30
-    I = mcs.Instance(nbs)
-    if I.maxdeg + int(I.has_field) > 8:
-        pytest.skip("served by the general-degree kernel")
-    sched = np.linspace(2.5, 0.0, S)
-    n = nbs.shape[-3]
-    s0 = (2 * np.random.RandomState(4).randint(2, size=(R, n)) - 1).astype(np.int8)
-    out = []
-    os.environ["MCS_PERSIST_CHECK"] = "1"
-    os.environ["MCS_CLUSTER"] = "0"
-    try:
-        for no_persist in (False, True):
-            if not no_persist:
-                os.environ["MCS_PERSIST"] = "1"
-            try:
-                st = mcs.State(I, mcs._lib.KIND_SA, R, 1)
-                st.upload_spins(s0)
-                l0 = I.launches
-                st.sa_sweeps(sched[:11], 2, seed=31)
-                st.sa_sweeps(sched[11:], 2, seed=31, sweep_offset=22)
-                nl = I.launches - l0
-                out.append((st.download_spins(), nl))
-                st.close()
-            finally:
-                os.environ.pop("MCS_PERSIST", None)
-    finally:
-        os.environ.pop("MCS_PERSIST_CHECK", None)
-        os.environ.pop("MCS_CLUSTER", None)
-    assert out[0][1] == 2 and out[1][1] >= 2 * S * 2  # two cooperative launches vs one launch per colour pass
-    assert not np.array_equal(out[0][0], s0)
-    assert np.array_equal(out[0][0], out[1][0])
-
-
 @pytest.mark.parametrize("csize", [1, 4, 8, 16])
 @pytest.mark.parametrize("case", ["torus16_R1024", "graph60_fields_R37", "torus6_noisy_R1", "torus20_fields_R200",
                                   "odd_ring_3colours_R70"])
