@@ -67,6 +67,8 @@ struct PiqmcPass {
     // sweep call from W and unpacked at its end: one 64-bit load per row instead of pk guarded loads and shifts
     uint64_t *Wp;
     long long gp;
+    int wpt;          // plain mode: words per thread (1, 2 or 4) ...
+    long long wstep;  // ... replica r0 + k wstep is the thread's k-th word (wstep = replicas of the launch / wpt)
 };
 
 __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
@@ -345,7 +347,7 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
 //       indices (see PiqmcPass::pk) and the Philox counter is the group's index, so results do not depend on how
 //       replicas are sharded over GPUs, windows or calls; members that lie outside this window are neither read
 //       nor written.
-template <int NPL, int WARPS, bool FULL, int FLD, int MODE>
+template <int NPL, int WARPS, bool FULL, int FLD, int MODE, bool MULTI = false>
 __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
     static_assert(!(FULL && MODE != MODE_PLAIN), "fused / packed modes are for P <= 32");
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     const unsigned si = blockIdx.y + 65535u * blockIdx.z;
     if (si >= (unsigned)a.nsites) return; // only when the colour class has more than 65535 sites (CTA-uniform)
     const int site = __ldg(&a.sites[si]);
-    const long long r = ((long long)blockIdx.x * WARPS + warp) * 32 + lane; // replica (PACK: group) of this thread
+    const long long r0 = ((long long)blockIdx.x * WARPS + warp) * 32 + lane; // first replica (PACK: group) of this thread
 
     // ---- per-site coefficients (CTA-uniform) and the acceptance-threshold table ---------------
     float c[NPL];
@@ -391,15 +393,22 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     // PACK: member m of this thread is local replica first + 32 m (global index (group0 + warp) 32 pk + 32 m + lane)
     const long long gwarp = (PACK ? a.gw_lo : 0) + (long long)blockIdx.x * WARPS + warp;
     const bool gw_ok = !PACK || gwarp < a.gw_lo + a.gw_n; // the last CTA of a packed launch may have spare warps
-    const long long first = PACK ? (a.group0 + gwarp) * 32 * pk + lane - (long long)a.replica_offset : r;
-    const uint64_t *Wr = a.W + first, *Wr2 = Wr + (FUSE ? a.half : 0);
+    const long long first0 = PACK ? (a.group0 + gwarp) * 32 * pk + lane - (long long)a.replica_offset : r0;
     uint64_t *Wn = NATIVE ? a.Wp + (gw_ok ? gwarp * 32 + lane : 0) : nullptr;
     const uint32_t gp = NATIVE ? (uint32_t)a.gp : 0u;
     uint32_t present = 0; // PACK: members that exist in this window
     if (PACK && !NATIVE && gw_ok)
         for (int m = 0; m < pk; ++m)
-            if (first + 32 * m >= 0 && first + 32 * m < a.nvalid) present |= 1u << m;
+            if (first0 + 32 * m >= 0 && first0 + 32 * m < a.nvalid) present |= 1u << m;
     mcs_pdl_wait(); // everything above depends on the instance and the schedule only
+    // Plain mode: a thread takes a.wpt words (replicas r0, r0 + wstep, ...) one after the other, so that the site's
+    // coefficients, neighbour indices and threshold table -- a quarter of the instructions of a one-word thread --
+    // are set up once for all of them.
+    // (MULTI is a template parameter: the one-word kernel keeps its straight-line code)
+    const int wpt = (MODE == MODE_PLAIN && MULTI) ? a.wpt : 1;
+    for (int kw = 0; kw < wpt; ++kw) {
+    const long long r = r0 + ((MODE == MODE_PLAIN && MULTI) ? kw * a.wstep : 0), first = PACK ? first0 : r;
+    const uint64_t *Wr = a.W + first, *Wr2 = Wr + (FUSE ? a.half : 0);
     auto load = [&](int row) -> uint64_t {
         if (NATIVE) return gw_ok ? Wn[(uint64_t)(uint32_t)row * gp] : 0ull;
         if (PACK) {
@@ -417,10 +426,12 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     uint64_t pl[NPL];
 #pragma unroll
     for (int j = 0; j < NPL; ++j) pl[j] = j < NQ ? (w ^ load(nb[j])) & pmask : w; // field plane: bit set <=> s = -1
-    if (WARPS == 1)
-        __syncwarp();
-    else
-        __syncthreads();
+    if (kw == 0) { // the table is published once; the first word's loads were issued before the barrier
+        if (WARPS == 1)
+            __syncwarp();
+        else
+            __syncthreads();
+    }
     const uint32_t *lut = s_lut;
     const uint32_t c0h[2] = {PACK ? (uint32_t)((a.group0 + gwarp) * 32 + lane) : a.replica_offset + (uint32_t)r,
                              a.replica_offset + (uint32_t)(r + a.half)};
@@ -527,6 +538,7 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     } else {
         a.W[(uint64_t)(uint32_t)site * rpad + r] = w;
     }
+    } // words of this thread
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1214,8 +1226,24 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
         return;
     }
     a.half = 0;
-    const dim3 grid((unsigned)(a.G / warps), ny, nz);
-    if (a.P == 64 && warps == 4)
+    // words per thread (P = 64, four-warp CTAs): the per-site set-up is shared by 2 or 4 replicas of a thread.  Measured
+    // at cfg3 (profiles/r02_wpt.log): 1.94e12 (one word) -> 1.95e12 (two) -> 2.00e12 attempts/s (four), also at 1024
+    // anneals; P = 40 does not gain (1.07e12 with one word, 1.05 / 1.07 with two / four) and keeps one.
+    a.wpt = 1;
+    if (warps == 4 && a.P == 64) {
+        int want = 4;
+        if (const char *e = getenv("MCS_WPT")) want = atoi(e);
+        for (int cand = 4; cand >= 2; cand /= 2)
+            if (cand <= want && (a.G / 4) % cand == 0) {
+                a.wpt = cand;
+                break;
+            }
+    }
+    a.wstep = (long long)(a.G / a.wpt) * 32;
+    const dim3 grid((unsigned)(a.G / warps / a.wpt), ny, nz);
+    if (a.P == 64 && warps == 4 && a.wpt > 1)
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD, MODE_PLAIN, true>, grid, dim3(128), s, a);
+    else if (a.P == 64 && warps == 4)
         mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD, MODE_PLAIN>, grid, dim3(128), s, a);
     else if (warps == 4)
         mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, MODE_PLAIN>, grid, dim3(128), s, a);
@@ -1324,6 +1352,8 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     a.gw_n = 0;
     a.Wp = nullptr;
     a.gp = 0;
+    a.wpt = 1;
+    a.wstep = 0;
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;

@@ -841,6 +841,34 @@ def test_packed_words_resident_in_hbm_equal_the_gathering_kernel(mcs, P, R, roff
         assert np.array_equal(out[0], o)
 
 
+@pytest.mark.parametrize("glob,fields", [(0, False), (1, False), (1, True)])
+def test_several_words_per_thread_do_not_change_any_decision(mcs, glob, fields, P=64):
+    """P = 64: a thread of the pass kernel takes 1, 2 or 4 replicas one after the other, sharing the site's set-up
+    (coefficients, neighbour indices, threshold table).  Counters belong to replicas, not to threads: bit-identical
+    states (with world-line moves and fields), also combined with two streams."""
+    nbs = inst.torus(8, seed=5, fields=fields)[1]
+    I = mcs.Instance(nbs)
+    R, S = 1024, 10
+    A, B = np.linspace(2.5, 0.05, S), np.linspace(0.3, 1.0, S)
+    out = []
+    for wpt, streams in (("1", "1"), ("2", "1"), ("4", "1"), ("4", "2"), (None, None)):
+        for k, v in (("MCS_WPT", wpt), ("MCS_STREAMS", streams)):
+            os.environ.pop(k, None)
+            if v:
+                os.environ[k] = v
+        try:
+            st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+            st.init_random(9)
+            st.piqmc_sweeps(A, B, 2, 0.05, global_moves=bool(glob), seed=77)
+            out.append(st.download_spins())
+            st.close()
+        finally:
+            os.environ.pop("MCS_WPT", None)
+            os.environ.pop("MCS_STREAMS", None)
+    for o in out[1:]:
+        assert np.array_equal(out[0], o)
+
+
 def test_zero_temperature_never_accepts_an_uphill_move(mcs):
     """T = 0 (the tail of the example's classical schedule, santoro80.py:260): the reference compares
     0 > rand()/RAND_MAX -- never.  A threshold of 0 means NEVER here too (mcs_accepts), not "once in 2^32": after a
