@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Words per thread of the plain PIQMC pass kernel (MCS_WPT = 1, 2, 4): cfg3 shape, 200 schedule steps."""
+"""Words per thread of the P = 64 PIQMC pass kernel (MCS_WPT = 1 .. 16): cfg3 shape, 200 schedule steps."""
 import json
 import os
 import sys
@@ -15,10 +15,10 @@ inst = mcs.Instance(nbs)
 N = inst.nspins
 S = 200
 A, B = np.linspace(3.0, 1e-8, S), np.ones(S)
-for P in (64, 40):
+for P in (64,):
     for R in (512, 1024, 4096):
         row = {"P": P, "R": R}
-        for wpt in ("1", "2", "4", None):
+        for wpt in ("1", "2", "4", "8", "16", None):
             os.environ.pop("MCS_WPT", None)
             if wpt:
                 os.environ["MCS_WPT"] = wpt

@@ -1226,14 +1226,14 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
         return;
     }
     a.half = 0;
-    // words per thread (P = 64, four-warp CTAs): the per-site set-up is shared by 2 or 4 replicas of a thread.  Measured
-    // at cfg3 (profiles/r02_wpt.log): 1.94e12 (one word) -> 1.95e12 (two) -> 2.00e12 attempts/s (four), also at 1024
-    // anneals; P = 40 does not gain (1.07e12 with one word, 1.05 / 1.07 with two / four) and keeps one.
+    // words per thread (P = 64, four-warp CTAs): the per-site set-up is shared by up to 16 replicas of a thread.  Measured
+    // at cfg3 (profiles/r02_wpt.log): 1.94e12 (one word) -> 1.95e12 (two) -> 2.00e12 (four) -> 2.02e12 (eight) ->
+    // 2.035e12 attempts/s (sixteen: one CTA per site and chunk); P = 40 does not gain and keeps one.
     a.wpt = 1;
     if (warps == 4 && a.P == 64) {
-        int want = 4;
+        int want = 16;
         if (const char *e = getenv("MCS_WPT")) want = atoi(e);
-        for (int cand = 4; cand >= 2; cand /= 2)
+        for (int cand = 16; cand >= 2; cand /= 2)
             if (cand <= want && (a.G / 4) % cand == 0) {
                 a.wpt = cand;
                 break;

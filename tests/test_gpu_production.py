@@ -843,7 +843,7 @@ def test_packed_words_resident_in_hbm_equal_the_gathering_kernel(mcs, P, R, roff
 
 @pytest.mark.parametrize("glob,fields", [(0, False), (1, False), (1, True)])
 def test_several_words_per_thread_do_not_change_any_decision(mcs, glob, fields, P=64):
-    """P = 64: a thread of the pass kernel takes 1, 2 or 4 replicas one after the other, sharing the site's set-up
+    """P = 64: a thread of the pass kernel takes 1, 2, 4 ... 16 replicas one after the other, sharing the site's set-up
     (coefficients, neighbour indices, threshold table).  Counters belong to replicas, not to threads: bit-identical
     states (with world-line moves and fields), also combined with two streams."""
     nbs = inst.torus(8, seed=5, fields=fields)[1]
@@ -851,7 +851,7 @@ def test_several_words_per_thread_do_not_change_any_decision(mcs, glob, fields, 
     R, S = 1024, 10
     A, B = np.linspace(2.5, 0.05, S), np.linspace(0.3, 1.0, S)
     out = []
-    for wpt, streams in (("1", "1"), ("2", "1"), ("4", "1"), ("4", "2"), (None, None)):
+    for wpt, streams in (("1", "1"), ("2", "1"), ("4", "1"), ("8", "1"), ("4", "2"), (None, None)):
         for k, v in (("MCS_WPT", wpt), ("MCS_STREAMS", streams)):
             os.environ.pop(k, None)
             if v:
