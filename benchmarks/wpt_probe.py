@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Words per thread of the P = 64 PIQMC pass kernel (MCS_WPT = 1 .. 16): cfg3 shape, 200 schedule steps."""
+"""Words per thread of the P = 64 PIQMC pass kernel (wW:n = W-warp CTAs, up to n words per thread): cfg3 shape,
+200 schedule steps."""
 import json
 import os
 import sys
@@ -16,11 +17,15 @@ N = inst.nspins
 S = 200
 A, B = np.linspace(3.0, 1e-8, S), np.ones(S)
 for P in (64,):
-    for R in (512, 1024, 4096):
+    for R in (128, 256, 512, 1024, 4096):
         row = {"P": P, "R": R}
-        for wpt in ("1", "2", "4", "8", "16", None):
+        for wpt in ("w4:1", "w4:16", "w1:16", "w1:64", None):
             os.environ.pop("MCS_WPT", None)
-            if wpt:
+            os.environ.pop("MCS_WPT_WARPS", None)
+            if wpt and wpt.startswith("w"):
+                os.environ["MCS_WPT_WARPS"] = wpt[1:].split(":")[0]
+                os.environ["MCS_WPT"] = wpt.split(":")[1]
+            elif wpt:
                 os.environ["MCS_WPT"] = wpt
             st = mcs.State(inst, mcs._lib.KIND_PIQMC, R, P)
             st.init_random(1)

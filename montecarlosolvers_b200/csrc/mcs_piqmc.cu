@@ -67,7 +67,8 @@ struct PiqmcPass {
     // sweep call from W and unpacked at its end: one 64-bit load per row instead of pk guarded loads and shifts
     uint64_t *Wp;
     long long gp;
-    int wpt;          // plain mode: words per thread (1, 2 or 4) ...
+    int chunks;       // launches of this colour pass in flight together (replica chunks on several streams)
+    int wpt;          // plain mode: words per thread ...
     long long wstep;  // ... replica r0 + k wstep is the thread's k-th word (wstep = replicas of the launch / wpt)
 };
 
@@ -1226,22 +1227,41 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
         return;
     }
     a.half = 0;
-    // words per thread (P = 64, four-warp CTAs): the per-site set-up is shared by up to 16 replicas of a thread.  Measured
-    // at cfg3 (profiles/r02_wpt.log): 1.94e12 (one word) -> 1.95e12 (two) -> 2.00e12 (four) -> 2.02e12 (eight) ->
-    // 2.035e12 attempts/s (sixteen: one CTA per site and chunk); P = 40 does not gain and keeps one.
+    // Words per thread (P = 64): a quarter of a one-word thread's instructions is set-up that depends on the site only, so
+    // a thread takes several replicas one after the other.  Measured at cfg3 (profiles/r02_wpt.log), four-warp CTAs:
+    // 1.94e12 (one word) -> 2.00e12 (four) -> 2.035e12 attempts/s (sixteen); ONE-warp CTAs (no CTA barrier, the warp
+    // builds its own table) with up to 64 words per thread: 2.08e12 at 4096 anneals, 2.09e12 at 1024, 2.06e12 at 512,
+    // 2.01e12 at 256 -- as long as the launches in flight keep a warp per site and chunk (at 128 anneals the one-word
+    // CTAs win: 1.68e12 against 1.55e12).  P < 64 (per-pair branches, fewer attempts per word) does not gain.
     a.wpt = 1;
-    if (warps == 4 && a.P == 64) {
-        int want = 16;
+    int cw = warps; // warps per CTA
+    if (a.P == 64) {
+        int want = 64, force_w = 0;
         if (const char *e = getenv("MCS_WPT")) want = atoi(e);
-        for (int cand = 16; cand >= 2; cand /= 2)
-            if (cand <= want && (a.G / 4) % cand == 0) {
-                a.wpt = cand;
-                break;
-            }
+        if (const char *e = getenv("MCS_WPT_WARPS")) force_w = atoi(e);
+        const bool narrow = force_w ? force_w == 1 : (long long)a.G * std::max(1, a.chunks) >= 8;
+        if (narrow) {
+            cw = 1;
+            for (int cand = 64; cand >= 2; cand /= 2)
+                if (cand <= want && a.G % cand == 0) {
+                    a.wpt = cand;
+                    break;
+                }
+        } else if (warps == 4) {
+            for (int cand = 16; cand >= 2; cand /= 2)
+                if (cand <= want && (a.G / 4) % cand == 0) {
+                    a.wpt = cand;
+                    break;
+                }
+        }
     }
     a.wstep = (long long)(a.G / a.wpt) * 32;
-    const dim3 grid((unsigned)(a.G / warps / a.wpt), ny, nz);
-    if (a.P == 64 && warps == 4 && a.wpt > 1)
+    const dim3 grid((unsigned)(a.G / cw / a.wpt), ny, nz);
+    if (a.P == 64 && cw == 1 && a.wpt > 1)
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, true, FLD, MODE_PLAIN, true>, grid, dim3(32), s, a);
+    else if (cw == 1)
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, MODE_PLAIN>, grid, dim3(32), s, a);
+    else if (a.P == 64 && warps == 4 && a.wpt > 1)
         mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD, MODE_PLAIN, true>, grid, dim3(128), s, a);
     else if (a.P == 64 && warps == 4)
         mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, true, FLD, MODE_PLAIN>, grid, dim3(128), s, a);
@@ -1354,6 +1374,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
     a.gp = 0;
     a.wpt = 1;
     a.wstep = 0;
+    a.chunks = 1;
     const int npl = std::max(1, inst->maxdeg + (inst->has_field ? 1 : 0));
     const int warps = (a.G % 4 == 0) ? 4 : (a.G % 2 == 0) ? 2 : 1;
     uint64_t sweep = sweep_offset;
@@ -1403,6 +1424,7 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
         nchunk = 2;
     if (const char *e = getenv("MCS_STREAMS"))
         if (can_chunk) nchunk = (int)std::max(1ll, std::min(std::min(4ll, packed_mode ? pk_gw / 4 : G0 / gran), atoll(e)));
+    a.chunks = nchunk;
     if (nchunk > 1 && !inst->ev_aux0) MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_aux0, cudaEventDisableTiming));
     for (int q = 0; q + 1 < nchunk; ++q) {
         if (!inst->s_aux[q]) {

@@ -843,30 +843,33 @@ def test_packed_words_resident_in_hbm_equal_the_gathering_kernel(mcs, P, R, roff
 
 @pytest.mark.parametrize("glob,fields", [(0, False), (1, False), (1, True)])
 def test_several_words_per_thread_do_not_change_any_decision(mcs, glob, fields, P=64):
-    """P = 64: a thread of the pass kernel takes 1, 2, 4 ... 16 replicas one after the other, sharing the site's set-up
-    (coefficients, neighbour indices, threshold table).  Counters belong to replicas, not to threads: bit-identical
-    states (with world-line moves and fields), also combined with two streams."""
+    """P = 64: a thread of the pass kernel takes up to 64 replicas one after the other, sharing the site's set-up
+    (coefficients, neighbour indices, threshold table), in one-warp CTAs (default) or four-warp CTAs.  Counters belong
+    to replicas, not to threads: bit-identical states (with world-line moves and fields), also combined with one and two
+    streams and a replica count that is not a multiple of 128."""
     nbs = inst.torus(8, seed=5, fields=fields)[1]
     I = mcs.Instance(nbs)
-    R, S = 1024, 10
+    S = 10
     A, B = np.linspace(2.5, 0.05, S), np.linspace(0.3, 1.0, S)
-    out = []
-    for wpt, streams in (("1", "1"), ("2", "1"), ("4", "1"), ("8", "1"), ("4", "2"), (None, None)):
-        for k, v in (("MCS_WPT", wpt), ("MCS_STREAMS", streams)):
-            os.environ.pop(k, None)
-            if v:
-                os.environ[k] = v
-        try:
-            st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
-            st.init_random(9)
-            st.piqmc_sweeps(A, B, 2, 0.05, global_moves=bool(glob), seed=77)
-            out.append(st.download_spins())
-            st.close()
-        finally:
-            os.environ.pop("MCS_WPT", None)
-            os.environ.pop("MCS_STREAMS", None)
-    for o in out[1:]:
-        assert np.array_equal(out[0], o)
+    for R in (1024, 352):
+        out = []
+        for wpt, warps, streams in (("1", "4", "1"), ("2", "4", "1"), ("16", "4", "2"), ("1", "1", "1"), ("4", "1", "1"),
+                                    ("64", "1", "2"), (None, None, None)):
+            for k, v in (("MCS_WPT", wpt), ("MCS_WPT_WARPS", warps), ("MCS_STREAMS", streams)):
+                os.environ.pop(k, None)
+                if v:
+                    os.environ[k] = v
+            try:
+                st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
+                st.init_random(9)
+                st.piqmc_sweeps(A, B, 2, 0.05, global_moves=bool(glob), seed=77)
+                out.append(st.download_spins())
+                st.close()
+            finally:
+                for k in ("MCS_WPT", "MCS_WPT_WARPS", "MCS_STREAMS"):
+                    os.environ.pop(k, None)
+        for o in out[1:]:
+            assert np.array_equal(out[0], o), R
 
 
 def test_zero_temperature_never_accepts_an_uphill_move(mcs):
