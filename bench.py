@@ -143,15 +143,16 @@ def roofline(achieved, peak, have_peaks, R, ms_per_launch, bytes_per_launch, n_p
             continue
     attempts_per_launch = bytes_per_launch / 0.25
     out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-           "traffic": args.traffic, "kernel": "piqmc_lut_pass_kernel<4,4,true,0,MODE_PLAIN>", "ms_per_launch": ms_per_launch,
+           "traffic": args.traffic, "kernel": "piqmc_lut_pass_kernel<4,1,true,0,MODE_PLAIN,MULTI> (one-warp CTAs, up to 64 world lines per thread)", "ms_per_launch": ms_per_launch,
            "algorithmic_bytes_per_launch": bytes_per_launch,
            "algorithmic_bytes_per_attempt": 0.25,
            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if have_peaks else "fallback 6650 GB/s",
            "note": "the sweep is instruction bound (Philox multiplies and the per-attempt threshold compare on the "
                    "ALU / FMA pipes), not HBM bound: see binding_unit, profiles/ and DESIGN.md section 4"}
     if prof:
-        # the profiled launch: grid_size CTAs of 128 threads, one 64-slice word per thread
-        prof_attempts = float(prof.get("grid_size", 102400)) * 128 * 64
+        # the profiled launch (profiles/summarize_ncu.py records what it covered; older captures: grid_size CTAs of
+        # 128 threads, one 64-slice word per thread)
+        prof_attempts = float(prof.get("attempts_in_launch", float(prof.get("grid_size", 102400)) * 128 * 64))
         scale = attempts_per_launch / prof_attempts
         if args.traffic is None:
             out["traffic"] = (prof["dram_bytes_read"] + prof["dram_bytes_write"]) * scale

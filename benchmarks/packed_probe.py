@@ -20,7 +20,8 @@ A, B = np.linspace(3.0, 1e-8, tau), np.ones(tau)
 for P, glob in ((20, True), (5, True), (21, False), (7, False)):
     for R in (4096, 512):
         row = {"P": P, "R": R, "global_moves": glob}
-        for name, env in (("two_per_word", {"MCS_NO_PACK": "1"}), ("gather", {"MCS_PACK_GATHER": "1"}), ("resident", {})):
+        for name, env in (("two_per_word", {"MCS_NO_PACK": "1"}), ("gather", {"MCS_PACK_GATHER": "1"}),
+                          ("resident_one_word_threads", {"MCS_PACK_ONE_WORD": "1"}), ("resident", {})):
             os.environ.update(env)
             st = mcs.State(inst, mcs._lib.KIND_PIQMC, R, P)
             st.init_random(1)

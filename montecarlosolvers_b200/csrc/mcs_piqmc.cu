@@ -348,8 +348,11 @@ __device__ __forceinline__ uint64_t phase(const uint64_t (&pl)[NPL], uint64_t w,
 //       indices (see PiqmcPass::pk) and the Philox counter is the group's index, so results do not depend on how
 //       replicas are sharded over GPUs, windows or calls; members that lie outside this window are neither read
 //       nor written.
+#ifndef MCS_LUT_MULTI_MINBLOCKS
+#define MCS_LUT_MULTI_MINBLOCKS 8
+#endif
 template <int NPL, int WARPS, bool FULL, int FLD, int MODE, bool MULTI = false>
-__global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
+__global__ void __launch_bounds__(WARPS * 32, (MULTI && WARPS == 1) ? MCS_LUT_MULTI_MINBLOCKS : MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_pass_kernel(const __grid_constant__ PiqmcPass a)
 {
     static_assert(!(FULL && MODE != MODE_PLAIN), "fused / packed modes are for P <= 32");
     constexpr bool FUSE = MODE == MODE_FUSE, PACK = MODE >= MODE_PACK, NATIVE = MODE == MODE_PACKN;
@@ -392,13 +395,12 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     // row offsets as one IMAD.WIDE.U32 each (site indices and Rpad are below 2^32)
     const uint32_t rpad = (uint32_t)a.Rpad;
     // PACK: member m of this thread is local replica first + 32 m (global index (group0 + warp) 32 pk + 32 m + lane)
-    const long long gwarp = (PACK ? a.gw_lo : 0) + (long long)blockIdx.x * WARPS + warp;
-    const bool gw_ok = !PACK || gwarp < a.gw_lo + a.gw_n; // the last CTA of a packed launch may have spare warps
-    const long long first0 = PACK ? (a.group0 + gwarp) * 32 * pk + lane - (long long)a.replica_offset : r0;
-    uint64_t *Wn = NATIVE ? a.Wp + (gw_ok ? gwarp * 32 + lane : 0) : nullptr;
+    const long long gwarp0 = (PACK ? a.gw_lo : 0) + (long long)blockIdx.x * WARPS + warp;
+    const bool gw_ok0 = !PACK || gwarp0 < a.gw_lo + a.gw_n; // the last CTA of a packed launch may have spare warps
+    const long long first0 = PACK ? (a.group0 + gwarp0) * 32 * pk + lane - (long long)a.replica_offset : r0;
     const uint32_t gp = NATIVE ? (uint32_t)a.gp : 0u;
     uint32_t present = 0; // PACK: members that exist in this window
-    if (PACK && !NATIVE && gw_ok)
+    if (PACK && !NATIVE && gw_ok0)
         for (int m = 0; m < pk; ++m)
             if (first0 + 32 * m >= 0 && first0 + 32 * m < a.nvalid) present |= 1u << m;
     mcs_pdl_wait(); // everything above depends on the instance and the schedule only
@@ -406,9 +408,14 @@ __global__ void __launch_bounds__(WARPS * 32, MCS_LUT_MINBLOCKS(NPL)) piqmc_lut_
     // coefficients, neighbour indices and threshold table -- a quarter of the instructions of a one-word thread --
     // are set up once for all of them.
     // (MULTI is a template parameter: the one-word kernel keeps its straight-line code)
-    const int wpt = (MODE == MODE_PLAIN && MULTI) ? a.wpt : 1;
+    // Resident packed words (MODE_PACKN) likewise: the thread's k-th word belongs to group warp gwarp0 + k wstep.
+    const int wpt = ((MODE == MODE_PLAIN || NATIVE) && MULTI) ? a.wpt : 1;
     for (int kw = 0; kw < wpt; ++kw) {
     const long long r = r0 + ((MODE == MODE_PLAIN && MULTI) ? kw * a.wstep : 0), first = PACK ? first0 : r;
+    const long long gwarp = gwarp0 + ((NATIVE && MULTI) ? kw * a.wstep : 0);
+    const bool gw_ok = (NATIVE && MULTI) ? gwarp < a.gw_lo + a.gw_n : gw_ok0;
+    if (NATIVE && MULTI && !gw_ok) break; // the last slab may be short (warp-uniform; never the first word)
+    uint64_t *Wn = NATIVE ? a.Wp + (gw_ok ? gwarp * 32 + lane : 0) : nullptr;
     const uint64_t *Wr = a.W + first, *Wr2 = Wr + (FUSE ? a.half : 0);
     auto load = [&](int row) -> uint64_t {
         if (NATIVE) return gw_ok ? Wn[(uint64_t)(uint32_t)row * gp] : 0ull;
@@ -1197,7 +1204,17 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
         a.half = 0;
         const dim3 grid((unsigned)((gw + wf - 1) / wf), ny, nz);
         constexpr int MP = LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN, MN = LutGeom<NPL>::FW == 8 ? MODE_PACKN : MODE_PLAIN;
-        if (a.Wp) {
+        if (a.Wp && gw * std::max(1, a.chunks) >= 8 && !getenv("MCS_PACK_ONE_WORD")) {
+            // one-warp CTAs, several packed words per thread (see the plain mode below): the thread's k-th word is in
+            // group warp gw_lo + blockIdx.x + k wstep
+            int want = 64;
+            if (const char *e = getenv("MCS_WPT")) want = atoi(e);
+            a.wpt = 1;
+            while (2 * a.wpt <= want && gw / (2 * a.wpt) >= 1) a.wpt *= 2;
+            a.wstep = (gw + a.wpt - 1) / a.wpt; // group warps per slab; the last slab may be short (guarded)
+            const dim3 g1((unsigned)a.wstep, ny, nz);
+            mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, MN, true>, g1, dim3(32), s, a);
+        } else if (a.Wp) {
             if (wf == 4)
                 mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 4, false, FLD, MN>, grid, dim3(128), s, a);
             else if (wf == 2)
@@ -1235,7 +1252,7 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
     // CTAs win: 1.68e12 against 1.55e12).  P < 64 (per-pair branches, fewer attempts per word) does not gain.
     a.wpt = 1;
     int cw = warps; // warps per CTA
-    if (a.P == 64) {
+    {
         int want = 64, force_w = 0;
         if (const char *e = getenv("MCS_WPT")) want = atoi(e);
         if (const char *e = getenv("MCS_WPT_WARPS")) force_w = atoi(e);
@@ -1247,7 +1264,7 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
                     a.wpt = cand;
                     break;
                 }
-        } else if (warps == 4) {
+        } else if (warps == 4 && a.P == 64) {
             for (int cand = 16; cand >= 2; cand /= 2)
                 if (cand <= want && (a.G / 4) % cand == 0) {
                     a.wpt = cand;
@@ -1259,6 +1276,8 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
     const dim3 grid((unsigned)(a.G / cw / a.wpt), ny, nz);
     if (a.P == 64 && cw == 1 && a.wpt > 1)
         mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, true, FLD, MODE_PLAIN, true>, grid, dim3(32), s, a);
+    else if (cw == 1 && a.wpt > 1)
+        mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, MODE_PLAIN, true>, grid, dim3(32), s, a);
     else if (cw == 1)
         mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, false, FLD, MODE_PLAIN>, grid, dim3(32), s, a);
     else if (a.P == 64 && warps == 4 && a.wpt > 1)

@@ -81,6 +81,10 @@ def as_json(path, out_path):
         "fma_pipe_cycles_active_pct": val("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
         "lsu_pipe_inst_pct_of_peak": val("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
         "registers_per_thread": int(val("launch__registers_per_thread")),
+        "block_size": int(val("launch__block_size")),
+        # profiles/capture.sh profiles bench.py's cfg3 workload (4096 anneals on one GPU): a launch of the pass kernel
+        # covers one 2048-replica chunk of one colour class = 3200 sites x 2048 world lines x 64 slices
+        "attempts_in_launch": 3200 * 2048 * 64,
     }
     json.dump(d, open(out_path, "w"), indent=1)
     return d

@@ -819,13 +819,15 @@ def test_packed_words_resident_in_hbm_equal_the_gathering_kernel(mcs, P, R, roff
     """Even P <= 20: the packed working words (floor(64 / P) world lines each, groups on GLOBAL replica indices) are
     built once per sweep call and the passes run on them (MODE_PACKN: one load per table row); MCS_PACK_GATHER=1
     gathers the members in every pass as before.  Same words, same counters, same decisions: bit-identical states,
-    with ragged counts, replica offsets inside a group, split schedules, and on one or two streams."""
+    with ragged counts, replica offsets inside a group, split schedules, on one or several streams, with one or
+    several packed words per thread."""
     nbs = inst.torus(8, seed=5)[1]
     I = mcs.Instance(nbs)
     S = 10
     A, B = np.linspace(2.5, 0.05, S), np.linspace(0.3, 1.0, S)
     out = []
-    for env in ({"MCS_PACK_GATHER": "1"}, {}, {"MCS_STREAMS": "1"}, {"MCS_STREAMS": "3"}):
+    for env in ({"MCS_PACK_GATHER": "1"}, {}, {"MCS_STREAMS": "1"}, {"MCS_STREAMS": "3"}, {"MCS_PACK_ONE_WORD": "1"},
+                {"MCS_WPT": "2"}):
         os.environ.update(env)
         try:
             st = mcs.State(I, mcs._lib.KIND_PIQMC, R, P)
