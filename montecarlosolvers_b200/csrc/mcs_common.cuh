@@ -111,6 +111,8 @@ struct mcs_state {
     size_t stage_bytes = 0;
     void *d_S16 = nullptr;    // dense sweeps: spins as bf16 +-1, [Cpad][Npad], column = (replica, slice)
     long long S16_cols = 0;
+    uint64_t *d_Wpk = nullptr; // PIQMC packed mode: the packed working words of a sweep call, [N][32 x group warps] (kept)
+    size_t Wpk_bytes = 0;
     double *d_eout = nullptr;    // per-replica energies of mcs_state_energies (kept: no cudaMalloc per call)
     size_t eout_bytes = 0;
     void *d_best = nullptr;      // best-slice results: ebest f64[R] | kbest i32[R] | conf i8[R][N]
@@ -582,8 +584,8 @@ __device__ __forceinline__ uint32_t mcs_accept_threshold(float dE, float nl2e_ov
 // use (mcs_piqmc.cu).  Returns false when the instance does not qualify.
 bool mcs_energy_tables(mcs_instance *inst);
 
-// PIQMC packed mode: floor(64 / P) (at most 6) world lines per working word -- even P up to 20, odd P from 3 to 21
-inline bool mcs_piqmc_packs(int P) { return (P & 1) ? (P >= 3 && P <= 21) : (P >= 2 && P <= 20); }
+// PIQMC packed mode: floor(64 / P) (at most 6) world lines per working word -- every P from 2 to 32
+inline bool mcs_piqmc_packs(int P) { return P >= 2 && P <= 32; }
 
 // kernels launchers implemented in the other translation units
 int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int64_t S, int mcsteps, float temp,

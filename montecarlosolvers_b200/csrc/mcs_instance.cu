@@ -327,6 +327,7 @@ static void state_release_device(mcs_state *st)
     cudaFree(st->d_cosz);
     cudaFree(st->d_stage);
     cudaFree(st->d_S16);
+    cudaFree(st->d_Wpk);
     cudaFree(st->d_eout);
     st->d_eout = nullptr;
     st->eout_bytes = 0;
@@ -334,6 +335,8 @@ static void state_release_device(mcs_state *st)
     st->d_best = nullptr;
     st->best_bytes = 0;
     st->d_S16 = nullptr;
+    st->d_Wpk = nullptr;
+    st->Wpk_bytes = 0;
     st->S16_cols = 0;
     cudaFree(st->d_labels);
     st->d_labels = nullptr;

@@ -1423,7 +1423,15 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
         pk_gw = ((long long)a.replica_offset + a.nvalid - 1) / blk - pk_group0 + 1;
         if (!getenv("MCS_PACK_GATHER") && (long long)S * mcsteps * inst->ncolors >= 4) {
             const long long n = inst->N * pk_gw * 32;
-            MCS_CUDA(cudaMallocAsync((void **)&d_Wp, (size_t)n * sizeof(uint64_t), inst->stream));
+            if (st->Wpk_bytes < (size_t)n * sizeof(uint64_t)) { // kept with the batch: no allocation per call
+                MCS_CUDA(cudaStreamSynchronize(inst->stream));
+                if (st->d_Wpk) MCS_CUDA(cudaFree(st->d_Wpk));
+                st->d_Wpk = nullptr;
+                st->Wpk_bytes = 0;
+                MCS_CUDA(cudaMalloc((void **)&st->d_Wpk, (size_t)n * sizeof(uint64_t)));
+                st->Wpk_bytes = (size_t)n * sizeof(uint64_t);
+            }
+            d_Wp = st->d_Wpk;
             piqmc_words_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(
                 a.W, d_Wp, inst->N, st->Rpad, pk_gw, pk_group0, (long long)a.replica_offset, a.nvalid, pk_n, P, 0);
             inst->launches++;
@@ -1518,7 +1526,6 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
         piqmc_words_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, inst->stream>>>(
             W0, d_Wp, inst->N, st->Rpad, pk_gw, pk_group0, (long long)roff0, valid0, pk_n, P, 1);
         inst->launches++;
-        MCS_CUDA(cudaFreeAsync(d_Wp, inst->stream));
     }
     if (d_lut4) MCS_CUDA(cudaFreeAsync(d_lut4, inst->stream));
     MCS_CUDA(mcs_take_launch_error());

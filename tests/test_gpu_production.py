@@ -445,7 +445,7 @@ def test_two_replicas_per_thread_do_not_change_any_decision(mcs, P):
         os.environ.pop("MCS_NO_PACK", None)
 
 
-@pytest.mark.parametrize("P", [2, 5, 6, 10, 20, 21])
+@pytest.mark.parametrize("P", [2, 5, 6, 10, 20, 21, 27, 32])
 def test_packed_groups_are_defined_on_global_replica_indices(mcs, P):
     """Even P <= 20 and odd P from 3 to 21: a thread owns floor(64 / P) (at most 6) replicas as consecutive P-bit segments of its working
     word (mcs_piqmc.cu, MODE_PACK); groups and Philox counters are functions of the GLOBAL replica index, so a shard
@@ -814,7 +814,7 @@ def test_piqmc_two_stream_chunks_equal_one_stream(mcs, P, glob):
 
 
 @pytest.mark.parametrize("P,R,roff,glob", [(20, 4096, 0, 1), (20, 333, 77, 1), (10, 1000, 64, 0), (16, 130, 5, 1), (2, 70, 0, 0),
-                                           (5, 900, 11, 1), (21, 200, 0, 0), (3, 70, 0, 1)])
+                                           (5, 900, 11, 1), (21, 200, 0, 0), (3, 70, 0, 1), (32, 700, 33, 1), (25, 1100, 0, 0)])
 def test_packed_words_resident_in_hbm_equal_the_gathering_kernel(mcs, P, R, roff, glob):
     """Even P <= 20: the packed working words (floor(64 / P) world lines each, groups on GLOBAL replica indices) are
     built once per sweep call and the passes run on them (MODE_PACKN: one load per table row); MCS_PACK_GATHER=1
