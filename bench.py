@@ -423,7 +423,7 @@ def run_configs(mcs, inst, peaks, which):
         out["cfg1"] = {"workload": "examples/santoro80.py protocol: 80x80 PIQMC P=20 with world-line moves "
                                    "(QuantumAnnealGlobal), tau=354, %d anneals" % R, "value": v, "unit": UNIT,
                        "ms": ms, "gpu_launches": (inst.launches - l0) // 3,
-                       "roofline": hbm_roofline(v, 0.25, peaks, "piqmc_lut_pass_kernel<4,4,false,0,MODE_PACKN> (three "
+                       "roofline": hbm_roofline(v, 0.25, peaks, "piqmc_lut_pass_kernel<4,1,false,0,MODE_PACKN,MULTI> (three "
                                                 "20-slice world lines per working word, packed words resident in HBM)", ms / (2 * tau))}
         st.close()
     if "cfg2" in which:  # sa.Anneal, 1024 restarts
