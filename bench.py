@@ -552,6 +552,13 @@ def run_configs(mcs, inst, peaks, which):
                           "note": "J is split hi + lo into two bf16 operands (16 mantissa bits): the tensor pipe "
                                   "executes twice the algorithmic flops; the sweep is bound by the 2048 sequential "
                                   "site decisions, not by the GEMM"}}
+        # the same sweeps with 256 replicas: 128 column groups of 64 = 128 of the 148 SMs busy instead of 64
+        st2 = mcs.State(di, K.KIND_PIQMC, 2 * R5, P5)
+        st2.init_random(1)
+        ms2 = timed(di, lambda: st2.piqmc_sweeps(A5, B5, 1, 1.0 / P5, global_moves=True, seed=2), reps=2)
+        o["replicas_256"] = {"value": S5 * n * 2 * cols / (ms2 * 1e-3), "unit": UNIT, "ms_per_sweep": ms2 / S5,
+                             "tensor_frac": 2 * flops / (ms2 * 1e-3) / 1e12 / tpeak}
+        st2.close()
         try:
             st.cluster_moves(1.0, 1.0, 1.0 / P5, nmoves=1, seed=3)
             ms_sw = timed(di, lambda: st.cluster_moves(1.0, 1.0, 1.0 / P5, nmoves=2, seed=3, sweep_offset=1), reps=1) / 2
