@@ -37,6 +37,9 @@ struct SaPass {
     uint32_t sweep_lo, sweep_hi;
     uint32_t word_offset; // replica_offset / 32
     uint32_t tie_thr;     // lazily refined uniforms (mcs_common.cuh)
+    long long Gs;         // words per row of V (= G unless the launch covers a chunk of the words)
+    int wpt;              // MULTI: words per thread ...
+    uint32_t wstep;       // ... the thread's k-th word is g0 + k wstep
 };
 
 // Index word of group Q (restarts 8 i + 7 - Q of the word, i = 0..3): plane p's bit of restart 8 i + 7 - Q goes
@@ -59,7 +62,9 @@ __device__ __forceinline__ uint32_t sa_gather_index(const uint32_t (&pl)[NPL], c
 // (complemented thresholds, see mcs_common.cuh) sits at a compile-time shared address and, for up to 6 planes,
 // the pattern index is kept pre-multiplied by 4 (= the LDS byte offset).  Groups 2q and 2q+1 share one Philox
 // call (lazily refined uniforms).  FLD: the instance has (1) / has no (0) field plane.
-template <int NPL, int WARPS, int FLD>
+// MULTI: a thread takes a.wpt words one after the other and shares the site's set-up (as the PIQMC pass kernel does:
+// one-warp CTAs, no register cap).
+template <int NPL, int WARPS, int FLD, bool MULTI = false>
 __global__ void __launch_bounds__(WARPS * 32, 8) sa_lut_pass_kernel(const __grid_constant__ SaPass a)
 {
     constexpr int ENT = 1 << NPL, NQ = NPL - FLD;
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sa_lut_pass_kernel(const __grid
     const unsigned si = blockIdx.y + 65535u * blockIdx.z;
     if (si >= (unsigned)a.nsites) return; // only when the colour class has more than 65535 sites (CTA-uniform)
     const int site = __ldg(&a.sites[si]);
-    const uint32_t g = ((uint32_t)blockIdx.x * WARPS + warp) * 32 + lane;
+    const uint32_t g0 = ((uint32_t)blockIdx.x * WARPS + warp) * 32 + lane;
 
     float c[NPL];
     int nb[NPL];
@@ -92,19 +97,24 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sa_lut_pass_kernel(const __grid
         s_lut[e] = ~mcs_accept_threshold(dE, a.nl2e_over_t);
     }
     // the state loads are issued BEFORE the barrier that publishes the table: their latency hides behind it
-    const uint32_t G32 = (uint32_t)a.G;
+    const uint32_t G32 = (uint32_t)a.G, Gs32 = (uint32_t)a.Gs;
+    mcs_pdl_wait(); // everything above depends on the instance and the schedule only
+    const int wpt = MULTI ? a.wpt : 1;
+    for (int kw = 0; kw < wpt; ++kw) {
+    const uint32_t g = g0 + (MULTI ? (uint32_t)kw * a.wstep : 0u);
     const bool live = g < G32;
     uint32_t *Vg = a.V + (live ? g : 0u);
-    mcs_pdl_wait(); // everything above depends on the instance and the schedule only
-    const uint32_t v = Vg[(uint64_t)(uint32_t)site * G32];
+    const uint32_t v = Vg[(uint64_t)(uint32_t)site * Gs32];
     uint32_t pl[NPL];
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) pl[j] = j < NQ ? v ^ Vg[(uint64_t)(uint32_t)nb[j] * G32] : v;
-    if (WARPS == 1)
-        __syncwarp();
-    else
-        __syncthreads();
-    if (!live) return;
+    for (int j = 0; j < NPL; ++j) pl[j] = j < NQ ? v ^ Vg[(uint64_t)(uint32_t)nb[j] * Gs32] : v;
+    if (kw == 0) {
+        if (WARPS == 1)
+            __syncwarp();
+        else
+            __syncthreads();
+    }
+    if (!live) continue;
     const uint32_t c0 = a.word_offset + g, c1 = (uint32_t)site, c2 = a.sweep_lo, c3hi = a.sweep_hi << 8;
     uint2 *bounce = s_bounce + threadIdx.x;
     uint32_t rej = 0, flags = 0;
@@ -130,7 +140,8 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sa_lut_pass_kernel(const __grid
         MCS_SA_REFINE(0) MCS_SA_REFINE(1) MCS_SA_REFINE(2) MCS_SA_REFINE(3)
 #undef MCS_SA_REFINE
     }
-    Vg[(uint64_t)(uint32_t)site * G32] = v ^ ~rej;
+    Vg[(uint64_t)(uint32_t)site * Gs32] = v ^ ~rej;
+    } // words of this thread
 }
 
 // general-degree pass: energy differences accumulated over the ELL row, one register per restart
@@ -574,6 +585,11 @@ void launch_lut_wf(int warps, cudaStream_t s, const SaPass &a)
 {
     // a.chunks = warps of work per site; `warps` divides it, so a CTA never straddles two sites
     const unsigned ny = (unsigned)std::min(a.nsites, 65535), nz = (unsigned)((a.nsites + 65534) / 65535);
+    if (a.wpt > 1) { // one-warp CTAs, a.wpt words per thread (the last slab may be short: guarded by g < G)
+        const dim3 g1((unsigned)(a.wstep / 32), ny, nz);
+        mcs_launch_pdl(sa_lut_pass_kernel<NPL, 1, FLD, true>, g1, dim3(32), s, a);
+        return;
+    }
     const dim3 grid((unsigned)(a.chunks / warps), ny, nz);
     if (warps == 4)
         mcs_launch_pdl(sa_lut_pass_kernel<NPL, 4, FLD>, grid, dim3(128), s, a);
@@ -770,6 +786,9 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
     a.nq = inst->maxdeg;
     a.field = inst->has_field ? 1 : 0;
     a.G = st->G;
+    a.Gs = st->G;
+    a.wpt = 1;
+    a.wstep = 0;
     a.chunks = (int)((st->G + 31) / 32);
     a.keys = mcs_philox_expand(seed);
     a.pow2 = mcs_pow2_make();
@@ -788,6 +807,32 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
         MCS_TRY(sa_try_cluster(st, sched, S, mcsteps, sweep_offset, npl, a, &done));
         if (done) return MCS_OK;
     }
+    // Larger batches (more than 2048 restarts: three or more warps of words per site; at 2048 two streams of one-warp
+    // launches are limited by the host's launch rate: 0.97e12 against 1.22e12 attempts/s): as in the PIQMC launcher, the words are
+    // cut into two chunks whose colour passes alternate on two streams, and a one-warp CTA takes all the words of its
+    // site and chunk one after the other (up to 64 per thread), sharing the site's set-up.  Same counters (global
+    // word index): identical results (tests).  MCS_SA_WPT=1 keeps one word per thread on one stream.
+    const int nwarps = a.chunks; // 32-word warps per site
+    int nchunk = 1, multi = 0;
+    if (lut && nwarps >= 3 && !(getenv("MCS_SA_WPT") && atoi(getenv("MCS_SA_WPT")) <= 1)) {
+        multi = 1;
+        nchunk = getenv("MCS_ONE_STREAM") ? 1 : 2;
+        if (const char *e = getenv("MCS_STREAMS")) nchunk = std::max(1, std::min(std::min(4, nwarps / 2), atoi(e)));
+    }
+    if (nchunk > 1 && !inst->ev_aux0) MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_aux0, cudaEventDisableTiming));
+    for (int q = 0; q + 1 < nchunk; ++q) {
+        if (!inst->s_aux[q]) {
+            MCS_CUDA(cudaStreamCreateWithFlags(&inst->s_aux[q], cudaStreamNonBlocking));
+            MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_aux1[q], cudaEventDisableTiming));
+        }
+    }
+    if (nchunk > 1) {
+        MCS_CUDA(cudaEventRecord(inst->ev_aux0, inst->stream));
+        for (int q = 0; q + 1 < nchunk; ++q) MCS_CUDA(cudaStreamWaitEvent(inst->s_aux[q], inst->ev_aux0, 0));
+    }
+    uint32_t *const V0 = a.V;
+    const uint32_t woff0 = a.word_offset;
+    const long long Gall = a.G;
     for (int64_t t = 0; t < S; ++t) {
         a.ell_J = inst->ell_J_at(t); // sa.NoisyAnneal: nbs[itemp] (sa.pyx:363-365)
         a.h = inst->h_at(t);
@@ -800,6 +845,23 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
                 a.sites = inst->d_order + inst->color_start[c];
                 a.nsites = inst->color_start[c + 1] - inst->color_start[c];
                 if (a.nsites == 0) continue;
+                if (multi) {
+                    for (int q = 0; q < nchunk; ++q) {
+                        const int w0 = nwarps * q / nchunk, w1 = nwarps * (q + 1) / nchunk; // warps of this chunk
+                        a.V = V0 + 32ll * w0;
+                        a.word_offset = woff0 + 32u * (uint32_t)w0;
+                        a.G = std::min(Gall, 32ll * w1) - 32ll * w0;
+                        int want = 64;
+                        if (const char *e = getenv("MCS_SA_WPT")) want = atoi(e);
+                        a.wpt = 1;
+                        while (2 * a.wpt <= want && 2 * a.wpt <= w1 - w0) a.wpt *= 2;
+                        a.wstep = 32u * (uint32_t)((w1 - w0 + a.wpt - 1) / a.wpt);
+                        if (a.wpt == 1) a.wpt = 2; // (the MULTI kernel with a second, out-of-range word: skipped)
+                        launch_lut(npl, 1, q ? inst->s_aux[q - 1] : inst->stream, a);
+                        inst->launches++;
+                    }
+                    continue;
+                }
                 const long long items = (long long)a.nsites * a.chunks;
                 if (lut)
                     launch_lut(npl, warps, inst->stream, a);
@@ -809,6 +871,10 @@ int mcs_launch_sa_sweeps(mcs_state *st, const double *sched, int64_t S, int mcst
                 inst->launches++;
             }
         }
+    }
+    for (int q = 0; q + 1 < nchunk; ++q) {
+        MCS_CUDA(cudaEventRecord(inst->ev_aux1[q], inst->s_aux[q]));
+        MCS_CUDA(cudaStreamWaitEvent(inst->stream, inst->ev_aux1[q], 0));
     }
     MCS_CUDA(mcs_take_launch_error());
     MCS_CUDA(cudaGetLastError());

@@ -874,6 +874,32 @@ def test_several_words_per_thread_do_not_change_any_decision(mcs, glob, fields, 
             assert np.array_equal(out[0], o), R
 
 
+@pytest.mark.parametrize("R,fields", [(2100, True), (4096, False), (5000, True), (9999, False)])
+def test_sa_multi_word_threads_and_two_streams_do_not_change_any_decision(mcs, R, fields):
+    """SA batches of more than 2048 restarts: the words of a site are cut into two chunks on two streams and a one-warp
+    CTA takes all the words of its site and chunk one after the other.  Counters are global word indices: bit-identical
+    to one word per thread on one stream (ragged restart counts, fields, split schedules, 1 - 3 streams)."""
+    nbs = inst.torus(8, seed=5, fields=fields)[1]
+    I = mcs.Instance(nbs)
+    S = 12
+    sched = np.linspace(2.5, 0.0, S)
+    out = []
+    for env in ({"MCS_SA_WPT": "1"}, {}, {"MCS_STREAMS": "1"}, {"MCS_STREAMS": "3"}, {"MCS_SA_WPT": "2"}):
+        os.environ.update(env)
+        try:
+            st = mcs.State(I, mcs._lib.KIND_SA, R, 1)
+            st.init_random(9)
+            st.sa_sweeps(sched[:5], 2, seed=31)
+            st.sa_sweeps(sched[5:], 2, seed=31, sweep_offset=10)
+            out.append(st.download_spins())
+            st.close()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    for o in out[1:]:
+        assert np.array_equal(out[0], o)
+
+
 def test_zero_temperature_never_accepts_an_uphill_move(mcs):
     """T = 0 (the tail of the example's classical schedule, santoro80.py:260): the reference compares
     0 > rand()/RAND_MAX -- never.  A threshold of 0 means NEVER here too (mcs_accepts), not "once in 2^32": after a
