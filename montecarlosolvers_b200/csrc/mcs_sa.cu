@@ -11,6 +11,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <set>
+#include <tuple>
 #include <vector>
 
 #include "mcs_common.cuh"
@@ -364,8 +368,10 @@ __device__ __forceinline__ void sa_divmod(int x, int d, float rcp, int &q, int &
     if (r >= d) r -= d, ++q;
 }
 
-template <int NPL, int FLD>
-__global__ void __launch_bounds__(1024, 1) sa_cluster_kernel(const __grid_constant__ SaCluster a)
+// TMAX = 512: CTAs of at most 512 threads compile without the 64-register cap (measured: 2.8 against 3.2 us per pass
+// at 448 restarts, 3.4 against 3.6 at 640; with 800 - 1000 items per CTA the 1024-thread form is faster).
+template <int NPL, int FLD, int TMAX>
+__global__ void __launch_bounds__(TMAX, 1) sa_cluster_kernel(const __grid_constant__ SaCluster a)
 {
     constexpr int ENT = 1 << NPL, NQ = NPL - FLD;
     static_assert(NPL <= 6, "byte index fields hold pattern * 4");
@@ -563,20 +569,22 @@ __global__ void __launch_bounds__(1024, 1) sa_cluster_kernel(const __grid_consta
 }
 
 template <int NPL>
-const void *sa_cluster_fn(int field)
+const void *sa_cluster_fn(int field, int tmax)
 {
-    return field ? (const void *)sa_cluster_kernel<NPL, 1> : (const void *)sa_cluster_kernel<NPL, 0>;
+    if (tmax == 512)
+        return field ? (const void *)sa_cluster_kernel<NPL, 1, 512> : (const void *)sa_cluster_kernel<NPL, 0, 512>;
+    return field ? (const void *)sa_cluster_kernel<NPL, 1, 1024> : (const void *)sa_cluster_kernel<NPL, 0, 1024>;
 }
 
-const void *sa_cluster_fn(int npl, int field)
+const void *sa_cluster_fn(int npl, int field, int tmax)
 {
     switch (npl) {
-    case 1: return sa_cluster_fn<1>(field);
-    case 2: return sa_cluster_fn<2>(field);
-    case 3: return sa_cluster_fn<3>(field);
-    case 4: return sa_cluster_fn<4>(field);
-    case 5: return sa_cluster_fn<5>(field);
-    default: return sa_cluster_fn<6>(field);
+    case 1: return sa_cluster_fn<1>(field, tmax);
+    case 2: return sa_cluster_fn<2>(field, tmax);
+    case 3: return sa_cluster_fn<3>(field, tmax);
+    case 4: return sa_cluster_fn<4>(field, tmax);
+    case 5: return sa_cluster_fn<5>(field, tmax);
+    default: return sa_cluster_fn<6>(field, tmax);
     }
 }
 
@@ -652,18 +660,38 @@ int sa_try_cluster(mcs_state *st, const double *sched, int64_t S, int mcsteps, u
     const int nloc = c.loc_base[inst->ncolors];
     c.nloc_pad = (nloc + 31) / 32 * 32;
     if (max_per > 1024) return MCS_OK;
-    const void *fn = sa_cluster_fn(npl, a.field);
+    const void *fn = sa_cluster_fn(npl, a.field, 1024);
     const int ent = 1 << npl, nq = npl - a.field;
     auto smem_for = [&](int wc, int threads) {
         return (size_t)c.nloc_pad * 4u * (size_t)(ent + wc + nq + npl + 1) + (size_t)threads * 32u;
     };
     // 1024 threads whatever the item count: the threads without an item build the next pass's tables meanwhile
     auto threads_for = [&](int wc) { return wc >= 0 ? 1024 : 0; };
+    // function attributes and occupancy answers are asked for ONCE per (device, function, geometry): repeated
+    // cudaFuncSetAttribute / cudaOccupancyMaxActiveClusters calls made single small calls erratically slow (spikes
+    // of 100 ms in the drop-in sa.Anneal on one configuration)
+    static std::mutex plan_mutex;
+    static std::set<std::tuple<int, const void *, bool>> attr_done;
+    static std::map<std::tuple<int, const void *, int, int, size_t>, int> occupancy_cache;
+    static std::map<int, int> smem_cache;
+    std::lock_guard<std::mutex> plan_lock(plan_mutex);
     int smem_max = 0;
-    MCS_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, inst->device));
+    if (smem_cache.count(inst->device)) {
+        smem_max = smem_cache[inst->device];
+    } else {
+        MCS_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, inst->device));
+        smem_cache[inst->device] = smem_max;
+    }
     if (smem_for(1, threads_for(1)) > (size_t)smem_max) return MCS_OK;
-    MCS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    if (csize > 8) MCS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    auto prepare_fn = [&](const void *f) -> cudaError_t {
+        const auto akey = std::make_tuple(inst->device, f, csize > 8);
+        if (attr_done.count(akey)) return cudaSuccess;
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        if (e == cudaSuccess && csize > 8) e = cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e == cudaSuccess) attr_done.insert(akey);
+        return e;
+    };
+    MCS_CUDA(prepare_fn(fn));
     // how many clusters are resident together (one CTA per SM: 1024 threads x 64 registers)
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -684,9 +712,15 @@ int sa_try_cluster(mcs_state *st, const double *sched, int64_t S, int mcsteps, u
         cfg.blockDim = dim3((unsigned)threads_for(w));
         cfg.dynamicSmemBytes = smem_for(w, threads_for(w));
         int ncl = 0;
-        if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess) {
-            cudaGetLastError();
-            return MCS_OK;
+        const auto key = std::make_tuple(inst->device, fn, csize, threads_for(w), (size_t)cfg.dynamicSmemBytes);
+        if (occupancy_cache.count(key)) {
+            ncl = occupancy_cache[key];
+        } else {
+            if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                return MCS_OK;
+            }
+            occupancy_cache[key] = ncl;
         }
         resident = ncl;
         if ((st->G + w - 1) / w <= ncl) {
@@ -709,11 +743,17 @@ int sa_try_cluster(mcs_state *st, const double *sched, int64_t S, int mcsteps, u
         wc = wc_max;
     }
     const long long nclusters = (st->G + wc - 1) / wc;
-    const int threads = threads_for(wc);
+    int threads = threads_for(wc);
+    if ((long long)max_per * wc <= 512 && !getenv("MCS_CLUSTER_1024")) { // the form without the register cap
+        threads = 512;
+        fn = sa_cluster_fn(npl, a.field, 512);
+        MCS_CUDA(prepare_fn(fn));
+    }
     std::vector<float> nl((size_t)S);
     for (int64_t t = 0; t < S; ++t) nl[(size_t)t] = (float)(-1.4426950408889634 / sched[t]); // sa.pyx:98
-    float *d_nl = nullptr;
-    MCS_CUDA(cudaMallocAsync((void **)&d_nl, (size_t)S * sizeof(float) + 64, inst->stream));
+    // the schedule goes to the batch's staging buffer (stream ordered with the conversions that also use it)
+    MCS_TRY(mcs_state_reserve_stage(st, (size_t)S * sizeof(float) + 64));
+    float *d_nl = reinterpret_cast<float *>(st->d_stage);
     MCS_CUDA(cudaMemcpyAsync(d_nl, nl.data(), (size_t)S * sizeof(float), cudaMemcpyHostToDevice, inst->stream));
     c.V = st->d_V;
     c.ell_idx = inst->d_ell_idx;
@@ -753,7 +793,6 @@ int sa_try_cluster(mcs_state *st, const double *sched, int64_t S, int mcsteps, u
         fprintf(stderr, "[mcs cluster] per pass: %.0f cycles item, %.0f arrive + tables, %.0f CTA barrier, %.0f cluster wait\n",
                 (double)hp[0] / passes, (double)hp[1] / passes, (double)hp[2] / passes, (double)hp[3] / passes);
     }
-    MCS_CUDA(cudaFreeAsync(d_nl, inst->stream));
     MCS_CUDA(le);
     if (getenv("MCS_CLUSTER_VERBOSE"))
         fprintf(stderr, "[mcs cluster] %lld clusters (%d resident) of %d CTAs x %d threads, %d words per cluster, %zu B smem, %lld passes\n",

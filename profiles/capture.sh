@@ -20,4 +20,12 @@ ncu --set full --clock-control none --import-source on -k regex:refdyn_ising_ker
 python benchmarks/sa_cluster_ncu.py > gpurun_out/cap_sa_cluster_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:sa_cluster_kernel -s 2 -c 1 -f \
     -o gpurun_out/cap_sa_cluster python benchmarks/sa_cluster_ncu.py > gpurun_out/cap_ncu5.log 2>&1
+# summaries on the box (the .ncu-rep files together exceed what gpurun copies back); the reports themselves are dropped
+python profiles/summarize_ncu.py --round r02 > gpurun_out/cap_summary.log 2>&1
+mkdir -p gpurun_out/profiles_out
+cp profiles/r02_launch_list.csv profiles/r02_piqmc_lut_pass_ncu.json profiles/r02_piqmc_lut_pass_ncu_full.txt gpurun_out/profiles_out/
+python profiles/summarize_ncu.py gpurun_out/cap_dense.ncu-rep > gpurun_out/profiles_out/r02_dense_kernel_ncu.txt 2>/dev/null
+python profiles/summarize_ncu.py gpurun_out/cap_refdyn.ncu-rep > gpurun_out/profiles_out/r02_refdyn_kernel_ncu.txt 2>/dev/null
+python profiles/summarize_ncu.py gpurun_out/cap_sa_cluster.ncu-rep > gpurun_out/profiles_out/r02_sa_cluster_kernel_ncu.txt 2>/dev/null
+rm -f gpurun_out/cap_dense.ncu-rep gpurun_out/cap_refdyn.ncu-rep gpurun_out/cap_piqmc_pass.ncu-rep
 echo "capture done: $(ls gpurun_out | grep cap_ | tr '\n' ' ')"
