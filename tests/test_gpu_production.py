@@ -599,6 +599,47 @@ def test_santoro_piqmc_residual_energy_matches_reference(mcs, tau, glob):
     _tier_c_same_order(name, got, _colored_stats()["cells"][name])
 
 
+def test_full_size_fast_paths_equal_the_plain_kernels(mcs):
+    """At the BASELINE lattice (80x80) and batch sizes: every faster execution added in round 2 reproduces the state
+    arrays of the plain one-word, one-stream, one-launch-per-pass kernels bit for bit -- cfg3 (P = 64, 4096 anneals:
+    one-warp CTAs with 64 words per thread on two streams), cfg1 (P = 20 with world-line moves: resident packed words,
+    several per thread), SA at 896 restarts (cluster-resident schedule) and at 8192 (multi-word, two streams) -- and
+    the fixed-order energies of the final states agree between the table kernel and the chain kernel."""
+    _, nbs, _, _ = inst.santoro()
+    I = mcs.Instance(nbs)
+    S = 6
+    A, B = np.linspace(3.0, 0.5, S), np.ones(S)
+
+    def run(kind, R, P, envs, glob=False, energies=True):
+        outs = []
+        for env in envs:
+            os.environ.update(env)
+            try:
+                st = mcs.State(I, kind, R, P)
+                st.init_random(11)
+                if kind == mcs._lib.KIND_PIQMC:
+                    st.piqmc_sweeps(A, B, 1, 1.0 / P, global_moves=glob, seed=5)
+                else:
+                    st.sa_sweeps(np.linspace(3.0, 0.5, S), 1, seed=5)
+                e = st.energies() if energies else None
+                outs.append((st.download_spins(), e))
+                st.close()
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+        for o in outs[1:]:
+            assert np.array_equal(outs[0][0], o[0])
+            if energies:
+                assert np.array_equal(outs[0][1], o[1])
+
+    plain = {"MCS_STREAMS": "1", "MCS_WPT": "1", "MCS_WPT_WARPS": "4", "MCS_ENERGY_CHAIN": "1"}
+    run(mcs._lib.KIND_PIQMC, 4096, 64, (plain, {}), energies=False)
+    run(mcs._lib.KIND_PIQMC, 512, 64, (plain, {}))
+    run(mcs._lib.KIND_PIQMC, 1000, 20, ({"MCS_PACK_GATHER": "1", "MCS_STREAMS": "1", "MCS_ENERGY_CHAIN": "1"}, {}), glob=True)
+    run(mcs._lib.KIND_SA, 896, 1, ({"MCS_CLUSTER": "0", "MCS_ENERGY_CHAIN": "1"}, {}))
+    run(mcs._lib.KIND_SA, 8192, 1, ({"MCS_SA_WPT": "1", "MCS_ENERGY_CHAIN": "1"}, {}))
+
+
 def test_full_size_properties_cfg3_shape(mcs):
     """BASELINE cfg3 shape (80x80, P = 64) at reduced replica count: size-independent properties.
     Energies never increase under a T -> 0, Gamma -> 0 quench; world lines align across slices;
