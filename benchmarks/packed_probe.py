@@ -17,7 +17,7 @@ inst = mcs.Instance(nbs)
 N = inst.nspins
 tau = 354
 A, B = np.linspace(3.0, 1e-8, tau), np.ones(tau)
-for P, glob in ((32, False), (32, True), (24, False), (27, True)):
+for P, glob in ((20, True), (32, True), (10, True)):
     for R in (4096, 512):
         row = {"P": P, "R": R, "global_moves": glob}
         for name, env in (("two_per_word", {"MCS_NO_PACK": "1"}), ("gather", {"MCS_PACK_GATHER": "1"}),

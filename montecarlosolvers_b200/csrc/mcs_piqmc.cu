@@ -72,6 +72,13 @@ struct PiqmcPass {
     long long wstep;  // ... replica r0 + k wstep is the thread's k-th word (wstep = replicas of the launch / wpt)
 };
 
+// float(v) for |v| <= 64 without the conversion unit (I2F runs at a quarter of the FMA rate): 2^23 + 64 + v is an
+// integer below 2^24, so its float bit pattern is 0x4B000000 + 64 + v and one exact subtraction gives v
+__device__ __forceinline__ float small_int_to_float(int v)
+{
+    return __int_as_float(0x4B000040 + v) - 8388672.0f;
+}
+
 __device__ __forceinline__ uint64_t rotl_ring(uint64_t w, int P, uint64_t mask)
 {
     return ((w << 1) | (w >> (P - 1))) & mask; // bit k <- bit k-1 (ring of P slices)
@@ -510,7 +517,7 @@ __global__ void __launch_bounds__(WARPS * 32, (MULTI && WARPS == 1) ? MCS_LUT_MU
                 float dE = 0.0f;
 #pragma unroll
                 for (int j = 0; j < NPL; ++j)
-                    dE += c[j] * (float)(P - 2 * __popcll((j < NQ ? pl[j] ^ flips : w) & seg));
+                    dE += c[j] * small_int_to_float(P - 2 * __popcll((j < NQ ? pl[j] ^ flips : w) & seg));
                 const uint32_t u = (m & 3) == 0 ? rnd[0] : (m & 3) == 1 ? rnd[1] : (m & 3) == 2 ? rnd[2] : rnd[3];
                 if (mcs_accepts(u, mcs_accept_threshold(dE, a.nl2e_over_t))) w ^= seg;
             }
@@ -520,10 +527,10 @@ __global__ void __launch_bounds__(WARPS * 32, (MULTI && WARPS == 1) ? MCS_LUT_MU
             for (int j = 0; j < NPL; ++j) {
                 const uint64_t x = (j < NQ ? pl[j] ^ flips : w) & pmask;
                 if (FUSE) {
-                    dE[0] += c[j] * (float)(P - 2 * __popc((uint32_t)x));
-                    dE[1] += c[j] * (float)(P - 2 * __popc((uint32_t)(x >> 32)));
+                    dE[0] += c[j] * small_int_to_float(P - 2 * __popc((uint32_t)x));
+                    dE[1] += c[j] * small_int_to_float(P - 2 * __popc((uint32_t)(x >> 32)));
                 } else {
-                    dE[0] += c[j] * (float)(P - 2 * __popcll(x));
+                    dE[0] += c[j] * small_int_to_float(P - 2 * __popcll(x));
                 }
             }
 #pragma unroll
@@ -631,12 +638,12 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_direct_pass_kernel(const __
         if (mcs_accepts(rnd[0], mcs_accept_threshold(dE, a.nl2e_over_t))) w ^= 1ull << k;
     }
     if (a.global_moves) {
-        float dE = hc * (float)(P - 2 * __popcll(w & pmask));
+        float dE = hc * small_int_to_float(P - 2 * __popcll(w & pmask));
         for (int j = 0; j < a.dpad; ++j) {
             const float cj = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
             const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
             const uint64_t x = (w ^ a.W[(long long)nbj * a.Rpad + r]) & pmask;
-            dE += cj * (float)(P - 2 * __popcll(x));
+            dE += cj * small_int_to_float(P - 2 * __popcll(x));
         }
         uint32_t rnd[4];
         mcs_philox4x32_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
@@ -750,15 +757,15 @@ __global__ void __launch_bounds__(kWarps * 32) piqmc_bath_pass_kernel(const __gr
                     x = (w ^ a.W[(long long)nb[j] * a.Rpad + r]) & pmask;
                 else
                     x = (a.field && j == a.nq) ? w : 0ull;
-                dE += c[j] * (float)(P - 2 * __popcll(x));
+                dE += c[j] * small_int_to_float(P - 2 * __popcll(x));
             }
         } else {
-            dE = hc * (float)(P - 2 * __popcll(w & pmask));
+            dE = hc * small_int_to_float(P - 2 * __popcll(w & pmask));
             for (int j = 0; j < a.dpad; ++j) {
                 const float cj = a.bcoef * __ldg(&a.ell_J[(long long)site * a.dpad + j]);
                 const int nbj = __ldg(&a.ell_idx[(long long)site * a.dpad + j]);
                 if (nbj == site) continue; // padding
-                dE += cj * (float)(P - 2 * __popcll((w ^ a.W[(long long)nbj * a.Rpad + r]) & pmask));
+                dE += cj * small_int_to_float(P - 2 * __popcll((w ^ a.W[(long long)nbj * a.Rpad + r]) & pmask));
             }
         }
         mcs_philox4x32_rk(c0, c1, c2, c3hi | MCS_TAG_GLOBAL, a.keys, rnd);
@@ -1204,9 +1211,10 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
         a.half = 0;
         const dim3 grid((unsigned)((gw + wf - 1) / wf), ny, nz);
         constexpr int MP = LutGeom<NPL>::FW == 8 ? MODE_PACK : MODE_PLAIN, MN = LutGeom<NPL>::FW == 8 ? MODE_PACKN : MODE_PLAIN;
-        if (a.Wp && gw * std::max(1, a.chunks) >= 8 && !getenv("MCS_PACK_ONE_WORD")) {
+        if (a.Wp && gw * std::max(1, a.chunks) >= 8 && (a.pk <= 4 || getenv("MCS_WPT")) && !getenv("MCS_PACK_ONE_WORD")) {
             // one-warp CTAs, several packed words per thread (see the plain mode below): the thread's k-th word is in
-            // group warp gw_lo + blockIdx.x + k wstep
+            // group warp gw_lo + blockIdx.x + k wstep.  Up to four world lines per word (P >= 13); with five or six the
+            // per-member world-line work dominates and one word per thread measured faster (P = 10: 1.04 against 1.01e12)
             int want = 64;
             if (const char *e = getenv("MCS_WPT")) want = atoi(e);
             a.wpt = 1;
