@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(WARPS * 32, (MULTI && WARPS == 1) ? MCS_LUT_MU
     const int wpt = ((MODE == MODE_PLAIN || NATIVE) && MULTI) ? a.wpt : 1;
     for (int kw = 0; kw < wpt; ++kw) {
     const long long r = r0 + ((MODE == MODE_PLAIN && MULTI) ? kw * a.wstep : 0), first = PACK ? first0 : r;
+    if (MODE == MODE_PLAIN && MULTI && r >= (long long)a.G * 32) break; // a short last slab (warp-uniform; never kw = 0)
     const long long gwarp = gwarp0 + ((NATIVE && MULTI) ? kw * a.wstep : 0);
     const bool gw_ok = (NATIVE && MULTI) ? gwarp < a.gw_lo + a.gw_n : gw_ok0;
     if (NATIVE && MULTI && !gw_ok) break; // the last slab may be short (warp-uniform; never the first word)
@@ -1265,13 +1266,12 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
         if (const char *e = getenv("MCS_WPT")) want = atoi(e);
         if (const char *e = getenv("MCS_WPT_WARPS")) force_w = atoi(e);
         const bool narrow = force_w ? force_w == 1 : (long long)a.G * std::max(1, a.chunks) >= 8;
-        if (narrow) {
+        if (narrow) { // any group count: slabs of ceil(G / wpt) groups, the last one may be short (guarded in the kernel)
             cw = 1;
-            for (int cand = 64; cand >= 2; cand /= 2)
-                if (cand <= want && a.G % cand == 0) {
-                    a.wpt = cand;
-                    break;
-                }
+            a.wpt = std::max(1, std::min(std::min(want, 64), a.G));
+            const int slab = (a.G + a.wpt - 1) / a.wpt;
+            a.wpt = (a.G + slab - 1) / slab;
+            a.wstep = (long long)slab * 32;
         } else if (warps == 4 && a.P == 64) {
             for (int cand = 16; cand >= 2; cand /= 2)
                 if (cand <= want && (a.G / 4) % cand == 0) {
@@ -1280,8 +1280,8 @@ static void launch_lut_wf(int warps, const PiqmcPass &a0, cudaStream_t s)
                 }
         }
     }
-    a.wstep = (long long)(a.G / a.wpt) * 32;
-    const dim3 grid((unsigned)(a.G / cw / a.wpt), ny, nz);
+    if (cw != 1 || a.wpt == 1) a.wstep = (long long)(a.G / a.wpt) * 32;
+    const dim3 grid((unsigned)(cw == 1 && a.wpt > 1 ? a.wstep / 32 : a.G / cw / a.wpt), ny, nz);
     if (a.P == 64 && cw == 1 && a.wpt > 1)
         mcs_launch_pdl(piqmc_lut_pass_kernel<NPL, 1, true, FLD, MODE_PLAIN, true>, grid, dim3(32), s, a);
     else if (cw == 1 && a.wpt > 1)
@@ -1452,13 +1452,18 @@ int mcs_launch_piqmc_sweeps(mcs_state *st, const double *A, const double *B, int
         max_sites = std::max(max_sites, (long long)(inst->color_start[c + 1] - inst->color_start[c]));
     // measured (profiles/r02_piqmc_streams.log): 2.1 us per pass saved at every size from 512 anneals up (56.1 -> 54.0 us
     // at 512: the per-GPU rate of the 8-GPU run equals the 1-GPU rate), nothing more with three streams
-    const long long gran = P <= 32 ? 8 : 4; // groups of 32 replicas per block: four-warp CTAs, two replicas per thread
+    // groups of 32 replicas per block: any for the one-warp CTAs of the plain mode, four for four-warp CTAs, eight with
+    // two replicas per thread
+    const char *force_warps = getenv("MCS_WPT_WARPS");
+    const long long gran = P <= 32 ? 8 : ((force_warps && atoi(force_warps) == 4) ? 4 : 1);
     int nchunk = 1;
     const bool can_chunk = lut_path && (packed_mode ? (d_Wp != nullptr && pk_gw >= 8) : G0 % gran == 0);
-    if (can_chunk && (packed_mode || G0 >= 2 * gran) && G0 * max_sites <= (long long)1 << 20 && !getenv("MCS_ONE_STREAM"))
+    if (can_chunk && (packed_mode || G0 >= std::max(2 * gran, 8ll)) && G0 * max_sites <= (long long)1 << 20 &&
+        !getenv("MCS_ONE_STREAM"))
         nchunk = 2;
     if (const char *e = getenv("MCS_STREAMS"))
-        if (can_chunk) nchunk = (int)std::max(1ll, std::min(std::min(4ll, packed_mode ? pk_gw / 4 : G0 / gran), atoll(e)));
+        if (can_chunk)
+            nchunk = (int)std::max(1ll, std::min(std::min(4ll, packed_mode ? pk_gw / 4 : G0 / std::max(gran, 4ll)), atoll(e)));
     a.chunks = nchunk;
     if (nchunk > 1 && !inst->ev_aux0) MCS_CUDA(cudaEventCreateWithFlags(&inst->ev_aux0, cudaEventDisableTiming));
     for (int q = 0; q + 1 < nchunk; ++q) {

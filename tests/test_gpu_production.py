@@ -894,7 +894,7 @@ def test_several_words_per_thread_do_not_change_any_decision(mcs, glob, fields, 
     I = mcs.Instance(nbs)
     S = 10
     A, B = np.linspace(2.5, 0.05, S), np.linspace(0.3, 1.0, S)
-    for R in (1024, 352):
+    for R in (1024, 352, 483):
         out = []
         for wpt, warps, streams in (("1", "4", "1"), ("2", "4", "1"), ("16", "4", "2"), ("1", "1", "1"), ("4", "1", "1"),
                                     ("64", "1", "2"), (None, None, None)):
