@@ -17,7 +17,7 @@ N = inst.nspins
 S = 200
 A, B = np.linspace(3.0, 1e-8, S), np.ones(S)
 for P in (64,):
-    for R in (128, 256, 512, 1024, 4096):
+    for R in (512, 4096):
         row = {"P": P, "R": R}
         for wpt in ("w4:1", "w4:16", "w1:16", "w1:64", None):
             os.environ.pop("MCS_WPT", None)

@@ -416,10 +416,11 @@ __global__ void __launch_bounds__(WARPS * 32, (MULTI && WARPS == 1) ? MCS_LUT_MU
     // are set up once for all of them.
     // (MULTI is a template parameter: the one-word kernel keeps its straight-line code)
     // Resident packed words (MODE_PACKN) likewise: the thread's k-th word belongs to group warp gwarp0 + k wstep.
-    const int wpt = ((MODE == MODE_PLAIN || NATIVE) && MULTI) ? a.wpt : 1;
+    int wpt = ((MODE == MODE_PLAIN || NATIVE) && MULTI) ? a.wpt : 1;
+    // a short last slab: fewer words for its threads (warp-uniform; decided here, not by a test inside the loop)
+    if (MODE == MODE_PLAIN && MULTI) wpt = (int)min((long long)wpt, ((long long)a.G * 32 - r0 + a.wstep - 1) / a.wstep);
     for (int kw = 0; kw < wpt; ++kw) {
     const long long r = r0 + ((MODE == MODE_PLAIN && MULTI) ? kw * a.wstep : 0), first = PACK ? first0 : r;
-    if (MODE == MODE_PLAIN && MULTI && r >= (long long)a.G * 32) break; // a short last slab (warp-uniform; never kw = 0)
     const long long gwarp = gwarp0 + ((NATIVE && MULTI) ? kw * a.wstep : 0);
     const bool gw_ok = (NATIVE && MULTI) ? gwarp < a.gw_lo + a.gw_n : gw_ok0;
     if (NATIVE && MULTI && !gw_ok) break; // the last slab may be short (warp-uniform; never the first word)
