@@ -8,7 +8,7 @@ Workload (BASELINE.json configs[2]): 80x80 PIQMC, P = 64 Trot
 independent anneals in total (sharded contiguously over the N ranks: strong scaling, no data-path
 collective), A = linspace(3, 1e-8, 1000), B = 1, mcsteps = 1, T = 1/P, each anneal started from
 Philox(seed, global anneal index) spins identical across slices.  One "step" = one full anneal of
-the rank's shard = 1000 sweeps = 2000 kernel launches (one per checkerboard colour per sweep).
+the rank's shard = 1000 sweeps = 2000 colour passes, each two launches (one per replica chunk, on two streams).
 `value` counts local single-spin attempts only: R * 1000 * 64 * 6400 per step over all ranks.
 
 Timing: W warm-up steps, then K steps bracketed by barrier + device sync, CUDA events recorded on the
